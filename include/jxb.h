@@ -1,0 +1,208 @@
+/*
+ * jxb.h -- C ABI of libjxb.so, the B200-native execution engine for the JaxABM hot path.
+ *
+ * The reference (a11to1n3/JaxABM) is pure Python on JAX and has no FFI of its own
+ * (SURVEY.md F1); this header therefore *defines* the boundary.  Every entry point
+ * names the reference interface it stands in for (path:line under /root/reference).
+ * The host side (jaxabm_b200/*.py) keeps the reference's Python API verbatim and
+ * binds these symbols with ctypes (see INTEGRATION.md for the stub a maintainer of
+ * the reference would add).
+ *
+ * Conventions
+ *   - plain C types only; all pointers are HOST pointers owned by the caller and are
+ *     only touched for the duration of the call;
+ *   - every function returns JXB_OK (0) or a negative jxb_status; jxb_last_error()
+ *     returns a thread-local NUL-terminated message owned by the library;
+ *   - the engine owns all device memory, its CUDA stream, events and graphs;
+ *   - calls on one jxb_model must be serialised by the caller;
+ *   - there is no CPU fallback: any call that needs a device fails with
+ *     JXB_ERR_NO_DEVICE when none is present.  The jxb_prng_* helpers are host-only
+ *     scalar key algebra (the reference does the same work on the host through
+ *     jax.random) and work without a GPU.
+ */
+#ifndef JXB_H_
+#define JXB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JXB_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  JXB_OK = 0,
+  JXB_ERR_INVALID = -1,    /* bad argument / unknown rule or program          */
+  JXB_ERR_NO_DEVICE = -2,  /* no CUDA device (there is no CPU fallback)        */
+  JXB_ERR_CUDA = -3,       /* a CUDA runtime call failed; see jxb_last_error() */
+  JXB_ERR_STATE = -4,      /* call order violated (e.g. run before init)       */
+  JXB_ERR_NCCL = -5,
+  JXB_ERR_UNSUPPORTED = -6
+} jxb_status;
+
+/* JAX threefry stream layouts (flag jax_threefry_partitionable; default flipped in
+ * JAX 0.5.0).  The reference pins only jax>=0.4.1 (requirements.txt:8-9).          */
+enum { JXB_RNG_LEGACY = 0, JXB_RNG_PARTITIONABLE = 1 };
+
+/* Registered agent rules: one hand-written fused update kernel each.               */
+enum {
+  JXB_RULE_RANDOM_WALKER = 1,   /* examples/basic_example.py:20-69                   */
+  JXB_RULE_SCALED_WALKER = 2,   /* same update; keyed init (roofline variant, N=2^26)*/
+  JXB_RULE_CONSUMER = 3,        /* tests/integration/test_integration.py:20-67       */
+  JXB_RULE_PRODUCER = 4,        /* tests/integration/test_integration.py:70-121      */
+  JXB_RULE_GROWTH = 5,          /* tests/unit/test_analysis.py:22-39 (DummyAgent)    */
+  JXB_RULE_INCREMENT = 6,       /* tests/unit/test_model.py:43-48   (DummyAgent)     */
+  JXB_RULE_WEALTH = 7,          /* tests/unit/test_agent.py:44-100  (TestAgent)      */
+  JXB_RULE_SCHELLING = 8,       /* layout examples/models/schelling_model.py:26-31   */
+  JXB_RULE_SIR = 9              /* layout jaxabm/agentpy.py:557,574-582              */
+};
+
+/* Registered model programs: the update_state_fn + metrics_fn pair that runs inside
+ * the step (jaxabm/model.py:182-200), fused into the tail of the step's kernels.    */
+enum {
+  JXB_PROGRAM_NONE = 0,         /* no env fn, no metrics (run() returns {})          */
+  JXB_PROGRAM_RANDOM_WALK = 1,  /* examples/basic_example.py:72-182                  */
+  JXB_PROGRAM_MARKET = 2,       /* tests/integration/test_integration.py:125-183     */
+  JXB_PROGRAM_GROWTH = 3,       /* tests/unit/test_analysis.py:105-128               */
+  JXB_PROGRAM_COUNTER = 4,      /* tests/unit/test_model.py:20-40                    */
+  JXB_PROGRAM_SCHELLING = 5,    /* builder-authored rule, DESIGN.md                  */
+  JXB_PROGRAM_SIR = 6           /* builder-authored rule, DESIGN.md                  */
+};
+
+#define JXB_MAX_TYPES 4
+#define JXB_MAX_PARAMS 16
+
+/* One agent collection (jaxabm/agent.py:69-90: AgentCollection(agent_type, num_agents)). */
+typedef struct {
+  int32_t rule;                   /* JXB_RULE_*                                      */
+  int64_t n_agents;               /* agents held by THIS engine (local shard)        */
+  int64_t global_offset;          /* index of local agent 0 in the whole population  */
+  int64_t global_n;               /* whole-population size (== n_agents on one GPU)  */
+  int32_t n_params;
+  float params[JXB_MAX_PARAMS];   /* rule constants (the agent_type's attributes)    */
+} jxb_type_desc;
+
+/* jaxabm/model.py:25-58 (Model.__init__) + add_agent_collection/add_env_state.      */
+typedef struct {
+  int32_t program;                /* JXB_PROGRAM_*                                   */
+  int32_t rng_mode;               /* JXB_RNG_*                                       */
+  int32_t n_types;
+  jxb_type_desc types[JXB_MAX_TYPES];   /* insertion order == key order (model.py:163) */
+  int32_t n_params;
+  double params[JXB_MAX_PARAMS];  /* Model(params=...) entries the program reads     */
+  int32_t grid_w, grid_h;         /* jaxabm/agentpy.py:480-493 Grid(shape, periodic) */
+  int32_t grid_periodic;
+  int32_t world_size, rank;       /* population sharding (1, 0 on a single GPU)      */
+} jxb_model_desc;
+
+typedef struct jxb_engine jxb_engine;
+typedef struct jxb_model jxb_model;
+
+int jxb_version(void);
+const char* jxb_last_error(void);
+
+/* ---- engine: one per process, bound to one device ------------------------------ */
+int jxb_engine_create(int device, jxb_engine** out);
+int jxb_engine_destroy(jxb_engine*);
+int jxb_engine_sm_count(jxb_engine*, int* out);
+/* kernels launched by this engine since creation (bench.py's "gpu_launches").       */
+int jxb_engine_launch_count(jxb_engine*, int64_t* out);
+
+/* ---- model ------------------------------------------------------------------------ */
+/* jaxabm/model.py:25-58,60-99: construct with collections, env layout and params.   */
+int jxb_model_create(jxb_engine*, const jxb_model_desc*, jxb_model** out);
+int jxb_model_destroy(jxb_model*);
+
+/* Field/env introspection so the host shim can size buffers (names mirror the
+ * reference's state-dict keys).  dtype: 0=f32, 1=i32, 2=bool(u8).                   */
+int jxb_model_n_fields(jxb_model*, int type, int* out);
+int jxb_model_field_info(jxb_model*, int type, int field, const char** name,
+                         int* dtype, int* width);
+int jxb_model_n_env(jxb_model*, int* out);
+int jxb_model_env_info(jxb_model*, int slot, const char** name, int* dtype);
+int jxb_model_n_metrics(jxb_model*, int* out);
+int jxb_model_metric_info(jxb_model*, int metric, const char** name, int* dtype);
+
+/* AgentCollection._states access (jaxabm/agent.py:179-196), host <-> HBM.           */
+int jxb_model_upload(jxb_model*, int type, int field, const void* host, size_t bytes);
+int jxb_model_download(jxb_model*, int type, int field, void* host, size_t bytes);
+/* vmap broadcast of an unbatched init value (jaxabm/agent.py:125-130).              */
+int jxb_model_fill(jxb_model*, int type, int field, const void* value, size_t bytes);
+/* Model.add_env_state (jaxabm/model.py:76-99); scalars travel as double.            */
+int jxb_model_set_env(jxb_model*, int slot, double value);
+int jxb_model_get_env(jxb_model*, int slot, double* value);
+/* change one constant of a collection's agent_type after construction (e.g. the
+ * 'wage_rate' a caller passes in model_state, tests/unit/test_agent.py:75-78).     */
+int jxb_model_set_type_param(jxb_model*, int type, int index, float value);
+
+/* Network env (jaxabm/agentpy.py:545-582): directed adjacency list int32[E,2]; the
+ * engine bins it by source into CSR in HBM.  Grid env for Schelling is derived from
+ * the uploaded 'position'/'type' fields by jxb_model_grid_rebuild.                  */
+int jxb_model_set_network(jxb_model*, const int32_t* edges, int64_t n_edges);
+int jxb_model_grid_rebuild(jxb_model*);
+/* env['grid'] (int32[W,H], -1 empty) as the reference lays it out
+ * (examples/models/schelling_model.py:119-131).                                     */
+int jxb_model_download_grid(jxb_model*, int32_t* host, size_t bytes);
+
+/* Model.initialize (jaxabm/model.py:118-144): keys = split(PRNGKey(seed), C+1);
+ * collection i is initialised on the device from keys[i+1] (agent.py:92-130).       */
+int jxb_model_init(jxb_model*, uint32_t seed_key0, uint32_t seed_key1);
+/* AgentCollection.init(key, cfg) for one collection (jaxabm/agent.py:92-130).       */
+int jxb_collection_init(jxb_model*, int type, uint32_t key0, uint32_t key1);
+/* AgentCollection.update(model_state, key, cfg) (jaxabm/agent.py:132-177): one fused
+ * update of one collection with the caller's key; env/metrics untouched.            */
+int jxb_collection_update(jxb_model*, int type, uint32_t key0, uint32_t key1);
+
+/* Model.run(steps) (jaxabm/model.py:218-262) = `steps` x Model.step (model.py:146-216)
+ * with no host round-trip inside.  metrics_out: [n_records][n_metrics] doubles where
+ * n_records = number of t in (t0, t0+steps] with t % collect_interval == 0; steps_out
+ * receives those t.  Either may be NULL.  device_seconds_out: CUDA-event time of the
+ * step loop on the engine's stream.                                                 */
+int jxb_model_run(jxb_model*, int steps, int collect_interval, double* metrics_out,
+                  int32_t* steps_out, int* n_records_out, double* device_seconds_out);
+int jxb_model_time_step(jxb_model*, int64_t* out);
+/* Seconds of the dominant kernel of the last run (CUDA events around every launch of
+ * it when profiling is enabled with jxb_model_set_profile(m, 1)).                   */
+int jxb_model_set_profile(jxb_model*, int enable);
+int jxb_model_profile(jxb_model*, double* dominant_kernel_seconds, int64_t* launches,
+                      const char** kernel_name);
+
+/* ---- ensembles (jaxabm/analysis.py:113-157 and :434-476) --------------------------- */
+/* R independent replicas of `desc`; replica r overrides params by
+ * param_slots/params[r][n_swept] (slot < 100: model param index; slot >= 100:
+ * 100 + 16*collection + rule-param index) and is seeded PRNGKey(seeds[r]).  env_init
+ * ([n_env] doubles, or NULL for the program defaults) is the add_env_state() layout every
+ * replica starts from.  The whole time loop of a replica runs on-chip.
+ * last_metrics_out: [R][n_metrics] doubles = results[m][-1] of every run.               */
+int jxb_ensemble_run(jxb_engine*, const jxb_model_desc* desc, int n_replicas,
+                     int n_swept, const int32_t* param_slots, const double* params,
+                     const uint32_t* seeds, const double* env_init, int steps,
+                     double* last_metrics_out, double* device_seconds_out);
+
+/* ---- population sharding across processes (one process per GPU) -------------------- */
+/* Attach an NCCL communicator: id_bytes = ncclUniqueId broadcast by the host shim
+ * over torch.distributed.  Used for the per-step env partial-sum all-reduce.         */
+int jxb_nccl_unique_id(void* id_bytes_out, size_t bytes);
+int jxb_engine_attach_nccl(jxb_engine*, const void* id_bytes, size_t bytes, int rank,
+                           int world_size);
+
+/* ---- host-only scalar key algebra (jax.random on the reference's host path) -------- */
+/* jax.random.split(key, n) -> out[n][2] (jaxabm/model.py:129,156; analysis.py:438).  */
+int jxb_prng_split(int rng_mode, const uint32_t key[2], int n, uint32_t* out);
+/* jax.random.bits(key, (n,)) 32-bit.                                                  */
+int jxb_prng_bits(int rng_mode, const uint32_t key[2], int64_t n, uint32_t* out);
+/* jax.random.uniform(key, (n,), minval, maxval) float32 (analysis.py:81).            */
+int jxb_prng_uniform(int rng_mode, const uint32_t key[2], int64_t n, float lo, float hi,
+                     float* out);
+/* jax.random.randint(key, (n,), lo, hi) int32 (agentpy.py:510-512; analysis.py:441). */
+int jxb_prng_randint(int rng_mode, const uint32_t key[2], int64_t n, int32_t lo,
+                     int32_t hi, int32_t* out);
+/* raw block function, for known-answer tests.                                         */
+int jxb_prng_threefry2x32(const uint32_t key[2], const uint32_t ctr[2], uint32_t out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JXB_H_ */

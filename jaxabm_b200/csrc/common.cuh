@@ -1,0 +1,183 @@
+// common.cuh -- device-side model view, control block and reduction helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/jxb.h"
+#include "prng.cuh"
+
+namespace jxb {
+
+constexpr int kMaxFields = 8;
+constexpr int kMaxEnv = 16;
+constexpr int kMaxMetrics = 8;
+constexpr int kThreads = 256;   // CTA size of the streaming kernels
+constexpr int kVec = 4;         // agents per thread per iteration (one float4 / int4 per field)
+
+// accumulator layout of one step (what the env/metrics tail consumes)
+constexpr int kFSum = 6;        // float sums  (promoted to double across blocks)
+constexpr int kFMax = 2;        // float maxima
+constexpr int kISum = 4;        // integer sums (exact)
+constexpr int kAcc = kFSum + kFMax + kISum;
+
+struct Acc {
+  float fsum[kFSum];
+  float fmax[kFMax];
+  int isum[kISum];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < kFSum; ++i) fsum[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kFMax; ++i) fmax[i] = -__int_as_float(0x7f800000);
+#pragma unroll
+    for (int i = 0; i < kISum; ++i) isum[i] = 0;
+  }
+};
+
+// device-resident control block: everything that changes from step to step lives here so
+// that one captured CUDA graph of a step can be replayed with no host-side arguments.
+struct Ctrl {
+  int step_in_run;        // index into the per-run key table
+  int n_recorded;         // history rows written this run
+  long long time_step;    // Model._time_step (persists across run() calls, model.py:203)
+  unsigned int ticket;    // last-block election for the fused step kernel
+  unsigned int ticket2;   // second election (Schelling move kernel / SIR)
+  // Schelling per-step scalars
+  unsigned int tile_ticket;
+  unsigned int n_unsat, n_empty;
+  long long total_moves;
+  double seg_sum;
+  long long seg_cnt;
+  long long n_satisfied;
+  // SIR per-step counts
+  long long sir_count[3];
+};
+
+struct TypeDev {
+  void* f[kMaxFields];
+  long long n;            // local agents
+  long long goff;         // global index of local agent 0
+  long long gn;           // global population (split(key, gn))
+  float p[JXB_MAX_PARAMS];
+  int rule;
+  int block_begin;        // first CTA of this type inside the fused launch
+  int block_count;
+};
+
+struct ModelDev {
+  TypeDev t[JXB_MAX_TYPES];
+  int n_types;
+  int program;
+  int collect_interval;
+  int has_env_fn;
+  double* env;            // [kMaxEnv]
+  double mp[JXB_MAX_PARAMS];
+  Ctrl* ctrl;
+  const uint32_t* keys;   // [steps][n_types+1][2] : coll keys then the update key
+  double* partials;       // [grid][kAcc]
+  double* metrics;        // [records][kMaxMetrics]
+  int* record_steps;      // [records]
+  int grid_blocks;
+  int world_size;
+  double* allreduce_buf;  // [kAcc] staging for the cross-rank partial-sum exchange
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-level reduction of an Acc into `out[kAcc]` doubles (valid in thread 0).
+// Fixed shuffle tree + fixed warp order: bit-reproducible for a fixed launch shape.
+__device__ __forceinline__ void block_reduce_acc(const Acc& a, double* smem /*[warps][kAcc]*/,
+                                                 double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kFSum; ++i) {
+    float v = warp_sum(a.fsum[i]);
+    if (lane == 0) smem[warp * kAcc + i] = (double)v;
+  }
+#pragma unroll
+  for (int i = 0; i < kFMax; ++i) {
+    float v = warp_max(a.fmax[i]);
+    if (lane == 0) smem[warp * kAcc + kFSum + i] = (double)v;
+  }
+#pragma unroll
+  for (int i = 0; i < kISum; ++i) {
+    int v = warp_sum(a.isum[i]);
+    if (lane == 0) smem[warp * kAcc + kFSum + kFMax + i] = (double)v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    const int i = threadIdx.x;
+    double r = smem[i];
+    const bool is_max = (i >= kFSum && i < kFSum + kFMax);
+    for (int w = 1; w < nw; ++w) {
+      double v = smem[w * kAcc + i];
+      r = is_max ? fmax(r, v) : r + v;
+    }
+    out[i] = r;
+  }
+}
+
+// streaming load/store helpers (read-once data: bypass L1 allocation)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int4 ld_stream(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream(int4* p, int4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// STREAM=true: HBM-resident state, read once per step (no L1 allocation);
+// STREAM=false: generic loads/stores (shared-memory or L2-resident replica state)
+template <bool STREAM, class V>
+__device__ __forceinline__ V ldv(const V* p) {
+  if (STREAM) return ld_stream(p);
+  return *p;
+}
+template <bool STREAM, class V>
+__device__ __forceinline__ void stv(V* p, V v) {
+  if (STREAM) st_stream(p, v);
+  else *p = v;
+}
+
+}  // namespace jxb

@@ -1,0 +1,1151 @@
+// engine.cu -- host side of libjxb.so: the C ABI of include/jxb.h.
+//
+// One engine per process, bound to one B200.  A model owns its struct-of-arrays agent
+// state, env scalars, key table and history ring in HBM; jxb_model_run() enqueues the
+// whole time loop (CUDA graph of fused step kernels) on the engine's stream and reads
+// the history back once at the end (jaxabm/model.py:218-262 without the per-step host
+// round trip).  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/jxb.h"
+#include "common.cuh"
+#include "rules.cuh"
+#include "schelling.cuh"
+#include "sir.cuh"
+#include "ensemble.cuh"
+
+using namespace jxb;
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return fail(JXB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+                  cudaGetErrorString(_e));                                                \
+  } while (0)
+
+extern "C" const char* jxb_last_error(void) { return g_err; }
+extern "C" int jxb_version(void) { return JXB_VERSION; }
+
+// ---------------------------------------------------------------------------------------
+// registries: state layout of every rule, env/metric layout of every program
+// dtype: 0 f32, 1 i32, 2 bool(u8), 3 f64 (a Python float in the reference)
+// ---------------------------------------------------------------------------------------
+struct FieldSpec { const char* name; int dtype; int width; };
+struct RuleSpec { int rule; int nf; FieldSpec f[kMaxFields]; };
+struct SlotSpec { const char* name; int dtype; double dflt; };
+struct ProgramSpec {
+  int program; int has_env_fn;
+  int n_env; SlotSpec env[kMaxEnv];
+  int n_metrics; SlotSpec metrics[kMaxMetrics];
+};
+
+static const RuleSpec kRules[] = {
+    {JXB_RULE_RANDOM_WALKER, 4, {{"position", 0, 2}, {"velocity", 0, 2}, {"color", 1, 1}, {"steps_taken", 1, 1}}},
+    {JXB_RULE_SCALED_WALKER, 4, {{"position", 0, 2}, {"velocity", 0, 2}, {"color", 1, 1}, {"steps_taken", 1, 1}}},
+    {JXB_RULE_CONSUMER, 4, {{"savings", 0, 1}, {"consumption", 0, 1}, {"utility", 0, 1}, {"income", 0, 1}}},
+    {JXB_RULE_PRODUCER, 3, {{"capital", 0, 1}, {"production", 0, 1}, {"profit", 0, 1}}},
+    {JXB_RULE_GROWTH, 1, {{"value", 0, 1}}},
+    {JXB_RULE_INCREMENT, 1, {{"value", 0, 1}}},
+    {JXB_RULE_WEALTH, 2, {{"wealth", 0, 1}, {"productivity", 0, 1}}},
+    {JXB_RULE_SCHELLING, 4, {{"type", 1, 1}, {"position", 1, 2}, {"satisfied", 2, 1}, {"moves", 1, 1}}},
+    {JXB_RULE_SIR, 1, {{"state", 1, 1}}},
+};
+
+static const ProgramSpec kPrograms[] = {
+    {JXB_PROGRAM_NONE, 0, 0, {}, 0, {}},
+    {JXB_PROGRAM_RANDOM_WALK, 1, 7,
+     {{"bounds_lo", 0, 0.0}, {"bounds_hi", 0, 1.0}, {"time", 1, 0}, {"mean_x", 3, 0.5}, {"mean_y", 3, 0.5},
+      {"num_red", 1, 0}, {"num_blue", 1, 0}},
+     7,
+     {{"mean_x", 3, 0}, {"mean_y", 3, 0}, {"mean_distance", 0, 0}, {"max_distance", 0, 0}, {"num_red", 1, 0},
+      {"num_blue", 1, 0}, {"time", 1, 0}}},
+    {JXB_PROGRAM_MARKET, 1, 5,
+     {{"price_level", 0, 1.0}, {"gdp", 0, 0}, {"unemployment", 0, 0}, {"total_consumption", 0, 0},
+      {"total_production", 0, 0}},
+     5,
+     {{"gdp", 0, 0}, {"price_level", 0, 0}, {"unemployment", 0, 0}, {"avg_utility", 0, 0}, {"avg_profit", 0, 0}}},
+    {JXB_PROGRAM_GROWTH, 1, 2, {{"price_level", 3, 1.0}, {"interest_rate", 3, 0.05}}, 3,
+     {{"avg_value", 0, 0}, {"price_level", 3, 0}, {"price_gap", 0, 0}}},
+    {JXB_PROGRAM_COUNTER, 1, 2, {{"counter", 1, 0}, {"increment", 0, 1.0}}, 2,
+     {{"total_value", 0, 0}, {"step_counter", 1, 0}}},
+    {JXB_PROGRAM_SCHELLING, 1, 3,
+     {{"segregation_index", 0, 0}, {"percent_satisfied", 0, 0}, {"total_moves", 1, 0}}, 3,
+     {{"percent_satisfied", 0, 0}, {"segregation_index", 0, 0}, {"total_moves", 1, 0}}},
+    {JXB_PROGRAM_SIR, 0, 0, {}, 3, {{"count_S", 1, 0}, {"count_I", 1, 0}, {"count_R", 1, 0}}},
+};
+
+static const RuleSpec* find_rule(int rule) {
+  for (const auto& r : kRules)
+    if (r.rule == rule) return &r;
+  return nullptr;
+}
+static const ProgramSpec* find_program(int p) {
+  for (const auto& r : kPrograms)
+    if (r.program == p) return &r;
+  return nullptr;
+}
+static size_t dtype_size(int dt) { return dt == 2 ? 1 : (dt == 3 ? 8 : 4); }
+
+// ---------------------------------------------------------------------------------------
+// NCCL through dlopen (only touched when a population is sharded across processes)
+// ---------------------------------------------------------------------------------------
+struct NcclId { char b[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.lib) return JXB_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return fail(JXB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  *(void**)&g_nccl.GetUniqueId = dlsym(g_nccl.lib, "ncclGetUniqueId");
+  *(void**)&g_nccl.CommInitRank = dlsym(g_nccl.lib, "ncclCommInitRank");
+  *(void**)&g_nccl.AllReduce = dlsym(g_nccl.lib, "ncclAllReduce");
+  *(void**)&g_nccl.CommDestroy = dlsym(g_nccl.lib, "ncclCommDestroy");
+  *(void**)&g_nccl.GetErrorString = dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
+    return fail(JXB_ERR_NCCL, "libnccl is missing required symbols");
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// engine / model objects
+// ---------------------------------------------------------------------------------------
+struct jxb_engine {
+  int device = 0;
+  int sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t launches = 0;
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+struct jxb_model {
+  jxb_engine* eng = nullptr;
+  jxb_model_desc desc{};
+  const ProgramSpec* prog = nullptr;
+  const RuleSpec* rules[JXB_MAX_TYPES] = {};
+  ModelDev dev{};
+  std::vector<void*> allocs;
+  Key rng{0, 0};
+  bool initialized = false;
+  bool collections_ready[JXB_MAX_TYPES] = {};
+  long long time_step = 0;
+  // per-run buffers
+  uint32_t* d_keys = nullptr; uint32_t* h_keys = nullptr; size_t keys_cap = 0;
+  double* d_metrics = nullptr; int* d_rec = nullptr; size_t rec_cap = 0;
+  // Schelling
+  bool has_grid = false; SchellingDev sd{}; long long pad = 0; float* d_ratio = nullptr;
+  bool grid_built = false; bool sat_dirty = false; long long n_empty_cells = 0;
+  // SIR
+  bool has_net = false; SirDev sv{}; bool net_built = false; long long nnz = 0;
+  // graphs: cached executable graphs of `chunk` consecutive steps
+  cudaGraphExec_t graph1 = nullptr, graphK = nullptr; int chunkK = 0;
+  const void* sig_keys = nullptr; const void* sig_metrics = nullptr; const void* sig_rec = nullptr; int sig_ci = 0;
+  // profiling of the dominant kernel
+  bool profile = false; double prof_seconds = 0; int64_t prof_launches = 0;
+  std::vector<cudaEvent_t> prof_events;
+  int step_blocks = 0;
+};
+
+template <class T>
+static int dev_alloc(jxb_model* m, T** p, size_t count) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 16)));
+  m->allocs.push_back(q);
+  *p = (T*)q;
+  return JXB_OK;
+}
+
+extern "C" int jxb_engine_create(int device, jxb_engine** out) {
+  if (!out) return fail(JXB_ERR_INVALID, "out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(JXB_ERR_NO_DEVICE, "no CUDA device visible (%s); libjxb has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(JXB_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+  CK(cudaSetDevice(device));
+  jxb_engine* eng = new jxb_engine();
+  eng->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  eng->sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&eng->ev0));
+  CK(cudaEventCreate(&eng->ev1));
+  *out = eng;
+  return JXB_OK;
+}
+
+extern "C" int jxb_engine_destroy(jxb_engine* eng) {
+  if (!eng) return JXB_OK;
+  cudaSetDevice(eng->device);
+  if (eng->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(eng->nccl_comm);
+  cudaEventDestroy(eng->ev0);
+  cudaEventDestroy(eng->ev1);
+  cudaStreamDestroy(eng->stream);
+  delete eng;
+  return JXB_OK;
+}
+
+extern "C" int jxb_engine_sm_count(jxb_engine* eng, int* out) {
+  if (!eng || !out) return fail(JXB_ERR_INVALID, "null argument");
+  *out = eng->sms;
+  return JXB_OK;
+}
+
+extern "C" int jxb_engine_launch_count(jxb_engine* eng, int64_t* out) {
+  if (!eng || !out) return fail(JXB_ERR_INVALID, "null argument");
+  *out = eng->launches;
+  return JXB_OK;
+}
+
+extern "C" int jxb_nccl_unique_id(void* id, size_t bytes) {
+  if (bytes < sizeof(NcclId)) return fail(JXB_ERR_INVALID, "need %zu bytes", sizeof(NcclId));
+  int rc = load_nccl();
+  if (rc) return rc;
+  int r = g_nccl.GetUniqueId(id);
+  if (r) return fail(JXB_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return JXB_OK;
+}
+
+extern "C" int jxb_engine_attach_nccl(jxb_engine* eng, const void* id, size_t bytes, int rank, int world) {
+  if (!eng || !id || bytes < sizeof(NcclId)) return fail(JXB_ERR_INVALID, "bad nccl id");
+  int rc = load_nccl();
+  if (rc) return rc;
+  CK(cudaSetDevice(eng->device));
+  NcclId nid;
+  memcpy(&nid, id, sizeof(nid));
+  int r = g_nccl.CommInitRank(&eng->nccl_comm, world, nid, rank);
+  if (r) return fail(JXB_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  eng->rank = rank;
+  eng->world = world;
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// model construction
+// ---------------------------------------------------------------------------------------
+static bool program_accepts(int program, int rule) {
+  switch (program) {
+    case JXB_PROGRAM_NONE: return rule != JXB_RULE_SCHELLING && rule != JXB_RULE_SIR;
+    case JXB_PROGRAM_RANDOM_WALK: return rule == JXB_RULE_RANDOM_WALKER || rule == JXB_RULE_SCALED_WALKER;
+    case JXB_PROGRAM_MARKET: return rule == JXB_RULE_CONSUMER || rule == JXB_RULE_PRODUCER;
+    case JXB_PROGRAM_GROWTH: return rule == JXB_RULE_GROWTH;
+    case JXB_PROGRAM_COUNTER: return rule == JXB_RULE_INCREMENT || rule == JXB_RULE_GROWTH;
+    case JXB_PROGRAM_SCHELLING: return rule == JXB_RULE_SCHELLING;
+    case JXB_PROGRAM_SIR: return rule == JXB_RULE_SIR;
+  }
+  return false;
+}
+
+static int validate_desc(const jxb_model_desc* d) {
+  if (!d) return fail(JXB_ERR_INVALID, "desc is NULL");
+  if (!find_program(d->program)) return fail(JXB_ERR_INVALID, "unknown program %d", d->program);
+  if (d->rng_mode != JXB_RNG_LEGACY && d->rng_mode != JXB_RNG_PARTITIONABLE)
+    return fail(JXB_ERR_INVALID, "unknown rng_mode %d", d->rng_mode);
+  if (d->n_types < 1 || d->n_types > JXB_MAX_TYPES)
+    return fail(JXB_ERR_INVALID, "No agent collections added to model");   // model.py:125-126
+  for (int i = 0; i < d->n_types; ++i) {
+    const jxb_type_desc& t = d->types[i];
+    if (!find_rule(t.rule))
+      return fail(JXB_ERR_INVALID, "collection %d: rule %d is not a registered agent rule", i, t.rule);
+    if (t.n_agents <= 0) return fail(JXB_ERR_INVALID, "num_agents must be a positive integer");
+    if (!program_accepts(d->program, t.rule))
+      return fail(JXB_ERR_INVALID, "program %d does not accept rule %d", d->program, t.rule);
+    if (t.global_n < t.n_agents || t.global_offset < 0 || t.global_offset + t.n_agents > t.global_n)
+      return fail(JXB_ERR_INVALID, "collection %d: bad shard [%lld,+%lld) of %lld", i,
+                  (long long)t.global_offset, (long long)t.n_agents, (long long)t.global_n);
+  }
+  if ((d->program == JXB_PROGRAM_SCHELLING || d->program == JXB_PROGRAM_SIR) && d->n_types != 1)
+    return fail(JXB_ERR_INVALID, "grid / network programs take exactly one collection");
+  if (d->program == JXB_PROGRAM_SCHELLING) {
+    if (d->grid_w <= 0 || d->grid_h <= 0) return fail(JXB_ERR_INVALID, "Schelling needs a Grid shape");
+    if ((long long)d->grid_w * d->grid_h >= (1ll << 31)) return fail(JXB_ERR_UNSUPPORTED, "grid too large");
+    if (d->types[0].n_agents > (long long)d->grid_w * d->grid_h)
+      return fail(JXB_ERR_INVALID, "more agents than cells");
+  }
+  return JXB_OK;
+}
+
+static void fill_type_dev(const jxb_type_desc& t, TypeDev& td) {
+  td.n = t.n_agents;
+  td.goff = t.global_offset;
+  td.gn = t.global_n;
+  td.rule = t.rule;
+  for (int k = 0; k < JXB_MAX_PARAMS; ++k) td.p[k] = k < t.n_params ? t.params[k] : 0.f;
+}
+
+static int plan_step_blocks(jxb_model* m);
+
+extern "C" int jxb_model_create(jxb_engine* eng, const jxb_model_desc* d, jxb_model** out) {
+  if (!eng || !out) return fail(JXB_ERR_INVALID, "null argument");
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  CK(cudaSetDevice(eng->device));
+  jxb_model* m = new jxb_model();
+  m->eng = eng;
+  m->desc = *d;
+  m->prog = find_program(d->program);
+  ModelDev& md = m->dev;
+  memset(&md, 0, sizeof(md));
+  md.n_types = d->n_types;
+  md.program = d->program;
+  md.collect_interval = 1;
+  md.has_env_fn = m->prog->has_env_fn;
+  md.world_size = d->world_size > 1 ? d->world_size : 1;
+  for (int k = 0; k < JXB_MAX_PARAMS; ++k) md.mp[k] = k < d->n_params ? d->params[k] : 0.0;
+#define TRY(x) do { rc = (x); if (rc) { jxb_model_destroy(m); return rc; } } while (0)
+  for (int i = 0; i < d->n_types; ++i) {
+    const jxb_type_desc& t = d->types[i];
+    m->rules[i] = find_rule(t.rule);
+    fill_type_dev(t, md.t[i]);
+    for (int f = 0; f < m->rules[i]->nf; ++f) {
+      const FieldSpec& fs = m->rules[i]->f[f];
+      unsigned char* p = nullptr;
+      // round up so vector tails of the 4-wide loops never fault
+      size_t bytes = (size_t)(t.n_agents + 8) * fs.width * dtype_size(fs.dtype);
+      TRY(dev_alloc(m, &p, bytes));
+      cudaMemsetAsync(p, 0, bytes, eng->stream);
+      md.t[i].f[f] = p;
+    }
+  }
+  TRY(dev_alloc(m, &md.env, kMaxEnv));
+  {
+    double h[kMaxEnv] = {0};
+    for (int i = 0; i < m->prog->n_env; ++i) h[i] = m->prog->env[i].dflt;
+    if (cudaMemcpy(md.env, h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) {
+      jxb_model_destroy(m);
+      return fail(JXB_ERR_CUDA, "env upload failed");
+    }
+  }
+  TRY(dev_alloc(m, &md.ctrl, 1));
+  cudaMemset(md.ctrl, 0, sizeof(Ctrl));
+  TRY(dev_alloc(m, &md.allreduce_buf, kAcc));
+  TRY(plan_step_blocks(m));
+  TRY(dev_alloc(m, &md.partials, (size_t)std::max(m->step_blocks, 1) * kAcc));
+
+  if (d->program == JXB_PROGRAM_SCHELLING) {
+    SchellingDev& sd = m->sd;
+    sd.W = d->grid_w; sd.H = d->grid_h; sd.periodic = d->grid_periodic ? 1 : 0;
+    sd.cells = (long long)sd.W * sd.H;
+    sd.ntiles = (int)((sd.cells + kTileCells - 1) / kTileCells);
+    m->pad = ((long long)sd.H + 16 + 15) / 16 * 16;
+    signed char* base = nullptr;
+    TRY(dev_alloc(m, &base, (size_t)(sd.cells + 2 * m->pad + 16)));
+    sd.ct = base + m->pad;
+    TRY(dev_alloc(m, &sd.cell_agent, (size_t)sd.cells));
+    const long long n = d->types[0].n_agents;
+    m->n_empty_cells = sd.cells - n;
+    TRY(dev_alloc(m, &sd.U, (size_t)n + 1));
+    TRY(dev_alloc(m, &sd.UA, (size_t)n + 1));
+    TRY(dev_alloc(m, &sd.E, (size_t)(sd.cells - n) + 1));
+    TRY(dev_alloc(m, &sd.tile_desc, (size_t)sd.ntiles));
+    TRY(dev_alloc(m, &sd.tile_seg_sum, (size_t)sd.ntiles));
+    TRY(dev_alloc(m, &sd.tile_seg_cnt, (size_t)sd.ntiles));
+    cudaMemset(sd.tile_desc, 0, sizeof(unsigned long long) * sd.ntiles);
+    // satisfaction / ratio tables in the reference's float32 arithmetic
+    const float thr = d->n_params > 0 ? (float)d->params[0] : 0.5f;
+    float ratio[10 * 16] = {0};
+    for (int o = 0; o < 10; ++o) {
+      unsigned int bits = 0;
+      for (int s = 0; s < 16; ++s) {
+        bool sat = (o == 0) || (s <= o && ((float)s / (float)o) >= thr);
+        if (sat) bits |= 1u << s;
+        if (o > 0 && s <= o) ratio[o * 16 + s] = (float)s / (float)o;
+      }
+      sd.sat_lut[o] = bits;
+    }
+    TRY(dev_alloc(m, &m->d_ratio, 160));
+    cudaMemcpy(m->d_ratio, ratio, sizeof(ratio), cudaMemcpyHostToDevice);
+    sd.ratio_lut = m->d_ratio;
+    m->has_grid = true;
+  }
+  if (d->program == JXB_PROGRAM_SIR) m->has_net = true;
+#undef TRY
+  cudaStreamSynchronize(eng->stream);
+  *out = m;
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_destroy(jxb_model* m) {
+  if (!m) return JXB_OK;
+  cudaSetDevice(m->eng->device);
+  cudaStreamSynchronize(m->eng->stream);
+  if (m->graph1) cudaGraphExecDestroy(m->graph1);
+  if (m->graphK) cudaGraphExecDestroy(m->graphK);
+  for (auto e : m->prof_events) cudaEventDestroy(e);
+  for (void* p : m->allocs) cudaFree(p);
+  if (m->d_keys) cudaFree(m->d_keys);
+  if (m->h_keys) cudaFreeHost(m->h_keys);
+  if (m->d_metrics) cudaFree(m->d_metrics);
+  if (m->d_rec) cudaFree(m->d_rec);
+  delete m;
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------
+#define NEED(m) if (!(m)) return fail(JXB_ERR_INVALID, "model is NULL")
+#define NEED_TYPE(m, type) \
+  if ((type) < 0 || (type) >= (m)->desc.n_types) return fail(JXB_ERR_INVALID, "type index %d out of range", (type))
+
+extern "C" int jxb_model_n_fields(jxb_model* m, int type, int* out) {
+  NEED(m); NEED_TYPE(m, type);
+  *out = m->rules[type]->nf;
+  return JXB_OK;
+}
+extern "C" int jxb_model_field_info(jxb_model* m, int type, int field, const char** name, int* dtype, int* width) {
+  NEED(m); NEED_TYPE(m, type);
+  if (field < 0 || field >= m->rules[type]->nf) return fail(JXB_ERR_INVALID, "field %d out of range", field);
+  const FieldSpec& f = m->rules[type]->f[field];
+  if (name) *name = f.name;
+  if (dtype) *dtype = f.dtype;
+  if (width) *width = f.width;
+  return JXB_OK;
+}
+extern "C" int jxb_model_n_env(jxb_model* m, int* out) { NEED(m); *out = m->prog->n_env; return JXB_OK; }
+extern "C" int jxb_model_env_info(jxb_model* m, int slot, const char** name, int* dtype) {
+  NEED(m);
+  if (slot < 0 || slot >= m->prog->n_env) return fail(JXB_ERR_INVALID, "env slot %d out of range", slot);
+  if (name) *name = m->prog->env[slot].name;
+  if (dtype) *dtype = m->prog->env[slot].dtype;
+  return JXB_OK;
+}
+extern "C" int jxb_model_n_metrics(jxb_model* m, int* out) { NEED(m); *out = m->prog->n_metrics; return JXB_OK; }
+extern "C" int jxb_model_metric_info(jxb_model* m, int k, const char** name, int* dtype) {
+  NEED(m);
+  if (k < 0 || k >= m->prog->n_metrics) return fail(JXB_ERR_INVALID, "metric %d out of range", k);
+  if (name) *name = m->prog->metrics[k].name;
+  if (dtype) *dtype = m->prog->metrics[k].dtype;
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// state access
+// ---------------------------------------------------------------------------------------
+static size_t field_bytes(jxb_model* m, int type, int field) {
+  const FieldSpec& f = m->rules[type]->f[field];
+  return (size_t)m->desc.types[type].n_agents * f.width * dtype_size(f.dtype);
+}
+
+static int sir_sync_from_api(jxb_model* m);
+static int sir_sync_to_api(jxb_model* m);
+static int schelling_export_satisfied(jxb_model* m);
+
+static int check_field(jxb_model* m, int type, int field, size_t bytes) {
+  NEED(m); NEED_TYPE(m, type);
+  if (field < 0 || field >= m->rules[type]->nf) return fail(JXB_ERR_INVALID, "field %d out of range", field);
+  if (bytes != field_bytes(m, type, field))
+    return fail(JXB_ERR_INVALID, "field '%s': expected %zu bytes, got %zu", m->rules[type]->f[field].name,
+                field_bytes(m, type, field), bytes);
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_upload(jxb_model* m, int type, int field, const void* host, size_t bytes) {
+  int rc = check_field(m, type, field, bytes);
+  if (rc) return rc;
+  CK(cudaSetDevice(m->eng->device));
+  CK(cudaMemcpyAsync(m->dev.t[type].f[field], host, bytes, cudaMemcpyHostToDevice, m->eng->stream));
+  CK(cudaStreamSynchronize(m->eng->stream));
+  if (m->has_net) return sir_sync_from_api(m);
+  if (m->has_grid && (field == 0 || field == 1)) m->grid_built = false;
+  if (m->has_grid && field == 2) m->sat_dirty = false;
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_download(jxb_model* m, int type, int field, void* host, size_t bytes) {
+  int rc = check_field(m, type, field, bytes);
+  if (rc) return rc;
+  CK(cudaSetDevice(m->eng->device));
+  if (m->has_net) { rc = sir_sync_to_api(m); if (rc) return rc; }
+  if (m->has_grid && field == 2 && m->sat_dirty) { rc = schelling_export_satisfied(m); if (rc) return rc; }
+  CK(cudaMemcpyAsync(host, m->dev.t[type].f[field], bytes, cudaMemcpyDeviceToHost, m->eng->stream));
+  CK(cudaStreamSynchronize(m->eng->stream));
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_fill(jxb_model* m, int type, int field, const void* value, size_t bytes) {
+  NEED(m); NEED_TYPE(m, type);
+  if (field < 0 || field >= m->rules[type]->nf) return fail(JXB_ERR_INVALID, "field %d out of range", field);
+  const FieldSpec& f = m->rules[type]->f[field];
+  if (bytes != f.width * dtype_size(f.dtype) || bytes > 16)
+    return fail(JXB_ERR_INVALID, "fill '%s': expected %zu bytes", f.name, f.width * dtype_size(f.dtype));
+  CK(cudaSetDevice(m->eng->device));
+  uint4 v = {0, 0, 0, 0};
+  memcpy(&v, value, bytes);
+  const long long n = m->desc.types[type].n_agents;
+  int blocks = (int)std::min<long long>((n * (long long)bytes + 255) / 256, m->eng->sms * 8);
+  fill_kernel<<<blocks, 256, 0, m->eng->stream>>>((unsigned char*)m->dev.t[type].f[field], n, (int)bytes, v);
+  m->eng->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(m->eng->stream));
+  if (m->has_net) return sir_sync_from_api(m);
+  if (m->has_grid && (field == 0 || field == 1)) m->grid_built = false;
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_set_env(jxb_model* m, int slot, double value) {
+  NEED(m);
+  if (slot < 0 || slot >= m->prog->n_env) return fail(JXB_ERR_INVALID, "env slot %d out of range", slot);
+  CK(cudaSetDevice(m->eng->device));
+  CK(cudaMemcpy(m->dev.env + slot, &value, sizeof(double), cudaMemcpyHostToDevice));
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_get_env(jxb_model* m, int slot, double* value) {
+  NEED(m);
+  if (slot < 0 || slot >= m->prog->n_env) return fail(JXB_ERR_INVALID, "env slot %d out of range", slot);
+  CK(cudaSetDevice(m->eng->device));
+  CK(cudaStreamSynchronize(m->eng->stream));
+  CK(cudaMemcpy(value, m->dev.env + slot, sizeof(double), cudaMemcpyDeviceToHost));
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_set_type_param(jxb_model* m, int type, int index, float value) {
+  NEED(m); NEED_TYPE(m, type);
+  if (index < 0 || index >= JXB_MAX_PARAMS) return fail(JXB_ERR_INVALID, "param index %d out of range", index);
+  m->dev.t[type].p[index] = value;
+  m->desc.types[type].params[index] = value;
+  // kernel arguments are baked into the cached step graphs
+  if (m->graph1) { cudaGraphExecDestroy(m->graph1); m->graph1 = nullptr; }
+  if (m->graphK) { cudaGraphExecDestroy(m->graphK); m->graphK = nullptr; }
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_time_step(jxb_model* m, int64_t* out) {
+  NEED(m);
+  *out = m->time_step;
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Schelling grid helpers
+// ---------------------------------------------------------------------------------------
+extern "C" int jxb_model_grid_rebuild(jxb_model* m) {
+  NEED(m);
+  if (!m->has_grid) return fail(JXB_ERR_STATE, "model has no Grid");
+  CK(cudaSetDevice(m->eng->device));
+  cudaStream_t s = m->eng->stream;
+  int* d_err = nullptr;
+  CK(cudaMalloc(&d_err, sizeof(int)));
+  CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+  const int blocks = m->eng->sms * 8;
+  grid_clear_kernel<<<blocks, 256, 0, s>>>(m->sd, m->pad);
+  grid_scatter_kernel<<<blocks, 256, 0, s>>>(m->sd, (const int*)m->dev.t[0].f[0], (const int2*)m->dev.t[0].f[1],
+                                            m->desc.types[0].n_agents, d_err);
+  m->eng->launches += 2;
+  int err = 0;
+  CK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  cudaFree(d_err);
+  CK(cudaGetLastError());
+  if (err == 1) return fail(JXB_ERR_INVALID, "an agent position lies outside the grid");
+  if (err == 2) return fail(JXB_ERR_INVALID, "two agents share a grid cell");
+  m->grid_built = true;
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_download_grid(jxb_model* m, int32_t* host, size_t bytes) {
+  NEED(m);
+  if (!m->has_grid) return fail(JXB_ERR_STATE, "model has no Grid");
+  if (bytes != (size_t)m->sd.cells * 4) return fail(JXB_ERR_INVALID, "grid is %lld int32", m->sd.cells);
+  CK(cudaSetDevice(m->eng->device));
+  if (!m->grid_built) { int rc = jxb_model_grid_rebuild(m); if (rc) return rc; }
+  int* tmp = nullptr;
+  CK(cudaMalloc(&tmp, bytes));
+  grid_export_kernel<<<m->eng->sms * 8, 256, 0, m->eng->stream>>>(m->sd, tmp);
+  m->eng->launches++;
+  CK(cudaMemcpyAsync(host, tmp, bytes, cudaMemcpyDeviceToHost, m->eng->stream));
+  CK(cudaStreamSynchronize(m->eng->stream));
+  cudaFree(tmp);
+  return JXB_OK;
+}
+
+static int schelling_export_satisfied(jxb_model* m) {
+  cudaStream_t s = m->eng->stream;
+  unsigned char* sat = (unsigned char*)m->dev.t[0].f[2];
+  CK(cudaMemsetAsync(sat, 1, (size_t)m->desc.types[0].n_agents, s));
+  satisfied_export_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->sd, m->dev.ctrl, sat);
+  m->eng->launches++;
+  CK(cudaGetLastError());
+  m->sat_dirty = false;
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// SIR network helpers
+// ---------------------------------------------------------------------------------------
+extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t n_edges) {
+  NEED(m);
+  if (!m->has_net) return fail(JXB_ERR_STATE, "model has no Network");
+  if (n_edges < 0 || n_edges >= (1ll << 31)) return fail(JXB_ERR_UNSUPPORTED, "edge count out of range");
+  CK(cudaSetDevice(m->eng->device));
+  const long long n = m->desc.types[0].n_agents;
+  // bin by source (counting sort); neighbour order inside a row is irrelevant to the rule
+  std::vector<unsigned int> row_ptr((size_t)n + 1, 0);
+  for (int64_t e = 0; e < n_edges; ++e) {
+    const int s = edges[2 * e], d = edges[2 * e + 1];
+    if (s < 0 || s >= n || d < 0 || d >= n) return fail(JXB_ERR_INVALID, "edge %lld references agent outside [0,%lld)", (long long)e, n);
+    row_ptr[(size_t)s + 1]++;
+  }
+  for (long long i = 0; i < n; ++i) row_ptr[i + 1] += row_ptr[i];
+  std::vector<int> col((size_t)std::max<int64_t>(n_edges, 1));
+  {
+    std::vector<unsigned int> cur(row_ptr.begin(), row_ptr.end() - 1);
+    for (int64_t e = 0; e < n_edges; ++e) col[cur[edges[2 * e]]++] = edges[2 * e + 1];
+  }
+  // row blocks: whole 32-row groups, greedy up to kSirTile entries / 1024 rows
+  std::vector<int> rb;
+  rb.push_back(0);
+  long long r = 0;
+  while (r < n) {
+    long long end = r;
+    const unsigned int e0 = row_ptr[r];
+    while (end < n) {
+      const long long g_end = std::min<long long>(end + 32, n);
+      const bool first = end == r;
+      if (!first && (row_ptr[g_end] - e0 > (unsigned)kSirTile || g_end - r > kThreads * kSirRowsPerThread)) break;
+      end = g_end;
+    }
+    rb.push_back((int)end);
+    r = end;
+  }
+  SirDev& sv = m->sv;
+  unsigned int* d_rp; int* d_col; int* d_rb; float* d_esc;
+  int rc;
+  if ((rc = dev_alloc(m, &d_rp, (size_t)n + 1))) return rc;
+  if ((rc = dev_alloc(m, &d_col, col.size()))) return rc;
+  if ((rc = dev_alloc(m, &d_rb, rb.size()))) return rc;
+  if ((rc = dev_alloc(m, &d_esc, kSirKCap + 1))) return rc;
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = dev_alloc(m, &sv.state8[b], (size_t)n + 32))) return rc;
+    if ((rc = dev_alloc(m, &sv.infbits[b], (size_t)(n + 31) / 32 + 1))) return rc;
+    cudaMemset(sv.state8[b], 0, (size_t)n + 32);
+    cudaMemset(sv.infbits[b], 0, ((size_t)(n + 31) / 32 + 1) * 4);
+  }
+  CK(cudaMemcpy(d_rp, row_ptr.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_col, col.data(), (size_t)n_edges * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_rb, rb.data(), rb.size() * 4, cudaMemcpyHostToDevice));
+  {
+    // escape[k] = (1-beta)^k as a float32 product chain (DESIGN.md "SIR rule")
+    std::vector<float> q(kSirKCap + 1);
+    const float b = 1.0f - m->desc.types[0].params[0];
+    q[0] = 1.0f;
+    for (int k = 1; k <= kSirKCap; ++k) { volatile float v = q[k - 1] * b; q[k] = v; }
+    CK(cudaMemcpy(d_esc, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
+  }
+  sv.row_ptr = d_rp; sv.col = d_col; sv.rb = d_rb; sv.nrb = (int)rb.size() - 1; sv.escape = d_esc;
+  if ((rc = dev_alloc(m, &sv.partials, (size_t)sv.nrb * 3))) return rc;
+  m->nnz = n_edges;
+  m->net_built = true;
+  return sir_sync_from_api(m);
+}
+
+static int sir_sync_from_api(jxb_model* m) {
+  if (!m->net_built) return JXB_OK;
+  const long long n = m->desc.types[0].n_agents;
+  const int cur = (int)(m->time_step & 1);
+  const int blocks = (int)((n + 255) / 256);
+  sir_pack_kernel<<<blocks, 256, 0, m->eng->stream>>>((const int*)m->dev.t[0].f[0], m->sv.state8[cur],
+                                                      m->sv.infbits[cur], n);
+  m->eng->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(m->eng->stream));
+  return JXB_OK;
+}
+
+static int sir_sync_to_api(jxb_model* m) {
+  if (!m->net_built) return JXB_OK;
+  const long long n = m->desc.types[0].n_agents;
+  const int cur = (int)(m->time_step & 1);
+  sir_unpack_kernel<<<m->eng->sms * 8, 256, 0, m->eng->stream>>>(m->sv.state8[cur], (int*)m->dev.t[0].f[0], n);
+  m->eng->launches++;
+  CK(cudaGetLastError());
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// initialisation (model.py:118-144, agent.py:92-130)
+// ---------------------------------------------------------------------------------------
+static int launch_init(jxb_model* m, int type, Key key) {
+  const TypeDev& t = m->dev.t[type];
+  int blocks = (int)std::min<long long>((t.n + 255) / 256, (long long)m->eng->sms * 16);
+  if (m->desc.rng_mode == JXB_RNG_PARTITIONABLE)
+    init_kernel<1><<<blocks, 256, 0, m->eng->stream>>>(t, key);
+  else
+    init_kernel<0><<<blocks, 256, 0, m->eng->stream>>>(t, key);
+  m->eng->launches++;
+  CK(cudaGetLastError());
+  m->collections_ready[type] = true;
+  return JXB_OK;
+}
+
+extern "C" int jxb_collection_init(jxb_model* m, int type, uint32_t k0, uint32_t k1) {
+  NEED(m); NEED_TYPE(m, type);
+  CK(cudaSetDevice(m->eng->device));
+  int rc = launch_init(m, type, Key{k0, k1});
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(m->eng->stream));
+  if (m->has_net) return sir_sync_from_api(m);
+  if (m->has_grid) m->grid_built = false;
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_init(jxb_model* m, uint32_t k0, uint32_t k1) {
+  NEED(m);
+  CK(cudaSetDevice(m->eng->device));
+  const int C = m->desc.n_types, mode = m->desc.rng_mode;
+  const Key root{k0, k1};
+  m->rng = split_child(mode, root, 0, C + 1);                       // model.py:129-130
+  for (int i = 0; i < C; ++i) {
+    int rc = launch_init(m, i, split_child(mode, root, i + 1, C + 1));   // model.py:133-137
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(m->eng->stream));
+  m->initialized = true;
+  if (m->has_net) return sir_sync_from_api(m);
+  if (m->has_grid) m->grid_built = false;
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// step launch plan
+// ---------------------------------------------------------------------------------------
+static int plan_step_blocks(jxb_model* m) {
+  ModelDev& md = m->dev;
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1>, kThreads, 0));
+  if (occ < 1) occ = 1;
+  const int budget = m->eng->sms * occ;
+  long long total = 0;
+  for (int i = 0; i < md.n_types; ++i) total += md.t[i].n;
+  int begin = 0;
+  for (int i = 0; i < md.n_types; ++i) {
+    const long long need = std::max<long long>(1, (md.t[i].n / kVec + kThreads - 1) / kThreads);
+    long long share = std::max<long long>(1, (long long)((double)budget * (double)md.t[i].n / (double)total));
+    int nb = (int)std::min(need, share);
+    md.t[i].block_begin = begin;
+    md.t[i].block_count = nb;
+    begin += nb;
+  }
+  md.grid_blocks = begin;
+  m->step_blocks = begin;
+  return JXB_OK;
+}
+
+// enqueue one Model.step (model.py:146-216) on the stream; capture-safe (no host-varying args)
+static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
+  jxb_engine* eng = m->eng;
+  const bool part = m->desc.rng_mode == JXB_RNG_PARTITIONABLE;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed) {
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    m->prof_events.push_back(e0); m->prof_events.push_back(e1);
+  }
+  switch (m->desc.program) {
+    case JXB_PROGRAM_SCHELLING: {
+      const SchellingDev& sd = m->sd;
+      const bool fast = (sd.H % 16) == 0;
+      if (timed) cudaEventRecord(e0, s);
+      if (fast) stencil_compact_kernel<true><<<sd.ntiles, kThreads, 0, s>>>(sd, m->dev.ctrl);
+      else stencil_compact_kernel<false><<<sd.ntiles, kThreads, 0, s>>>(sd, m->dev.ctrl);
+      if (timed) cudaEventRecord(e1, s);
+      const long long work = std::max<long long>(std::max<long long>(m->n_empty_cells, sd.ntiles), 1);
+      const int blocks = (int)((work + kThreads - 1) / kThreads);
+      if (part) move_kernel<1><<<blocks, kThreads, 0, s>>>(sd, m->dev);
+      else move_kernel<0><<<blocks, kThreads, 0, s>>>(sd, m->dev);
+      eng->launches += 2;
+      break;
+    }
+    case JXB_PROGRAM_SIR: {
+      if (timed) cudaEventRecord(e0, s);
+      if (part) sir_step_kernel<1><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
+      else sir_step_kernel<0><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
+      if (timed) cudaEventRecord(e1, s);
+      eng->launches += 1;
+      break;
+    }
+    default: {
+      if (timed) cudaEventRecord(e0, s);
+      if (part) step_kernel<1><<<m->step_blocks, kThreads, 0, s>>>(m->dev);
+      else step_kernel<0><<<m->step_blocks, kThreads, 0, s>>>(m->dev);
+      if (timed) cudaEventRecord(e1, s);
+      eng->launches += 1;
+      if (m->dev.world_size > 1) {
+        // sharded population: sum/max/int slots are exchanged as three small all-reduces
+        if (!eng->nccl_comm) return fail(JXB_ERR_STATE, "sharded model but no NCCL communicator attached");
+        double* buf = m->dev.allreduce_buf;
+        int r = g_nccl.AllReduce(buf, buf, kFSum, /*ncclFloat64*/ 8, /*ncclSum*/ 0, eng->nccl_comm, s);
+        if (!r) r = g_nccl.AllReduce(buf + kFSum, buf + kFSum, kFMax, 8, /*ncclMax*/ 2, eng->nccl_comm, s);
+        if (!r) r = g_nccl.AllReduce(buf + kFSum + kFMax, buf + kFSum + kFMax, kISum, 8, 0, eng->nccl_comm, s);
+        if (r) return fail(JXB_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        tail_kernel<<<1, 32, 0, s>>>(m->dev);
+        eng->launches += 1;
+      }
+    }
+  }
+  CK(cudaGetLastError());
+  return JXB_OK;
+}
+
+static int build_graph(jxb_model* m, int chunk, cudaGraphExec_t* out) {
+  cudaStream_t s = m->eng->stream;
+  cudaGraph_t g = nullptr;
+  const int64_t before = m->eng->launches;
+  CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  for (int i = 0; i < chunk; ++i) {
+    int rc = enqueue_step(m, s, false);
+    if (rc) { cudaStreamEndCapture(s, &g); if (g) cudaGraphDestroy(g); return rc; }
+  }
+  CK(cudaStreamEndCapture(s, &g));
+  m->eng->launches = before;   // capture enqueued nothing
+  cudaError_t e = cudaGraphInstantiate(out, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(JXB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  return JXB_OK;
+}
+
+static int launches_per_step(jxb_model* m) {
+  if (m->desc.program == JXB_PROGRAM_SCHELLING) return 2;
+  return (m->dev.world_size > 1) ? 2 : 1;
+}
+
+extern "C" int jxb_model_set_profile(jxb_model* m, int enable) {
+  NEED(m);
+  m->profile = enable != 0;
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_profile(jxb_model* m, double* seconds, int64_t* launches, const char** name) {
+  NEED(m);
+  if (seconds) *seconds = m->prof_seconds;
+  if (launches) *launches = m->prof_launches;
+  if (name) {
+    switch (m->desc.program) {
+      case JXB_PROGRAM_SCHELLING: *name = "stencil_compact_kernel"; break;
+      case JXB_PROGRAM_SIR: *name = "sir_step_kernel"; break;
+      default: *name = "step_kernel";
+    }
+  }
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Model.run (model.py:218-262)
+// ---------------------------------------------------------------------------------------
+extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, double* metrics_out,
+                             int32_t* steps_out, int* n_records_out, double* device_seconds_out) {
+  NEED(m);
+  if (!m->initialized)
+    return fail(JXB_ERR_STATE, "Model must be initialized before stepping. Call initialize() first.");
+  if (steps < 0) return fail(JXB_ERR_INVALID, "steps must be >= 0");
+  if (collect_interval < 1) return fail(JXB_ERR_INVALID, "collect_interval must be >= 1");
+  jxb_engine* eng = m->eng;
+  CK(cudaSetDevice(eng->device));
+  cudaStream_t s = eng->stream;
+  if (m->has_grid && !m->grid_built) { int rc = jxb_model_grid_rebuild(m); if (rc) return rc; }
+  if (m->has_net && !m->net_built) return fail(JXB_ERR_STATE, "SIR model has no network; call jxb_model_set_network");
+  if (m->dev.world_size > 1 && !eng->nccl_comm) return fail(JXB_ERR_STATE, "sharded model but no NCCL communicator attached");
+
+  const int C = m->desc.n_types, mode = m->desc.rng_mode, stride = (C + 1) * 2;
+  // ---- key schedule of the whole run (model.py:156,164,183), host scalar work ----------
+  if ((size_t)steps * stride > m->keys_cap) {
+    if (m->d_keys) cudaFree(m->d_keys);
+    if (m->h_keys) cudaFreeHost(m->h_keys);
+    m->keys_cap = (size_t)std::max(steps, 16) * stride;
+    CK(cudaMalloc(&m->d_keys, m->keys_cap * 4));
+    CK(cudaMallocHost(&m->h_keys, m->keys_cap * 4));
+  }
+  for (int t = 0; t < steps; ++t) {
+    Key step_key = split_child(mode, m->rng, 1, 2);
+    m->rng = split_child(mode, m->rng, 0, 2);
+    uint32_t* row = m->h_keys + (size_t)t * stride;
+    for (int c = 0; c < C; ++c) {
+      Key ck = split_child(mode, step_key, 1, 2);
+      step_key = split_child(mode, step_key, 0, 2);
+      row[2 * c] = ck.a; row[2 * c + 1] = ck.b;
+    }
+    Key uk{0, 0};
+    if (m->prog->has_env_fn) uk = split_child(mode, step_key, 1, 2);
+    row[2 * C] = uk.a; row[2 * C + 1] = uk.b;
+  }
+  if (steps) CK(cudaMemcpyAsync(m->d_keys, m->h_keys, (size_t)steps * stride * 4, cudaMemcpyHostToDevice, s));
+  m->dev.keys = m->d_keys;
+
+  // ---- history ring ---------------------------------------------------------------------
+  const long long t0 = m->time_step;
+  const int n_rec = (int)((t0 + steps) / collect_interval - t0 / collect_interval);
+  if ((size_t)n_rec + 1 > m->rec_cap) {
+    if (m->d_metrics) cudaFree(m->d_metrics);
+    if (m->d_rec) cudaFree(m->d_rec);
+    m->rec_cap = (size_t)n_rec + 64;
+    CK(cudaMalloc(&m->d_metrics, m->rec_cap * kMaxMetrics * sizeof(double)));
+    CK(cudaMalloc(&m->d_rec, m->rec_cap * sizeof(int)));
+  }
+  m->dev.metrics = m->d_metrics;
+  m->dev.record_steps = m->d_rec;
+  m->dev.collect_interval = collect_interval;
+  {
+    // reset the per-run counters, keep the persistent ones
+    int zeros[2] = {0, 0};
+    CK(cudaMemcpyAsync(&m->dev.ctrl->step_in_run, zeros, sizeof(zeros), cudaMemcpyHostToDevice, s));
+  }
+  static const bool use_graph = getenv("JXB_NO_GRAPH") == nullptr;
+  const bool graphs = use_graph && !m->profile && m->dev.world_size == 1 && steps > 0;
+  if (graphs) {
+    // kernel arguments (the ModelDev snapshot) are baked into a captured graph: rebuild the
+    // two cached graphs (1 step, 32 steps) whenever a pointer or the interval changed
+    const bool changed = !m->graph1 || m->sig_keys != m->d_keys || m->sig_metrics != m->d_metrics ||
+                         m->sig_rec != m->d_rec || m->sig_ci != collect_interval;
+    if (changed) {
+      if (m->graph1) { cudaGraphExecDestroy(m->graph1); m->graph1 = nullptr; }
+      if (m->graphK) { cudaGraphExecDestroy(m->graphK); m->graphK = nullptr; }
+      int rc = build_graph(m, 1, &m->graph1);
+      if (rc) return rc;
+      m->chunkK = 32;
+      rc = build_graph(m, m->chunkK, &m->graphK);
+      if (rc) return rc;
+      m->sig_keys = m->d_keys; m->sig_metrics = m->d_metrics; m->sig_rec = m->d_rec; m->sig_ci = collect_interval;
+    }
+  }
+  for (auto e : m->prof_events) cudaEventDestroy(e);
+  m->prof_events.clear();
+
+  CK(cudaEventRecord(eng->ev0, s));
+  if (graphs) {
+    int left = steps;
+    while (left >= m->chunkK) { CK(cudaGraphLaunch(m->graphK, s)); left -= m->chunkK; }
+    while (left > 0) { CK(cudaGraphLaunch(m->graph1, s)); --left; }
+    eng->launches += (int64_t)steps * launches_per_step(m);
+  } else {
+    for (int t = 0; t < steps; ++t) {
+      int rc = enqueue_step(m, s, m->profile);
+      if (rc) return rc;
+    }
+  }
+  CK(cudaEventRecord(eng->ev1, s));
+  if (metrics_out && n_rec)
+    CK(cudaMemcpyAsync(metrics_out, m->d_metrics, (size_t)n_rec * kMaxMetrics * sizeof(double),
+                       cudaMemcpyDeviceToHost, s));
+  if (steps_out && n_rec)
+    CK(cudaMemcpyAsync(steps_out, m->d_rec, (size_t)n_rec * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+  if (device_seconds_out) *device_seconds_out = (double)ms * 1e-3;
+  if (n_records_out) *n_records_out = n_rec;
+  if (m->profile) {
+    double tot = 0;
+    for (size_t i = 0; i + 1 < m->prof_events.size(); i += 2) {
+      float k = 0;
+      cudaEventElapsedTime(&k, m->prof_events[i], m->prof_events[i + 1]);
+      tot += k;
+    }
+    m->prof_seconds = tot * 1e-3;
+    m->prof_launches = (int64_t)m->prof_events.size() / 2;
+  }
+  m->time_step = t0 + steps;
+  if (m->has_grid && steps > 0) m->sat_dirty = true;
+  return JXB_OK;
+}
+
+// AgentCollection.update with the caller's key (agent.py:132-177); env/metrics untouched
+extern "C" int jxb_collection_update(jxb_model* m, int type, uint32_t k0, uint32_t k1) {
+  NEED(m); NEED_TYPE(m, type);
+  if (!m->collections_ready[type])
+    return fail(JXB_ERR_STATE, "Agent collection not initialized. Call init() first.");   // agent.py:150-151
+  if (m->has_grid || m->has_net)
+    return fail(JXB_ERR_UNSUPPORTED, "grid / network collections step through Model.step only");
+  CK(cudaSetDevice(m->eng->device));
+  const TypeDev& t = m->dev.t[type];
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((t.n / kVec + kThreads - 1) / kThreads,
+                                                                     (long long)m->eng->sms * 8));
+  (void)k0; (void)k1;   // registered well-mixed rules draw nothing in update(); the key is unobservable
+  if (m->desc.rng_mode == JXB_RNG_PARTITIONABLE)
+    collection_update_kernel<1><<<blocks, kThreads, 0, m->eng->stream>>>(m->dev, type);
+  else
+    collection_update_kernel<0><<<blocks, kThreads, 0, m->eng->stream>>>(m->dev, type);
+  m->eng->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(m->eng->stream));
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// ensembles
+// ---------------------------------------------------------------------------------------
+extern "C" int jxb_ensemble_run(jxb_engine* eng, const jxb_model_desc* d, int R, int n_swept,
+                                const int32_t* slots, const double* params, const uint32_t* seeds,
+                                const double* env_init, int steps, double* last_metrics_out,
+                                double* device_seconds_out) {
+  if (!eng) return fail(JXB_ERR_INVALID, "engine is NULL");
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  if (R <= 0 || steps < 0 || !seeds || !last_metrics_out) return fail(JXB_ERR_INVALID, "bad ensemble arguments");
+  if (n_swept < 0 || n_swept > kEnsMaxSwept || (n_swept && (!slots || !params)))
+    return fail(JXB_ERR_INVALID, "bad swept-parameter table");
+  if (d->program == JXB_PROGRAM_SCHELLING || d->program == JXB_PROGRAM_SIR)
+    return fail(JXB_ERR_UNSUPPORTED, "grid / network programs run replicas through jxb_model_run");
+  CK(cudaSetDevice(eng->device));
+  cudaStream_t s = eng->stream;
+  const ProgramSpec* prog = find_program(d->program);
+  EnsDev ed;
+  memset(&ed, 0, sizeof(ed));
+  ed.program = d->program; ed.n_types = d->n_types; ed.has_env_fn = prog->has_env_fn;
+  ed.n_env = prog->n_env; ed.n_metrics = prog->n_metrics;
+  ed.R = R; ed.steps = steps; ed.n_swept = n_swept;
+  for (int i = 0; i < n_swept; ++i) {
+    ed.slots[i] = slots[i];
+    const int sl = slots[i];
+    const bool ok = (sl >= 0 && sl < JXB_MAX_PARAMS) ||
+                    (sl >= 100 && (sl - 100) / 16 < d->n_types);
+    if (!ok) return fail(JXB_ERR_INVALID, "swept slot %d is not a parameter of this model", sl);
+  }
+  for (int k = 0; k < JXB_MAX_PARAMS; ++k) ed.mp[k] = k < d->n_params ? d->params[k] : 0.0;
+  for (int k = 0; k < prog->n_env; ++k) ed.env0[k] = env_init ? env_init[k] : prog->env[k].dflt;
+  size_t off = 0;
+  for (int i = 0; i < d->n_types; ++i) {
+    fill_type_dev(d->types[i], ed.t[i]);
+    const RuleSpec* rs = find_rule(d->types[i].rule);
+    for (int f = 0; f < rs->nf; ++f) {
+      ed.t[i].f[f] = (void*)off;
+      size_t bytes = (size_t)(d->types[i].n_agents + 8) * rs->f[f].width * dtype_size(rs->f[f].dtype);
+      off += (bytes + 15) / 16 * 16;
+    }
+  }
+  ed.state_bytes = off;
+  ed.use_smem = off <= kEnsSmemBudget;
+  int grid;
+  size_t dyn = 0;
+  if (ed.use_smem) {
+    dyn = off;
+    grid = std::min(R, eng->sms * (off <= kEnsSmemBudget / 2 ? 2 : 1));
+  } else {
+    // keep all live replica slots inside L2 (~64 MB) when possible, at least one CTA per SM
+    long long fit = (long long)((64ull << 20) / off);
+    grid = (int)std::min<long long>(R, std::max<long long>(eng->sms, std::min<long long>(fit, 2ll * eng->sms)));
+  }
+  double* d_params = nullptr; uint32_t* d_seeds = nullptr; double* d_out = nullptr; unsigned char* d_scratch = nullptr;
+  auto cleanup = [&]() { cudaFree(d_params); cudaFree(d_seeds); cudaFree(d_out); cudaFree(d_scratch); };
+#define ECK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return fail(JXB_ERR_CUDA, \
+    "%s failed: %s", #call, cudaGetErrorString(_e)); } } while (0)
+  ECK(cudaMalloc(&d_params, std::max<size_t>((size_t)R * std::max(n_swept, 1) * sizeof(double), 16)));
+  ECK(cudaMalloc(&d_seeds, (size_t)R * 4));
+  ECK(cudaMalloc(&d_out, (size_t)R * kMaxMetrics * sizeof(double)));
+  if (!ed.use_smem) ECK(cudaMalloc(&d_scratch, (size_t)grid * off));
+  if (n_swept) ECK(cudaMemcpyAsync(d_params, params, (size_t)R * n_swept * sizeof(double), cudaMemcpyHostToDevice, s));
+  ECK(cudaMemcpyAsync(d_seeds, seeds, (size_t)R * 4, cudaMemcpyHostToDevice, s));
+  ed.params = d_params; ed.seeds = d_seeds; ed.out = d_out; ed.scratch = d_scratch;
+  const bool part = d->rng_mode == JXB_RNG_PARTITIONABLE;
+  if (dyn > 48 * 1024) {
+    if (part) ECK(cudaFuncSetAttribute(ensemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    else ECK(cudaFuncSetAttribute(ensemble_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  }
+  ECK(cudaEventRecord(eng->ev0, s));
+  if (part) ensemble_kernel<1><<<grid, kEnsThreads, dyn, s>>>(ed);
+  else ensemble_kernel<0><<<grid, kEnsThreads, dyn, s>>>(ed);
+  eng->launches++;
+  ECK(cudaGetLastError());
+  ECK(cudaEventRecord(eng->ev1, s));
+  std::vector<double> tmp((size_t)R * kMaxMetrics);
+  ECK(cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  ECK(cudaStreamSynchronize(s));
+  float ms = 0;
+  ECK(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
+#undef ECK
+  if (device_seconds_out) *device_seconds_out = ms * 1e-3;
+  for (int r = 0; r < R; ++r)
+    for (int k = 0; k < prog->n_metrics; ++k)
+      last_metrics_out[(size_t)r * prog->n_metrics + k] = tmp[(size_t)r * kMaxMetrics + k];
+  cleanup();
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-only key algebra
+// ---------------------------------------------------------------------------------------
+static bool mode_ok(int mode) { return mode == JXB_RNG_LEGACY || mode == JXB_RNG_PARTITIONABLE; }
+
+extern "C" int jxb_prng_threefry2x32(const uint32_t key[2], const uint32_t ctr[2], uint32_t out[2]) {
+  threefry2x32(key[0], key[1], ctr[0], ctr[1], out[0], out[1]);
+  return JXB_OK;
+}
+
+extern "C" int jxb_prng_split(int mode, const uint32_t key[2], int n, uint32_t* out) {
+  if (!mode_ok(mode) || n < 0 || !out) return fail(JXB_ERR_INVALID, "bad split arguments");
+  for (int j = 0; j < n; ++j) {
+    Key c = split_child(mode, Key{key[0], key[1]}, (uint64_t)j, (uint64_t)n);
+    out[2 * j] = c.a; out[2 * j + 1] = c.b;
+  }
+  return JXB_OK;
+}
+
+static uint32_t host_bits(int mode, Key k, uint64_t j, uint64_t n) {
+  return mode == 1 ? bits_elem<1>(k, j, n) : bits_elem<0>(k, j, n);
+}
+
+extern "C" int jxb_prng_bits(int mode, const uint32_t key[2], int64_t n, uint32_t* out) {
+  if (!mode_ok(mode) || n < 0 || !out) return fail(JXB_ERR_INVALID, "bad bits arguments");
+  for (int64_t j = 0; j < n; ++j) out[j] = host_bits(mode, Key{key[0], key[1]}, (uint64_t)j, (uint64_t)n);
+  return JXB_OK;
+}
+
+extern "C" int jxb_prng_uniform(int mode, const uint32_t key[2], int64_t n, float lo, float hi, float* out) {
+  if (!mode_ok(mode) || n < 0 || !out) return fail(JXB_ERR_INVALID, "bad uniform arguments");
+  for (int64_t j = 0; j < n; ++j)
+    out[j] = bits_to_uniform(host_bits(mode, Key{key[0], key[1]}, (uint64_t)j, (uint64_t)n), lo, hi);
+  return JXB_OK;
+}
+
+extern "C" int jxb_prng_randint(int mode, const uint32_t key[2], int64_t n, int32_t lo, int32_t hi, int32_t* out) {
+  if (!mode_ok(mode) || n < 0 || !out) return fail(JXB_ERR_INVALID, "bad randint arguments");
+  const Key k{key[0], key[1]};
+  const Key k1 = split_child(mode, k, 0, 2), k2 = split_child(mode, k, 1, 2);
+  uint32_t span = hi <= lo ? 1u : (uint32_t)((int64_t)hi - (int64_t)lo);
+  uint32_t mult = (1u << 16) % span;
+  mult = (uint32_t)(mult * mult) % span;
+  for (int64_t j = 0; j < n; ++j) {
+    const uint32_t hb = host_bits(mode, k1, (uint64_t)j, (uint64_t)n);
+    const uint32_t lb = host_bits(mode, k2, (uint64_t)j, (uint64_t)n);
+    const uint32_t off = (uint32_t)((hb % span) * mult + (lb % span)) % span;
+    out[j] = (int32_t)((int64_t)lo + (int64_t)off);
+  }
+  return JXB_OK;
+}

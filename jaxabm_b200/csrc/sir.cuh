@@ -1,0 +1,198 @@
+// sir.cuh -- SIR epidemic on a Network (C3): CSR neighbour aggregation as a segmented
+// reduction over ballot words, fused with the per-agent threefry draw and transition.
+//
+// Layout in HBM (DESIGN.md "SIR"):
+//   row_ptr uint32[N+1], col int32[nnz]   adjacency binned by source from env
+//                                         'network_edges' (jaxabm/agentpy.py:557,574-582)
+//   state8  int8[2][N]                    S/I/R, double-buffered (pre-step snapshot
+//                                         semantics of jaxabm/model.py:160)
+//   infbits uint32[2][ceil(N/32)]         "is infected" bitmap the gathers hit (L2-resident)
+//   rb      int32[nrb+1]                  row blocks: 32-row aligned, <= kSirTile adjacency
+//                                         entries unless a single 32-row group exceeds it
+//
+// One CTA per row block.  The CTA streams its adjacency entries tile by tile (coalesced),
+// turns each gathered infected bit into one bit of a warp ballot, prefix-sums the ballot
+// popcounts, and every row reads its infected-neighbour count as a difference of two
+// ranks.  Rows then draw u = uniform(split(coll_key, N)[i]) (jaxabm/agent.py:156) and
+// transition; the new infected bitmap word of each 32-row group is a plain ballot store.
+#pragma once
+#include "common.cuh"
+
+namespace jxb {
+
+constexpr int kSirTile = 2048;                 // adjacency entries per tile
+constexpr int kSirWords = kSirTile / 32;       // 64 ballot words
+constexpr int kSirRowsPerThread = 4;           // <= 1024 rows per row block
+constexpr int kSirKCap = 4095;
+
+struct SirDev {
+  const unsigned int* row_ptr;
+  const int* col;
+  signed char* state8[2];
+  unsigned int* infbits[2];
+  const int* rb;
+  int nrb;
+  const float* escape;     // q[k] = fl32(q[k-1]*fl32(1-beta)), k <= kSirKCap
+  long long* partials;     // [nrb][3] new S/I/R counts per row block
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, const ModelDev md) {
+  __shared__ unsigned int s_words[kSirWords + 1];
+  __shared__ unsigned int s_pref[kSirWords + 1];
+  __shared__ int s_red[3][kThreads / 32];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Ctrl* ctrl = md.ctrl;
+  const TypeDev& t = md.t[0];
+  const int cur = (int)(ctrl->time_step & 1), nxt = cur ^ 1;
+  const int r0 = sv.rb[blockIdx.x], r1 = sv.rb[blockIdx.x + 1];
+  const unsigned int e0 = sv.row_ptr[r0], e1 = sv.row_ptr[r1];
+  const unsigned int* inf = sv.infbits[cur];
+
+  unsigned int lo[kSirRowsPerThread], hi[kSirRowsPerThread];
+  int k[kSirRowsPerThread];
+#pragma unroll
+  for (int i = 0; i < kSirRowsPerThread; ++i) {
+    const int r = r0 + i * kThreads + tid;
+    k[i] = 0;
+    lo[i] = hi[i] = 0;
+    if (r < r1) { lo[i] = sv.row_ptr[r]; hi[i] = sv.row_ptr[r + 1]; }
+  }
+
+  for (unsigned int ts = e0; ts < e1; ts += kSirTile) {
+#pragma unroll
+    for (int j = 0; j < kSirTile / kThreads; ++j) {
+      const unsigned int e = ts + j * kThreads + tid;
+      unsigned int bit = 0;
+      if (e < e1) {
+        const int c = __ldcs(sv.col + e);                       // streamed once
+        bit = (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;         // gather: L1/L2-resident bitmap
+      }
+      const unsigned int w = __ballot_sync(0xffffffffu, bit);
+      if (lane == 0) s_words[j * (kThreads / 32) + warp] = w;
+    }
+    if (tid == 0) s_words[kSirWords] = 0;
+    __syncthreads();
+    if (warp == 0) {  // exclusive prefix of the 64 popcounts (+ total in slot 64)
+      const unsigned int a = __popc(s_words[2 * lane]), b = __popc(s_words[2 * lane + 1]);
+      unsigned int inc = a + b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      s_pref[2 * lane] = inc - a - b;
+      s_pref[2 * lane + 1] = inc - b;
+      if (lane == 31) s_pref[kSirWords] = inc;
+    }
+    __syncthreads();
+    const unsigned int te = ts + kSirTile;
+#pragma unroll
+    for (int i = 0; i < kSirRowsPerThread; ++i) {
+      const unsigned int a = lo[i] > ts ? lo[i] : ts, b = hi[i] < te ? hi[i] : te;
+      if (b > a) {
+        const unsigned int xa = a - ts, xb = b - ts;
+        const unsigned int ra = s_pref[xa >> 5] + __popc(s_words[xa >> 5] & ((1u << (xa & 31)) - 1u));
+        const unsigned int rb = s_pref[xb >> 5] + __popc(s_words[xb >> 5] & ((1u << (xb & 31)) - 1u));
+        k[i] += (int)(rb - ra);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- transitions ------------------------------------------------------------------------
+  const int step = ctrl->step_in_run;
+  const uint32_t* kp = md.keys + (size_t)step * (md.n_types + 1) * 2;
+  const Key ck = {kp[0], kp[1]};
+  const float gamma = t.p[1];
+  int cS = 0, cI = 0, cR = 0;
+#pragma unroll
+  for (int i = 0; i < kSirRowsPerThread; ++i) {
+    const int r = r0 + i * kThreads + tid;
+    const bool active = r < r1 && r < t.n;
+    int s = 0;
+    if (active) {
+      s = sv.state8[cur][r];
+      const bool need = (s == 0 && k[i] > 0) || s == 1;
+      if (need) {
+        const Key ak = split_child<MODE>(ck, (unsigned long long)(t.goff + r), (unsigned long long)t.gn);
+        const float u = bits_to_uniform(bits_scalar<MODE>(ak), 0.f, 1.f);
+        if (s == 0) {
+          const float p = 1.0f - __ldg(sv.escape + (k[i] < kSirKCap ? k[i] : kSirKCap));
+          if (u < p) s = 1;
+        } else if (u < gamma) {
+          s = 2;
+        }
+      }
+      sv.state8[nxt][r] = (signed char)s;
+      cS += (s == 0); cI += (s == 1); cR += (s == 2);
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, active && s == 1);
+    // rows of a warp-iteration form one 32-aligned group -> one whole bitmap word
+    const int rg = r0 + i * kThreads + warp * 32;
+    if (lane == 0 && rg < r1 && rg < t.n) sv.infbits[nxt][rg >> 5] = w;
+  }
+  cS = warp_sum(cS); cI = warp_sum(cI); cR = warp_sum(cR);
+  if (lane == 0) { s_red[0][warp] = cS; s_red[1][warp] = cI; s_red[2][warp] = cR; }
+  __syncthreads();
+  if (tid < 3) {
+    long long v = 0;
+    for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
+    sv.partials[(size_t)blockIdx.x * 3 + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&ctrl->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- tail: exact integer fold + metrics row (count_S, count_I, count_R) ---------------------
+  __shared__ long long s_tot[3][kThreads / 32];
+  long long v[3] = {0, 0, 0};
+  for (int b = tid; b < (int)gridDim.x; b += kThreads) {
+    v[0] += __ldcg(sv.partials + (size_t)b * 3 + 0);
+    v[1] += __ldcg(sv.partials + (size_t)b * 3 + 1);
+    v[2] += __ldcg(sv.partials + (size_t)b * 3 + 2);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+    if (lane == 0) s_tot[j][warp] = v[j];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long c[3] = {0, 0, 0};
+    for (int j = 0; j < 3; ++j)
+      for (int w = 0; w < kThreads / 32; ++w) c[j] += s_tot[j][w];
+    ctrl->ticket = 0;
+    ctrl->sir_count[0] = c[0]; ctrl->sir_count[1] = c[1]; ctrl->sir_count[2] = c[2];
+    const long long tsn = ctrl->time_step + 1;
+    if ((tsn % md.collect_interval) == 0) {
+      double* row = md.metrics + (size_t)ctrl->n_recorded * kMaxMetrics;
+      row[0] = (double)c[0]; row[1] = (double)c[1]; row[2] = (double)c[2];
+      md.record_steps[ctrl->n_recorded] = (int)tsn;
+      ctrl->n_recorded += 1;
+    }
+    ctrl->time_step = tsn;
+    ctrl->step_in_run += 1;
+  }
+}
+
+// API column 'state' int32[N]  <->  packed int8 + infected bitmap
+__global__ void sir_pack_kernel(const int* state, signed char* s8, unsigned int* bits, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int s = 0;
+  if (i < n) { s = state[i]; s8[i] = (signed char)s; }
+  const unsigned int w = __ballot_sync(0xffffffffu, i < n && s == 1);
+  if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = w;
+}
+
+__global__ void sir_unpack_kernel(const signed char* s8, int* state, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    state[i] = (int)s8[i];
+}
+
+}  // namespace jxb

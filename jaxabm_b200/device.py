@@ -1,0 +1,222 @@
+"""Thin object wrapper over a ``jxb_model`` handle (device-resident model state)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+
+
+class TypeSpec:
+    """One collection of a device model: rule, local/global population, rule constants."""
+
+    def __init__(self, rule: str, n_agents: int, params: Sequence[float] = (),
+                 global_offset: int = 0, global_n: Optional[int] = None):
+        self.rule = rule
+        self.n_agents = int(n_agents)
+        self.params = [float(p) for p in params]
+        self.global_offset = int(global_offset)
+        self.global_n = int(global_n) if global_n is not None else int(n_agents)
+
+
+def make_desc(program: str, types: Sequence[TypeSpec], params: Sequence[float] = (),
+              rng_mode: Optional[int] = None, grid: Optional[Tuple[int, int, bool]] = None,
+              world_size: int = 1, rank: int = 0) -> nat.ModelDesc:
+    d = nat.ModelDesc()
+    d.program = nat.PROGRAM[program]
+    d.rng_mode = nat.default_rng_mode() if rng_mode is None else int(rng_mode)
+    d.n_types = len(types)
+    if len(types) > nat.MAX_TYPES:
+        raise ValueError(f"at most {nat.MAX_TYPES} agent collections per model")
+    for i, t in enumerate(types):
+        td = d.types[i]
+        td.rule = nat.RULE[t.rule]
+        td.n_agents = t.n_agents
+        td.global_offset = t.global_offset
+        td.global_n = t.global_n
+        td.n_params = len(t.params)
+        for k, v in enumerate(t.params):
+            td.params[k] = v
+    d.n_params = len(params)
+    for k, v in enumerate(params):
+        d.params[k] = float(v)
+    if grid is not None:
+        d.grid_w, d.grid_h, d.grid_periodic = int(grid[0]), int(grid[1]), int(bool(grid[2]))
+    d.world_size, d.rank = world_size, rank
+    return d
+
+
+class DeviceModel:
+    def __init__(self, desc: nat.ModelDesc, engine: Optional[nat.Engine] = None):
+        self.engine = engine or nat.engine()
+        self.desc = desc
+        self.handle = C.c_void_p()
+        self._lib = nat.lib()
+        nat.check(self._lib.jxb_model_create(self.engine.handle, C.byref(desc), C.byref(self.handle)))
+        self.n_types = desc.n_types
+        self.fields: List[List[Tuple[str, np.dtype, int]]] = []
+        for t in range(self.n_types):
+            nf = C.c_int()
+            nat.check(self._lib.jxb_model_n_fields(self.handle, t, C.byref(nf)))
+            fl = []
+            for f in range(nf.value):
+                name, dt, w = C.c_char_p(), C.c_int(), C.c_int()
+                nat.check(self._lib.jxb_model_field_info(self.handle, t, f, C.byref(name), C.byref(dt), C.byref(w)))
+                fl.append((name.value.decode(), nat.DTYPES[dt.value], w.value))
+            self.fields.append(fl)
+        n = C.c_int()
+        nat.check(self._lib.jxb_model_n_env(self.handle, C.byref(n)))
+        self.env_slots: List[Tuple[str, np.dtype]] = []
+        for s in range(n.value):
+            name, dt = C.c_char_p(), C.c_int()
+            nat.check(self._lib.jxb_model_env_info(self.handle, s, C.byref(name), C.byref(dt)))
+            self.env_slots.append((name.value.decode(), nat.DTYPES[dt.value]))
+        nat.check(self._lib.jxb_model_n_metrics(self.handle, C.byref(n)))
+        self.metric_slots: List[Tuple[str, np.dtype]] = []
+        for s in range(n.value):
+            name, dt = C.c_char_p(), C.c_int()
+            nat.check(self._lib.jxb_model_metric_info(self.handle, s, C.byref(name), C.byref(dt)))
+            self.metric_slots.append((name.value.decode(), nat.DTYPES[dt.value]))
+
+    def close(self):
+        if self.handle:
+            self._lib.jxb_model_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- fields -------------------------------------------------------------------
+    def field_index(self, t: int, name: str) -> int:
+        for i, (n, _, _) in enumerate(self.fields[t]):
+            if n == name:
+                return i
+        raise KeyError(name)
+
+    def n_agents(self, t: int) -> int:
+        return int(self.desc.types[t].n_agents)
+
+    def _shape(self, t: int, f: int):
+        _, dt, w = self.fields[t][f]
+        n = self.n_agents(t)
+        return ((n,) if w == 1 else (n, w)), dt
+
+    def download(self, t: int, f: int) -> np.ndarray:
+        shape, dt = self._shape(t, f)
+        out = np.empty(shape, dtype=dt)
+        nat.check(self._lib.jxb_model_download(self.handle, t, f, nat.ptr(out), out.nbytes))
+        return out
+
+    def upload(self, t: int, f: int, value) -> None:
+        shape, dt = self._shape(t, f)
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), shape))
+        nat.check(self._lib.jxb_model_upload(self.handle, t, f, nat.ptr(a), a.nbytes))
+
+    def fill(self, t: int, f: int, value) -> None:
+        _, dt, w = self.fields[t][f]
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), (w,)))
+        nat.check(self._lib.jxb_model_fill(self.handle, t, f, nat.ptr(a), a.nbytes))
+
+    # ---- env ----------------------------------------------------------------------
+    def env_index(self, name: str) -> Optional[int]:
+        for i, (n, _) in enumerate(self.env_slots):
+            if n == name:
+                return i
+        return None
+
+    def set_env(self, slot: int, value) -> None:
+        nat.check(self._lib.jxb_model_set_env(self.handle, slot, float(value)))
+
+    def get_env(self, slot: int):
+        v = C.c_double()
+        nat.check(self._lib.jxb_model_get_env(self.handle, slot, C.byref(v)))
+        dt = self.env_slots[slot][1]
+        return float(v.value) if dt == np.float64 else dt(v.value)
+
+    def set_type_param(self, t: int, index: int, value: float) -> None:
+        nat.check(self._lib.jxb_model_set_type_param(self.handle, t, index, float(value)))
+
+    # ---- structure ----------------------------------------------------------------
+    def set_network(self, edges) -> None:
+        e = np.ascontiguousarray(np.asarray(edges, dtype=np.int32).reshape(-1, 2))
+        nat.check(self._lib.jxb_model_set_network(self.handle, nat.ptr(e), e.shape[0]))
+
+    def grid_rebuild(self) -> None:
+        nat.check(self._lib.jxb_model_grid_rebuild(self.handle))
+
+    def download_grid(self) -> np.ndarray:
+        out = np.empty((self.desc.grid_w, self.desc.grid_h), dtype=np.int32)
+        nat.check(self._lib.jxb_model_download_grid(self.handle, nat.ptr(out), out.nbytes))
+        return out
+
+    # ---- time loop ----------------------------------------------------------------
+    def init(self, key) -> None:
+        k = np.asarray(key, dtype=np.uint32).reshape(2)
+        nat.check(self._lib.jxb_model_init(self.handle, int(k[0]), int(k[1])))
+
+    def collection_init(self, t: int, key) -> None:
+        k = np.asarray(key, dtype=np.uint32).reshape(2)
+        nat.check(self._lib.jxb_collection_init(self.handle, t, int(k[0]), int(k[1])))
+
+    def collection_update(self, t: int, key) -> None:
+        k = np.asarray(key, dtype=np.uint32).reshape(2)
+        nat.check(self._lib.jxb_collection_update(self.handle, t, int(k[0]), int(k[1])))
+
+    @property
+    def time_step(self) -> int:
+        v = C.c_int64()
+        nat.check(self._lib.jxb_model_time_step(self.handle, C.byref(v)))
+        return v.value
+
+    def run(self, steps: int, collect_interval: int = 1):
+        """-> (record_steps int32[n], metrics float64[n, n_metrics], device_seconds)."""
+        t0 = self.time_step
+        n_rec = (t0 + steps) // collect_interval - t0 // collect_interval
+        m = np.zeros((max(n_rec, 1), nat.MAX_METRICS), dtype=np.float64)
+        st = np.zeros(max(n_rec, 1), dtype=np.int32)
+        n = C.c_int()
+        secs = C.c_double()
+        nat.check(self._lib.jxb_model_run(self.handle, int(steps), int(collect_interval), nat.ptr(m), nat.ptr(st),
+                                          C.byref(n), C.byref(secs)))
+        return st[:n.value], m[:n.value, :len(self.metric_slots)], secs.value
+
+    def set_profile(self, on: bool) -> None:
+        nat.check(self._lib.jxb_model_set_profile(self.handle, int(on)))
+
+    def profile(self):
+        s, n, name = C.c_double(), C.c_int64(), C.c_char_p()
+        nat.check(self._lib.jxb_model_profile(self.handle, C.byref(s), C.byref(n), C.byref(name)))
+        return s.value, n.value, name.value.decode()
+
+
+PROGRAM_ENV = {   # env slot names per program (csrc/engine.cu kPrograms)
+    "none": [], "random_walk": ["bounds_lo", "bounds_hi", "time", "mean_x", "mean_y", "num_red", "num_blue"],
+    "market": ["price_level", "gdp", "unemployment", "total_consumption", "total_production"],
+    "growth": ["price_level", "interest_rate"], "counter": ["counter", "increment"],
+    "schelling": ["segregation_index", "percent_satisfied", "total_moves"], "sir": [],
+}
+PROGRAM_N_METRICS = {0: 0, 1: 7, 2: 5, 3: 3, 4: 2, 5: 3, 6: 3}
+
+
+def ensemble_run(desc: nat.ModelDesc, slots: Sequence[int], params: np.ndarray, seeds: np.ndarray,
+                 steps: int, env_init: Optional[np.ndarray] = None, engine: Optional[nat.Engine] = None):
+    """-> (last_metrics float64[R, n_metrics], device_seconds)."""
+    eng = engine or nat.engine()
+    seeds = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint32))
+    R = seeds.shape[0]
+    slots_a = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
+    params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(R, len(slots_a)))
+    n_m = PROGRAM_N_METRICS[int(desc.program)]
+    out = np.zeros((R, max(n_m, 1)), dtype=np.float64)
+    env = None if env_init is None else np.ascontiguousarray(np.asarray(env_init, dtype=np.float64))
+    secs = C.c_double()
+    nat.check(nat.lib().jxb_ensemble_run(eng.handle, C.byref(desc), R, len(slots_a), nat.ptr(slots_a),
+                                         nat.ptr(params), nat.ptr(seeds),
+                                         None if env is None else nat.ptr(env), int(steps), nat.ptr(out),
+                                         C.byref(secs)))
+    return out[:, :n_m], secs.value

@@ -1,0 +1,253 @@
+"""Model loop: same public surface as ``jaxabm/model.py:18-285``, time loop on the device.
+
+``Model.run(steps)`` enqueues the whole loop of ``model.py:240-241`` as CUDA graphs of
+fused step kernels (agent updates -> deterministic reduction -> ``update_state_fn`` +
+``metrics_fn`` tail -> history row) and reads the history back once.  The PRNG key
+schedule of ``model.py:129-130,156,164,183`` is reproduced bit for bit.
+"""
+from __future__ import annotations
+
+import time
+from typing import Any, Callable, Dict, List, Optional
+
+import numpy as np
+
+from . import _native as nat
+from .agent import AgentCollection, UnregisteredRuleError, rule_of
+from .core import ModelConfig
+from .device import DeviceModel, make_desc
+from . import random as jrandom
+
+# per program: names of the Model(params=...) entries the device tail reads, with the
+# defaults the reference's functions use (None = required key, KeyError if absent)
+PROGRAM_PARAMS = {
+    "none": [],
+    "random_walk": [],          # slot 0 is the internal 'metrics live' flag
+    "market": [("price_adjustment_rate", 0.1)],          # test_integration.py:136
+    "growth": [("adjustment_rate", None), ("target_price", None)],   # test_analysis.py:109
+    "counter": [],
+    "schelling": [("similarity_threshold", 0.5)],
+    "sir": [],
+}
+# collections a program's functions look up by name (reference dict keys)
+PROGRAM_COLLECTIONS = {
+    "market": {"consumer": "consumers", "producer": "producers"},
+    "growth": {"growth": "consumers"},
+    "counter": {"increment": "consumers", "growth": "consumers"},
+}
+
+
+def program_of(update_state_fn, metrics_fn) -> str:
+    names = set()
+    for fn in (update_state_fn, metrics_fn):
+        if fn is None:
+            continue
+        p = getattr(fn, "jxb_program", None)
+        if p is None:
+            raise UnregisteredRuleError(
+                f"{getattr(fn, '__qualname__', fn)!r} is not a registered model function: the engine runs "
+                "update_state_fn / metrics_fn as the fused tail of the step kernel and needs a registered "
+                f"program ({sorted(nat.PROGRAM)}); decorate with jaxabm_b200.rules.program or use the "
+                "functions shipped in jaxabm_b200.rules. There is no CPU fallback.")
+        names.add(p)
+    if not names:
+        return "none"
+    if len(names) > 1:
+        raise UnregisteredRuleError(f"update_state_fn and metrics_fn belong to different programs: {sorted(names)}")
+    return names.pop()
+
+
+class Model:
+    """Core model class (``jaxabm/model.py:18``)."""
+
+    def __init__(self, params: Optional[Dict[str, Any]] = None, config: Optional[ModelConfig] = None,
+                 update_state_fn: Optional[Callable] = None, metrics_fn: Optional[Callable] = None):
+        self.config = config or ModelConfig()
+        self._rng = jrandom.PRNGKey(self.config.seed)                       # model.py:46
+        self._agent_collections: Dict[str, AgentCollection] = {}
+        self._env_state: Dict[str, Any] = {}
+        self._state: Optional[Dict[str, Any]] = None
+        self._params = params or {}
+        self._update_state_fn = update_state_fn
+        self._metrics_fn = metrics_fn
+        self._time_step = 0
+        self._history: List[Dict[str, Any]] = []
+        self._is_initialized = False
+        self._dev: Optional[DeviceModel] = None
+        self._program: Optional[str] = None
+        self.last_device_seconds = 0.0
+
+    # ---- construction ---------------------------------------------------------------------
+    def add_agent_collection(self, name: str, agent_collection: AgentCollection) -> None:
+        if self._is_initialized:
+            raise RuntimeError("Cannot add agent collections after model is initialized")   # model.py:71-72
+        self._agent_collections[name] = agent_collection
+
+    def add_env_state(self, name: str, value: Any) -> None:                 # model.py:76-99
+        if self._is_initialized and self._state is not None:
+            self._state.setdefault("env", {})[name] = value
+        self._env_state[name] = value
+        if self._dev is not None:
+            self._push_env(name, value)
+
+    def _push_env(self, name: str, value: Any) -> None:
+        dev = self._dev
+        if name == "bounds":
+            b = np.asarray(value, dtype=np.float32).reshape(-1)
+            for nm, v in (("bounds_lo", b[0]), ("bounds_hi", b[1])):
+                s = dev.env_index(nm)
+                if s is not None:
+                    dev.set_env(s, v)
+            return
+        if name == "network_edges" and self._program == "sir":
+            dev.set_network(value)
+            return
+        s = dev.env_index(name)
+        if s is not None and np.ndim(value) == 0:
+            dev.set_env(s, value)
+
+    def model_state(self) -> Dict[str, Any]:                                # model.py:101-116
+        state = {"time_step": self._time_step, "env": self._env_state}
+        for name, c in self._agent_collections.items():
+            state[f"agents_{name}"] = c.states
+        return state
+
+    # ---- initialisation --------------------------------------------------------------------
+    def initialize(self) -> None:                                           # model.py:118-144
+        if not self._agent_collections:
+            raise ValueError("No agent collections added to model")
+        program = program_of(self._update_state_fn, self._metrics_fn)
+        specs = [c.type_spec() for c in self._agent_collections.values()]
+        wanted = PROGRAM_COLLECTIONS.get(program)
+        if wanted:
+            for name, spec in zip(self._agent_collections, specs):
+                if spec.rule in wanted and wanted[spec.rule] != name:
+                    raise UnregisteredRuleError(
+                        f"program {program!r} looks its {spec.rule} collection up as {wanted[spec.rule]!r} "
+                        f"(as the reference functions do); it was added as {name!r}")
+        mparams = []
+        for key, default in PROGRAM_PARAMS[program]:
+            if key in self._params:
+                mparams.append(float(self._params[key]))
+            elif default is None:
+                raise KeyError(key)
+            else:
+                mparams.append(float(default))
+        if program == "random_walk":
+            # compute_metrics looks the walkers up under a fixed collection name
+            # (examples/basic_example.py:151); under any other name it reports 0.0 distances
+            want = getattr(getattr(self, "_facade", None), "jxb_metrics_collection", "walkers")
+            names = list(self._agent_collections)
+            mparams = [1.0 if (names and names[0] == want) else 0.0]
+        grid = None
+        if program == "schelling":
+            shape = self._env_state.get("grid_shape")
+            if shape is None:
+                raise ValueError("Schelling needs a Grid: env state 'grid_shape' is missing")
+            grid = (int(shape[0]), int(shape[1]), bool(self._env_state.get("grid_periodic", False)))
+        desc = make_desc(program, specs, mparams, rng_mode=self.config.rng_mode, grid=grid)
+        self._dev = DeviceModel(desc)
+        self._program = program
+        for name, value in list(self._env_state.items()):
+            self._push_env(name, value)
+        # keys = split(_rng, C+1); _rng = keys[0]; collection i <- keys[i+1]     (model.py:129-137)
+        keys = jrandom.split(self._rng, len(self._agent_collections) + 1, desc.rng_mode)
+        self._dev.init(self._rng)
+        self._rng = keys[0]
+        for i, c in enumerate(self._agent_collections.values()):
+            c._attach(self._dev, i, self.config, keys[i + 1])
+            host_init = getattr(c.agent_type, "jxb_host_init", None)
+            if callable(host_init):
+                for fname, value in host_init(self.config).items():
+                    self._dev.fill(i, self._dev.field_index(i, fname), value)
+        self._is_initialized = True
+        self._state = {"env": self._env_state.copy()}                       # model.py:142-144
+
+    # ---- stepping ---------------------------------------------------------------------------
+    def _metric_names(self) -> List[tuple]:
+        slots = list(enumerate(self._dev.metric_slots))
+        if self._program == "market":
+            have = {s.rule for s in (c.type_spec() for c in self._agent_collections.values())}
+            if "consumer" not in have:
+                slots = [x for x in slots if x[1][0] != "avg_utility"]
+            if "producer" not in have:
+                slots = [x for x in slots if x[1][0] != "avg_profit"]
+        if self._program == "counter":
+            have = set(self._agent_collections)
+            if "consumers" not in have:
+                slots = [x for x in slots if x[1][0] != "total_value"]
+        if self._metrics_fn is None:
+            return []
+        return slots
+
+    @staticmethod
+    def _cast(v: float, dt):
+        if dt == np.float64:
+            return float(v)
+        if dt == np.int32:
+            return np.int32(int(v))
+        return dt(v)
+
+    def _pull_env(self) -> None:
+        if self._update_state_fn is None:
+            return
+        for s, (name, _) in enumerate(self._dev.env_slots):
+            if name in ("bounds_lo", "bounds_hi"):
+                continue
+            if name in self._env_state or self._program not in ("random_walk", "counter"):
+                self._env_state[name] = self._dev.get_env(s)
+
+    def _advance(self, steps: int, collect_interval: int) -> List[Dict[str, Any]]:
+        """Run `steps` steps on the device; return the history rows they produced."""
+        rec_steps, rec, secs = self._dev.run(steps, collect_interval)
+        self.last_device_seconds = secs
+        self._time_step += steps
+        names = self._metric_names()
+        rows = [{"time_step": int(rec_steps[r]),
+                 "metrics": {name: self._cast(rec[r, k], dt) for k, (name, dt) in names}}
+                for r in range(len(rec_steps))]
+        self._pull_env()
+        return rows
+
+    def step(self) -> Dict[str, Any]:                                       # model.py:146-216
+        if not self._is_initialized:
+            raise RuntimeError("Model must be initialized before stepping. Call initialize() first.")
+        row = self._advance(1, 1)[0]
+        if self.config.track_history and self._time_step % self.config.collect_interval == 0:
+            self._history.append(row)                                       # model.py:206-213
+        return row["metrics"]
+
+    def run(self, steps: Optional[int] = None) -> Dict[str, List[Any]]:     # model.py:218-262
+        if not self._is_initialized:
+            self.initialize()
+        steps_to_run = steps if steps is not None else self.config.steps
+        if self.config.track_history:
+            self._history = []
+        start = time.time()
+        ci = self.config.collect_interval if self.config.track_history else (1 << 30)
+        rows = self._advance(int(steps_to_run), ci)
+        if self.config.track_history:
+            self._history.extend(rows)
+        elapsed = max(time.time() - start, 1e-12)
+        print(f"Ran {steps_to_run} steps in {elapsed:.2f}s ({steps_to_run / elapsed:.1f} steps/sec)")
+        if self.config.track_history and self._history:
+            metrics: Dict[str, List[Any]] = {"step": [h["time_step"] for h in self._history]}
+            for name in self._history[0]["metrics"].keys():
+                metrics[name] = [h["metrics"][name] for h in self._history]
+            return metrics
+        return {}
+
+    @property
+    def agent_collections(self) -> Dict[str, AgentCollection]:
+        return self._agent_collections
+
+    @property
+    def state(self) -> Dict[str, Any]:                                      # model.py:273-285
+        if self._state is None:
+            self._state = {"env": self._env_state.copy()}
+        return self._state
+
+    def jit_step(self) -> Callable:
+        """``model.py:287-342``: nothing in the reference calls it; here every step already is a
+        compiled kernel, so this returns the bound ``step``."""
+        return self.step

@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """The in-tree library must exist before any test imports the package."""
+    import __graft_entry__ as g
+    g.build()
+
+
+@pytest.fixture(params=[0, 1], ids=["legacy", "partitionable"])
+def mode(request):
+    return request.param
