@@ -264,14 +264,17 @@ __device__ inline void program_tail(const ModelDev& md, const double* tot, doubl
 __device__ inline void finish_step(const ModelDev& md, const double* tot) {
   Ctrl* c = md.ctrl;
   const long long t = c->time_step + 1;
-  double* row = md.metrics + (size_t)c->n_recorded * kMaxMetrics;
-  double scratch[kMaxMetrics];
-  const bool rec = (t % md.collect_interval) == 0;
-  double* m = rec ? row : scratch;
+  // metrics are formed in a local row and copied out with plain global stores (selecting
+  // between a global row and a local scratch pointer made nvcc 12.9 infer the local
+  // address space for the tail's stores and drop them)
+  double m[kMaxMetrics];
 #pragma unroll
   for (int i = 0; i < kMaxMetrics; ++i) m[i] = 0.0;
   program_tail(md, tot, md.env, m);
-  if (rec) {
+  if ((t % md.collect_interval) == 0) {
+    double* row = md.metrics + (size_t)c->n_recorded * kMaxMetrics;
+#pragma unroll
+    for (int i = 0; i < kMaxMetrics; ++i) row[i] = m[i];
     md.record_steps[c->n_recorded] = (int)t;
     c->n_recorded += 1;
   }
