@@ -106,9 +106,13 @@ class DeviceModel:
         n = self.n_agents(t)
         return ((n,) if w == 1 else (n, w)), dt
 
-    def download(self, t: int, f: int) -> np.ndarray:
+    def download(self, t: int, f: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Copy one state column to the host (into ``out`` -- e.g. a pinned buffer -- if given)."""
         shape, dt = self._shape(t, f)
-        out = np.empty(shape, dtype=dt)
+        if out is None:
+            out = np.empty(shape, dtype=dt)
+        elif out.shape != shape or out.dtype != dt or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous {dt} array of shape {shape}")
         nat.check(self._lib.jxb_model_download(self.handle, t, f, nat.ptr(out), out.nbytes))
         return out
 
