@@ -145,6 +145,9 @@ int jxb_model_grid_rebuild(jxb_model*);
 /* env['grid'] (int32[W,H], -1 empty) as the reference lays it out
  * (examples/models/schelling_model.py:119-131).                                     */
 int jxb_model_download_grid(jxb_model*, int32_t* host, size_t bytes);
+/* env['empty_cells'] (examples/models/schelling_model.py:133-139) as cell ids x*H+y in slot
+ * order, int32[W*H - n_agents].                                                          */
+int jxb_model_download_empty_cells(jxb_model*, int32_t* host, size_t bytes);
 
 /* Model.initialize (jaxabm/model.py:118-144): keys = split(PRNGKey(seed), C+1);
  * collection i is initialised on the device from keys[i+1] (agent.py:92-130).       */

@@ -75,6 +75,7 @@ SIGNATURES = {
     "jxb_model_set_network": (C.c_int, [_P, _P, C.c_int64]),
     "jxb_model_grid_rebuild": (C.c_int, [_P]),
     "jxb_model_download_grid": (C.c_int, [_P, _P, C.c_size_t]),
+    "jxb_model_download_empty_cells": (C.c_int, [_P, _P, C.c_size_t]),
     "jxb_model_init": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
     "jxb_collection_init": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32]),
     "jxb_collection_update": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32]),

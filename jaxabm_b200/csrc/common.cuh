@@ -41,14 +41,9 @@ struct Ctrl {
   int n_recorded;         // history rows written this run
   long long time_step;    // Model._time_step (persists across run() calls, model.py:203)
   unsigned int ticket;    // last-block election for the fused step kernel
-  unsigned int ticket2;   // second election (Schelling move kernel / SIR)
   // Schelling per-step scalars
-  unsigned int tile_ticket;
-  unsigned int n_unsat, n_empty;
+  unsigned int n_unsat, n_moved;
   long long total_moves;
-  double seg_sum;
-  long long seg_cnt;
-  long long n_satisfied;
   // SIR per-step counts
   long long sir_count[3];
 };

@@ -169,7 +169,7 @@ struct jxb_model {
   double* d_metrics = nullptr; int* d_rec = nullptr; size_t rec_cap = 0;
   // Schelling
   bool has_grid = false; SchellingDev sd{}; long long pad = 0; float* d_ratio = nullptr;
-  bool grid_built = false; bool sat_dirty = false; long long n_empty_cells = 0;
+  bool grid_built = false; bool sat_dirty = false; long long n_empty_cells = 0; int sch_blocks = 0;
   // SIR
   bool has_net = false; SirDev sv{}; bool net_built = false; long long nnz = 0;
   // graphs: cached executable graphs of `chunk` consecutive steps
@@ -371,28 +371,38 @@ extern "C" int jxb_model_create(jxb_engine* eng, const jxb_model_desc* d, jxb_mo
     TRY(dev_alloc(m, &sd.cell_agent, (size_t)sd.cells));
     const long long n = d->types[0].n_agents;
     m->n_empty_cells = sd.cells - n;
+    sd.n_empty = (unsigned int)(sd.cells - n);
     TRY(dev_alloc(m, &sd.U, (size_t)n + 1));
-    TRY(dev_alloc(m, &sd.UA, (size_t)n + 1));
+    TRY(dev_alloc(m, &sd.MA, (size_t)n + 1));
     TRY(dev_alloc(m, &sd.E, (size_t)(sd.cells - n) + 1));
-    TRY(dev_alloc(m, &sd.tile_desc, (size_t)sd.ntiles));
-    TRY(dev_alloc(m, &sd.tile_seg_sum, (size_t)sd.ntiles));
-    TRY(dev_alloc(m, &sd.tile_seg_cnt, (size_t)sd.ntiles));
-    cudaMemset(sd.tile_desc, 0, sizeof(unsigned long long) * sd.ntiles);
-    // satisfaction / ratio tables in the reference's float32 arithmetic
-    const float thr = d->n_params > 0 ? (float)d->params[0] : 0.5f;
-    float ratio[10 * 16] = {0};
-    for (int o = 0; o < 10; ++o) {
-      unsigned int bits = 0;
-      for (int s = 0; s < 16; ++s) {
-        bool sat = (o == 0) || (s <= o && ((float)s / (float)o) >= thr);
-        if (sat) bits |= 1u << s;
-        if (o > 0 && s <= o) ratio[o * 16 + s] = (float)s / (float)o;
-      }
-      sd.sat_lut[o] = bits;
+    TRY(dev_alloc(m, &sd.mask16, (size_t)(sd.cells + 15) / 16 + 16));
+    {
+      // persistent cooperative grid: every CTA must be co-resident
+      int occ = 0;
+      cudaError_t oe = (sd.H % 16 == 0)
+          ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, schelling_run_kernel<true, 1>, kThreads, 0)
+          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, schelling_run_kernel<false, 1>, kThreads, 0);
+      if (oe != cudaSuccess || occ < 1) { jxb_model_destroy(m); return fail(JXB_ERR_CUDA, "occupancy query failed"); }
+      int bps = occ;
+      if (const char* ev = getenv("JXB_SCH_BPS")) bps = std::max(1, std::min(occ, atoi(ev)));
+      else bps = std::min(occ, 4);
+      m->sch_blocks = (int)std::max<long long>(1, std::min<long long>((long long)eng->sms * bps, (sd.cells + 511) / 512));
     }
-    TRY(dev_alloc(m, &m->d_ratio, 160));
-    cudaMemcpy(m->d_ratio, ratio, sizeof(ratio), cudaMemcpyHostToDevice);
-    sd.ratio_lut = m->d_ratio;
+    {
+      BlkPart* bp = nullptr;
+      TRY(dev_alloc(m, &bp, (size_t)2 * m->sch_blocks));
+      sd.blk_part = bp;
+    }
+    // least number of same-type neighbours that satisfies an agent with o occupied neighbours,
+    // evaluated in the rule's float32 arithmetic: same/o >= threshold
+    const float thr = d->n_params > 0 ? (float)d->params[0] : 0.5f;
+    sd.need_lut = 0;
+    for (int o = 1; o <= 8; ++o) {
+      int need = o + 1;
+      for (int sm = 0; sm <= o; ++sm)
+        if (((float)sm / (float)o) >= thr) { need = sm; break; }
+      sd.need_lut |= (unsigned long long)need << (4 * o);
+    }
     m->has_grid = true;
   }
   if (d->program == JXB_PROGRAM_SIR) m->has_net = true;
@@ -563,17 +573,22 @@ extern "C" int jxb_model_grid_rebuild(jxb_model* m) {
   CK(cudaSetDevice(m->eng->device));
   cudaStream_t s = m->eng->stream;
   int* d_err = nullptr;
-  CK(cudaMalloc(&d_err, sizeof(int)));
-  CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+  CK(cudaMalloc(&d_err, 2 * sizeof(int)));
+  CK(cudaMemsetAsync(d_err, 0, 2 * sizeof(int), s));
   const int blocks = m->eng->sms * 8;
   grid_clear_kernel<<<blocks, 256, 0, s>>>(m->sd, m->pad);
   grid_scatter_kernel<<<blocks, 256, 0, s>>>(m->sd, (const int*)m->dev.t[0].f[0], (const int2*)m->dev.t[0].f[1],
                                             m->desc.types[0].n_agents, d_err);
-  m->eng->launches += 2;
+  // env['empty_cells']: ascending empty cells of the freshly built grid
+  empty_list_kernel<<<1, 1024, 0, s>>>(m->sd, (unsigned int*)(d_err + 1));
+  m->eng->launches += 3;
   int err = 0;
+  unsigned int n_empty = 0;
   CK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&n_empty, d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   cudaFree(d_err);
+  if (!err && n_empty != m->sd.n_empty) err = 2;
   CK(cudaGetLastError());
   if (err == 1) return fail(JXB_ERR_INVALID, "an agent position lies outside the grid");
   if (err == 2) return fail(JXB_ERR_INVALID, "two agents share a grid cell");
@@ -594,6 +609,17 @@ extern "C" int jxb_model_download_grid(jxb_model* m, int32_t* host, size_t bytes
   CK(cudaMemcpyAsync(host, tmp, bytes, cudaMemcpyDeviceToHost, m->eng->stream));
   CK(cudaStreamSynchronize(m->eng->stream));
   cudaFree(tmp);
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_download_empty_cells(jxb_model* m, int32_t* host, size_t bytes) {
+  NEED(m);
+  if (!m->has_grid) return fail(JXB_ERR_STATE, "model has no Grid");
+  if (bytes != (size_t)m->sd.n_empty * 4) return fail(JXB_ERR_INVALID, "empty_cells holds %u int32", m->sd.n_empty);
+  CK(cudaSetDevice(m->eng->device));
+  if (!m->grid_built) { int rc = jxb_model_grid_rebuild(m); if (rc) return rc; }
+  if (bytes) CK(cudaMemcpyAsync(host, m->sd.E, bytes, cudaMemcpyDeviceToHost, m->eng->stream));
+  CK(cudaStreamSynchronize(m->eng->stream));
   return JXB_OK;
 }
 
@@ -779,20 +805,6 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
     m->prof_events.push_back(e0); m->prof_events.push_back(e1);
   }
   switch (m->desc.program) {
-    case JXB_PROGRAM_SCHELLING: {
-      const SchellingDev& sd = m->sd;
-      const bool fast = (sd.H % 16) == 0;
-      if (timed) cudaEventRecord(e0, s);
-      if (fast) stencil_compact_kernel<true><<<sd.ntiles, kThreads, 0, s>>>(sd, m->dev.ctrl);
-      else stencil_compact_kernel<false><<<sd.ntiles, kThreads, 0, s>>>(sd, m->dev.ctrl);
-      if (timed) cudaEventRecord(e1, s);
-      const long long work = std::max<long long>(std::max<long long>(m->n_empty_cells, sd.ntiles), 1);
-      const int blocks = (int)((work + kThreads - 1) / kThreads);
-      if (part) move_kernel<1><<<blocks, kThreads, 0, s>>>(sd, m->dev);
-      else move_kernel<0><<<blocks, kThreads, 0, s>>>(sd, m->dev);
-      eng->launches += 2;
-      break;
-    }
     case JXB_PROGRAM_SIR: {
       if (timed) cudaEventRecord(e0, s);
       if (part) sir_step_kernel<1><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
@@ -841,8 +853,18 @@ static int build_graph(jxb_model* m, int chunk, cudaGraphExec_t* out) {
   return JXB_OK;
 }
 
+// Schelling: the whole run is ONE cooperative launch (csrc/schelling.cuh)
+static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
+  const bool fast = (m->sd.H % 16) == 0, part = m->desc.rng_mode == JXB_RNG_PARTITIONABLE;
+  void* args[] = {(void*)&m->sd, (void*)&m->dev, (void*)&steps};
+  const void* fn = fast ? (part ? (const void*)schelling_run_kernel<true, 1> : (const void*)schelling_run_kernel<true, 0>)
+                        : (part ? (const void*)schelling_run_kernel<false, 1> : (const void*)schelling_run_kernel<false, 0>);
+  CK(cudaLaunchCooperativeKernel(fn, dim3(m->sch_blocks), dim3(kThreads), args, 0, s));
+  m->eng->launches += 1;
+  return JXB_OK;
+}
+
 static int launches_per_step(jxb_model* m) {
-  if (m->desc.program == JXB_PROGRAM_SCHELLING) return 2;
   return (m->dev.world_size > 1) ? 2 : 1;
 }
 
@@ -858,7 +880,7 @@ extern "C" int jxb_model_profile(jxb_model* m, double* seconds, int64_t* launche
   if (launches) *launches = m->prof_launches;
   if (name) {
     switch (m->desc.program) {
-      case JXB_PROGRAM_SCHELLING: *name = "stencil_compact_kernel"; break;
+      case JXB_PROGRAM_SCHELLING: *name = "schelling_run_kernel"; break;
       case JXB_PROGRAM_SIR: *name = "sir_step_kernel"; break;
       default: *name = "step_kernel";
     }
@@ -927,7 +949,8 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
     CK(cudaMemcpyAsync(&m->dev.ctrl->step_in_run, zeros, sizeof(zeros), cudaMemcpyHostToDevice, s));
   }
   static const bool use_graph = getenv("JXB_NO_GRAPH") == nullptr;
-  const bool graphs = use_graph && !m->profile && m->dev.world_size == 1 && steps > 0;
+  const bool persistent = m->desc.program == JXB_PROGRAM_SCHELLING;
+  const bool graphs = use_graph && !persistent && !m->profile && m->dev.world_size == 1 && steps > 0;
   if (graphs) {
     // kernel arguments (the ModelDev snapshot) are baked into a captured graph: rebuild the
     // two cached graphs (1 step, 32 steps) whenever a pointer or the interval changed
@@ -948,7 +971,9 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   m->prof_events.clear();
 
   CK(cudaEventRecord(eng->ev0, s));
-  if (graphs) {
+  if (persistent) {
+    if (steps > 0) { int rc = launch_schelling(m, steps, s); if (rc) return rc; }
+  } else if (graphs) {
     int left = steps;
     while (left >= m->chunkK) { CK(cudaGraphLaunch(m->graphK, s)); left -= m->chunkK; }
     while (left > 0) { CK(cudaGraphLaunch(m->graph1, s)); --left; }
@@ -971,7 +996,10 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   CK(cudaEventElapsedTime(&ms, eng->ev0, eng->ev1));
   if (device_seconds_out) *device_seconds_out = (double)ms * 1e-3;
   if (n_records_out) *n_records_out = n_rec;
-  if (m->profile) {
+  if (m->profile && persistent) {
+    m->prof_seconds = (double)ms * 1e-3;      // the persistent kernel IS the run: time per step = total / steps
+    m->prof_launches = steps;
+  } else if (m->profile) {
     double tot = 0;
     for (size_t i = 0; i + 1 < m->prof_events.size(); i += 2) {
       float k = 0;

@@ -1,45 +1,53 @@
-// schelling.cuh -- Schelling segregation on a Grid (C2): cell-binned occupancy, Moore-8
-// stencil, single-pass stream compaction of movers / empty cells, keyed matching.
+// schelling.cuh -- Schelling segregation on a Grid (C2): the whole time loop as ONE
+// persistent cooperative kernel (cell-binned occupancy, Moore-8 stencil by byte-SWAR adds,
+// ordered compaction of the unsatisfied agents, keyed conflict-free matching to empty cells).
 //
 // Layout in HBM (DESIGN.md "Schelling"):
 //   cell_type  int8  [pad | W*H | pad]   -1 empty, else agent type   (env['grid'] of
 //              examples/models/schelling_model.py:119-131, packed 4x narrower)
 //   cell_agent int32 [W*H]               the binning: which agent sits in the cell
+//   E          uint32[e]                 env['empty_cells'] (schelling_model.py:133-139) as
+//              cell ids; slot j is refilled with the mover's old cell, so it is maintained
+//              in O(movers) per step and never rebuilt
 //   type/position/moves per agent        API-visible SoA (schelling_model.py:26-31)
 // The pad holds one halo row on each side (0xFF = empty, or the wrapped row when
 // Grid(periodic=True), jaxabm/agentpy.py:480) so vertical neighbours are plain offsets.
 //
-// Step = 2 launches:
-//   stencil_compact_kernel : per 4096-cell tile, neighbour counts by byte-SWAR adds,
-//       satisfied / empty flags, block scan + decoupled look-back across tiles, and the
-//       ordered lists U (unsatisfied cells, ascending cell id), UA (their agents) and
-//       E (empty cells, ascending) written straight from registers -- no flag array.
-//   move_kernel : mover k < min(u,e): U[piU(k)] -> E[piE(k)] with two keyed Feistel
-//       bijections (round keys = bits(coll_key, (8,))); conflict-free by construction;
-//       last CTA folds the per-tile partials and writes the step's metrics row.
+// Per step, inside the kernel (3 grid-wide barriers, no host round trip, no launch):
+//   phase 1  every CTA sweeps its contiguous range of 4096-cell tiles: neighbour counts by
+//            SWAR byte adds, per-cell satisfaction against a packed threshold table, a 16-bit
+//            "unsatisfied" mask per thread (2 B per 16 cells), exact integer partials for the
+//            segregation index; publishes its unsatisfied count.
+//   phase 2  exclusive prefix over the CTA counts (each CTA folds its predecessors), ordered
+//            write of U = unsatisfied cells ascending; CTA 0 writes the step's metrics row.
+//   phase 3  mover k < min(u, e): agent in U[piU(k)] -> E[piE(k)], E[piE(k)] <- old cell;
+//            piU / piE are keyed Feistel bijections with round keys bits(coll_key, (8,)).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace jxb {
 
-constexpr int kTileCells = 4096;          // cells per CTA tile
+namespace cg = cooperative_groups;
+
+constexpr int kTileCells = 4096;          // cells per tile (256 threads x 16)
 constexpr int kCellsPerThread = 16;       // one uint4 of the packed grid
 
 struct SchellingDev {
   signed char* ct;        // points at cell 0 (halo/pad on both sides)
   int* cell_agent;
-  unsigned int* U;        // unsatisfied cells, ascending
-  int* UA;                // agent sitting in U[k]
-  unsigned int* E;        // empty cells, ascending
-  unsigned long long* tile_desc;
-  double* tile_seg_sum;   // per-tile sum of same/occupied
-  int* tile_seg_cnt;
+  unsigned int* U;        // unsatisfied cells of the current step, ascending
+  unsigned int* E;        // empty-cell slots
+  int* MA;                // agents moved in the last step (for the lazy 'satisfied' column)
+  unsigned short* mask16; // unsatisfied mask per 16 cells
+  void* blk_part;                 // BlkPart[2][grid]: per-CTA partials (double-buffered by step parity)
   int W, H;               // W rows (x), H columns (y): cell = x*H + y
   long long cells;
   int ntiles;
   int periodic;
-  unsigned int sat_lut[10];     // bit s of sat_lut[o]: satisfied with s same of o occupied
-  const float* ratio_lut;       // [10*16] same/occupied in float32 (0 where occ == 0)
+  unsigned int n_empty;   // e: constant (agents are conserved)
+  unsigned long long need_lut;    // nibble o: least `same` that satisfies an agent with o occupied neighbours
 };
 
 __device__ __forceinline__ unsigned int pack_row(unsigned int w) {
@@ -53,36 +61,60 @@ __device__ __forceinline__ unsigned int pack_cell(int v) {
   return v < 0 ? 0u : (1u | ((unsigned)(v & 1) << 4));
 }
 
-constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPre = 2ull << 62;
-constexpr unsigned long long kCntMask = (1ull << 31) - 1;
+__device__ __forceinline__ int ldct(const signed char* p) { return (int)__ldcg(p); }
 
+// ---------------------------------------------------------------------------------------
+// decision table: index = h | code << 8, h = (#type1 << 4) | #occupied among the 8 neighbours,
+// code = 0 type-0 agent, 1 type-1 agent, 3 empty cell.  Entry packs everything the sweep needs
+// so that ONE add per cell accumulates all partials:
+//   bits  0..12  same * (840 / occupied)      (840 = lcm(1..8): same/occupied as an exact integer)
+//   bit   20     agent is unsatisfied
+//   bit   26     agent has at least one occupied neighbour
+// ---------------------------------------------------------------------------------------
+constexpr int kLutSize = 1024;
+constexpr unsigned int kLutUnsat = 1u << 20, kLutOcc = 1u << 26;
+
+__device__ __forceinline__ unsigned int lut_entry(unsigned int idx, unsigned long long need_lut) {
+  const unsigned int h = idx & 0xFFu, code = idx >> 8;
+  const unsigned int o = h & 0xFu, n1 = h >> 4;
+  if (code > 1 || o > 8 || n1 > o) return 0u;
+  const unsigned int same = code ? n1 : o - n1;
+  const unsigned int need = (unsigned int)(need_lut >> (4 * o)) & 0xFu;
+  unsigned int e = 0;
+  if (o) e = same * (840u / o) | kLutOcc;
+  if (same < need) e |= kLutUnsat;
+  return e;
+}
+
+// neighbour counts of the 16 cells [c0, c0+16) of one lane; a warp covers 512 consecutive cells.
+// Horizontal neighbours across lanes come from shuffles, across warps from 3 extra byte loads.
 template <bool FAST>
-__global__ void __launch_bounds__(kThreads) stencil_compact_kernel(const SchellingDev sd, Ctrl* ctrl) {
-  __shared__ unsigned int sC[kTileCells / 4 + 2];   // vertical sums, packed, +1 word each side
-  __shared__ unsigned int s_warp[kThreads / 32];
-  __shared__ unsigned int s_tile, s_base_u, s_base_e;
-  __shared__ double s_seg[kThreads / 32];
-  __shared__ int s_cnt[kThreads / 32];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(&ctrl->tile_ticket, 1u);
-  __syncthreads();
-  const unsigned int tile = s_tile;
-  const long long c0 = (long long)tile * kTileCells + (long long)tid * kCellsPerThread;
+__device__ __forceinline__ void chunk_counts(const SchellingDev& sd, long long c0, bool in_range,
+                                             unsigned int (&mid)[4], unsigned int (&Hc)[4]) {
+  const int lane = threadIdx.x & 31;
   const int H = sd.H;
   const signed char* ct = sd.ct;
-
-  unsigned int mid[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-  unsigned int Hc[4];                     // per byte: low nibble #occupied, high nibble #type1
-  bool in_range = c0 < sd.cells;
-
   if (FAST) {
-    // H % 16 == 0: the 16 cells of a thread never straddle a row; rows are 16B aligned
+    // H % 16 == 0: the 16 cells of a lane never straddle a row; rows are 16 B aligned
     unsigned int C[4] = {0, 0, 0, 0}, Pm[4] = {0, 0, 0, 0};
+    unsigned int left = 0, right = 0;
+    bool own_left = true, own_right = true;
     if (in_range) {
-      const uint4 u = *(const uint4*)(ct + c0 - H);
-      const uint4 m = *(const uint4*)(ct + c0);
-      const uint4 d = *(const uint4*)(ct + c0 + H);
+      const uint4 u = __ldcg((const uint4*)(ct + c0 - H));
+      const uint4 m = __ldcg((const uint4*)(ct + c0));
+      const uint4 d = __ldcg((const uint4*)(ct + c0 + H));
+      const int col = (int)(c0 % H);
+      own_left = lane == 0 || col == 0;
+      own_right = lane == 31 || col + kCellsPerThread == H;
+      // the cell left of my 16 (lane 0 of the warp, or my cells start a row: wraps if periodic)
+      if (own_left && (col != 0 || sd.periodic)) {
+        const long long e = col == 0 ? c0 - 1 + H : c0 - 1;
+        left = pack_cell(ldct(ct + e - H)) + pack_cell(ldct(ct + e)) + pack_cell(ldct(ct + e + H));
+      }
+      if (own_right && (col + kCellsPerThread != H || sd.periodic)) {
+        const long long e = col + kCellsPerThread == H ? c0 + kCellsPerThread - H : c0 + kCellsPerThread;
+        right = pack_cell(ldct(ct + e - H)) + pack_cell(ldct(ct + e)) + pack_cell(ldct(ct + e + H));
+      }
       mid[0] = m.x; mid[1] = m.y; mid[2] = m.z; mid[3] = m.w;
       Pm[0] = pack_row(m.x); Pm[1] = pack_row(m.y); Pm[2] = pack_row(m.z); Pm[3] = pack_row(m.w);
       C[0] = pack_row(u.x) + Pm[0] + pack_row(d.x);
@@ -90,47 +122,18 @@ __global__ void __launch_bounds__(kThreads) stencil_compact_kernel(const Schelli
       C[2] = pack_row(u.z) + Pm[2] + pack_row(d.z);
       C[3] = pack_row(u.w) + Pm[3] + pack_row(d.w);
     }
-    unsigned int* myC = sC + 1 + tid * 4;
-    myC[0] = C[0]; myC[1] = C[1]; myC[2] = C[2]; myC[3] = C[3];
-    // tile-edge words: the cell just left of the tile and just right of it
-    if (tid == 0) {
-      const long long e = (long long)tile * kTileCells - 1;
-      sC[0] = (pack_cell(ct[e - H]) + pack_cell(ct[e]) + pack_cell(ct[e + H])) << 24;
-    }
-    if (tid == kThreads - 1) {
-      const long long e = (long long)(tile + 1) * kTileCells;
-      unsigned int v = 0;
-      if (e < sd.cells + H) v = pack_cell(ct[e - H]) + pack_cell(ct[e]) + pack_cell(ct[e + H]);
-      sC[kTileCells / 4 + 1] = v;
-    }
-    __syncthreads();
-    if (in_range) {
-      unsigned int left = myC[-1] >> 24;        // vertical sum of the cell left of my 16
-      unsigned int right = myC[4] & 0xFFu;      // and right of them
-      const int col = (int)(c0 % H);
-      if (col == 0) {
-        left = 0;
-        if (sd.periodic) {
-          const long long e = c0 - 1 + H;       // (row, H-1) and its vertical neighbours
-          left = pack_cell(ct[e - H]) + pack_cell(ct[e]) + pack_cell(ct[e + H]);
-        }
-      }
-      if (col + kCellsPerThread == H) {
-        right = 0;
-        if (sd.periodic) {
-          const long long e = c0 + kCellsPerThread - H;   // (row, 0)
-          right = pack_cell(ct[e - H]) + pack_cell(ct[e]) + pack_cell(ct[e + H]);
-        }
-      }
-      // horizontal 3-sum per byte, minus the centre cell
+    // whole warp, converged: vertical sums of the neighbouring lanes' edge cells
+    const unsigned int sl = __shfl_up_sync(0xffffffffu, C[3], 1) >> 24;
+    const unsigned int sr = __shfl_down_sync(0xffffffffu, C[0], 1) & 0xFFu;
+    if (!own_left) left = sl;
+    if (!own_right) right = sr;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned int prev = j == 0 ? (left << 24) : C[j - 1];
-        const unsigned int next = j == 3 ? right : C[j + 1];
-        const unsigned int l = __funnelshift_l(prev, C[j], 8);   // byte i <- byte i-1
-        const unsigned int r = __funnelshift_r(C[j], next, 8);   // byte i <- byte i+1
-        Hc[j] = l + C[j] + r - Pm[j];
-      }
+    for (int j = 0; j < 4; ++j) {
+      const unsigned int prev = j == 0 ? (left << 24) : C[j - 1];
+      const unsigned int next = j == 3 ? right : C[j + 1];
+      const unsigned int l = __funnelshift_l(prev, C[j], 8);   // byte i <- byte i-1
+      const unsigned int r = __funnelshift_r(C[j], next, 8);   // byte i <- byte i+1
+      Hc[j] = l + C[j] + r - Pm[j];
     }
   } else {
     // generic shape: per-cell byte loads with explicit column handling
@@ -143,15 +146,15 @@ __global__ void __launch_bounds__(kThreads) stencil_compact_kernel(const Schelli
           int v = -1;
           unsigned int h = 0;
           if (c < sd.cells) {
-            v = ct[c];
+            v = ldct(ct + c);
             const int col = (int)(c % H);
             for (int dy = -1; dy <= 1; ++dy) {
               int cc = col + dy;
               long long shift = dy;
               if (cc < 0) { if (!sd.periodic) continue; shift += H; }
               if (cc >= H) { if (!sd.periodic) continue; shift -= H; }
-              h += pack_cell(ct[c + shift - H]) + pack_cell(ct[c + shift + H]);
-              if (dy != 0) h += pack_cell(ct[c + shift]);
+              h += pack_cell(ldct(ct + c + shift - H)) + pack_cell(ldct(ct + c + shift + H));
+              if (dy != 0) h += pack_cell(ldct(ct + c + shift));
             }
           }
           mw |= ((unsigned int)(v & 0xFF)) << (8 * b);
@@ -162,214 +165,203 @@ __global__ void __launch_bounds__(kThreads) stencil_compact_kernel(const Schelli
       }
     }
   }
-
-  // ---- per-cell decisions -----------------------------------------------------------
-  unsigned int unsat = 0, empty = 0;      // 16-bit masks over my cells
-  float seg = 0.f;
-  int segc = 0;
-  if (in_range) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int idx = j * 4 + b;
-        if (c0 + idx >= sd.cells) continue;
-        const unsigned int v = (mid[j] >> (8 * b)) & 0xFFu;
-        if (v == 0xFFu) {
-          empty |= 1u << idx;
-          continue;
-        }
-        const unsigned int h = (Hc[j] >> (8 * b)) & 0xFFu;
-        const unsigned int o = h & 0xFu, n1 = h >> 4;
-        const unsigned int same = v ? n1 : o - n1;
-        const unsigned int sat = (sd.sat_lut[o] >> same) & 1u;
-        if (!sat) unsat |= 1u << idx;
-        if (o) {
-          seg += __ldg(sd.ratio_lut + o * 16 + same);
-          segc += 1;
-        }
-      }
-    }
-  }
-
-  // ---- block scan of (unsat | empty << 16) counts ------------------------------------
-  const unsigned int cnt = __popc(unsat) | (__popc(empty) << 16);
-  unsigned int inc = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  {
-    double sv = warp_sum((double)seg);
-    int sc = warp_sum(segc);
-    if (lane == 0) { s_seg[warp] = sv; s_cnt[warp] = sc; }
-  }
-  __syncthreads();
-  unsigned int warp_off = 0, block_tot = 0;
-#pragma unroll
-  for (int w = 0; w < kThreads / 32; ++w) {
-    if (w < warp) warp_off += s_warp[w];
-    block_tot += s_warp[w];
-  }
-  const unsigned int excl = warp_off + inc - cnt;
-
-  // ---- decoupled look-back across tiles (warp 0) --------------------------------------
-  if (warp == 0) {
-    const unsigned long long agg =
-        ((unsigned long long)(block_tot & 0xFFFFu) << 31) | (unsigned long long)(block_tot >> 16);
-    unsigned long long prefix = 0;
-    volatile unsigned long long* desc = sd.tile_desc;
-    if (tile == 0) {
-      if (lane == 0) desc[0] = kFlagPre | agg;
-    } else {
-      if (lane == 0) desc[tile] = kFlagAgg | agg;
-      long long pred = (long long)tile - 1 - lane;
-      while (true) {
-        unsigned long long d = 0;
-        if (pred >= 0) {
-          do { d = desc[pred]; } while ((d >> 62) == 0);
-        } else {
-          d = kFlagPre;   // before tile 0: zero prefix
-        }
-        const unsigned int is_pre = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-        unsigned long long contrib = d & ((1ull << 62) - 1);
-        if (is_pre) {
-          const int first = __ffs(is_pre) - 1;       // nearest predecessor holding a full prefix
-          if (lane > first) contrib = 0;
-        }
-        // sum the two 31-bit fields separately (no cross-field carry: totals < 2^31)
-        unsigned long long a = contrib >> 31, b = contrib & kCntMask;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          a += __shfl_xor_sync(0xffffffffu, a, o);
-          b += __shfl_xor_sync(0xffffffffu, b, o);
-        }
-        prefix += (a << 31) | b;
-        if (is_pre) break;
-        pred -= 32;
-      }
-      if (lane == 0) {
-        const unsigned long long incl =
-            (((prefix >> 31) + (agg >> 31)) << 31) | ((prefix & kCntMask) + (agg & kCntMask));
-        __threadfence();
-        desc[tile] = kFlagPre | incl;
-      }
-    }
-    if (lane == 0) {
-      s_base_u = (unsigned int)(prefix >> 31);
-      s_base_e = (unsigned int)(prefix & kCntMask);
-      double sv = 0; int sc = 0;
-      for (int w = 0; w < kThreads / 32; ++w) { sv += s_seg[w]; sc += s_cnt[w]; }
-      sd.tile_seg_sum[tile] = sv;
-      sd.tile_seg_cnt[tile] = sc;
-      if ((int)tile == sd.ntiles - 1) {
-        ctrl->n_unsat = s_base_u + (block_tot & 0xFFFFu);
-        ctrl->n_empty = s_base_e + (block_tot >> 16);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- ordered writes -------------------------------------------------------------------
-  unsigned int pu = s_base_u + (excl & 0xFFFFu);
-  unsigned int pe = s_base_e + (excl >> 16);
-  while (unsat) {
-    const int b = __ffs(unsat) - 1;
-    unsat &= unsat - 1;
-    const unsigned int c = (unsigned int)(c0 + b);
-    sd.U[pu] = c;
-    sd.UA[pu] = sd.cell_agent[c];
-    ++pu;
-  }
-  while (empty) {
-    const int b = __ffs(empty) - 1;
-    empty &= empty - 1;
-    sd.E[pe++] = (unsigned int)(c0 + b);
-  }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) move_kernel(const SchellingDev sd, const ModelDev md) {
+struct __align__(16) BlkPart {
+  unsigned int unsat, occ;          // #unsatisfied, #agents with an occupied neighbour
+  unsigned long long num;           // sum of same * 840 / occupied
+};
+
+template <bool FAST, int MODE>
+__global__ void __launch_bounds__(kThreads) schelling_run_kernel(const SchellingDev sd, const ModelDev md, int steps) {
+  __shared__ unsigned int s_lut[kLutSize];
+  __shared__ unsigned int s_u32[kThreads / 32];
+  __shared__ unsigned long long s_u64[kThreads / 32];
+  __shared__ unsigned int s_occ[kThreads / 32];
   __shared__ unsigned int s_rk[8];
-  __shared__ int s_last;
-  __shared__ double s_d[kThreads / 32];
-  __shared__ long long s_c[kThreads / 32];
+  __shared__ unsigned int s_prefix, s_total;
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kChunkCells = 32 * kCellsPerThread;     // 512 cells per warp pass
+  const int B = gridDim.x, b = blockIdx.x;
   Ctrl* ctrl = md.ctrl;
-  const unsigned int u = ctrl->n_unsat, e = ctrl->n_empty;
-  const unsigned int m = u < e ? u : e;
   const TypeDev& t = md.t[0];
-  if (threadIdx.x < 8) {
-    const int step = ctrl->step_in_run;
-    const uint32_t* kp = md.keys + (size_t)step * (md.n_types + 1) * 2;
-    Key ck = {kp[0], kp[1]};
-    s_rk[threadIdx.x] = bits_elem<MODE>(ck, threadIdx.x, 8);
-  }
-  __syncthreads();
-  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < sd.ntiles) sd.tile_desc[k] = 0;     // re-arm the look-back for the next step
-  if (k < m) {
-    const Feistel fu = make_feistel(u, s_rk), fe = make_feistel(e, s_rk + 4);
-    const unsigned int ku = feistel_permute(fu, (unsigned int)k);
-    const unsigned int src = sd.U[ku];
-    const int a = sd.UA[ku];
-    const unsigned int dst = sd.E[feistel_permute(fe, (unsigned int)k)];
-    const signed char ty = sd.ct[src];
-    sd.ct[dst] = ty;
-    sd.ct[src] = (signed char)-1;
-    sd.cell_agent[dst] = a;
-    sd.cell_agent[src] = -1;
-    if (sd.periodic) {
-      const long long H = sd.H, cells = sd.cells;
-      if (dst < H) sd.ct[dst + cells] = ty;
-      if (dst >= cells - H) sd.ct[(long long)dst - cells] = ty;
-      if (src < H) sd.ct[src + cells] = (signed char)-1;
-      if (src >= cells - H) sd.ct[(long long)src - cells] = (signed char)-1;
+  // contiguous range of 512-cell chunks owned by this CTA (so that U comes out in cell order)
+  const long long nchunks = (sd.cells + kChunkCells - 1) / kChunkCells;
+  const long long k0 = nchunks * b / B, k1 = nchunks * (b + 1) / B;
+  const unsigned int e = sd.n_empty;
+  const int step0 = ctrl->step_in_run;           // 0 at launch; read by everyone before anyone writes
+  BlkPart* blk_part = (BlkPart*)sd.blk_part;
+  for (int i = tid; i < kLutSize; i += kThreads) s_lut[i] = lut_entry(i, sd.need_lut);
+
+  for (int s = 0; s < steps; ++s) {
+    // ------------------------------------------------------------------ phase 1: stencil sweep
+    if (tid < 8) {
+      const uint32_t* kp = md.keys + (size_t)(step0 + s) * (md.n_types + 1) * 2;
+      const Key ck = {kp[0], kp[1]};
+      s_rk[tid] = bits_elem<MODE>(ck, tid, 8);
     }
-    ((int2*)t.f[1])[a] = make_int2((int)(dst / sd.H), (int)(dst % sd.H));
-    ((int*)t.f[3])[a] += 1;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->ticket2, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  // ---- tail: fold per-tile partials in tile order, write the metrics row ----------------
-  double sv = 0;
-  long long sc = 0;
-  for (int i = threadIdx.x; i < sd.ntiles; i += blockDim.x) {
-    sv += __ldcg(sd.tile_seg_sum + i);
-    sc += __ldcg(sd.tile_seg_cnt + i);
-  }
-  sv = warp_sum(sv);
+    __syncthreads();
+    BlkPart* part = blk_part + (size_t)(s & 1) * B;      // double-buffered by step parity: a CTA may
+    unsigned int my_unsat = 0, my_occ = 0;                // start step s+1 while others still fold step s
+    unsigned long long my_num = 0;
+    for (long long ch = k0 + warp; ch < k1; ch += kWarps) {
+      const long long c0 = ch * kChunkCells + (long long)lane * kCellsPerThread;
+      const bool in_range = c0 < sd.cells;
+      unsigned int mid[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+      unsigned int Hc[4] = {0, 0, 0, 0};
+      chunk_counts<FAST>(sd, c0, in_range, mid, Hc);
+      unsigned int unsat = 0, acc = 0;
+      if (in_range) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
-  if ((threadIdx.x & 31) == 0) { s_d[threadIdx.x >> 5] = sv; s_c[threadIdx.x >> 5] = sc; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    sv = 0; sc = 0;
-    for (int w = 0; w < kThreads / 32; ++w) { sv += s_d[w]; sc += s_c[w]; }
-    ctrl->ticket2 = 0;
-    ctrl->tile_ticket = 0;
-    ctrl->total_moves += m;
-    ctrl->n_satisfied = t.gn - u;
-    ctrl->seg_sum = sv;
-    ctrl->seg_cnt = sc;
-    const long long ts = ctrl->time_step + 1;
-    if ((ts % md.collect_interval) == 0) {
-      double* row = md.metrics + (size_t)ctrl->n_recorded * kMaxMetrics;
-      row[0] = (double)(float)((double)(t.gn - u) / (double)t.gn);          // percent_satisfied
-      row[1] = (double)(float)(sv / (double)(sc > 0 ? sc : 1));             // segregation_index
-      row[2] = (double)(int)ctrl->total_moves;                              // total_moves (int32)
-      md.record_steps[ctrl->n_recorded] = (int)ts;
-      ctrl->n_recorded += 1;
+        for (int j = 0; j < 4; ++j) {
+          // code per byte: bit0 = type, bit1 = empty  (0xFF -> 3)
+          const unsigned int cw = (mid[j] & 0x01010101u) | ((mid[j] >> 6) & 0x02020202u);
+          const unsigned int lo = __byte_perm(Hc[j], cw, 0x5140);   // [h0, code0, h1, code1]
+          const unsigned int hi = __byte_perm(Hc[j], cw, 0x7362);   // [h2, code2, h3, code3]
+          const unsigned int e0 = s_lut[lo & 0xFFFFu], e1 = s_lut[lo >> 16];
+          const unsigned int e2 = s_lut[hi & 0xFFFFu], e3 = s_lut[hi >> 16];
+          acc += e0 + e1 + e2 + e3;
+          unsat |= ((e0 >> 20) & 1u) << (4 * j) | ((e1 >> 20) & 1u) << (4 * j + 1) |
+                   ((e2 >> 20) & 1u) << (4 * j + 2) | ((e3 >> 20) & 1u) << (4 * j + 3);
+        }
+        sd.mask16[c0 >> 4] = (unsigned short)unsat;
+      }
+      my_unsat += (acc >> 20) & 0x1Fu;
+      my_occ += acc >> 26;
+      my_num += acc & 0xFFFFFu;
     }
-    md.env[0] = (double)(float)(sv / (double)(sc > 0 ? sc : 1));
-    md.env[1] = (double)(float)((double)(t.gn - u) / (double)t.gn);
-    md.env[2] = (double)(int)ctrl->total_moves;
-    ctrl->time_step = ts;
-    ctrl->step_in_run += 1;
+    {
+      const unsigned int a = warp_sum((int)my_unsat), o = warp_sum((int)my_occ);
+      unsigned long long n = my_num;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+      if (lane == 0) { s_u32[warp] = a; s_occ[warp] = o; s_u64[warp] = n; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      BlkPart p = {0, 0, 0};
+      for (int w = 0; w < kWarps; ++w) { p.unsat += s_u32[w]; p.occ += s_occ[w]; p.num += s_u64[w]; }
+      part[b] = p;
+    }
+    grid.sync();
+
+    // ------------------------------------------------------------------ phase 2: ordered U
+    {
+      unsigned int before = 0, all = 0, occ = 0;
+      unsigned long long num = 0;
+      for (int i = tid; i < B; i += kThreads) {
+        const uint4 raw = __ldcg((const uint4*)(part + i));
+        all += raw.x;
+        if (i < b) before += raw.x;
+        occ += raw.y;
+        num += ((unsigned long long)raw.w << 32) | raw.z;
+      }
+      before = warp_sum((int)before);
+      all = warp_sum((int)all);
+      occ = warp_sum((int)occ);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) num += __shfl_xor_sync(0xffffffffu, num, d);
+      __syncthreads();
+      __shared__ unsigned int s_all[kWarps];
+      if (lane == 0) { s_u32[warp] = before; s_all[warp] = all; s_occ[warp] = occ; s_u64[warp] = num; }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned int p = 0, a = 0, oc = 0;
+        unsigned long long nm = 0;
+        for (int w = 0; w < kWarps; ++w) { p += s_u32[w]; a += s_all[w]; oc += s_occ[w]; nm += s_u64[w]; }
+        s_prefix = p;
+        s_total = a;
+        if (b == 0) {
+          // metrics row of this step (pre-step configuration; DESIGN.md "Schelling rule")
+          const unsigned int u = a, m = u < e ? u : e;
+          const long long ts = ctrl->time_step + 1;
+          ctrl->total_moves += m;
+          ctrl->n_unsat = u;
+          ctrl->n_moved = m;
+          const double segv = (double)(float)((double)nm / 840.0 / (double)(oc ? oc : 1));
+          const double psat = (double)(float)((double)(t.gn - u) / (double)t.gn);
+          if ((ts % md.collect_interval) == 0) {
+            double* row = md.metrics + (size_t)ctrl->n_recorded * kMaxMetrics;
+            row[0] = psat;
+            row[1] = segv;
+            row[2] = (double)(int)ctrl->total_moves;
+            md.record_steps[ctrl->n_recorded] = (int)ts;
+            ctrl->n_recorded += 1;
+          }
+          md.env[0] = segv;
+          md.env[1] = psat;
+          md.env[2] = (double)(int)ctrl->total_moves;
+          ctrl->time_step = ts;
+          ctrl->step_in_run += 1;
+        }
+      }
+      __syncthreads();
+    }
+    const unsigned int u = s_total;
+    const unsigned int m = u < e ? u : e;
+    if (u > 0) {                   // uniform across the grid
+      unsigned int base = s_prefix;
+      for (long long ch0 = k0; ch0 < k1; ch0 += kWarps) {
+        const long long ch = ch0 + warp;
+        const long long c0 = ch * kChunkCells + (long long)lane * kCellsPerThread;
+        unsigned int unsat = (ch < k1 && c0 < sd.cells) ? (unsigned int)sd.mask16[c0 >> 4] : 0u;
+        const unsigned int cnt = __popc(unsat);
+        unsigned int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += v;
+        }
+        __syncthreads();
+        if (lane == 31) s_u32[warp] = inc;
+        __syncthreads();
+        unsigned int woff = 0, ttot = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          if (w < warp) woff += s_u32[w];
+          ttot += s_u32[w];
+        }
+        unsigned int pu = base + woff + inc - cnt;
+        while (unsat) {
+          const int q = __ffs(unsat) - 1;
+          unsat &= unsat - 1;
+          sd.U[pu++] = (unsigned int)(c0 + q);
+        }
+        base += ttot;
+      }
+    }
+    if (m == 0) continue;          // uniform: nobody moves, the grid is unchanged
+    grid.sync();
+
+    // ------------------------------------------------------------------ phase 3: moves
+    {
+      const Feistel fu = make_feistel(u, s_rk), fe = make_feistel(e, s_rk + 4);
+      for (unsigned int k = (unsigned int)b * kThreads + tid; k < m; k += (unsigned int)B * kThreads) {
+        const unsigned int src = __ldcg(sd.U + feistel_permute(fu, k));
+        const unsigned int j = feistel_permute(fe, k);
+        const unsigned int dst = __ldcg(sd.E + j);
+        const int a = __ldcg(sd.cell_agent + src);
+        const signed char ty = (signed char)ldct(sd.ct + src);
+        sd.E[j] = src;
+        sd.MA[k] = a;
+        sd.ct[dst] = ty;
+        sd.ct[src] = (signed char)-1;
+        sd.cell_agent[dst] = a;
+        sd.cell_agent[src] = -1;
+        if (sd.periodic) {
+          const long long H = sd.H, cells = sd.cells;
+          if (dst < H) sd.ct[dst + cells] = ty;
+          if (dst >= cells - H) sd.ct[(long long)dst - cells] = ty;
+          if (src < H) sd.ct[src + cells] = (signed char)-1;
+          if (src >= cells - H) sd.ct[(long long)src - cells] = (signed char)-1;
+        }
+        ((int2*)t.f[1])[a] = make_int2((int)(dst / sd.H), (int)(dst % sd.H));
+        ((int*)t.f[3])[a] += 1;
+      }
+    }
+    grid.sync();
   }
 }
 
@@ -401,19 +393,51 @@ __global__ void grid_scatter_kernel(const SchellingDev sd, const int* type, cons
   }
 }
 
+// env['empty_cells'] = ascending empty cells (schelling_model.py:133-139): single CTA ordered
+// compaction, run once when the grid is (re)built from uploaded positions
+__global__ void empty_list_kernel(const SchellingDev sd, unsigned int* count_out) {
+  __shared__ unsigned int s_w[32];
+  __shared__ unsigned int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (long long c0 = 0; c0 < sd.cells; c0 += blockDim.x) {
+    const long long c = c0 + tid;
+    const bool emp = c < sd.cells && sd.ct[c] < 0;
+    const unsigned int bal = __ballot_sync(0xffffffffu, emp);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    unsigned int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_w[w];
+    if (emp) sd.E[off + __popc(bal & ((1u << lane) - 1u))] = (unsigned int)c;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int tot = 0;
+      for (int w = 0; w < nw; ++w) tot += s_w[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *count_out = s_base;
+}
+
 __global__ void grid_export_kernel(const SchellingDev sd, int* out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < sd.cells;
        i += (long long)gridDim.x * blockDim.x)
     out[i] = (int)sd.ct[i];
 }
 
-// 'satisfied' column (schelling_model.py:29) of the last step, materialised on demand:
-// everyone is satisfied except the agents listed in UA[0..n_unsat)
+// 'satisfied' column (schelling_model.py:29) of the last step, materialised on demand: everyone
+// is satisfied except the agents moved in that step (MA) and the unsatisfied agents that stayed
+// (still sitting in their U cell)
 __global__ void satisfied_export_kernel(const SchellingDev sd, const Ctrl* ctrl, unsigned char* sat) {
-  const unsigned int u = ctrl->n_unsat;
+  const unsigned int u = ctrl->n_unsat, m = ctrl->n_moved;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < u;
-       i += (long long)gridDim.x * blockDim.x)
-    sat[sd.UA[i]] = 0;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < m) sat[sd.MA[i]] = 0;
+    const int a = sd.cell_agent[sd.U[i]];
+    if (a >= 0) sat[a] = 0;
+  }
 }
 
 }  // namespace jxb

@@ -158,6 +158,14 @@ class DeviceModel:
         nat.check(self._lib.jxb_model_download_grid(self.handle, nat.ptr(out), out.nbytes))
         return out
 
+    def download_empty_cells(self) -> np.ndarray:
+        """env['empty_cells'] as int32[e, 2] (x, y) pairs in slot order."""
+        e = int(self.desc.grid_w) * int(self.desc.grid_h) - self.n_agents(0)
+        ids = np.empty(e, dtype=np.int32)
+        nat.check(self._lib.jxb_model_download_empty_cells(self.handle, nat.ptr(ids), ids.nbytes))
+        h = int(self.desc.grid_h)
+        return np.stack([ids // h, ids % h], axis=1).astype(np.int32)
+
     # ---- time loop ----------------------------------------------------------------
     def init(self, key) -> None:
         k = np.asarray(key, dtype=np.uint32).reshape(2)

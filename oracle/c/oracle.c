@@ -147,14 +147,16 @@ void orc_key_schedule(int mode, uint32_t rng[2], int C, int has_env_fn, int step
  * One Schelling step (DESIGN.md "Schelling rule").
  *   grid  int32[W*H]  in: pre-step grid (-1 empty / type), out: grid rebuilt from the moved agents
  *   type  int32[n], pos int32[n][2] (in/out), satisfied uint8[n] (out), moves int32[n] (in/out)
- *   scratch: cell_agent int32[W*H], U int32[n], E int32[W*H]   (caller-allocated)
+ *   E     int32[e]    in/out: env['empty_cells'] as cell ids in slot order (a mover's old cell
+ *                     takes the slot of the cell it moved to)
+ *   scratch: cell_agent int32[W*H], U int32[n]   (caller-allocated)
  * Returns the number of movers; *seg_sum / *seg_cnt give sum and count of same/occupied over
  * agents with at least one occupied neighbour (pre-step grid); *n_unsat the unsatisfied count.
  * ------------------------------------------------------------------------------------------ */
 int64_t orc_schelling_step(int W, int H, int periodic, float thr, int mode, const uint32_t coll_key[2],
                            int64_t n, const int32_t* type, int32_t* pos, uint8_t* satisfied, int32_t* moves,
-                           int32_t* grid, int32_t* cell_agent, int32_t* U, int32_t* E, double* seg_sum,
-                           int64_t* seg_cnt, int64_t* n_unsat) {
+                           int32_t* grid, int32_t* cell_agent, int32_t* U, int32_t* E, int64_t e,
+                           double* seg_sum, int64_t* seg_cnt, int64_t* n_unsat) {
   const int64_t cells = (int64_t)W * H;
   double ssum = 0.0;
   int64_t scnt = 0;
@@ -182,12 +184,11 @@ int64_t orc_schelling_step(int W, int H, int periodic, float thr, int mode, cons
     satisfied[i] = (uint8_t)(occ == 0 || frac >= thr);
     cell_agent[(int64_t)x * H + y] = (int32_t)i;
   }
-  /* ordered compaction: unsatisfied agents by ascending cell id, empty cells ascending */
-  int64_t u = 0, e = 0;
+  /* ordered compaction: unsatisfied agents by ascending cell id */
+  int64_t u = 0;
   for (int64_t c = 0; c < cells; ++c) {
     const int a = cell_agent[c];
-    if (a < 0) E[e++] = (int32_t)c;
-    else if (!satisfied[a]) U[u++] = a;
+    if (a >= 0 && !satisfied[a]) U[u++] = a;
   }
   const int64_t m = u < e ? u : e;
   uint32_t rk[8];
@@ -196,8 +197,10 @@ int64_t orc_schelling_step(int W, int H, int periodic, float thr, int mode, cons
 #pragma omp parallel for schedule(static)
   for (int64_t k = 0; k < m; ++k) {
     const int a = U[feistel_permute(&fu, (uint32_t)k)];
-    const int64_t dst = E[feistel_permute(&fe, (uint32_t)k)];
+    const uint32_t j = feistel_permute(&fe, (uint32_t)k);
+    const int64_t dst = E[j];
     const int64_t src = (int64_t)pos[2 * a] * H + pos[2 * a + 1];
+    E[j] = (int32_t)src;
     grid[dst] = type[a];
     grid[src] = -1;
     pos[2 * a] = (int32_t)(dst / H);

@@ -27,8 +27,8 @@ def lib():
         L.orc_schelling_step.restype = C.c_int64
         L.orc_schelling_step.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                         C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
-                                         C.POINTER(C.c_int64)]
+                                         C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_key_schedule.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_market_step.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
@@ -72,7 +72,7 @@ class SchellingFast:
         self.grid[self.pos[:, 0].astype(np.int64) * self.G + self.pos[:, 1]] = self.type
         self._cell_agent = np.empty(self.G * self.G, dtype=np.int32)
         self._U = np.empty(self.n, dtype=np.int32)
-        self._E = np.empty(self.G * self.G, dtype=np.int32)
+        self.E = np.ascontiguousarray(np.nonzero(self.grid < 0)[0].astype(np.int32))   # env['empty_cells']
         _, _, _, rng = key_schedule(seed, 1, True, 0, mode)
         self._rng = rng
         self.total_moves = 0
@@ -88,8 +88,8 @@ class SchellingFast:
             ck = np.ascontiguousarray(coll[t, 0])
             m = lib().orc_schelling_step(self.G, self.G, self.periodic, self.thr, self.mode, _p(ck), self.n,
                                          _p(self.type), _p(self.pos), _p(self.satisfied), _p(self.moves),
-                                         _p(self.grid), _p(self._cell_agent), _p(self._U), _p(self._E),
-                                         C.byref(ssum), C.byref(scnt), C.byref(nu))
+                                         _p(self.grid), _p(self._cell_agent), _p(self._U), _p(self.E),
+                                         self.E.shape[0], C.byref(ssum), C.byref(scnt), C.byref(nu))
             self.total_moves += int(m)
             self.time_step += 1
             out["step"].append(self.time_step)

@@ -374,10 +374,17 @@ class SchellingAgent:
     """State layout of ``SchellingSocialAgent`` (``schelling_model.py:26-31``):
     ``type i32, position i32[2], satisfied bool, moves i32``.  The rule is collective
     (a matching of movers to empty cells), so it is expressed on whole columns with
-    the collection key -- it is not a per-agent ``vmap`` body."""
+    the collection key -- it is not a per-agent ``vmap`` body.
+
+    DESIGN.md "Schelling rule": (1) every agent is satisfied iff it has no occupied Moore
+    neighbour or same/occupied >= threshold (float32), on the pre-step grid; (2) U = the
+    unsatisfied agents by ascending cell id, E = env['empty_cells'] in slot order; (3) with
+    rk = bits(coll_key, (8,)), mover k < min(|U|, |E|) is the agent U[piU(k)], it moves to
+    the cell in slot piE(k) and its old cell takes that slot."""
 
     def __init__(self, similarity_threshold=0.5):
         self.similarity_threshold = similarity_threshold
+        self.last_moves = None       # (slots, old cells) of the latest step, for the env phase
 
     def init_batch(self, cfg, keys):                             # schelling_model.py:26-31
         return {"type": 0, "position": unbatched(np.zeros(2, dtype=i32)),
@@ -398,13 +405,16 @@ class SchellingAgent:
         cell = x.astype(np.int64) * G1 + y
         unsat = np.nonzero(~satisfied)[0]
         U = unsat[np.argsort(cell[unsat], kind="stable")]        # unsatisfied agents, by cell id
-        E = np.nonzero(grid.reshape(-1) < 0)[0]                  # empty cells, ascending
+        ec = np.asarray(env["empty_cells"], dtype=np.int64).reshape(-1, 2)
+        E = ec[:, 0] * G1 + ec[:, 1]                             # empty cells, slot order
         u, e = len(U), len(E)
         m = min(u, e)
         rk = jl.random_bits(coll_key, (8,), cfg.rng_mode)
         k = np.arange(m, dtype=np.uint32)
         src = U[jl.feistel_permute(k, u, rk[0:4]).astype(np.int64)]
-        dst = E[jl.feistel_permute(k, e, rk[4:8]).astype(np.int64)]
+        slots = jl.feistel_permute(k, e, rk[4:8]).astype(np.int64)
+        dst = E[slots]
+        self.last_moves = (slots, cell[src])
         pos = s["position"].copy()
         pos[src, 0] = (dst // G1).astype(i32)
         pos[src, 1] = (dst % G1).astype(i32)
@@ -413,25 +423,33 @@ class SchellingAgent:
         return {"type": s["type"], "position": pos, "satisfied": satisfied, "moves": moves}
 
 
-def schelling_update_state(env, agent_states, params, key):
-    """Env phase: segregation index from the pre-step grid, then rebuild the grid and the
-    empty-cell list from the moved agents (``schelling_model.py:119-139`` layout)."""
-    a = agent_states["agents"]
-    grid = np.asarray(env["grid"], dtype=i32)
-    occ, t0, t1 = moore_counts(grid, bool(env.get("grid_periodic", False)))
-    same = np.where(grid == 0, t0, t1)
-    sel = (grid >= 0) & (occ > 0)
-    ratios = (same[sel].astype(f32) / occ[sel].astype(f32)).astype(f32)
-    seg = f32(np.sum(ratios, dtype=np.float64) / max(1, ratios.size))
-    new_grid = -np.ones_like(grid)
-    new_grid[a["position"][:, 0], a["position"][:, 1]] = a["type"]
-    new = dict(env)
-    new["grid"] = new_grid
-    new["empty_cells"] = np.column_stack(np.nonzero(new_grid < 0)).astype(i32)
-    new["segregation_index"] = seg
-    new["percent_satisfied"] = f32(np.mean(a["satisfied"], dtype=np.float64))
-    new["total_moves"] = i32(np.sum(a["moves"], dtype=np.int64))
-    return new
+def make_schelling_update_state(agent_type):
+    def schelling_update_state(env, agent_states, params, key):
+        """Env phase: segregation index from the pre-step grid, grid rebuilt from the moved agents,
+        vacated cells written into the empty-cell slots their movers took
+        (``schelling_model.py:119-139`` layout)."""
+        a = agent_states["agents"]
+        grid = np.asarray(env["grid"], dtype=i32)
+        G1 = grid.shape[1]
+        occ, t0, t1 = moore_counts(grid, bool(env.get("grid_periodic", False)))
+        same = np.where(grid == 0, t0, t1)
+        sel = (grid >= 0) & (occ > 0)
+        ratios = (same[sel].astype(f32) / occ[sel].astype(f32)).astype(f32)
+        seg = f32(np.sum(ratios, dtype=np.float64) / max(1, ratios.size))
+        new_grid = -np.ones_like(grid)
+        new_grid[a["position"][:, 0], a["position"][:, 1]] = a["type"]
+        ec = np.asarray(env["empty_cells"], dtype=i32).reshape(-1, 2).copy()
+        slots, old_cells = agent_type.last_moves
+        ec[slots, 0] = (old_cells // G1).astype(i32)
+        ec[slots, 1] = (old_cells % G1).astype(i32)
+        new = dict(env)
+        new["grid"] = new_grid
+        new["empty_cells"] = ec
+        new["segregation_index"] = seg
+        new["percent_satisfied"] = f32(np.mean(a["satisfied"], dtype=np.float64))
+        new["total_moves"] = i32(np.sum(a["moves"], dtype=np.int64))
+        return new
+    return schelling_update_state
 
 
 def schelling_metrics(env, agent_states, params):               # schelling_model.py:172-196 (keys)
@@ -457,9 +475,10 @@ def create_schelling_model(grid_size=20, n_agents=300, ratio=0.5, similarity_thr
     if config is None:
         config = ModelConfig(seed=seed)
     types, pos = schelling_initial_layout(grid_size, n_agents, ratio, seed)
-    coll = AgentCollection(SchellingAgent(similarity_threshold), n_agents)
+    agent_type = SchellingAgent(similarity_threshold)
+    coll = AgentCollection(agent_type, n_agents)
     model = Model(params={"similarity_threshold": similarity_threshold}, config=config,
-                  update_state_fn=schelling_update_state, metrics_fn=schelling_metrics)
+                  update_state_fn=make_schelling_update_state(agent_type), metrics_fn=schelling_metrics)
     model.add_agent_collection("agents", coll)
     grid = -np.ones((grid_size, grid_size), dtype=i32)
     grid[pos[:, 0], pos[:, 1]] = types

@@ -153,6 +153,7 @@ def test_schelling(mode, g0, n, periodic):
     assert np.array_equal(series(r, "percent_satisfied"), series(orr, "percent_satisfied"))
     np.testing.assert_allclose(series(r, "segregation_index"), series(orr, "segregation_index"), rtol=1e-6)
     assert np.array_equal(m._dev.download_grid(), om._env_state["grid"])
+    assert np.array_equal(m._dev.download_empty_cells(), om._env_state["empty_cells"])
     # continue the same models: state and key chain persist across run() calls (model.py:203)
     r2, orr2 = m.run(steps=3), om.run(steps=3)
     assert list(r2["step"]) == list(orr2["step"]) == [steps + 1, steps + 2, steps + 3]
