@@ -1,0 +1,202 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared
+symbol, the host key algebra is bit-compatible, the Python API mirrors the reference's
+contract (errors, defaults, bookkeeping) -- no kernel is launched here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import jaxabm_b200 as jx
+from jaxabm_b200 import _native as nat, dist, ensemble, random as jr
+from jaxabm_b200.rules import contract, growth, market, random_walk, schelling, sir
+from oracle import jaxlike as jl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "jxb.h")).read()
+    declared = set(re.findall(r"\b(jxb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 35
+    lib = nat.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"libjxb.so does not export {name}"
+    assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
+    assert lib.jxb_version() == 100
+
+
+def test_no_device_fails_loudly():
+    import ctypes as C
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    h = C.c_void_p()
+    rc = nat.lib().jxb_engine_create(0, C.byref(h))
+    assert rc == -2 and b"no CPU fallback" in nat.lib().jxb_last_error()
+    with pytest.raises(nat.JxbError):
+        market.create_economy_model().run(steps=1)
+
+
+def test_host_prng_matches_oracle_and_kats(mode):
+    assert jr.threefry2x32([0, 0], [0, 0]).tolist() == [0x6B200159, 0x99BA4EFE]
+    assert jr.threefry2x32([0x13198A2E, 0x03707344], [0x243F6A88, 0x85A308D3]).tolist() == [0xC4923A9C, 0x483DF7A0]
+    assert jr.split(jr.PRNGKey(0), 2, 0).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    assert jr.split(jr.PRNGKey(0), 2, 1).tolist() == [[1797259609, 2579123966], [928981903, 3453687069]]
+    for seed in (0, 42, 12345):
+        k = jr.PRNGKey(seed)
+        assert np.array_equal(k, jl.PRNGKey(seed))
+        for n in (1, 2, 3, 8, 33):
+            assert np.array_equal(jr.split(k, n, mode), jl.split(k, n, mode))
+            assert np.array_equal(jr.bits(k, (n,), mode), jl.random_bits(k, (n,), mode))
+            assert np.array_equal(jr.uniform(k, (n,), -2.0, 5.0, mode), jl.uniform(k, (n,), -2.0, 5.0, mode))
+            assert np.array_equal(jr.randint(k, (n,), 0, 1_000_000, mode), jl.randint(k, (n,), 0, 1_000_000, mode))
+        assert np.array_equal(jr.bits(k, (), mode), jl.random_bits(k, (), mode))
+        assert np.array_equal(jr.permutation(k, np.arange(37), mode), jl.permutation(k, np.arange(37), mode))
+
+
+def test_lhs_samples_follow_the_reference_schedule(mode, monkeypatch):
+    """analysis.py:67-95 restated with the oracle's jax.random."""
+    monkeypatch.setenv("JXB_RNG_MODE", "legacy" if mode == 0 else "partitionable")
+    ranges = {"growth_rate": (0.05, 0.2), "adjustment_rate": (0.05, 0.3), "x": (-1.0, 1.0)}
+    sa = jx.SensitivityAnalysis(growth.create_test_model, ranges, ["avg_value"], num_samples=17, seed=3)
+    key = jl.PRNGKey(3)
+    key, sub = jl.split(key, 2, mode)
+    pts = np.linspace(0, 1, 18, dtype=np.float32)[:-1]
+    pts = (pts + jl.uniform(sub, (17,), mode=mode) / np.float32(17)).astype(np.float32)
+    want = np.zeros((17, 3), dtype=np.float32)
+    for i in range(3):
+        key, sub = jl.split(key, 2, mode)
+        want[:, i] = jl.permutation(sub, pts, mode)
+    for i, (lo, hi) in enumerate(ranges.values()):
+        want[:, i] = want[:, i] * np.float32(hi - lo) + np.float32(lo)
+    assert np.array_equal(sa.samples, want)
+    for j, (lo, hi) in enumerate(ranges.values()):      # one sample per stratum
+        strata = np.floor((np.sort(sa.samples[:, j]) - lo) / (hi - lo) * 17).astype(int)
+        assert strata.tolist() == list(range(17))
+    with pytest.raises(ValueError):
+        sa.sobol_indices()                                   # analysis.py:180-181
+
+
+def test_api_contract_without_device():
+    assert jx.ModelConfig().__dict__ | {"rng_mode": None} == {"seed": 0, "steps": 100, "track_history": True,
+                                                              "collect_interval": 1, "rng_mode": None}
+    for bad in (0, -3, 2.5, "7"):
+        with pytest.raises(ValueError):
+            jx.AgentCollection(contract.IncrementAgent(), bad)           # agent.py:83-84
+    m = jx.JaxModel()
+    with pytest.raises(ValueError):
+        m.initialize()                                                   # model.py:125-126
+    with pytest.raises(RuntimeError):
+        m.step()                                                         # model.py:152-153
+    c = jx.AgentCollection(contract.IncrementAgent(), 4)
+    with pytest.raises(ValueError):
+        c.update({}, jr.PRNGKey(0), jx.ModelConfig())                    # agent.py:150-151
+    with pytest.raises(TypeError):
+        c.init(jr.PRNGKey(0), {"seed": 0})                               # agent.py:103-104
+    assert c.states is None and c.get_states() is None
+
+    class Unknown(jx.AgentType):
+        pass
+
+    m = jx.JaxModel()
+    m.add_agent_collection("x", jx.AgentCollection(Unknown(), 3))
+    with pytest.raises(jx.UnregisteredRuleError):
+        m.initialize()
+    m = jx.JaxModel(update_state_fn=lambda e, a, p, k: e)
+    m.add_agent_collection("consumers", jx.AgentCollection(contract.IncrementAgent(), 3))
+    with pytest.raises(jx.UnregisteredRuleError):
+        m.initialize()
+
+    class MyModel(jx.Model):
+        def step(self):
+            pass
+
+    with pytest.raises(jx.UnregisteredRuleError):
+        MyModel({"steps": 1}).run()
+    with pytest.raises(NotImplementedError):
+        jx.CoreModelCalibrator(growth.create_test_model, {"growth_rate": 0.1}, {"avg_value": 1.0}, method="dqn")
+    with pytest.raises(ValueError):
+        jx.CoreModelCalibrator(growth.create_test_model, {"growth_rate": 0.1}, {"avg_value": 1.0}, method="gradient")
+    assert set(jx.__all__) >= {"Agent", "AgentList", "Environment", "Grid", "Network", "Model", "Results",
+                               "AgentType", "AgentCollection", "JaxModel", "ModelConfig", "SensitivityAnalysis",
+                               "ModelCalibrator", "convert_to_numpy", "format_time", "run_parallel_simulations"}
+
+
+def test_facade_host_objects():
+    class M(jx.Model):
+        pass
+
+    m = M({"seed": 5})
+    assert m.seed == 5 and m.steps == 100
+    net = jx.Network(m, directed=False)
+    net.add_edge(0, 1)
+    net.add_edge(1, 2)
+    net.add_edge(2, 2)
+    e = m.env.network_edges
+    assert e.dtype == np.int32 and e.tolist() == [[0, 1], [1, 0], [1, 2], [2, 1], [2, 2]]      # agentpy.py:574-582
+    assert net.get_neighbors(1).tolist() == [0, 2]
+    d = jx.Network(M(), directed=True)
+    d.add_edges([[0, 1], [0, 2], [3, 0]])
+    assert d.get_neighbors(0).tolist() == [1, 2]
+    g = jx.Grid(m, (7, 9), periodic=True)
+    assert m.env.grid_shape == (7, 9) and m.env.grid_periodic is True
+    al = m.add_agents(6, schelling.SchellingSocialAgent)
+    assert al.name == "schellingsocialagents" and len(al) == 6                                 # agentpy.py:960-961
+    g.position_agents(al)                                                                      # silently nothing before init
+    res = jx.Results({"step": [1, 2], "x": [0.5, 0.25], "agents.a.v": [np.zeros(3), np.ones(3)]})
+    assert "x" in res and res["x"][-1] == 0.25 and len(res.variables.a.v) == 2
+    assert jx.format_time(12.345) == "12.35s" and jx.format_time(125) == "2m 5.00s" and jx.format_time(3723) == "1h 2m 3.00s"
+    p = jx.Parameter("a", bounds=(0.0, 1.0))
+    s = jx.Sample({"a": p, "b": 3}, n=4, seed=1)
+    assert len(s) == 4 and all(0 <= x["a"] <= 1 and x["b"] == 3 for x in s)
+    with pytest.raises(AttributeError):
+        an = jx.SensitivityAnalyzer(random_walk.RandomWalkModel, {"n_agents": p}, n_samples=2)
+        an._sa = object.__new__(jx.SensitivityAnalysis)
+        an._sa.results = {}
+        an.calculate_sensitivity("morris")                                                     # agentpy.py:1363-1364
+
+
+def test_ensemble_plan_is_pure_host_logic():
+    models = [growth.create_test_model(initial_value=1.0, num_agents=50,
+                                       params={"growth_rate": 0.05 + 0.01 * i, "adjustment_rate": 0.1 * (i % 3 + 1)},
+                                       config=jx.ModelConfig(seed=1000 + i)) for i in range(6)]
+    assert ensemble.batchable(models)
+    desc, slots, params, seeds, env0 = ensemble.plan(models)
+    assert desc.program == nat.PROGRAM["growth"] and desc.n_types == 1 and desc.types[0].n_agents == 50
+    assert slots == [0, 100] and params.shape == (6, 2) and seeds.tolist() == list(range(1000, 1006))
+    assert params[:, 1].tolist() == [float(np.float32(1.0 + 0.05 + 0.01 * i)) for i in range(6)]
+    assert env0[:2].tolist() == [1.0, 0.05]
+    mixed = models[:2] + [market.create_economy_model()]
+    assert not ensemble.batchable(mixed)
+    assert not ensemble.batchable([object()])
+    mk = [market.create_economy_model(params={"productivity": 1.0 + 0.1 * i}, config=jx.ModelConfig(seed=i)) for i in range(3)]
+    _, slots, params, _, _ = ensemble.plan(mk)
+    assert slots == [100 + 16 + 1] and np.allclose(params[:, 0], [1.0, 1.1, 1.2])
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 8, 8192, 8191):
+        for w in (1, 2, 3, 8):
+            b = [dist.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+    assert dist.rank_world() == (0, 1) and dist.max_over_ranks(3.5) == 3.5
+    a = np.arange(6.0).reshape(3, 2)
+    assert dist.gather_rows(a, 3) is a
+
+
+def test_synthetic_generators():
+    from jaxabm_b200 import synthetic
+    e = synthetic.scale_free_edges(5000, 4, 1)
+    assert e.dtype == np.int32 and e.shape[1] == 2 and e.min() >= 0 and e.max() < 5000
+    assert np.array_equal(np.sort(e[: len(e) // 2], axis=0)[:, ::1], np.sort(e[len(e) // 2:][:, ::-1], axis=0))
+    deg = np.bincount(e[:, 0], minlength=5000)
+    assert deg.max() > 20 * np.median(deg)                                                     # heavy tail
+    assert np.array_equal(e, synthetic.scale_free_edges(5000, 4, 1))
+    t, p = schelling.initial_layout(32, 700, 0.5, 3)
+    assert len({(a, b) for a, b in p.tolist()}) == 700 and t.sum() == 350
