@@ -1,14 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the JaxABM hot path on B200 (contract in the task statement).
 
-  python bench.py --gpus N --steps K --warmup W [--workload schelling|market|walk|sir]
+  python bench.py --gpus N --steps K --warmup W [--workload schelling|market|walk|sir|ensemble]
   python bench.py --impl reference ...      # the CPU restatement timed on the host cores
 
 Metric (BASELINE.json): agent-steps/sec, device-timed.  A "step" is one Model.step() of the
 workload (jaxabm/model.py:146-216).  Default workload = BASELINE.json configs[1]: Schelling
-segregation on a 4096x4096 Grid with 13 M agents.  With N > 1 every rank runs an independent
-replica of the workload on its own GPU (ensemble sharding, no data-path collective):
-scaling = "weak", value = sum of agent-steps over ranks / max device time over ranks.
+segregation on a 4096x4096 Grid with 13 M agents; its timed region is K steps of the run that
+STARTS FROM THE SEEDED INITIAL LAYOUT (so it covers the active phase in which millions of agents
+move as well as the converged tail), default K = 1000 = the configured run length.  With N > 1
+every rank runs an independent replica of the workload on its own GPU (ensemble sharding, no
+data-path collective): scaling = "weak", value = sum of agent-steps over ranks / max device time
+over ranks.  `--workload market --shard` instead splits ONE population across the ranks (strong
+scaling, per-step cross-rank reduction of the env partial sums).
 """
 from __future__ import annotations
 
@@ -29,133 +33,295 @@ METRIC = "agent_steps_per_sec"
 UNIT = "agent-steps/s"
 
 
+def _pin(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+
+def _pinned_like(shape, dtype):
+    import torch
+    return torch.empty(shape, dtype=dtype).pin_memory()
+
+
 # ------------------------------------------------------------------------------------------
-# workloads
+# workloads.  Protocol:
+#   fresh()            -> model whose state is resident in HBM, ready for step 1 (untimed)
+#   stationary         -> True: per-step cost does not depend on t (warm up and time one model);
+#                         False: the timed run starts from a fresh model
+#   api_bytes(res,K)   -> SURVEY.md 8(d) algorithmic bytes of K steps (reference API dtypes)
+#   engine_bytes(res,K)-> same in the engine's packed layout (what the kernels must move)
+#   e2e(K)             -> (wall_s, h2d_bytes, d2h_bytes) through the public API with host buffers
+#   cpu_run(steps)     -> (seconds, threads, what) on the CPU oracle
 # ------------------------------------------------------------------------------------------
 class SchellingWorkload:
     """C2: Schelling 4096x4096, 13,000,000 agents (77.5 % fill), threshold 0.5, Moore-8."""
     name = "schelling_4096x4096_13M"
     dtype = "i8/i32"
+    default_steps = 1000
+    stationary = False
+    kernel = "schelling_run_kernel"
+    l2_note = ("no flush (one persistent launch runs all K steps); active-phase working set "
+               "(agents SoA + cell arrays + U/E lists, ~360 MB) exceeds the 126 MB L2; the packed "
+               "grid (16.8 MB) is L2-resident by design once the population has converged")
 
     def __init__(self, rank, grid=4096, n=13_000_000):
         from jaxabm_b200.rules import schelling
         self.grid, self.n, self.seed = grid, n, 42 + rank
         self.types, self.positions = schelling.initial_layout(grid, n, 0.5, self.seed)
         self.agents = n
+        self._pins = None
 
-    def make(self):
+    def fresh(self):
         import jaxabm_b200 as jx
         from jaxabm_b200.rules import schelling
-        return schelling.create_schelling_model(self.grid, self.n, seed=self.seed, types=self.types,
-                                                positions=self.positions,
-                                                config=jx.ModelConfig(seed=self.seed))
+        m = schelling.create_schelling_model(self.grid, self.n, seed=self.seed, types=self.types,
+                                             positions=self.positions, config=jx.ModelConfig(seed=self.seed))
+        m._dev.grid_rebuild()                       # cell binning of the uploaded layout (untimed setup)
+        return m
 
-    def pinned_inputs(self):
+    def movers(self, res):
+        """agents moved during the (fresh) run: total_moves is cumulative since model creation"""
+        return int(res["total_moves"][-1]) if len(res.get("total_moves", [])) else 0
+
+    def unsat_sum(self, res):
+        ps = np.array([float(v) for v in res["percent_satisfied"]], dtype=np.float64)
+        return float(np.sum((1.0 - ps) * self.n))
+
+    def api_bytes(self, res, K):
+        """29 B/agent + 8 B/cell per step + 16 B per mover."""
+        return (29 * self.n + 8 * self.grid * self.grid) * K + 16 * self.movers(res)
+
+    def engine_bytes(self, res, K):
+        """Packed layout: 1 B/cell sweep + 2 B/16 cells mask per step; 4 B per unsatisfied agent
+        (U list); per mover U/E/cell_agent/type/position/moves accesses = 41 B."""
+        cells = self.grid * self.grid
+        return (cells + cells // 8) * K + 4 * self.unsat_sum(res) + 41 * self.movers(res)
+
+    def e2e(self, K):
+        """Upload type+position from pinned host memory -> Model.run(K) -> read back
+        position/moves/satisfied + the metrics history, all through the public API."""
         import torch
-        t = torch.from_numpy(self.types).pin_memory()
-        p = torch.from_numpy(self.positions).pin_memory()
-        outs = {"position": torch.empty((self.n, 2), dtype=torch.int32).pin_memory(),
-                "moves": torch.empty(self.n, dtype=torch.int32).pin_memory(),
-                "satisfied": torch.empty(self.n, dtype=torch.bool).pin_memory()}
-        return {"type": t, "position": p}, outs
-
-    def e2e_run(self, model, ins, outs, steps):
-        """Public-API call with host buffers: upload state -> run -> read results back."""
-        st = model.agent_collections["agents"].states
-        st["type"] = ins["type"].numpy()
-        st["position"] = ins["position"].numpy()
-        res = model.run(steps=steps)
-        dev = model._dev
+        if self._pins is None:
+            self._pins = ({"type": _pin(self.types), "position": _pin(self.positions)},
+                          {"position": _pinned_like((self.n, 2), torch.int32),
+                           "moves": _pinned_like((self.n,), torch.int32),
+                           "satisfied": _pinned_like((self.n,), torch.bool)})
+        ins, outs = self._pins
+        import jaxabm_b200 as jx
+        from jaxabm_b200.rules import schelling
+        t0 = time.perf_counter()
+        m = schelling.create_schelling_model(self.grid, self.n, seed=self.seed, types=ins["type"].numpy(),
+                                             positions=ins["position"].numpy(),
+                                             config=jx.ModelConfig(seed=self.seed))
+        res = m.run(steps=K)
+        dev = m._dev
         for k, buf in outs.items():
             dev.download(0, dev.field_index(0, k), out=buf.numpy())
-        h2d = ins["type"].numel() * 4 + ins["position"].numel() * 4
-        d2h = sum(b.numel() * b.element_size() for b in outs.values()) + steps * (3 * 8 + 4)
-        return res, h2d, d2h
-
-    def kernel_bytes(self, res):
-        """Algorithmic bytes of ONE launch of the dominant kernel (stencil_compact_kernel) in the
-        engine's layout: packed grid read once (1 B/cell) + ordered lists written
-        (U, UA: 4 B each + 4 B cell_agent read per unsatisfied agent; E: 4 B per empty cell)."""
-        cells = self.grid * self.grid
-        ps = np.array([float(v) for v in res["percent_satisfied"]])
-        u = float(np.mean((1.0 - ps) * self.n))
-        e = cells - self.n
-        return cells * 1 + u * 12 + e * 4
-
-    def api_bytes_per_step(self):
-        """SURVEY.md 8(d) figure in the reference's API-visible dtypes: 29 B/agent + 8 B/cell."""
-        return 29 * self.n + 8 * self.grid * self.grid
+        wall = time.perf_counter() - t0
+        h2d = sum(b.numel() * b.element_size() for b in ins.values())
+        d2h = sum(b.numel() * b.element_size() for b in outs.values()) + K * (3 * 8 + 4)
+        del m
+        return wall, h2d, d2h, ("create model + upload type/position from pinned host memory, Model.run(K), "
+                                "read back position/moves/satisfied + the metrics history")
 
     def cpu_run(self, steps):
         from oracle import cfast
         f = cfast.SchellingFast(self.grid, self.types, self.positions, seed=self.seed, mode=1)
         t0 = time.perf_counter()
         f.run(steps)
-        return time.perf_counter() - t0, cfast.num_threads()
+        return (time.perf_counter() - t0, cfast.num_threads(),
+                f"first {steps} full-size steps of {self.name} (from the same seeded layout) on the C/OpenMP oracle")
 
 
 class MarketWorkload:
     """C4-A: 45 M consumers + 5 M producers, well-mixed, env-level reductions fused in the step."""
     name = "market_45M_consumers_5M_producers"
     dtype = "f32"
+    default_steps = 100
+    stationary = True
+    kernel = "step_kernel"
+    l2_note = "no flush: per-step state traffic (0.98 GB) exceeds the 126 MB L2"
 
-    def __init__(self, rank, nc=45_000_000, npr=5_000_000):
-        self.nc, self.npr, self.seed = nc, npr, 42 + rank
+    def __init__(self, rank, nc=45_000_000, npr=5_000_000, world=1, shard=False):
+        self.nc, self.npr, self.seed = nc, npr, 42 + (0 if shard else rank)
+        self.rank, self.world, self.shard = rank, world, shard
         self.agents = nc + npr
 
-    def make(self):
+    def fresh(self):
         import jaxabm_b200 as jx
         from jaxabm_b200.rules import market
         m = market.create_economy_model(num_consumers=self.nc, num_producers=self.npr,
                                         config=jx.ModelConfig(seed=self.seed))
+        if self.shard:
+            from jaxabm_b200 import sharding
+            sharding.shard_model(m)
         m.initialize()
         return m
 
-    def pinned_inputs(self):
-        return None, None
+    def api_bytes(self, res, K):
+        return (32 * self.nc + 24 * self.npr) * K
 
-    def kernel_bytes(self, res):
+    def engine_bytes(self, res, K):
         # consumers: read savings+income, write savings+consumption+utility = 20 B; producers:
-        # read capital, write capital+production+profit = 16 B (in-place; 'income' is not rewritten)
-        return 20 * self.nc + 16 * self.npr
+        # read capital, write capital+production+profit = 16 B (in place; 'income' is not rewritten)
+        return (20 * self.nc + 16 * self.npr) * K
 
-    def api_bytes_per_step(self):
-        return 32 * self.nc + 24 * self.npr
+    def e2e(self, K):
+        """initialize() on the device from the seed (the reference's init_state draws), run(K),
+        read every state column back to pinned host memory."""
+        import torch
+        t0 = time.perf_counter()
+        m = self.fresh()
+        m.run(steps=K)
+        d2h = 0
+        for name, c in m.agent_collections.items():
+            st = c.states
+            for k in st:
+                a = st[k]
+                d2h += a.nbytes
+        wall = time.perf_counter() - t0
+        del m
+        return wall, 0, d2h + K * 5 * 8, ("create + initialize on device (keys from the seed), Model.run(K), "
+                                          "download all 7 state columns + the metrics history")
 
     def cpu_run(self, steps):
-        raise NotImplementedError
+        from oracle import cfast
+        n_c, n_p = self.nc // 10, self.npr // 10
+        f = cfast.MarketFast(n_c, n_p, seed=self.seed, mode=1)
+        t0 = time.perf_counter()
+        f.run(steps)
+        secs = (time.perf_counter() - t0) * 10.0
+        return secs, cfast.num_threads(), (f"{steps} steps on a 1/10 population sample ({n_c}+{n_p} agents, "
+                                            "time scaled x10) on the C/OpenMP oracle")
 
 
 class WalkWorkload:
     """C1 scaled: 2^26 random walkers (48 B/agent-step), fused distance reductions."""
     name = "random_walk_2^26"
     dtype = "f32"
+    default_steps = 50
+    stationary = True
+    kernel = "step_kernel"
+    l2_note = "no flush: per-step state traffic (3.2 GB) exceeds the 126 MB L2"
 
     def __init__(self, rank, n=1 << 26):
         self.n, self.seed = n, 42 + rank
         self.agents = n
 
-    def make(self):
+    def fresh(self):
         import jaxabm_b200 as jx
         from jaxabm_b200.rules import random_walk
         m = random_walk.create_scaled_walk_model(self.n, config=jx.ModelConfig(seed=self.seed))
         m.initialize()
         return m
 
-    def pinned_inputs(self):
-        return None, None
+    def api_bytes(self, res, K):
+        return 48 * self.n * K
 
-    def kernel_bytes(self, res):
-        return 48 * self.n
+    engine_bytes = api_bytes
 
-    def api_bytes_per_step(self):
-        return 48 * self.n
+    def e2e(self, K):
+        t0 = time.perf_counter()
+        m = self.fresh()
+        m.run(steps=K)
+        d2h = 0
+        st = m.agent_collections["walkers"].states
+        for k in st:
+            d2h += st[k].nbytes
+        wall = time.perf_counter() - t0
+        del m
+        return wall, 0, d2h + K * 7 * 8, "create + initialize on device, Model.run(K), download all 4 state columns"
 
     def cpu_run(self, steps):
         raise NotImplementedError
 
 
-WORKLOADS = {"schelling": SchellingWorkload, "market": MarketWorkload, "walk": WalkWorkload}
+class SirWorkload:
+    """C3: SIR on a synthetic scale-free Network, 10 M agents / ~100 M adjacency entries."""
+    name = "sir_10M_agents_100M_adjacency"
+    dtype = "i8/u32"
+    default_steps = 100
+    stationary = False
+    kernel = "sir_step_kernel"
+    l2_note = "no flush: adjacency (400 MB) is streamed every step and exceeds the 126 MB L2"
+
+    def __init__(self, rank, n=10_000_000, m=5):
+        from jaxabm_b200 import synthetic
+        self.n, self.seed = n, 42 + rank
+        self.edges = synthetic.scale_free_edges(n, m, self.seed)
+        self.nnz = int(self.edges.shape[0])
+        self.agents = n
+
+    def fresh(self):
+        import jaxabm_b200 as jx
+        from jaxabm_b200.rules import sir
+        m = sir.create_sir_model(self.n, self.edges, beta=0.05, gamma=0.1, initial_infected=0.01,
+                                 seed=self.seed, config=jx.ModelConfig(seed=self.seed))
+        m.initialize()
+        return m
+
+    def api_bytes(self, res, K):
+        """row_ptr 4(N+1) + col 4 nnz + state read 4N + state write 4N."""
+        return (4 * (self.n + 1) + 4 * self.nnz + 8 * self.n) * K
+
+    def engine_bytes(self, res, K):
+        """row_ptr + col streamed; int8 state read+write; infected bitmap read + write."""
+        return (4 * (self.n + 1) + 4 * self.nnz + 2 * self.n + 2 * (self.n // 8)) * K
+
+    def e2e(self, K):
+        t0 = time.perf_counter()
+        m = self.fresh()
+        m.run(steps=K)
+        st = m.agent_collections["agents"].states["state"]
+        wall = time.perf_counter() - t0
+        del m
+        return wall, self.edges.nbytes, st.nbytes + K * 3 * 8, ("create model, bin network_edges into CSR and upload, "
+                                                               "initialize, Model.run(K), download 'state'")
+
+    def cpu_run(self, steps):
+        raise NotImplementedError
+
+
+class EnsembleWorkload:
+    """C5: 8,192 parameter samples x 100k agents x K steps (K = 200 in the config) of
+    tests/unit/test_analysis.py's create_test_model, one ensemble launch."""
+    name = "sensitivity_sweep_8192x100k"
+    dtype = "f32"
+    default_steps = 200
+    stationary = True
+    kernel = "ensemble_kernel"
+    l2_note = "replica state (400 KB) lives in one CTA's L2-resident slot for its whole run; HBM sees only results"
+
+    def __init__(self, rank, world=1, samples=8192, n=100_000):
+        self.samples_total, self.n = samples, n
+        lo = samples * rank // world
+        hi = samples * (rank + 1) // world
+        self.lo, self.hi = lo, hi
+        self.agents = (hi - lo) * n
+
+    def plan(self, K):
+        import jaxabm_b200 as jx
+        from jaxabm_b200 import ensemble
+        from jaxabm_b200.rules import growth
+        rng = np.random.RandomState(0)
+        g = rng.uniform(0.05, 0.2, self.samples_total)
+        a = rng.uniform(0.05, 0.3, self.samples_total)
+        models = [growth.create_test_model(params={"growth_rate": float(g[i]), "adjustment_rate": float(a[i])},
+                                           config=jx.ModelConfig(seed=i + 1000, steps=K), num_agents=self.n)
+                  for i in range(self.lo, self.hi)]
+        return ensemble.plan(models)
+
+    def api_bytes(self, res, K):
+        return 8 * self.agents * K
+
+    engine_bytes = api_bytes
+
+    def cpu_run(self, steps):
+        raise NotImplementedError
+
+
+WORKLOADS = {"schelling": SchellingWorkload, "market": MarketWorkload, "walk": WalkWorkload, "sir": SirWorkload,
+             "ensemble": EnsembleWorkload}
 
 
 # ------------------------------------------------------------------------------------------
@@ -173,9 +339,10 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            time.sleep(0.25)                       # first sample lands before the timed region
         except Exception:
             self.proc = None
 
@@ -203,13 +370,15 @@ def load_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured"
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
             pass
-    return 6650.0, "fallback"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def load_traffic(workload):
+    """profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from
+    an `ncu --set full` capture, stored per step of the captured launch."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
@@ -221,21 +390,23 @@ def load_traffic(workload):
 
 def reference_arm(args, rank, world):
     """CPU restatement of the reference's path (oracle/c, OpenMP over the host cores) on the same
-    workload; under torchrun only rank 0 works."""
+    workload; under torchrun only rank 0 works.  JAX is not installable in this image, so the
+    reference itself cannot run (DESIGN.md "Reference install")."""
     if rank != 0:
         return
     wl = WORKLOADS[args.workload](0)
-    for _ in range(min(args.warmup, 1)):
+    steps = args.steps if args.steps is not None else wl.default_steps
+    cpu_steps = max(1, min(steps, args.cpu_steps * 5))        # bounded sample: at most 200 full-size steps
+    if args.warmup:
         wl.cpu_run(1)
-    secs, threads = wl.cpu_run(args.steps)
-    value = wl.agents * args.steps / secs
+    secs, threads, what = wl.cpu_run(cpu_steps)
+    value = wl.agents * cpu_steps / secs
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+            "steps": cpu_steps, "warmup": min(args.warmup, 1), "ms_per_step": secs / cpu_steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
             "data": "synthetic", "config": {"workload": wl.name},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} full-size steps of {wl.name} on the C/OpenMP oracle "
-                                       "(JAX is not installable here, so the reference itself cannot run)"},
+                             "sample": what + " (JAX is not installable here, so the reference itself cannot run)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -243,12 +414,14 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps K (default: the workload's run length)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="schelling", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", action="store_true", help="market: split ONE population over the ranks")
     ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -268,7 +441,7 @@ def main():
         g.build()
     if world > 1:
         td.barrier()
-    import jaxabm_b200 as jx
+    import jaxabm_b200 as jx  # noqa: F401
     from jaxabm_b200 import _native as nat
 
     def sync_all():
@@ -277,78 +450,131 @@ def main():
             td.barrier()
             torch.cuda.synchronize()
 
-    wl = WORKLOADS[args.workload](rank)
-    eng = nat.engine()
-    model = wl.make()
-    model.run(steps=args.warmup)                       # untimed warm-up (also builds the CUDA graphs)
-
-    # ---- timed region: exactly K steps, device-timed on the engine's stream ------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    sync_all()
-    l0 = eng.launch_count
-    res = model.run(steps=args.steps)
-    dev_s = model.last_device_seconds
-    sync_all()
-    launches = eng.launch_count - l0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    max_s = float(t.item())
-    total_agents = wl.agents * world
-    value = total_agents * args.steps / max_s
-
-    # ---- dominant kernel: CUDA events around every launch of it over K more steps ---------------
-    model._dev.set_profile(True)
-    res_p = model.run(steps=args.steps)
-    ksecs, klaunches, kname = model._dev.profile()
-    model._dev.set_profile(False)
-    peak, peak_kind = load_peak()
-    kbytes = wl.kernel_bytes(res_p)
-    achieved = kbytes / (ksecs / max(klaunches, 1)) / 1e9
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_kind": f"of {peak_kind}", "traffic": load_traffic(args.workload),
-                "bytes_per_launch": kbytes, "us_per_launch": ksecs / max(klaunches, 1) * 1e6,
-                "kernel_share_of_step": (ksecs / max(klaunches, 1)) / (model.last_device_seconds / args.steps),
-                "api_layout_gbs": wl.api_bytes_per_step() / (max_s / args.steps) / 1e9}
-
-    # ---- end to end through the public API with pinned host buffers --------------------------------
-    e2e = None
-    ins, outs = wl.pinned_inputs()
-    if ins is not None:
-        m2 = wl.make()
-        wl.e2e_run(m2, ins, outs, 3)                    # warm-up of the same call
-        sync_all()
-        t0 = time.perf_counter()
-        _, h2d, d2h = wl.e2e_run(m2, ins, outs, args.steps)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        tt = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
         if world > 1:
-            td.all_reduce(tt, op=td.ReduceOp.MAX)
-        e2e = {"value": total_agents * args.steps / float(tt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-               "what": "upload type+position from pinned host memory, Model.run(K), read back "
-                       "position/moves/satisfied + the metrics history"}
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    eng = nat.engine()
+    if args.workload == "ensemble":
+        wl = EnsembleWorkload(rank, world)
+    elif args.workload == "market":
+        wl = MarketWorkload(rank, world=world, shard=args.shard)
+    else:
+        wl = WORKLOADS[args.workload](rank)
+    K = args.steps if args.steps is not None else wl.default_steps
+    sampler = ClockSampler(local)
+    total_agents = wl.agents * (1 if (args.workload == "market" and args.shard) else world)
+    if args.workload == "ensemble":
+        total_agents = wl.samples_total * wl.n
+    extra = {}
+
+    if args.workload == "ensemble":
+        from jaxabm_b200.device import ensemble_run
+        desc, slots, params, seeds, env0 = wl.plan(K)
+        for _ in range(args.warmup):
+            ensemble_run(desc, slots, params[:64], seeds[:64], min(K, 20), env0)
+        if rank == 0:
+            sampler.start()
+        sync_all()
+        l0 = eng.launch_count
+        t0 = time.perf_counter()
+        vals, dev_s = ensemble_run(desc, slots, params, seeds, K, env0)     # host params in, last metrics out
+        wall = time.perf_counter() - t0
+        sync_all()
+        launches = eng.launch_count - l0
+        clocks = sampler.stop() if rank == 0 else None
+        max_s = max_over_ranks(dev_s)
+        max_wall = max_over_ranks(wall)
+        res = None
+        ksecs, klaunches = dev_s, 1
+        extra["runs_per_sec"] = wl.samples_total / max_s
+        e2e = {"value": total_agents * K / max_wall, "unit": UNIT,
+               "h2d_bytes_per_step": (params.nbytes + seeds.nbytes) / K, "d2h_bytes_per_step": vals.nbytes / K,
+               "runs_per_sec": wl.samples_total / max_wall,
+               "what": "jxb_ensemble_run with host parameter/seed tables in, last-metric rows out (wall clock)"}
+    else:
+        # ---- warm-up (W untimed steps) then the timed region: exactly K steps, device-timed ----------
+        model = wl.fresh()
+        model.run(steps=args.warmup)
+        if not wl.stationary:
+            del model
+            model = wl.fresh()                     # the timed run starts from the seeded initial state
+        if rank == 0:
+            sampler.start()
+        sync_all()
+        l0 = eng.launch_count
+        res = model.run(steps=K)
+        dev_s = model.last_device_seconds
+        sync_all()
+        launches = eng.launch_count - l0
+        clocks = sampler.stop() if rank == 0 else None
+        max_s = max_over_ranks(dev_s)
+        # ---- dominant kernel: its own CUDA-event time -------------------------------------------------
+        if wl.kernel == "schelling_run_kernel":
+            ksecs, klaunches = dev_s, 1            # the persistent kernel IS the timed region (one launch)
+        else:
+            pm = model if wl.stationary else wl.fresh()
+            pm._dev.set_profile(True)              # events around every launch, no graph
+            res = pm.run(steps=K)
+            ksecs, klaunches, _ = pm._dev.profile()
+            pm._dev.set_profile(False)
+            if pm is not model:
+                del pm
+        # ---- end to end through the public API with host buffers ------------------------------------------
+        e2e = None
+        if not args.no_e2e and not (args.workload == "market" and args.shard):
+            del model
+            wl.e2e(min(K, 3))                      # warm-up of the same call
+            sync_all()
+            wall, h2d, d2h, what = wl.e2e(K)
+            torch.cuda.synchronize()
+            e2e = {"value": total_agents * K / max_over_ranks(wall), "unit": UNIT, "h2d_bytes_per_step": h2d / K,
+                   "d2h_bytes_per_step": d2h / K, "what": what}
+
+    value = total_agents * K / max_s
+    peak, peak_kind = load_peak()
+    api_b = wl.api_bytes(res, K) / max(klaunches, 1)
+    eng_b = wl.engine_bytes(res, K) / max(klaunches, 1)
+    per_launch = ksecs / max(klaunches, 1)
+    traffic = load_traffic(args.workload)
+    roofline = {"bound": "hbm", "kernel": wl.kernel, "achieved": api_b / per_launch / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": api_b / per_launch / 1e9 / peak, "peak_kind": peak_kind,
+                "traffic": (traffic or {}).get("dram_bytes_per_step", None) and traffic["dram_bytes_per_step"] *
+                           (K if klaunches == 1 else 1),
+                "traffic_source": (traffic or {}).get("source"),
+                "bytes_per_launch": api_b, "us_per_launch": per_launch * 1e6, "launches_timed": int(klaunches),
+                "kernel_share_of_step": min(1.0, ksecs / dev_s) if dev_s > 0 else None,
+                "engine_layout": {"bytes_per_launch": eng_b, "achieved": eng_b / per_launch / 1e9,
+                                  "frac": eng_b / per_launch / 1e9 / peak},
+                "note": "achieved/frac use SURVEY.md 8(d) algorithmic bytes in the reference's API dtypes; "
+                        "engine_layout uses the bytes the packed HBM layout actually has to move "
+                        "(frac > 1 on the API figure means the engine moves fewer bytes than the reference layout implies)"}
     if rank != 0:
         return
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
-            secs, threads = wl.cpu_run(args.cpu_steps)
+            secs, threads, what = wl.cpu_run(args.cpu_steps)
             cpu = {"value": wl.agents * args.cpu_steps / secs, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{args.cpu_steps} full-size steps of {wl.name} on the C/OpenMP oracle ({secs:.1f} s)"}
+                   "sample": f"{what} ({secs:.1f} s)"}
         except NotImplementedError:
             cpu = None
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": max_s / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-            "config": {"workload": wl.name, "agents_per_gpu": wl.agents,
-                       "parallelism": f"replica-per-gpu x{world}" if world > 1 else "single-gpu",
-                       "l2": "no flush: resident state (agents SoA + cell arrays + lists, >400 MB) exceeds the 126 MB L2"},
+    par = "single-gpu"
+    if world > 1:
+        par = (f"one population sharded over {world} gpus (per-step env partial-sum exchange)"
+               if (args.workload == "market" and args.shard) else
+               (f"replica blocks over {world} gpus" if args.workload == "ensemble" else f"replica-per-gpu x{world}"))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "ms_per_step": max_s / K * 1e3, "higher_is_better": True,
+            "scaling": "strong" if (args.workload in ("ensemble",) or args.shard) else "weak",
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+            "config": {"workload": wl.name, "agents_per_gpu": wl.agents, "parallelism": par, "l2": wl.l2_note,
+                       "timed_region": ("K steps from the seeded initial state (fresh model after the warm-up model)"
+                                        if not wl.stationary else "K steps after W warm-up steps on the same model")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    line.update(extra)
     print(json.dumps(line), flush=True)
 
 

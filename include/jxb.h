@@ -191,6 +191,17 @@ int jxb_nccl_unique_id(void* id_bytes_out, size_t bytes);
 int jxb_engine_attach_nccl(jxb_engine*, const void* id_bytes, size_t bytes, int rank,
                            int world_size);
 
+/* Peer-memory exchange (the product path): every rank exports the CUDA IPC handle of its
+ * exchange buffer, the host shim all-gathers the JXB_IPC_HANDLE_BYTES-byte handles and every
+ * rank maps its peers' buffers over NVLink.  The step kernel's last CTA then stores its
+ * partial-sum row into every peer, waits for the peers' rows and folds them in rank order:
+ * update + reduction + exchange in ONE kernel, no NCCL launch on the step path.
+ * JXB_EXCHANGE=nccl selects the NCCL all-reduce path instead (kept as the comparison arm). */
+#define JXB_IPC_HANDLE_BYTES 64
+int jxb_engine_p2p_export(jxb_engine*, void* handle_out, size_t bytes);
+int jxb_engine_p2p_attach(jxb_engine*, const void* handles, size_t bytes_each, int rank,
+                          int world_size);
+
 /* ---- host-only scalar key algebra (jax.random on the reference's host path) -------- */
 /* jax.random.split(key, n) -> out[n][2] (jaxabm/model.py:129,156; analysis.py:438).  */
 int jxb_prng_split(int rng_mode, const uint32_t key[2], int n, uint32_t* out);

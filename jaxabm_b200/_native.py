@@ -87,6 +87,8 @@ SIGNATURES = {
                                    C.POINTER(C.c_double)]),
     "jxb_nccl_unique_id": (C.c_int, [_P, C.c_size_t]),
     "jxb_engine_attach_nccl": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int]),
+    "jxb_engine_p2p_export": (C.c_int, [_P, _P, C.c_size_t]),
+    "jxb_engine_p2p_attach": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int]),
     "jxb_prng_split": (C.c_int, [C.c_int, _P, C.c_int, _P]),
     "jxb_prng_bits": (C.c_int, [C.c_int, _P, C.c_int64, _P]),
     "jxb_prng_uniform": (C.c_int, [C.c_int, _P, C.c_int64, C.c_float, C.c_float, _P]),

@@ -48,6 +48,20 @@ struct Ctrl {
   long long sir_count[3];
 };
 
+// cross-rank exchange of the per-step env partial sums (population sharding, one process per
+// GPU): every rank owns one XchgBuf in its HBM and maps its peers' buffers through CUDA IPC
+// (NVLink / NVSwitch peer memory).  The last CTA of a rank's step kernel stores its totals row
+// into slot [parity][rank] of EVERY rank's buffer, publishes a sequence flag, waits for the
+// world_size flags in its own buffer and folds the rows in rank order -- one kernel does the
+// update, the reduction and the exchange; all ranks fold identical values in identical order.
+constexpr int kMaxPeers = 8;
+struct XchgBuf {
+  double row[2][kMaxPeers][kAcc];
+  unsigned int flag[2][kMaxPeers];
+  unsigned int seq;       // sharded steps completed by this rank since the peers were attached
+  unsigned int err;       // set when a peer's flag did not arrive within the spin budget
+};
+
 struct TypeDev {
   void* f[kMaxFields];
   long long n;            // local agents
@@ -74,7 +88,10 @@ struct ModelDev {
   int* record_steps;      // [records]
   int grid_blocks;
   int world_size;
-  double* allreduce_buf;  // [kAcc] staging for the cross-rank partial-sum exchange
+  double* allreduce_buf;  // [kAcc] staging for the cross-rank partial-sum exchange (NCCL path)
+  int rank;
+  int exchange;           // 0 none, 1 in-kernel peer-memory exchange, 2 NCCL all-reduce + tail kernel
+  XchgBuf* xpeer[kMaxPeers];   // every rank's buffer as mapped into this process (own = local)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

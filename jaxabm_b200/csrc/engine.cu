@@ -151,6 +151,10 @@ struct jxb_engine {
   int64_t launches = 0;
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // peer-memory exchange (CUDA IPC over NVLink): own buffer + every rank's buffer as mapped here
+  XchgBuf* xlocal = nullptr;
+  XchgBuf* xpeer[kMaxPeers] = {};
+  bool p2p = false;
 };
 
 struct jxb_model {
@@ -215,6 +219,9 @@ extern "C" int jxb_engine_destroy(jxb_engine* eng) {
   if (!eng) return JXB_OK;
   cudaSetDevice(eng->device);
   if (eng->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(eng->nccl_comm);
+  for (int p = 0; p < kMaxPeers; ++p)
+    if (eng->xpeer[p] && eng->xpeer[p] != eng->xlocal) cudaIpcCloseMemHandle(eng->xpeer[p]);
+  if (eng->xlocal) cudaFree(eng->xlocal);
   cudaEventDestroy(eng->ev0);
   cudaEventDestroy(eng->ev1);
   cudaStreamDestroy(eng->stream);
@@ -254,6 +261,43 @@ extern "C" int jxb_engine_attach_nccl(jxb_engine* eng, const void* id, size_t by
   if (r) return fail(JXB_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   eng->rank = rank;
   eng->world = world;
+  return JXB_OK;
+}
+
+// peer-memory exchange: every rank exports the IPC handle of its XchgBuf, the host shim
+// all-gathers the handles (torch.distributed) and every rank maps its peers' buffers.
+extern "C" int jxb_engine_p2p_export(jxb_engine* eng, void* handle_out, size_t bytes) {
+  if (!eng || !handle_out || bytes < sizeof(cudaIpcMemHandle_t))
+    return fail(JXB_ERR_INVALID, "need %zu bytes for the IPC handle", sizeof(cudaIpcMemHandle_t));
+  CK(cudaSetDevice(eng->device));
+  if (!eng->xlocal) {
+    CK(cudaMalloc((void**)&eng->xlocal, sizeof(XchgBuf)));
+    CK(cudaMemset(eng->xlocal, 0, sizeof(XchgBuf)));
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, eng->xlocal));
+  memset(handle_out, 0, bytes);
+  memcpy(handle_out, &h, sizeof(h));
+  return JXB_OK;
+}
+
+extern "C" int jxb_engine_p2p_attach(jxb_engine* eng, const void* handles, size_t bytes_each, int rank, int world) {
+  if (!eng || !handles || bytes_each < sizeof(cudaIpcMemHandle_t)) return fail(JXB_ERR_INVALID, "bad IPC handle table");
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(JXB_ERR_INVALID, "rank %d / world %d out of range (max %d peers)", rank, world, kMaxPeers);
+  if (!eng->xlocal) return fail(JXB_ERR_STATE, "call jxb_engine_p2p_export first");
+  CK(cudaSetDevice(eng->device));
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) { eng->xpeer[p] = eng->xlocal; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)p * bytes_each, sizeof(h));
+    void* q = nullptr;
+    CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    eng->xpeer[p] = (XchgBuf*)q;
+  }
+  eng->rank = rank;
+  eng->world = world;
+  eng->p2p = true;
   return JXB_OK;
 }
 
@@ -328,6 +372,26 @@ extern "C" int jxb_model_create(jxb_engine* eng, const jxb_model_desc* d, jxb_mo
   md.collect_interval = 1;
   md.has_env_fn = m->prog->has_env_fn;
   md.world_size = d->world_size > 1 ? d->world_size : 1;
+  md.rank = d->rank;
+  md.exchange = 0;
+  if (md.world_size > 1) {
+    static const bool force_nccl = getenv("JXB_EXCHANGE") && !strcmp(getenv("JXB_EXCHANGE"), "nccl");
+    if (eng->p2p && !force_nccl) {
+      if (eng->world != md.world_size || eng->rank != md.rank) {
+        delete m;
+        return fail(JXB_ERR_INVALID, "model shard (rank %d of %d) does not match the attached peers (rank %d of %d)",
+                    md.rank, md.world_size, eng->rank, eng->world);
+      }
+      md.exchange = 1;
+      for (int p = 0; p < md.world_size; ++p) md.xpeer[p] = eng->xpeer[p];
+    } else if (eng->nccl_comm) {
+      md.exchange = 2;
+    } else {
+      delete m;
+      return fail(JXB_ERR_STATE, "sharded model but neither peer memory (jxb_engine_p2p_attach) nor an NCCL "
+                                 "communicator (jxb_engine_attach_nccl) is attached");
+    }
+  }
   for (int k = 0; k < JXB_MAX_PARAMS; ++k) md.mp[k] = k < d->n_params ? d->params[k] : 0.0;
 #define TRY(x) do { rc = (x); if (rc) { jxb_model_destroy(m); return rc; } } while (0)
   for (int i = 0; i < d->n_types; ++i) {
@@ -573,15 +637,16 @@ extern "C" int jxb_model_grid_rebuild(jxb_model* m) {
   CK(cudaSetDevice(m->eng->device));
   cudaStream_t s = m->eng->stream;
   int* d_err = nullptr;
-  CK(cudaMalloc(&d_err, 2 * sizeof(int)));
+  CK(cudaMalloc(&d_err, (2 + (size_t)m->sd.ntiles) * sizeof(int)));
   CK(cudaMemsetAsync(d_err, 0, 2 * sizeof(int), s));
   const int blocks = m->eng->sms * 8;
   grid_clear_kernel<<<blocks, 256, 0, s>>>(m->sd, m->pad);
   grid_scatter_kernel<<<blocks, 256, 0, s>>>(m->sd, (const int*)m->dev.t[0].f[0], (const int2*)m->dev.t[0].f[1],
                                             m->desc.types[0].n_agents, d_err);
   // env['empty_cells']: ascending empty cells of the freshly built grid
-  empty_list_kernel<<<1, 1024, 0, s>>>(m->sd, (unsigned int*)(d_err + 1));
-  m->eng->launches += 3;
+  empty_count_kernel<<<m->sd.ntiles, kThreads, 0, s>>>(m->sd, (unsigned int*)(d_err + 2));
+  empty_write_kernel<<<m->sd.ntiles, kThreads, 0, s>>>(m->sd, (const unsigned int*)(d_err + 2), (unsigned int*)(d_err + 1));
+  m->eng->launches += 4;
   int err = 0;
   unsigned int n_empty = 0;
   CK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -819,8 +884,8 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       else step_kernel<0><<<m->step_blocks, kThreads, 0, s>>>(m->dev);
       if (timed) cudaEventRecord(e1, s);
       eng->launches += 1;
-      if (m->dev.world_size > 1) {
-        // sharded population: sum/max/int slots are exchanged as three small all-reduces
+      if (m->dev.exchange == 2) {
+        // NCCL path (JXB_EXCHANGE=nccl or no peer memory): sum/max/int slots as three small all-reduces
         if (!eng->nccl_comm) return fail(JXB_ERR_STATE, "sharded model but no NCCL communicator attached");
         double* buf = m->dev.allreduce_buf;
         int r = g_nccl.AllReduce(buf, buf, kFSum, /*ncclFloat64*/ 8, /*ncclSum*/ 0, eng->nccl_comm, s);
@@ -865,7 +930,7 @@ static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
 }
 
 static int launches_per_step(jxb_model* m) {
-  return (m->dev.world_size > 1) ? 2 : 1;
+  return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
 }
 
 extern "C" int jxb_model_set_profile(jxb_model* m, int enable) {
@@ -903,7 +968,6 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   cudaStream_t s = eng->stream;
   if (m->has_grid && !m->grid_built) { int rc = jxb_model_grid_rebuild(m); if (rc) return rc; }
   if (m->has_net && !m->net_built) return fail(JXB_ERR_STATE, "SIR model has no network; call jxb_model_set_network");
-  if (m->dev.world_size > 1 && !eng->nccl_comm) return fail(JXB_ERR_STATE, "sharded model but no NCCL communicator attached");
 
   const int C = m->desc.n_types, mode = m->desc.rng_mode, stride = (C + 1) * 2;
   // ---- key schedule of the whole run (model.py:156,164,183), host scalar work ----------
@@ -950,7 +1014,7 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   }
   static const bool use_graph = getenv("JXB_NO_GRAPH") == nullptr;
   const bool persistent = m->desc.program == JXB_PROGRAM_SCHELLING;
-  const bool graphs = use_graph && !persistent && !m->profile && m->dev.world_size == 1 && steps > 0;
+  const bool graphs = use_graph && !persistent && !m->profile && m->dev.exchange != 2 && steps > 0;
   if (graphs) {
     // kernel arguments (the ModelDev snapshot) are baked into a captured graph: rebuild the
     // two cached graphs (1 step, 32 steps) whenever a pointer or the interval changed
@@ -1011,6 +1075,11 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   }
   m->time_step = t0 + steps;
   if (m->has_grid && steps > 0) m->sat_dirty = true;
+  if (m->dev.exchange == 1) {
+    unsigned int xerr = 0;
+    CK(cudaMemcpy(&xerr, &eng->xlocal->err, sizeof(xerr), cudaMemcpyDeviceToHost));
+    if (xerr) return fail(JXB_ERR_NCCL, "peer exchange timed out: a rank did not publish its partial sums");
+  }
   return JXB_OK;
 }
 

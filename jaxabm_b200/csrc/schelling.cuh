@@ -393,32 +393,75 @@ __global__ void grid_scatter_kernel(const SchellingDev sd, const int* type, cons
   }
 }
 
-// env['empty_cells'] = ascending empty cells (schelling_model.py:133-139): single CTA ordered
-// compaction, run once when the grid is (re)built from uploaded positions
-__global__ void empty_list_kernel(const SchellingDev sd, unsigned int* count_out) {
-  __shared__ unsigned int s_w[32];
-  __shared__ unsigned int s_base;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  if (tid == 0) s_base = 0;
+// env['empty_cells'] = ascending empty cells (schelling_model.py:133-139): two-pass ordered
+// compaction over 4096-cell tiles (one CTA per tile, 16 cells per thread), run when the grid is
+// (re)built from uploaded positions.  Pass 1 counts the empty cells of every tile; pass 2 folds
+// the counts of the preceding tiles (exclusive prefix, fixed order) and writes the tile's cells.
+__device__ __forceinline__ unsigned int empty_mask16(const SchellingDev& sd, long long c0) {
+  unsigned int mask = 0;
+#pragma unroll
+  for (int q = 0; q < kCellsPerThread; ++q)
+    if (c0 + q < sd.cells && sd.ct[c0 + q] < 0) mask |= 1u << q;
+  return mask;
+}
+
+__global__ void __launch_bounds__(kThreads) empty_count_kernel(const SchellingDev sd, unsigned int* tile_count) {
+  __shared__ unsigned int s_w[kThreads / 32];
+  const int tid = threadIdx.x;
+  const long long c0 = (long long)blockIdx.x * kTileCells + (long long)tid * kCellsPerThread;
+  const unsigned int cnt = warp_sum((int)__popc(empty_mask16(sd, c0)));
+  if ((tid & 31) == 0) s_w[tid >> 5] = cnt;
   __syncthreads();
-  for (long long c0 = 0; c0 < sd.cells; c0 += blockDim.x) {
-    const long long c = c0 + tid;
-    const bool emp = c < sd.cells && sd.ct[c] < 0;
-    const unsigned int bal = __ballot_sync(0xffffffffu, emp);
-    if (lane == 0) s_w[warp] = __popc(bal);
-    __syncthreads();
-    unsigned int off = s_base;
-    for (int w = 0; w < warp; ++w) off += s_w[w];
-    if (emp) sd.E[off + __popc(bal & ((1u << lane) - 1u))] = (unsigned int)c;
-    __syncthreads();
-    if (tid == 0) {
-      unsigned int tot = 0;
-      for (int w = 0; w < nw; ++w) tot += s_w[w];
-      s_base += tot;
-    }
-    __syncthreads();
+  if (tid == 0) {
+    unsigned int tot = 0;
+    for (int w = 0; w < kThreads / 32; ++w) tot += s_w[w];
+    tile_count[blockIdx.x] = tot;
   }
-  if (tid == 0) *count_out = s_base;
+}
+
+__global__ void __launch_bounds__(kThreads) empty_write_kernel(const SchellingDev sd, const unsigned int* tile_count,
+                                                               unsigned int* count_out) {
+  __shared__ unsigned int s_w[kThreads / 32];
+  __shared__ unsigned int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // exclusive prefix of the preceding tiles' counts
+  unsigned int before = 0;
+  for (int i = tid; i < (int)blockIdx.x; i += kThreads) before += tile_count[i];
+  before = warp_sum((int)before);
+  if (lane == 0) s_w[warp] = before;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int tot = 0;
+    for (int w = 0; w < kThreads / 32; ++w) tot += s_w[w];
+    s_base = tot;
+  }
+  __syncthreads();
+  const long long c0 = (long long)blockIdx.x * kTileCells + (long long)tid * kCellsPerThread;
+  unsigned int mask = empty_mask16(sd, c0);
+  const unsigned int cnt = __popc(mask);
+  unsigned int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  __syncthreads();
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  unsigned int woff = 0, ttot = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    if (w < warp) woff += s_w[w];
+    ttot += s_w[w];
+  }
+  unsigned int pos = s_base + woff + inc - cnt;
+  while (mask) {
+    const int q = __ffs(mask) - 1;
+    mask &= mask - 1;
+    if (pos < sd.n_empty) sd.E[pos] = (unsigned int)(c0 + q);   // more only if two agents share a cell
+    ++pos;
+  }
+  if (blockIdx.x == gridDim.x - 1 && tid == 0) *count_out = s_base + ttot;
 }
 
 __global__ void grid_export_kernel(const SchellingDev sd, int* out) {

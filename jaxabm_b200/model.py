@@ -75,6 +75,7 @@ class Model:
         self._is_initialized = False
         self._dev: Optional[DeviceModel] = None
         self._program: Optional[str] = None
+        self._shard = None            # (rank, world) when split across GPUs (sharding.shard_model)
         self.last_device_seconds = 0.0
 
     # ---- construction ---------------------------------------------------------------------
@@ -145,7 +146,18 @@ class Model:
             if shape is None:
                 raise ValueError("Schelling needs a Grid: env state 'grid_shape' is missing")
             grid = (int(shape[0]), int(shape[1]), bool(self._env_state.get("grid_periodic", False)))
-        desc = make_desc(program, specs, mparams, rng_mode=self.config.rng_mode, grid=grid)
+        rank, world = self._shard or (0, 1)
+        if world > 1:
+            if program in ("schelling", "sir"):
+                raise UnregisteredRuleError("grid / network programs are not population-sharded; run replicas")
+            from .dist import shard_bounds
+            for spec in specs:
+                lo, hi = shard_bounds(spec.n_agents, rank, world)
+                if hi <= lo:
+                    raise ValueError(f"collection of {spec.n_agents} agents cannot be split over {world} ranks")
+                spec.global_n, spec.global_offset, spec.n_agents = spec.n_agents, lo, hi - lo
+        desc = make_desc(program, specs, mparams, rng_mode=self.config.rng_mode, grid=grid,
+                         world_size=world, rank=rank)
         self._dev = DeviceModel(desc)
         self._program = program
         for name, value in list(self._env_state.items()):

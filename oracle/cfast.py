@@ -97,3 +97,43 @@ class SchellingFast:
             out["segregation_index"].append(np.float32(ssum.value / max(1, scnt.value)))
             out["total_moves"].append(np.int32(self.total_moves))
         return out
+
+
+class MarketFast:
+    """Consumer/producer market (C4-A) on the C oracle: same initial state as
+    ``oracle.rules.create_economy_model(...)`` (incomes / capital from the per-agent keys of
+    ``Model.initialize``), stepped by ``orc_market_step``."""
+
+    def __init__(self, num_consumers, num_producers, base_income=1.0, propensity_to_consume=0.8,
+                 initial_capital=10.0, productivity=1.0, reinvestment_rate=0.3, price_adjustment_rate=0.1,
+                 seed=0, mode=1):
+        self.nc, self.np_ = int(num_consumers), int(num_producers)
+        self.ptc, self.prd, self.rr, self.rate = (np.float32(propensity_to_consume), np.float32(productivity),
+                                                  np.float32(reinvestment_rate), np.float32(price_adjustment_rate))
+        keys = jl.split(jl.PRNGKey(seed), 3, mode)                  # model.py:129-137
+        u_c = jl.uniform_scalar_batched(jl.split(keys[1], self.nc, mode), mode=mode)
+        u_p = jl.uniform_scalar_batched(jl.split(keys[2], self.np_, mode), mode=mode)
+        f32 = np.float32
+        self.income = (f32(base_income) * (f32(0.8) + f32(0.4) * u_c)).astype(f32)
+        self.capital = (f32(initial_capital) * (f32(0.8) + f32(0.4) * u_p)).astype(f32)
+        self.savings = np.zeros(self.nc, f32)
+        self.consumption = np.zeros(self.nc, f32)
+        self.utility = np.zeros(self.nc, f32)
+        self.production = np.zeros(self.np_, f32)
+        self.profit = np.zeros(self.np_, f32)
+        self.env = np.array([1.0, 0.0, 0.0, 0.0, 0.0], dtype=f32)
+
+    def run(self, steps: int):
+        out = {"gdp": [], "price_level": [], "unemployment": [], "avg_utility": [], "avg_profit": []}
+        su, sp = C.c_double(), C.c_double()
+        for _ in range(steps):
+            lib().orc_market_step(self.nc, _p(self.savings), _p(self.consumption), _p(self.utility), _p(self.income),
+                                  C.c_float(self.ptc), self.np_, _p(self.capital), _p(self.production),
+                                  _p(self.profit), C.c_float(self.prd), C.c_float(self.rr), C.c_float(self.rate),
+                                  _p(self.env), C.byref(su), C.byref(sp))
+            out["price_level"].append(np.float32(self.env[0]))
+            out["gdp"].append(np.float32(self.env[1]))
+            out["unemployment"].append(np.float32(self.env[2]))
+            out["avg_utility"].append(np.float32(su.value / max(self.nc, 1)))
+            out["avg_profit"].append(np.float32(sp.value / max(self.np_, 1)))
+        return out
