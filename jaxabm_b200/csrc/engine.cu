@@ -176,6 +176,9 @@ struct jxb_model {
   bool grid_built = false; bool sat_dirty = false; long long n_empty_cells = 0; int sch_blocks = 0;
   // SIR
   bool has_net = false; SirDev sv{}; bool net_built = false; long long nnz = 0;
+  // SIR formulation: 0 pull (CSR ballot-segmented sweep of all edges, fused transitions),
+  // 1 push (infected rows scatter-add into k32, then the transition kernel)
+  int sir_mode = 1; int sir_tblocks = 0;
   // graphs: cached executable graphs of `chunk` consecutive steps
   cudaGraphExec_t graph1 = nullptr, graphK = nullptr; int chunkK = 0;
   const void* sig_keys = nullptr; const void* sig_metrics = nullptr; const void* sig_rec = nullptr; int sig_ci = 0;
@@ -762,9 +765,25 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     CK(cudaMemcpy(d_esc, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
   }
   sv.row_ptr = d_rp; sv.col = d_col; sv.rb = d_rb; sv.nrb = (int)rb.size() - 1; sv.escape = d_esc;
-  if ((rc = dev_alloc(m, &sv.partials, (size_t)sv.nrb * 3))) return rc;
+  if ((rc = dev_alloc(m, &sv.partials, (size_t)std::max<long long>(sv.nrb, (n + kThreads * kSirRowsPerThread - 1) / (kThreads * kSirRowsPerThread)) * 3 + 3))) return rc;
   m->nnz = n_edges;
   m->net_built = true;
+  {
+    // push formulation: counters + the static list of heavy rows
+    std::vector<int> heavy;
+    for (long long i = 0; i < n; ++i)
+      if (row_ptr[i + 1] - row_ptr[i] > (unsigned)kSirHeavy) heavy.push_back((int)i);
+    int* d_heavy = nullptr;
+    if ((rc = dev_alloc(m, &d_heavy, heavy.size() + 1))) return rc;
+    if (!heavy.empty()) CK(cudaMemcpy(d_heavy, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice));
+    if ((rc = dev_alloc(m, &sv.k32, (size_t)n + 32))) return rc;
+    CK(cudaMemset(sv.k32, 0, ((size_t)n + 32) * 4));
+    sv.heavy = d_heavy;
+    sv.n_heavy = (int)heavy.size();
+    m->sir_tblocks = (int)((n + kThreads * kSirRowsPerThread - 1) / (kThreads * kSirRowsPerThread));
+    const char* mode = getenv("JXB_SIR_MODE");
+    m->sir_mode = (mode && !strcmp(mode, "pull")) ? 0 : 1;
+  }
   return sir_sync_from_api(m);
 }
 
@@ -872,8 +891,15 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
   switch (m->desc.program) {
     case JXB_PROGRAM_SIR: {
       if (timed) cudaEventRecord(e0, s);
-      if (part) sir_step_kernel<1><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
-      else sir_step_kernel<0><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
+      if (m->sir_mode == 1) {
+        sir_push_kernel<<<m->eng->sms * 8, kThreads, 0, s>>>(m->sv, m->dev);
+        if (part) sir_transition_kernel<1><<<m->sir_tblocks, kThreads, 0, s>>>(m->sv, m->dev);
+        else sir_transition_kernel<0><<<m->sir_tblocks, kThreads, 0, s>>>(m->sv, m->dev);
+        eng->launches += 1;
+      } else {
+        if (part) sir_step_kernel<1><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
+        else sir_step_kernel<0><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
+      }
       if (timed) cudaEventRecord(e1, s);
       eng->launches += 1;
       break;
@@ -930,6 +956,7 @@ static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
 }
 
 static int launches_per_step(jxb_model* m) {
+  if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 1 ? 2 : 1;
   return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
 }
 
@@ -946,7 +973,7 @@ extern "C" int jxb_model_profile(jxb_model* m, double* seconds, int64_t* launche
   if (name) {
     switch (m->desc.program) {
       case JXB_PROGRAM_SCHELLING: *name = "schelling_run_kernel"; break;
-      case JXB_PROGRAM_SIR: *name = "sir_step_kernel"; break;
+      case JXB_PROGRAM_SIR: *name = m->sir_mode == 1 ? "sir_push_kernel+sir_transition_kernel" : "sir_step_kernel"; break;
       default: *name = "step_kernel";
     }
   }

@@ -33,22 +33,44 @@ struct SirDev {
   const int* rb;
   int nrb;
   const float* escape;     // q[k] = fl32(q[k-1]*fl32(1-beta)), k <= kSirKCap
-  long long* partials;     // [nrb][3] new S/I/R counts per row block
+  long long* partials;     // [max(nrb, transition CTAs)][3] new S/I/R counts per CTA
+  unsigned int* k32;       // push formulation: infected-neighbour counters (zero between steps)
+  const int* heavy;        // rows with more than kSirHeavy adjacency entries
+  int n_heavy;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, const ModelDev md) {
-  __shared__ unsigned int s_words[kSirWords + 1];
-  __shared__ unsigned int s_pref[kSirWords + 1];
-  __shared__ int s_red[3][kThreads / 32];
-  __shared__ int s_last;
+// ---------------------------------------------------------------------------------------
+// infected-bit gather policies.
+//   GatherGlobal : bitmap read through L1/L2.  A warp-wide random gather costs one L1tex
+//                  wavefront per distinct 128 B line (~1 lane / cycle / SM) -- this is what bounds
+//                  the plain kernel, not HBM.
+//   (A variant that sliced the bitmap over the shared memories of an 8-CTA cluster and gathered
+//   through distributed shared memory measured 6x SLOWER -- 4.1 ms vs 0.64 ms per step at C3 --
+//   and was removed: divergent ld.shared::cluster gathers serialise per lane.  DESIGN.md 4.3.)
+// ---------------------------------------------------------------------------------------
+struct GatherGlobal {
+  const unsigned int* inf;
+  __device__ __forceinline__ unsigned int operator()(int c) const {
+    return (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;
+  }
+};
+
+struct SirSmem {
+  unsigned int words[kSirWords + 1];
+  unsigned int pref[kSirWords + 1];
+  int red[3][kThreads / 32];
+};
+
+// one row block: neighbour counts by ballot-segmented reduction, threefry draw, transition,
+// new bitmap words, per-block S/I/R partial counts.
+template <int MODE, class Gather>
+__device__ __forceinline__ void sir_row_block(const SirDev& sv, const ModelDev& md, const Gather& gather, int rbi,
+                                              int cur, const Key ck, SirSmem& sm) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  Ctrl* ctrl = md.ctrl;
   const TypeDev& t = md.t[0];
-  const int cur = (int)(ctrl->time_step & 1), nxt = cur ^ 1;
-  const int r0 = sv.rb[blockIdx.x], r1 = sv.rb[blockIdx.x + 1];
+  const int nxt = cur ^ 1;
+  const int r0 = sv.rb[rbi], r1 = sv.rb[rbi + 1];
   const unsigned int e0 = sv.row_ptr[r0], e1 = sv.row_ptr[r1];
-  const unsigned int* inf = sv.infbits[cur];
 
   unsigned int lo[kSirRowsPerThread], hi[kSirRowsPerThread];
   int k[kSirRowsPerThread];
@@ -61,30 +83,34 @@ __global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, con
   }
 
   for (unsigned int ts = e0; ts < e1; ts += kSirTile) {
+    // all loads of the tile first (memory-level parallelism), then the gathers, then the ballots
+    int cols[kSirTile / kThreads];
 #pragma unroll
     for (int j = 0; j < kSirTile / kThreads; ++j) {
       const unsigned int e = ts + j * kThreads + tid;
-      unsigned int bit = 0;
-      if (e < e1) {
-        const int c = __ldcs(sv.col + e);                       // streamed once
-        bit = (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;         // gather: L1/L2-resident bitmap
-      }
-      const unsigned int w = __ballot_sync(0xffffffffu, bit);
-      if (lane == 0) s_words[j * (kThreads / 32) + warp] = w;
+      cols[j] = e < e1 ? __ldcs(sv.col + e) : -1;                 // streamed once
     }
-    if (tid == 0) s_words[kSirWords] = 0;
+    unsigned int bits[kSirTile / kThreads];
+#pragma unroll
+    for (int j = 0; j < kSirTile / kThreads; ++j) bits[j] = cols[j] >= 0 ? gather(cols[j]) : 0u;
+#pragma unroll
+    for (int j = 0; j < kSirTile / kThreads; ++j) {
+      const unsigned int w = __ballot_sync(0xffffffffu, bits[j]);
+      if (lane == 0) sm.words[j * (kThreads / 32) + warp] = w;
+    }
+    if (tid == 0) sm.words[kSirWords] = 0;
     __syncthreads();
     if (warp == 0) {  // exclusive prefix of the 64 popcounts (+ total in slot 64)
-      const unsigned int a = __popc(s_words[2 * lane]), b = __popc(s_words[2 * lane + 1]);
+      const unsigned int a = __popc(sm.words[2 * lane]), b = __popc(sm.words[2 * lane + 1]);
       unsigned int inc = a + b;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += v;
       }
-      s_pref[2 * lane] = inc - a - b;
-      s_pref[2 * lane + 1] = inc - b;
-      if (lane == 31) s_pref[kSirWords] = inc;
+      sm.pref[2 * lane] = inc - a - b;
+      sm.pref[2 * lane + 1] = inc - b;
+      if (lane == 31) sm.pref[kSirWords] = inc;
     }
     __syncthreads();
     const unsigned int te = ts + kSirTile;
@@ -93,8 +119,8 @@ __global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, con
       const unsigned int a = lo[i] > ts ? lo[i] : ts, b = hi[i] < te ? hi[i] : te;
       if (b > a) {
         const unsigned int xa = a - ts, xb = b - ts;
-        const unsigned int ra = s_pref[xa >> 5] + __popc(s_words[xa >> 5] & ((1u << (xa & 31)) - 1u));
-        const unsigned int rb = s_pref[xb >> 5] + __popc(s_words[xb >> 5] & ((1u << (xb & 31)) - 1u));
+        const unsigned int ra = sm.pref[xa >> 5] + __popc(sm.words[xa >> 5] & ((1u << (xa & 31)) - 1u));
+        const unsigned int rb = sm.pref[xb >> 5] + __popc(sm.words[xb >> 5] & ((1u << (xb & 31)) - 1u));
         k[i] += (int)(rb - ra);
       }
     }
@@ -102,9 +128,6 @@ __global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, con
   }
 
   // ---- transitions ------------------------------------------------------------------------
-  const int step = ctrl->step_in_run;
-  const uint32_t* kp = md.keys + (size_t)step * (md.n_types + 1) * 2;
-  const Key ck = {kp[0], kp[1]};
   const float gamma = t.p[1];
   int cS = 0, cI = 0, cR = 0;
 #pragma unroll
@@ -134,23 +157,23 @@ __global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, con
     if (lane == 0 && rg < r1 && rg < t.n) sv.infbits[nxt][rg >> 5] = w;
   }
   cS = warp_sum(cS); cI = warp_sum(cI); cR = warp_sum(cR);
-  if (lane == 0) { s_red[0][warp] = cS; s_red[1][warp] = cI; s_red[2][warp] = cR; }
+  if (lane == 0) { sm.red[0][warp] = cS; sm.red[1][warp] = cI; sm.red[2][warp] = cR; }
   __syncthreads();
   if (tid < 3) {
     long long v = 0;
-    for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
-    sv.partials[(size_t)blockIdx.x * 3 + tid] = v;
+    for (int w = 0; w < kThreads / 32; ++w) v += sm.red[tid][w];
+    sv.partials[(size_t)rbi * 3 + tid] = v;
   }
-  __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&ctrl->ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // ---- tail: exact integer fold + metrics row (count_S, count_I, count_R) ---------------------
+}
+
+// last CTA: exact integer fold over the row blocks + metrics row (count_S, count_I, count_R)
+__device__ __forceinline__ void sir_tail(const SirDev& sv, const ModelDev& md, int nparts) {
   __shared__ long long s_tot[3][kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Ctrl* ctrl = md.ctrl;
   long long v[3] = {0, 0, 0};
-  for (int b = tid; b < (int)gridDim.x; b += kThreads) {
+  for (int b = tid; b < nparts; b += kThreads) {
     v[0] += __ldcg(sv.partials + (size_t)b * 3 + 0);
     v[1] += __ldcg(sv.partials + (size_t)b * 3 + 1);
     v[2] += __ldcg(sv.partials + (size_t)b * 3 + 2);
@@ -178,6 +201,132 @@ __global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, con
     ctrl->time_step = tsn;
     ctrl->step_in_run += 1;
   }
+}
+
+// plain variant: one CTA per row block, bitmap gathered through L1/L2
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, const ModelDev md) {
+  __shared__ SirSmem sm;
+  __shared__ int s_last;
+  Ctrl* ctrl = md.ctrl;
+  const int cur = (int)(ctrl->time_step & 1);
+  const uint32_t* kp = md.keys + (size_t)ctrl->step_in_run * (md.n_types + 1) * 2;
+  const Key ck = {kp[0], kp[1]};
+  GatherGlobal g{sv.infbits[cur]};
+  sir_row_block<MODE>(sv, md, g, blockIdx.x, cur, ck, sm);
+  __threadfence();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  sir_tail(sv, md, sv.nrb);
+}
+
+// ---------------------------------------------------------------------------------------
+// push formulation (frontier-driven): only the adjacency rows of INFECTED agents are read.
+//   sir_push_kernel       for every infected row j, for every neighbour i: k32[i] += 1
+//                         (fire-and-forget L2 reductions; k32 is L2-resident, 4 B / agent)
+//   sir_transition_kernel per agent: k = k32[i] (re-zeroed), draw, transition, new bitmap word,
+//                         S/I/R partial counts; last CTA folds + metrics row.
+// Work is proportional to the infected agents' edges instead of all edges, the counts are the same
+// exact integers as in the pull kernel, so the two formulations are bit-identical.
+// Rows longer than kSirHeavy entries (static list built with the CSR) are spread over a whole
+// CTA; all other rows are handled by one warp per 32-row group, lanes striding the row.
+// ---------------------------------------------------------------------------------------
+constexpr int kSirHeavy = 2048;
+
+__device__ __forceinline__ void red_add_u32(unsigned int* p, unsigned int v) {
+  asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads) sir_push_kernel(const SirDev sv, const ModelDev md) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const Ctrl* ctrl = md.ctrl;
+  const int cur = (int)(ctrl->time_step & 1);
+  const unsigned int* inf = sv.infbits[cur];
+  const long long n = md.t[0].n;
+  // heavy rows: one CTA per row, all threads stride the row
+  for (int h = blockIdx.x; h < sv.n_heavy; h += gridDim.x) {
+    const int r = sv.heavy[h];
+    if (!((__ldg(inf + (r >> 5)) >> (r & 31)) & 1u)) continue;
+    const unsigned int lo = sv.row_ptr[r], hi = sv.row_ptr[r + 1];
+    for (unsigned int e = lo + tid; e < hi; e += kThreads) red_add_u32(sv.k32 + __ldcs(sv.col + e), 1u);
+  }
+  // all other rows: one warp per 32-row group
+  const long long ngroups = (n + 31) >> 5;
+  const long long wstride = (long long)gridDim.x * (kThreads / 32);
+  for (long long g = (long long)blockIdx.x * (kThreads / 32) + (tid >> 5); g < ngroups; g += wstride) {
+    unsigned int word = __ldg(inf + g);
+    if (!word) continue;
+    // lanes fetch the 33 row pointers of the group once
+    const long long rbase = g << 5;
+    const unsigned int my_lo = (rbase + lane <= n) ? sv.row_ptr[rbase + lane] : 0u;
+    const unsigned int last = (rbase + 32 <= n) ? sv.row_ptr[rbase + 32] : sv.row_ptr[n];
+    while (word) {
+      const int b = __ffs(word) - 1;
+      word &= word - 1;
+      const unsigned int lo = __shfl_sync(0xffffffffu, my_lo, b);
+      const unsigned int hi = b == 31 ? last : __shfl_sync(0xffffffffu, my_lo, (b + 1) & 31);
+      if (hi - lo > (unsigned)kSirHeavy) continue;             // done by the heavy-row pass
+      for (unsigned int e = lo + lane; e < hi; e += 32) red_add_u32(sv.k32 + __ldcs(sv.col + e), 1u);
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) sir_transition_kernel(const SirDev sv, const ModelDev md) {
+  __shared__ int s_red[3][kThreads / 32];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Ctrl* ctrl = md.ctrl;
+  const TypeDev& t = md.t[0];
+  const int cur = (int)(ctrl->time_step & 1), nxt = cur ^ 1;
+  const uint32_t* kp = md.keys + (size_t)ctrl->step_in_run * (md.n_types + 1) * 2;
+  const Key ck = {kp[0], kp[1]};
+  const float gamma = t.p[1];
+  int cS = 0, cI = 0, cR = 0;
+#pragma unroll
+  for (int i = 0; i < kSirRowsPerThread; ++i) {
+    const long long r = (long long)blockIdx.x * (kThreads * kSirRowsPerThread) + i * kThreads + tid;
+    const bool active = r < t.n;
+    int s = 0;
+    if (active) {
+      s = sv.state8[cur][r];
+      const unsigned int k = __ldcg(sv.k32 + r);
+      if (k) sv.k32[r] = 0u;
+      const bool need = (s == 0 && k > 0) || s == 1;
+      if (need) {
+        const Key ak = split_child<MODE>(ck, (unsigned long long)(t.goff + r), (unsigned long long)t.gn);
+        const float u = bits_to_uniform(bits_scalar<MODE>(ak), 0.f, 1.f);
+        if (s == 0) {
+          const float p = 1.0f - __ldg(sv.escape + (k < (unsigned)kSirKCap ? k : (unsigned)kSirKCap));
+          if (u < p) s = 1;
+        } else if (u < gamma) {
+          s = 2;
+        }
+      }
+      sv.state8[nxt][r] = (signed char)s;
+      cS += (s == 0); cI += (s == 1); cR += (s == 2);
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, active && s == 1);
+    const long long rg = (long long)blockIdx.x * (kThreads * kSirRowsPerThread) + i * kThreads + warp * 32;
+    if (lane == 0 && rg < t.n) sv.infbits[nxt][rg >> 5] = w;
+  }
+  cS = warp_sum(cS); cI = warp_sum(cI); cR = warp_sum(cR);
+  if (lane == 0) { s_red[0][warp] = cS; s_red[1][warp] = cI; s_red[2][warp] = cR; }
+  __syncthreads();
+  if (tid < 3) {
+    long long v = 0;
+    for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
+    sv.partials[(size_t)blockIdx.x * 3 + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&ctrl->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  sir_tail(sv, md, (int)gridDim.x);
 }
 
 // API column 'state' int32[N]  <->  packed int8 + infected bitmap
