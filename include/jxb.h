@@ -56,7 +56,9 @@ enum {
   JXB_RULE_INCREMENT = 6,       /* tests/unit/test_model.py:43-48   (DummyAgent)     */
   JXB_RULE_WEALTH = 7,          /* tests/unit/test_agent.py:44-100  (TestAgent)      */
   JXB_RULE_SCHELLING = 8,       /* layout examples/models/schelling_model.py:26-31   */
-  JXB_RULE_SIR = 9              /* layout jaxabm/agentpy.py:557,574-582              */
+  JXB_RULE_SIR = 9,             /* layout jaxabm/agentpy.py:557,574-582              */
+  JXB_RULE_HOUSEHOLD = 10,      /* examples/models/advanced_economic_model.py:57-296 */
+  JXB_RULE_CONSUMER_FIRM = 11   /* examples/models/advanced_economic_model.py:299-581*/
 };
 
 /* Registered model programs: the update_state_fn + metrics_fn pair that runs inside
@@ -68,11 +70,13 @@ enum {
   JXB_PROGRAM_GROWTH = 3,       /* tests/unit/test_analysis.py:105-128               */
   JXB_PROGRAM_COUNTER = 4,      /* tests/unit/test_model.py:20-40                    */
   JXB_PROGRAM_SCHELLING = 5,    /* builder-authored rule, DESIGN.md                  */
-  JXB_PROGRAM_SIR = 6           /* builder-authored rule, DESIGN.md                  */
+  JXB_PROGRAM_SIR = 6,          /* builder-authored rule, DESIGN.md                  */
+  JXB_PROGRAM_ECONOMY = 7       /* examples/models/advanced_economic_model.py:1461-1905 */
 };
 
 #define JXB_MAX_TYPES 4
 #define JXB_MAX_PARAMS 16
+#define JXB_MAX_METRICS 32      /* row stride (doubles) of metrics_out / last_metrics_out scratch */
 
 /* One agent collection (jaxabm/agent.py:69-90: AgentCollection(agent_type, num_agents)). */
 typedef struct {
@@ -116,7 +120,7 @@ int jxb_model_create(jxb_engine*, const jxb_model_desc*, jxb_model** out);
 int jxb_model_destroy(jxb_model*);
 
 /* Field/env introspection so the host shim can size buffers (names mirror the
- * reference's state-dict keys).  dtype: 0=f32, 1=i32, 2=bool(u8).                   */
+ * reference's state-dict keys).  dtype: 0=f32, 1=i32, 2=bool(u8), 3=f64 (Python float). */
 int jxb_model_n_fields(jxb_model*, int type, int* out);
 int jxb_model_field_info(jxb_model*, int type, int field, const char** name,
                          int* dtype, int* width);
@@ -161,7 +165,7 @@ int jxb_collection_update(jxb_model*, int type, uint32_t key0, uint32_t key1);
 /* Model.run(steps) (jaxabm/model.py:218-262) = `steps` x Model.step (model.py:146-216)
  * with no host round-trip inside.  metrics_out: [n_records][n_metrics] doubles where
  * n_records = number of t in (t0, t0+steps] with t % collect_interval == 0; steps_out
- * receives those t.  Either may be NULL.  device_seconds_out: CUDA-event time of the
+ * receives those t.  A metrics row is JXB_MAX_METRICS doubles wide.  Either may be NULL.  device_seconds_out: CUDA-event time of the
  * step loop on the engine's stream.                                                 */
 int jxb_model_run(jxb_model*, int steps, int collect_interval, double* metrics_out,
                   int32_t* steps_out, int* n_records_out, double* device_seconds_out);

@@ -16,13 +16,13 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libjxb.so")
 
 MAX_TYPES = 4
 MAX_PARAMS = 16
-MAX_METRICS = 8
+MAX_METRICS = 32
 
 RNG_LEGACY, RNG_PARTITIONABLE = 0, 1
 
 RULE = dict(random_walker=1, scaled_walker=2, consumer=3, producer=4, growth=5, increment=6,
-            wealth=7, schelling=8, sir=9)
-PROGRAM = dict(none=0, random_walk=1, market=2, growth=3, counter=4, schelling=5, sir=6)
+            wealth=7, schelling=8, sir=9, household=10, consumer_firm=11)
+PROGRAM = dict(none=0, random_walk=1, market=2, growth=3, counter=4, schelling=5, sir=6, economy=7)
 
 DTYPES = {0: np.float32, 1: np.int32, 2: np.bool_, 3: np.float64}
 

@@ -8,9 +8,9 @@
 
 namespace jxb {
 
-constexpr int kMaxFields = 8;
-constexpr int kMaxEnv = 16;
-constexpr int kMaxMetrics = 8;
+constexpr int kMaxFields = 20;
+constexpr int kMaxEnv = 32;
+constexpr int kMaxMetrics = 32;
 constexpr int kThreads = 256;   // CTA size of the streaming kernels
 constexpr int kVec = 4;         // agents per thread per iteration (one float4 / int4 per field)
 

@@ -71,6 +71,17 @@ static const RuleSpec kRules[] = {
     {JXB_RULE_WEALTH, 2, {{"wealth", 0, 1}, {"productivity", 0, 1}}},
     {JXB_RULE_SCHELLING, 4, {{"type", 1, 1}, {"position", 1, 2}, {"satisfied", 2, 1}, {"moves", 1, 1}}},
     {JXB_RULE_SIR, 1, {{"state", 1, 1}}},
+    {JXB_RULE_HOUSEHOLD, 15,
+     {{"savings", 0, 1}, {"income", 0, 1}, {"bank_deposits", 0, 1}, {"cash", 0, 1}, {"debt", 0, 1},
+      {"propensity_to_consume", 0, 1}, {"propensity_to_save", 0, 1}, {"risk_aversion", 0, 1}, {"employed", 2, 1},
+      {"productivity", 0, 1}, {"labor_supply", 0, 1}, {"consumption", 0, 1}, {"utility", 0, 1},
+      {"taxes_paid", 0, 1}, {"transfers_received", 0, 1}}},
+    {JXB_RULE_CONSUMER_FIRM, 19,
+     {{"capital_stock", 0, 1}, {"production_capacity", 0, 1}, {"inventory", 0, 1}, {"cash", 0, 1}, {"revenue", 0, 1},
+      {"profit", 0, 1}, {"debt", 0, 1}, {"production_efficiency", 0, 1}, {"labor_demand", 0, 1},
+      {"energy_usage", 0, 1}, {"goods_produced", 0, 1}, {"goods_sold", 0, 1}, {"price", 0, 1}, {"markup_rate", 0, 1},
+      {"labor_elasticity", 0, 1}, {"capital_elasticity", 0, 1}, {"energy_elasticity", 0, 1}, {"age", 1, 1},
+      {"is_active", 2, 1}}},
 };
 
 static const ProgramSpec kPrograms[] = {
@@ -94,6 +105,25 @@ static const ProgramSpec kPrograms[] = {
      {{"segregation_index", 0, 0}, {"percent_satisfied", 0, 0}, {"total_moves", 1, 0}}, 3,
      {{"percent_satisfied", 0, 0}, {"segregation_index", 0, 0}, {"total_moves", 1, 0}}},
     {JXB_PROGRAM_SIR, 0, 0, {}, 3, {{"count_S", 1, 0}, {"count_I", 1, 0}, {"count_R", 1, 0}}},
+    // env slot order == the EE_* enum of csrc/economy.cuh; defaults are the .get() defaults of the reference
+    {JXB_PROGRAM_ECONOMY, 1, EE_COUNT,
+     {{"wage_rate", 0, 1.0}, {"price_level", 0, 1.0}, {"interest_rate", 0, 0.05}, {"gdp", 0, 0.1}, {"gdp_growth", 0, 0.0},
+      {"total_labor_supply", 0, 0.0}, {"total_labor_demand", 0, 0.0}, {"employment_rate", 0, 1.0},
+      {"unemployment_rate", 0, 0.0}, {"time_step", 1, 0}, {"climate_impact", 3, 1.0}, {"pandemic_impact", 3, 1.0},
+      {"tax_rate", 3, 0.2}, {"energy_price", 3, 1.0}, {"job_market_condition", 3, 1.0}, {"goods_availability", 3, 1.0},
+      {"consumer_goods_demand", 3, 100.0}, {"consumer_goods_price", 3, 1.0}, {"capital_goods_price", 3, 2.0},
+      {"inflation_rate", 3, 0.0}, {"debt_to_gdp", 3, 0.0}, {"avg_utility", 3, 0.0}, {"income_per_capita", 3, 0.0},
+      {"govt_spending", 3, 0.0}, {"energy_supply", 3, 0.0}, {"capital_goods_demand", 3, 0.0}, {"total_income", 0, 0.0},
+      {"_total_income_set", 1, 0}, {"_gini", 0, 0.0}},
+     29,
+     {{"gdp", 0, 0}, {"gdp_growth", 0, 0}, {"inflation", 0, 0}, {"unemployment", 0, 0}, {"wage_rate", 0, 0},
+      {"interest_rate", 0, 0}, {"goods_availability", 0, 0}, {"labor_market_tightness", 0, 0}, {"consumer_price", 0, 0},
+      {"capital_price", 0, 0}, {"energy_price", 0, 0}, {"utility", 0, 0}, {"income_per_capita", 0, 0},
+      {"inequality", 0, 0}, {"consumer_sector_share", 0, 0}, {"capital_sector_share", 0, 0},
+      {"energy_sector_share", 0, 0}, {"govt_sector_share", 0, 0}, {"technology_level", 0, 0},
+      {"capital_investment", 0, 0}, {"energy_demand", 0, 0}, {"energy_supply", 0, 0}, {"renewable_share", 0, 0},
+      {"carbon_emissions", 0, 0}, {"sustainability_index", 0, 0}, {"debt_to_gdp", 0, 0}, {"climate_impact", 0, 0},
+      {"pandemic_impact", 0, 0}, {"economic_health", 0, 0}}},
 };
 
 static const RuleSpec* find_rule(int rule) {
@@ -179,6 +209,8 @@ struct jxb_model {
   // SIR formulation: 0 pull (CSR ballot-segmented sweep of all edges, fused transitions),
   // 1 push (infected rows scatter-add into k32, then the transition kernel)
   int sir_mode = 1; int sir_tblocks = 0;
+  // economy (C4-B)
+  bool has_eco = false; EcoDev eco{}; int eco_hh = -1;
   // graphs: cached executable graphs of `chunk` consecutive steps
   cudaGraphExec_t graph1 = nullptr, graphK = nullptr; int chunkK = 0;
   const void* sig_keys = nullptr; const void* sig_metrics = nullptr; const void* sig_rec = nullptr; int sig_ci = 0;
@@ -309,13 +341,15 @@ extern "C" int jxb_engine_p2p_attach(jxb_engine* eng, const void* handles, size_
 // ---------------------------------------------------------------------------------------
 static bool program_accepts(int program, int rule) {
   switch (program) {
-    case JXB_PROGRAM_NONE: return rule != JXB_RULE_SCHELLING && rule != JXB_RULE_SIR;
+    case JXB_PROGRAM_NONE: return rule != JXB_RULE_SCHELLING && rule != JXB_RULE_SIR && rule != JXB_RULE_HOUSEHOLD &&
+                                  rule != JXB_RULE_CONSUMER_FIRM;
     case JXB_PROGRAM_RANDOM_WALK: return rule == JXB_RULE_RANDOM_WALKER || rule == JXB_RULE_SCALED_WALKER;
     case JXB_PROGRAM_MARKET: return rule == JXB_RULE_CONSUMER || rule == JXB_RULE_PRODUCER;
     case JXB_PROGRAM_GROWTH: return rule == JXB_RULE_GROWTH;
     case JXB_PROGRAM_COUNTER: return rule == JXB_RULE_INCREMENT || rule == JXB_RULE_GROWTH;
     case JXB_PROGRAM_SCHELLING: return rule == JXB_RULE_SCHELLING;
     case JXB_PROGRAM_SIR: return rule == JXB_RULE_SIR;
+    case JXB_PROGRAM_ECONOMY: return rule == JXB_RULE_HOUSEHOLD || rule == JXB_RULE_CONSUMER_FIRM;
   }
   return false;
 }
@@ -473,6 +507,23 @@ extern "C" int jxb_model_create(jxb_engine* eng, const jxb_model_desc* d, jxb_mo
     m->has_grid = true;
   }
   if (d->program == JXB_PROGRAM_SIR) m->has_net = true;
+  if (d->program == JXB_PROGRAM_ECONOMY) {
+    if (md.world_size > 1) { jxb_model_destroy(m); return fail(JXB_ERR_UNSUPPORTED, "the economy program is not population-sharded (Gini needs a global rank)"); }
+    EcoDev& ed = m->eco;
+    TRY(dev_alloc(m, &ed.partials, (size_t)std::max(m->step_blocks, 1) * kEcoAcc));
+    TRY(dev_alloc(m, &ed.bin_count, (size_t)kGiniBins));
+    TRY(dev_alloc(m, &ed.bin_base, (size_t)kGiniBins));
+    TRY(dev_alloc(m, &ed.scan_sums, (size_t)kGiniBins / kGiniScanTile));
+    TRY(dev_alloc(m, &ed.ticket2, 4));
+    cudaMemsetAsync(ed.bin_count, 0, (size_t)kGiniBins * 4, eng->stream);
+    cudaMemsetAsync(ed.ticket2, 0, 16, eng->stream);
+    for (int i = 0; i < d->n_types; ++i)
+      if (d->types[i].rule == JXB_RULE_HOUSEHOLD) m->eco_hh = i;
+    const long long nh = m->eco_hh >= 0 ? d->types[m->eco_hh].n_agents : 0;
+    ed.gini_blocks = (int)std::max<long long>(1, std::min<long long>((nh + kThreads - 1) / kThreads, (long long)eng->sms * 8));
+    TRY(dev_alloc(m, &ed.gini_partials, (size_t)ed.gini_blocks * 2));
+    m->has_eco = true;
+  }
 #undef TRY
   cudaStreamSynchronize(eng->stream);
   *out = m;
@@ -780,7 +831,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     CK(cudaMemset(sv.k32, 0, ((size_t)n + 32) * 4));
     sv.heavy = d_heavy;
     sv.n_heavy = (int)heavy.size();
-    m->sir_tblocks = (int)((n + kThreads * kSirRowsPerThread - 1) / (kThreads * kSirRowsPerThread));
+    m->sir_tblocks = (int)std::max<long long>(1, std::min<long long>((n + kThreads * kSirRowsPerThread - 1) / (kThreads * kSirRowsPerThread), (long long)m->eng->sms * 8));
     const char* mode = getenv("JXB_SIR_MODE");
     m->sir_mode = (mode && !strcmp(mode, "pull")) ? 0 : 1;
   }
@@ -904,6 +955,30 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       eng->launches += 1;
       break;
     }
+    case JXB_PROGRAM_ECONOMY: {
+      if (timed) cudaEventRecord(e0, s);
+      if (part) economy_step_kernel<1><<<m->step_blocks, kThreads, 0, s>>>(m->dev, m->eco);
+      else economy_step_kernel<0><<<m->step_blocks, kThreads, 0, s>>>(m->dev, m->eco);
+      if (timed) cudaEventRecord(e1, s);
+      eng->launches += 1;
+      const int hh = m->eco_hh;
+      if (hh >= 0) {
+        const float* income = (const float*)m->dev.t[hh].f[1];
+        const long long nh = m->dev.t[hh].n;
+        gini_count_kernel<<<m->eco.gini_blocks, kThreads, 0, s>>>(income, nh, m->eco.bin_count);
+        gini_scan_sums_kernel<<<kGiniBins / kGiniScanTile, kThreads, 0, s>>>(m->eco.bin_count, m->eco.scan_sums);
+        gini_scan_top_kernel<<<1, 1024, 0, s>>>(m->eco.scan_sums, kGiniBins / kGiniScanTile);
+        gini_scan_apply_kernel<<<kGiniBins / kGiniScanTile, kThreads, 0, s>>>(m->eco.bin_count, m->eco.scan_sums, m->eco.bin_base);
+        eng->launches += 4;
+      }
+      gini_accumulate_kernel<<<hh >= 0 ? m->eco.gini_blocks : 1, kThreads, 0, s>>>(m->dev, m->eco, hh);
+      eng->launches += 1;
+      if (hh >= 0) {
+        gini_clear_kernel<<<m->eco.gini_blocks, kThreads, 0, s>>>((const float*)m->dev.t[hh].f[1], m->dev.t[hh].n, m->eco.bin_count);
+        eng->launches += 1;
+      }
+      break;
+    }
     default: {
       if (timed) cudaEventRecord(e0, s);
       if (part) step_kernel<1><<<m->step_blocks, kThreads, 0, s>>>(m->dev);
@@ -957,6 +1032,7 @@ static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
 
 static int launches_per_step(jxb_model* m) {
   if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 1 ? 2 : 1;
+  if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->eco_hh >= 0 ? 7 : 2;
   return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
 }
 
@@ -973,6 +1049,7 @@ extern "C" int jxb_model_profile(jxb_model* m, double* seconds, int64_t* launche
   if (name) {
     switch (m->desc.program) {
       case JXB_PROGRAM_SCHELLING: *name = "schelling_run_kernel"; break;
+      case JXB_PROGRAM_ECONOMY: *name = "economy_step_kernel"; break;
       case JXB_PROGRAM_SIR: *name = m->sir_mode == 1 ? "sir_push_kernel+sir_transition_kernel" : "sir_step_kernel"; break;
       default: *name = "step_kernel";
     }
@@ -1115,8 +1192,8 @@ extern "C" int jxb_collection_update(jxb_model* m, int type, uint32_t k0, uint32
   NEED(m); NEED_TYPE(m, type);
   if (!m->collections_ready[type])
     return fail(JXB_ERR_STATE, "Agent collection not initialized. Call init() first.");   // agent.py:150-151
-  if (m->has_grid || m->has_net)
-    return fail(JXB_ERR_UNSUPPORTED, "grid / network collections step through Model.step only");
+  if (m->has_grid || m->has_net || m->has_eco)
+    return fail(JXB_ERR_UNSUPPORTED, "grid / network / economy collections step through Model.step only");
   CK(cudaSetDevice(m->eng->device));
   const TypeDev& t = m->dev.t[type];
   const int blocks = (int)std::max<long long>(1, std::min<long long>((t.n / kVec + kThreads - 1) / kThreads,

@@ -12,6 +12,7 @@
 // -fmad=false so a*b+c is two roundings exactly as XLA-CPU/NumPy evaluate the unfused ops.
 #pragma once
 #include "common.cuh"
+#include "economy.cuh"
 
 namespace jxb {
 
@@ -485,6 +486,47 @@ __device__ __forceinline__ void init_agent(const TypeDev& t, Key key, long long 
         Key ak = split_child<MODE>(key, gi, (unsigned long long)t.gn);
         float u = bits_to_uniform(bits_scalar<MODE>(ak), 0.f, 1.f);
         ((int*)t.f[0])[i] = (u < t.p[2]) ? 1 : 0;
+        break;
+      }
+      case JXB_RULE_HOUSEHOLD: {  // advanced_economic_model.py:84-136
+        const Key ak = split_child<MODE>(key, gi, (unsigned long long)t.gn);
+        const float n1 = normal_scalar<MODE>(split_child<MODE>(ak, 0, 4));
+        const float savings = t.p[0] * expf(n1 * 0.5f);
+        const float n2 = normal_scalar<MODE>(split_child<MODE>(ak, 1, 4));
+        const float income_factor = jmax(0.3f, n2 * 0.2f + 1.0f);
+        const float consume_adj = beta52<MODE>(split_child<MODE>(ak, 2, 4)) * 0.4f + 0.6f;
+        const bool employed = bits_to_uniform(bits_scalar<MODE>(split_child<MODE>(ak, 3, 4)), 0.f, 1.f) < 0.95f;
+        ((float*)t.f[0])[i] = savings;
+        ((float*)t.f[1])[i] = t.p[1] * income_factor;
+        ((float*)t.f[2])[i] = savings * 0.7f;
+        ((float*)t.f[3])[i] = savings * 0.3f;
+        ((float*)t.f[4])[i] = 0.f;
+        ((float*)t.f[5])[i] = t.p[2] * consume_adj;
+        ((float*)t.f[6])[i] = t.p[3];
+        ((float*)t.f[7])[i] = t.p[5];
+        ((unsigned char*)t.f[8])[i] = employed ? 1 : 0;
+        ((float*)t.f[9])[i] = t.p[4] * income_factor;
+        ((float*)t.f[10])[i] = employed ? 1.0f : 0.0f;
+        for (int f = 11; f <= 14; ++f) ((float*)t.f[f])[i] = 0.f;
+        break;
+      }
+      case JXB_RULE_CONSUMER_FIRM: {  // advanced_economic_model.py:329-387
+        const Key ak = split_child<MODE>(key, gi, (unsigned long long)t.gn);
+        const float capital = t.p[0] * expf(normal_scalar<MODE>(split_child<MODE>(ak, 0, 3)) * 0.5f);
+        const float eff = t.p[2] * jmax(0.5f, normal_scalar<MODE>(split_child<MODE>(ak, 1, 3)) * 0.2f + 1.0f);
+        const float markup = t.p[6] * (beta52<MODE>(split_child<MODE>(ak, 2, 3)) * 0.3f + 0.1f);
+        ((float*)t.f[0])[i] = capital;
+        ((float*)t.f[1])[i] = eff * powf(capital, t.p[4]);
+        ((float*)t.f[2])[i] = 0.f;
+        ((float*)t.f[3])[i] = t.p[1];
+        ((float*)t.f[4])[i] = 0.f; ((float*)t.f[5])[i] = 0.f; ((float*)t.f[6])[i] = 0.f;
+        ((float*)t.f[7])[i] = eff;
+        for (int f = 8; f <= 11; ++f) ((float*)t.f[f])[i] = 0.f;
+        ((float*)t.f[12])[i] = 1.0f;
+        ((float*)t.f[13])[i] = markup;
+        ((float*)t.f[14])[i] = t.p[3]; ((float*)t.f[15])[i] = t.p[4]; ((float*)t.f[16])[i] = t.p[5];
+        ((int*)t.f[17])[i] = 0;
+        ((unsigned char*)t.f[18])[i] = 1;
         break;
       }
       default: break;

@@ -212,7 +212,7 @@ PROGRAM_ENV = {   # env slot names per program (csrc/engine.cu kPrograms)
     "growth": ["price_level", "interest_rate"], "counter": ["counter", "increment"],
     "schelling": ["segregation_index", "percent_satisfied", "total_moves"], "sir": [],
 }
-PROGRAM_N_METRICS = {0: 0, 1: 7, 2: 5, 3: 3, 4: 2, 5: 3, 6: 3}
+PROGRAM_N_METRICS = {0: 0, 1: 7, 2: 5, 3: 3, 4: 2, 5: 3, 6: 3, 7: 29}
 
 
 def ensemble_run(desc: nat.ModelDesc, slots: Sequence[int], params: np.ndarray, seeds: np.ndarray,

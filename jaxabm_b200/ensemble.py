@@ -52,7 +52,7 @@ def batchable(models: Sequence[Any]) -> bool:
         sigs = [_signature(m) for m in models]
     except Exception:
         return False
-    if sigs[0][0] in ("schelling", "sir"):
+    if sigs[0][0] in ("schelling", "sir", "economy"):
         return False
     # env must still be at the program defaults the device kernel starts from
     return all(s[3] == sigs[0][3] for s in sigs)

@@ -28,12 +28,21 @@ PROGRAM_PARAMS = {
     "counter": [],
     "schelling": [("similarity_threshold", 0.5)],
     "sir": [],
+    "economy": [],
 }
+# env entries the economy program needs to find in env_state: update_environment's final dict
+# comprehension (advanced_economic_model.py:1731-1735) keeps every PRE-EXISTING entry outside its
+# exclusion list, and the device program bakes that in for the layout of create_economy_model
+ECONOMY_ENV_REQUIRED = ("wage_rate", "price_level", "interest_rate", "gdp", "tax_rate", "energy_price",
+                        "job_market_condition", "goods_availability", "consumer_goods_demand", "consumer_goods_price",
+                        "capital_goods_price", "inflation_rate", "debt_to_gdp", "avg_utility", "income_per_capita",
+                        "govt_spending", "energy_supply", "capital_goods_demand", "climate_impact", "pandemic_impact")
 # collections a program's functions look up by name (reference dict keys)
 PROGRAM_COLLECTIONS = {
     "market": {"consumer": "consumers", "producer": "producers"},
     "growth": {"growth": "consumers"},
     "counter": {"increment": "consumers", "growth": "consumers"},
+    "economy": {"household": "households", "consumer_firm": "consumer_firms"},
 }
 
 
@@ -140,6 +149,14 @@ class Model:
             want = getattr(getattr(self, "_facade", None), "jxb_metrics_collection", "walkers")
             names = list(self._agent_collections)
             mparams = [1.0 if (names and names[0] == want) else 0.0]
+        if program == "economy":
+            missing = [k for k in ECONOMY_ENV_REQUIRED if k not in self._env_state]
+            if missing:
+                raise UnregisteredRuleError(
+                    "the economy program implements update_environment for the env layout of "
+                    f"create_economy_model; env_state lacks {missing}")
+            if self._params.get("enable_climate_module") or self._params.get("enable_pandemic_module"):
+                raise UnregisteredRuleError("the climate / pandemic modules are not registered device programs")
         grid = None
         if program == "schelling":
             shape = self._env_state.get("grid_shape")
@@ -148,7 +165,7 @@ class Model:
             grid = (int(shape[0]), int(shape[1]), bool(self._env_state.get("grid_periodic", False)))
         rank, world = self._shard or (0, 1)
         if world > 1:
-            if program in ("schelling", "sir"):
+            if program in ("schelling", "sir", "economy"):
                 raise UnregisteredRuleError("grid / network programs are not population-sharded; run replicas")
             from .dist import shard_bounds
             for spec in specs:
@@ -204,7 +221,9 @@ class Model:
         if self._update_state_fn is None:
             return
         for s, (name, _) in enumerate(self._dev.env_slots):
-            if name in ("bounds_lo", "bounds_hi"):
+            if name in ("bounds_lo", "bounds_hi") or name.startswith("_"):
+                continue
+            if self._program == "economy" and name == "total_income" and self._time_step == 0:
                 continue
             if name in self._env_state or self._program not in ("random_walk", "counter"):
                 self._env_state[name] = self._dev.get_env(s)

@@ -14,6 +14,7 @@ module                 mirrors
 ``rules.market``       ``tests/integration/test_integration.py:20-283`` (C4-A)
 ``rules.growth``       ``tests/unit/test_analysis.py:22-144`` (C5)
 ``rules.contract``     ``tests/unit/test_model.py:20-48``, ``tests/unit/test_agent.py:44-100``
+``rules.economy``      ``examples/models/advanced_economic_model.py`` (C4-B)
 ``rules.schelling``    layout of ``examples/models/schelling_model.py`` + DESIGN.md rule (C2)
 ``rules.sir``          layout of ``jaxabm/agentpy.py:530-615`` + DESIGN.md rule (C3)
 =====================  ===============================================================
@@ -32,4 +33,4 @@ def program(name: str):
     return deco
 
 
-from . import contract, growth, market, random_walk, schelling, sir  # noqa: E402,F401
+from . import contract, economy, growth, market, random_walk, schelling, sir  # noqa: E402,F401
