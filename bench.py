@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the JaxABM hot path on B200 (contract in the task statement).
 
-  python bench.py --gpus N --steps K --warmup W [--workload schelling|market|walk|sir|ensemble]
+  python bench.py --gpus N --steps K --warmup W [--workload schelling|market|economy|walk|sir|ensemble]
   python bench.py --impl reference ...      # the CPU restatement timed on the host cores
 
 Metric (BASELINE.json): agent-steps/sec, device-timed.  A "step" is one Model.step() of the
@@ -195,6 +195,52 @@ class MarketWorkload:
                                             "time scaled x10) on the C/OpenMP oracle")
 
 
+class EconomyWorkload:
+    """C4-B: 49 M households + 1 M consumer-goods firms (advanced_economic_model.py), per-agent threefry
+    draws every step, 14 fused env reductions, Gini by histogram rank."""
+    name = "economy_49M_households_1M_firms"
+    dtype = "f32"
+    default_steps = 50
+    stationary = True
+    kernel = "economy_step_kernel"
+    l2_note = "no flush: per-step state traffic (3.3 GB) exceeds the 126 MB L2"
+
+    def __init__(self, rank, nh=49_000_000, nf=1_000_000):
+        self.nh, self.nf, self.seed = nh, nf, 42 + rank
+        self.agents = nh + nf
+
+    def fresh(self):
+        import jaxabm_b200 as jx
+        from jaxabm_b200.rules import economy
+        m = economy.create_economy_model(self.nh, self.nf, config=jx.ModelConfig(seed=self.seed))
+        m.initialize()
+        return m
+
+    def api_bytes(self, res, K):
+        """households 57 B read + 57 B write, firms 73 B + 73 B."""
+        return (114 * self.nh + 146 * self.nf) * K
+
+    def engine_bytes(self, res, K):
+        # households: read 7 f32 + employed, write 9 f32 + employed = 66 B (constant columns are not
+        # rewritten); firms: read 11 f32 + age, write 11 f32 + age + is_active = 97 B
+        return (66 * self.nh + 97 * self.nf) * K
+
+    def e2e(self, K):
+        t0 = time.perf_counter()
+        m = self.fresh()
+        m.run(steps=K)
+        d2h = 0
+        for name in ("income", "savings", "employed"):
+            d2h += m.agent_collections["households"].states[name].nbytes
+        wall = time.perf_counter() - t0
+        del m
+        return wall, 0, d2h + K * 29 * 8, ("create + initialize on device (keys from the seed), Model.run(K), "
+                                           "download households' income/savings/employed + the metrics history")
+
+    def cpu_run(self, steps):
+        raise NotImplementedError
+
+
 class WalkWorkload:
     """C1 scaled: 2^26 random walkers (48 B/agent-step), fused distance reductions."""
     name = "random_walk_2^26"
@@ -321,7 +367,7 @@ class EnsembleWorkload:
 
 
 WORKLOADS = {"schelling": SchellingWorkload, "market": MarketWorkload, "walk": WalkWorkload, "sir": SirWorkload,
-             "ensemble": EnsembleWorkload}
+             "ensemble": EnsembleWorkload, "economy": EconomyWorkload}
 
 
 # ------------------------------------------------------------------------------------------

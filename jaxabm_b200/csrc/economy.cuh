@@ -7,8 +7,8 @@
 //   compute_metrics           :1741-1905 -> eco_compute_metrics    (29 metrics, Gini)
 //
 // One model step = economy_step_kernel (both collections in one launch, 14 float sums + 1 count as
-// per-CTA partial rows, last CTA folds them and runs update_environment) -> Gini kernels (rank of
-// every household income by a 22-bit radix histogram: count, scan, rank-weighted sum) whose last
+// per-CTA partial rows + the 22-bit radix histogram of the new household incomes; last CTA folds the
+// rows and runs update_environment) -> Gini kernels (scan of the histogram, rank-weighted sum) whose last
 // CTA runs compute_metrics and appends the history row.  All of it is captured in the step graph.
 //
 // Arithmetic: float32 in the reference's operation order (-fmad=false); Python-float env entries
@@ -180,9 +180,11 @@ __device__ __forceinline__ void household_one(HouseholdIO& h, float rv, const Ec
   h.transfers = transfers;
 }
 
+__device__ __forceinline__ unsigned int gini_bin(float x);
+
 template <int MODE>
 __device__ __forceinline__ void rule_household(const TypeDev& t, const double* env, Key ck, int lb, float* fs,
-                                               int& employed_count) {
+                                               int& employed_count, unsigned int* bin_count) {
   const EcoEnvView v = eco_env_view(env);
   const float init_inc = t.p[1];
   const float two_init_inc = (float)(2.0 * (double)t.p[1]);
@@ -208,6 +210,9 @@ __device__ __forceinline__ void rule_household(const TypeDev& t, const double* e
     fs[0] += h.labor_supply; fs[1] += h.consumption; fs[2] += h.savings; fs[3] += h.deposits;
     fs[4] += h.income; fs[5] += h.utility;
     employed_count += h.employed ? 1 : 0;
+    // Gini histogram of the NEW incomes (metrics are computed on the post-update state): a
+    // fire-and-forget L2 reduction whose latency hides behind the streaming loads
+    atomicAdd(bin_count + gini_bin(h.income), 1u);
   }
 }
 
@@ -390,24 +395,25 @@ __device__ inline void eco_compute_metrics(const double* env, float gini, double
 // step kernel: both collections in one launch; last CTA folds partial rows in a fixed order and
 // runs update_environment.  (Metrics + history row follow in gini_accumulate_kernel.)
 // ---------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(kThreads) economy_step_kernel(const ModelDev md, const EcoDev ed) {
+// One launch per collection (RULE is a template parameter so that the household path is not
+// compiled with the firm path's register footprint); the launches of a step share the election
+// ticket: the last CTA of the LAST launch folds all `total_ctas` partial rows.
+template <int MODE, int RULE>
+__global__ void __launch_bounds__(kThreads) economy_step_kernel(const ModelDev md, const EcoDev ed, int ti,
+                                                                int row_offset, int total_ctas) {
   __shared__ double s_red[(kThreads / 32) * kEcoAcc];
   __shared__ double s_tot[kEcoAcc];
   __shared__ int s_last;
-  int ti = 0;
-  for (int i = 1; i < md.n_types; ++i)
-    if ((int)blockIdx.x >= md.t[i].block_begin) ti = i;
   const TypeDev& t = md.t[ti];
-  const int lb = blockIdx.x - t.block_begin;
+  const int lb = blockIdx.x;
   const uint32_t* kp = md.keys + (size_t)md.ctrl->step_in_run * (md.n_types + 1) * 2;
   const Key ck = {kp[2 * ti], kp[2 * ti + 1]};
   float fs[kEcoF];
 #pragma unroll
   for (int i = 0; i < kEcoF; ++i) fs[i] = 0.f;
   int emp = 0;
-  if (t.rule == JXB_RULE_HOUSEHOLD) rule_household<MODE>(t, md.env, ck, lb, fs, emp);
-  else if (t.rule == JXB_RULE_CONSUMER_FIRM) rule_firm<MODE>(t, md.env, ck, lb, fs);
+  if (RULE == JXB_RULE_HOUSEHOLD) rule_household<MODE>(t, md.env, ck, lb, fs, emp, ed.bin_count);
+  else rule_firm<MODE>(t, md.env, ck, lb, fs);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < kEcoF; ++i) {
@@ -422,17 +428,17 @@ __global__ void __launch_bounds__(kThreads) economy_step_kernel(const ModelDev m
   if (threadIdx.x < kEcoAcc) {
     double r = 0.0;
     for (int w = 0; w < kThreads / 32; ++w) r += s_red[w * kEcoAcc + threadIdx.x];
-    ed.partials[(size_t)blockIdx.x * kEcoAcc + threadIdx.x] = r;
+    ed.partials[(size_t)(row_offset + blockIdx.x) * kEcoAcc + threadIdx.x] = r;
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&md.ctrl->ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) s_last = (atomicAdd(&md.ctrl->ticket, 1u) == (unsigned)total_ctas - 1u);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   for (int i = warp; i < kEcoAcc; i += kThreads / 32) {
     double r = 0.0;
-    for (int b = lane; b < (int)gridDim.x; b += 32) r += __ldcg(ed.partials + (size_t)b * kEcoAcc + i);
+    for (int b = lane; b < total_ctas; b += 32) r += __ldcg(ed.partials + (size_t)b * kEcoAcc + i);
     r = warp_sum(r);
     if (lane == 0) s_tot[i] = r;
   }
@@ -454,11 +460,6 @@ __device__ __forceinline__ unsigned int gini_bin(float x) {
   unsigned int b = __float_as_uint(x);
   b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
   return b >> (32 - kGiniBits);
-}
-
-__global__ void __launch_bounds__(kThreads) gini_count_kernel(const float* income, long long n, unsigned int* bin_count) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    atomicAdd(bin_count + gini_bin(__ldg(income + i)), 1u);
 }
 
 // exclusive scan of the bin counts: per-tile sums, scan of the sums, per-tile rescan
@@ -593,12 +594,6 @@ __global__ void __launch_bounds__(kThreads) gini_accumulate_kernel(const ModelDe
       c->step_in_run += 1;
     }
   }
-}
-
-// zero the bins the step's incomes touched (cheaper than a 16 MB memset when N is small)
-__global__ void __launch_bounds__(kThreads) gini_clear_kernel(const float* income, long long n, unsigned int* bin_count) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    bin_count[gini_bin(__ldg(income + i))] = 0u;
 }
 
 }  // namespace jxb

@@ -910,6 +910,26 @@ extern "C" int jxb_model_init(jxb_model* m, uint32_t k0, uint32_t k1) {
 // ---------------------------------------------------------------------------------------
 static int plan_step_blocks(jxb_model* m) {
   ModelDev& md = m->dev;
+  if (md.program == JXB_PROGRAM_ECONOMY) {
+    // one launch per collection, each a single resident wave of its own kernel
+    int begin = 0;
+    for (int i = 0; i < md.n_types; ++i) {
+      int occ = 0;
+      if (md.t[i].rule == JXB_RULE_HOUSEHOLD)
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, economy_step_kernel<1, JXB_RULE_HOUSEHOLD>, kThreads, 0));
+      else
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, economy_step_kernel<1, JXB_RULE_CONSUMER_FIRM>, kThreads, 0));
+      if (occ < 1) occ = 1;
+      const long long need = std::max<long long>(1, (md.t[i].n + kThreads - 1) / kThreads);
+      const int nb = (int)std::min<long long>(need, (long long)m->eng->sms * occ);
+      md.t[i].block_begin = begin;
+      md.t[i].block_count = nb;
+      begin += nb;
+    }
+    md.grid_blocks = begin;
+    m->step_blocks = begin;
+    return JXB_OK;
+  }
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1>, kThreads, 0));
   if (occ < 1) occ = 1;
@@ -957,26 +977,30 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
     }
     case JXB_PROGRAM_ECONOMY: {
       if (timed) cudaEventRecord(e0, s);
-      if (part) economy_step_kernel<1><<<m->step_blocks, kThreads, 0, s>>>(m->dev, m->eco);
-      else economy_step_kernel<0><<<m->step_blocks, kThreads, 0, s>>>(m->dev, m->eco);
+      for (int ti = 0; ti < m->desc.n_types; ++ti) {
+        const TypeDev& t = m->dev.t[ti];
+        const bool hhk = t.rule == JXB_RULE_HOUSEHOLD;
+        if (part) {
+          if (hhk) economy_step_kernel<1, JXB_RULE_HOUSEHOLD><<<t.block_count, kThreads, 0, s>>>(m->dev, m->eco, ti, t.block_begin, m->step_blocks);
+          else economy_step_kernel<1, JXB_RULE_CONSUMER_FIRM><<<t.block_count, kThreads, 0, s>>>(m->dev, m->eco, ti, t.block_begin, m->step_blocks);
+        } else {
+          if (hhk) economy_step_kernel<0, JXB_RULE_HOUSEHOLD><<<t.block_count, kThreads, 0, s>>>(m->dev, m->eco, ti, t.block_begin, m->step_blocks);
+          else economy_step_kernel<0, JXB_RULE_CONSUMER_FIRM><<<t.block_count, kThreads, 0, s>>>(m->dev, m->eco, ti, t.block_begin, m->step_blocks);
+        }
+        eng->launches += 1;
+      }
       if (timed) cudaEventRecord(e1, s);
-      eng->launches += 1;
       const int hh = m->eco_hh;
       if (hh >= 0) {
-        const float* income = (const float*)m->dev.t[hh].f[1];
-        const long long nh = m->dev.t[hh].n;
-        gini_count_kernel<<<m->eco.gini_blocks, kThreads, 0, s>>>(income, nh, m->eco.bin_count);
         gini_scan_sums_kernel<<<kGiniBins / kGiniScanTile, kThreads, 0, s>>>(m->eco.bin_count, m->eco.scan_sums);
         gini_scan_top_kernel<<<1, 1024, 0, s>>>(m->eco.scan_sums, kGiniBins / kGiniScanTile);
         gini_scan_apply_kernel<<<kGiniBins / kGiniScanTile, kThreads, 0, s>>>(m->eco.bin_count, m->eco.scan_sums, m->eco.bin_base);
-        eng->launches += 4;
+        eng->launches += 3;
       }
       gini_accumulate_kernel<<<hh >= 0 ? m->eco.gini_blocks : 1, kThreads, 0, s>>>(m->dev, m->eco, hh);
       eng->launches += 1;
-      if (hh >= 0) {
-        gini_clear_kernel<<<m->eco.gini_blocks, kThreads, 0, s>>>((const float*)m->dev.t[hh].f[1], m->dev.t[hh].n, m->eco.bin_count);
-        eng->launches += 1;
-      }
+      // bins back to zero for the next step's histogram (16 MB memset node)
+      if (hh >= 0) CK(cudaMemsetAsync(m->eco.bin_count, 0, (size_t)kGiniBins * 4, s));
       break;
     }
     default: {
@@ -1032,7 +1056,7 @@ static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
 
 static int launches_per_step(jxb_model* m) {
   if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 1 ? 2 : 1;
-  if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->eco_hh >= 0 ? 7 : 2;
+  if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? 4 : 1);
   return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
 }
 

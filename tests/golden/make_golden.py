@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from oracle import jaxlike as jl, rules as orules, runtime as ort  # noqa: E402
+from oracle import economy as oeco, jaxlike as jl, rules as orules, runtime as ort  # noqa: E402
 from jaxabm_b200.synthetic import ring_lattice_edges  # noqa: E402  (host-side generator, no device needed)
 
 
@@ -51,6 +51,14 @@ def main():
                                      config=ort.ModelConfig(seed=0, rng_mode=mode))
         for k, v in series(g.run(steps=30)).items():
             out[f"growth_{tag}_{k}"] = v
+        ec = oeco.create_economy_model(1200, 30, config=ort.ModelConfig(seed=42, rng_mode=mode))
+        ec.initialize()
+        out[f"economy_{tag}_init_income"] = ec.agent_collections["households"].states["income"].copy()
+        out[f"economy_{tag}_init_ptc"] = ec.agent_collections["households"].states["propensity_to_consume"].copy()
+        out[f"economy_{tag}_init_capital"] = ec.agent_collections["consumer_firms"].states["capital_stock"].copy()
+        for k, v in series(ec.run(steps=8)).items():
+            out[f"economy_{tag}_{k}"] = v
+        out[f"economy_{tag}_employed"] = ec.agent_collections["households"].states["employed"]
         key = jl.PRNGKey(42)
         out[f"prng_{tag}_split5"] = jl.split(key, 5, mode)
         out[f"prng_{tag}_uniform9"] = jl.uniform(key, (9,), -1.0, 3.0, mode)

@@ -95,3 +95,40 @@ def test_economy_unregistered_parts_raise():
         economy.create_economy_model(100, 10, num_capital_firms=5)
     with pytest.raises(jx.UnregisteredRuleError):
         economy.create_economy_model(100, 10, enable_climate_module=True)
+
+
+def test_economy_against_frozen_fixture(mode):
+    """CUDA path vs the committed oracle fixture (tests/golden/oracle_golden.npz)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden.npz"))
+    tag = "legacy" if mode == 0 else "part"
+    m = economy.create_economy_model(1200, 30, config=jx.ModelConfig(seed=42, rng_mode=mode))
+    m.initialize()
+    assert np.allclose(m.agent_collections["households"].states["income"], gold[f"economy_{tag}_init_income"], rtol=2e-6)
+    assert np.allclose(m.agent_collections["consumer_firms"].states["capital_stock"],
+                       gold[f"economy_{tag}_init_capital"], rtol=2e-6)
+    r = m.run(steps=3)
+    for k in ("gdp", "wage_rate", "interest_rate", "unemployment", "inequality"):
+        assert np.allclose([float(v) for v in r[k]], gold[f"economy_{tag}_{k}"][:3], rtol=RTOL, atol=1e-6), k
+
+
+def test_economy_full_size_properties():
+    """C4-B at bench size (49 M households + 1 M firms): employment flags stay boolean, every household
+    was updated, the fused reductions equal host reductions of the downloaded columns, and the
+    histogram-rank Gini equals the sorted formula evaluated on the host in float64."""
+    nh, nf = 49_000_000, 1_000_000
+    m = economy.create_economy_model(nh, nf, config=jx.ModelConfig(seed=42, rng_mode=1))
+    r = m.run(steps=2)
+    hh = m.agent_collections["households"].states
+    emp = hh["employed"]
+    assert emp.dtype == np.bool_ and emp.shape == (nh,)
+    assert float(r["unemployment"][-1]) == pytest.approx(100.0 * (1.0 - emp.mean(dtype=np.float64)), rel=1e-5)
+    inc = hh["income"].astype(np.float64)
+    assert np.isfinite(inc).all() and (inc >= 0).all()
+    x = np.sort(inc)
+    n = x.shape[0]
+    gini = 2.0 * np.dot(np.arange(1, n + 1, dtype=np.float64), x) / (n * x.sum()) - (n + 1) / n
+    assert float(r["inequality"][-1]) == pytest.approx(gini, rel=2e-5)
+    assert float(m._env_state["total_labor_supply"]) == pytest.approx(float(hh["labor_supply"].sum(dtype=np.float64)), rel=1e-6)
+    cf = m.agent_collections["consumer_firms"].states
+    assert (cf["age"] == 2).all()
