@@ -46,6 +46,9 @@ struct Ctrl {
   long long total_moves;
   // SIR per-step counts
   long long sir_count[3];
+  // SIR direction choice for the NEXT step (0 pull over susceptible rows, 1 push from infected rows)
+  int sir_mode;
+  long long sir_deg[2];     // adjacency entries of the susceptible / infected rows after the step
 };
 
 // cross-rank exchange of the per-step env partial sums (population sharding, one process per

@@ -206,9 +206,11 @@ struct jxb_model {
   bool grid_built = false; bool sat_dirty = false; long long n_empty_cells = 0; int sch_blocks = 0;
   // SIR
   bool has_net = false; SirDev sv{}; bool net_built = false; long long nnz = 0;
-  // SIR formulation: 0 pull (CSR ballot-segmented sweep of all edges, fused transitions),
-  // 1 push (infected rows scatter-add into k32, then the transition kernel)
-  int sir_mode = 1; int sir_tblocks = 0;
+  // SIR formulation (JXB_SIR_MODE): 0 "pull" = CSR ballot-segmented sweep of ALL edges, fused
+  // transitions; 1 "push" = infected rows scatter-add into k32 + transition kernel; 2 "pull_s" = pull
+  // over the susceptible rows only; 3 "auto" (default) = direction-optimising, the step's tail picks
+  // push or pull_s for the next step on the device
+  int sir_mode = 3; int sir_tblocks = 0;
   // economy (C4-B)
   bool has_eco = false; EcoDev eco{}; int eco_hh = -1;
   // graphs: cached executable graphs of `chunk` consecutive steps
@@ -816,7 +818,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     CK(cudaMemcpy(d_esc, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
   }
   sv.row_ptr = d_rp; sv.col = d_col; sv.rb = d_rb; sv.nrb = (int)rb.size() - 1; sv.escape = d_esc;
-  if ((rc = dev_alloc(m, &sv.partials, (size_t)std::max<long long>(sv.nrb, (n + kThreads * kSirRowsPerThread - 1) / (kThreads * kSirRowsPerThread)) * 3 + 3))) return rc;
+  if ((rc = dev_alloc(m, &sv.partials, (size_t)std::max<long long>(std::max<long long>(sv.nrb, (long long)m->eng->sms * 8), (n + kThreads * kSirRowsPerThread - 1) / (kThreads * kSirRowsPerThread)) * 3 + 3))) return rc;
   m->nnz = n_edges;
   m->net_built = true;
   {
@@ -833,7 +835,15 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     sv.n_heavy = (int)heavy.size();
     m->sir_tblocks = (int)std::max<long long>(1, std::min<long long>((n + kThreads * kSirRowsPerThread - 1) / (kThreads * kSirRowsPerThread), (long long)m->eng->sms * 8));
     const char* mode = getenv("JXB_SIR_MODE");
-    m->sir_mode = (mode && !strcmp(mode, "pull")) ? 0 : 1;
+    m->sir_mode = 3;
+    if (mode && !strcmp(mode, "pull")) m->sir_mode = 0;
+    else if (mode && !strcmp(mode, "push")) m->sir_mode = 1;
+    else if (mode && !strcmp(mode, "pull_s")) m->sir_mode = 2;
+    sv.auto_mode = m->sir_mode == 3;
+    const int dev_mode = m->sir_mode == 2 ? 0 : 1;       // auto starts in the push direction
+    CK(cudaMemcpy(&m->dev.ctrl->sir_mode, &dev_mode, sizeof(int), cudaMemcpyHostToDevice));
+    const size_t max_ctas = (size_t)std::max<long long>(m->sir_tblocks, (long long)m->eng->sms * 8);
+    if ((rc = dev_alloc(m, &sv.degsum, max_ctas * 2 + 2))) return rc;
   }
   return sir_sync_from_api(m);
 }
@@ -962,14 +972,22 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
   switch (m->desc.program) {
     case JXB_PROGRAM_SIR: {
       if (timed) cudaEventRecord(e0, s);
-      if (m->sir_mode == 1) {
-        sir_push_kernel<<<m->eng->sms * 8, kThreads, 0, s>>>(m->sv, m->dev);
-        if (part) sir_transition_kernel<1><<<m->sir_tblocks, kThreads, 0, s>>>(m->sv, m->dev);
-        else sir_transition_kernel<0><<<m->sir_tblocks, kThreads, 0, s>>>(m->sv, m->dev);
-        eng->launches += 1;
-      } else {
+      if (m->sir_mode == 0) {
         if (part) sir_step_kernel<1><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
         else sir_step_kernel<0><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
+      } else {
+        const int pgrid = m->eng->sms * 8;
+        if (m->sir_mode != 2) {          // push direction (self-gated on ctrl->sir_mode in auto mode)
+          sir_push_kernel<<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
+          if (part) sir_transition_kernel<1><<<m->sir_tblocks, kThreads, 0, s>>>(m->sv, m->dev);
+          else sir_transition_kernel<0><<<m->sir_tblocks, kThreads, 0, s>>>(m->sv, m->dev);
+          eng->launches += 1;
+        }
+        if (m->sir_mode != 1) {          // pull direction
+          if (part) sir_pull_s_kernel<1><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
+          else sir_pull_s_kernel<0><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
+          if (m->sir_mode == 3) eng->launches += 1;
+        }
       }
       if (timed) cudaEventRecord(e1, s);
       eng->launches += 1;
@@ -1055,7 +1073,7 @@ static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
 }
 
 static int launches_per_step(jxb_model* m) {
-  if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 1 ? 2 : 1;
+  if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 3 : (m->sir_mode == 1 ? 2 : 1);
   if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? 4 : 1);
   return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
 }
@@ -1074,7 +1092,10 @@ extern "C" int jxb_model_profile(jxb_model* m, double* seconds, int64_t* launche
     switch (m->desc.program) {
       case JXB_PROGRAM_SCHELLING: *name = "schelling_run_kernel"; break;
       case JXB_PROGRAM_ECONOMY: *name = "economy_step_kernel"; break;
-      case JXB_PROGRAM_SIR: *name = m->sir_mode == 1 ? "sir_push_kernel+sir_transition_kernel" : "sir_step_kernel"; break;
+      case JXB_PROGRAM_SIR:
+        *name = m->sir_mode == 0 ? "sir_step_kernel" : (m->sir_mode == 1 ? "sir_push_kernel+sir_transition_kernel"
+                : (m->sir_mode == 2 ? "sir_pull_s_kernel" : "sir_push_kernel+sir_transition_kernel|sir_pull_s_kernel"));
+        break;
       default: *name = "step_kernel";
     }
   }

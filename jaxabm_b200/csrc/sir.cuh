@@ -37,6 +37,8 @@ struct SirDev {
   unsigned int* k32;       // push formulation: infected-neighbour counters (zero between steps)
   const int* heavy;        // rows with more than kSirHeavy adjacency entries
   int n_heavy;
+  long long* degsum;       // [CTAs][2] adjacency entries of the new susceptible / infected rows per CTA
+  int auto_mode;           // 1: the step's tail picks push or pull for the next step (direction-optimising)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -167,30 +169,41 @@ __device__ __forceinline__ void sir_row_block(const SirDev& sv, const ModelDev& 
   __syncthreads();
 }
 
-// last CTA: exact integer fold over the row blocks + metrics row (count_S, count_I, count_R)
-__device__ __forceinline__ void sir_tail(const SirDev& sv, const ModelDev& md, int nparts) {
-  __shared__ long long s_tot[3][kThreads / 32];
+// last CTA: exact integer fold over the per-CTA partials + metrics row (count_S, count_I, count_R);
+// with_deg: also folds the adjacency sizes of the new S / I sets and picks the cheaper direction for
+// the next step (cost model in DESIGN.md 4.3: an L2 reduction per infected-row entry + the
+// transition pass, against a bitmap gather per susceptible-row entry).
+__device__ __forceinline__ void sir_tail(const SirDev& sv, const ModelDev& md, int nparts, bool with_deg) {
+  __shared__ long long s_tot[5][kThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   Ctrl* ctrl = md.ctrl;
-  long long v[3] = {0, 0, 0};
+  long long v[5] = {0, 0, 0, 0, 0};
   for (int b = tid; b < nparts; b += kThreads) {
     v[0] += __ldcg(sv.partials + (size_t)b * 3 + 0);
     v[1] += __ldcg(sv.partials + (size_t)b * 3 + 1);
     v[2] += __ldcg(sv.partials + (size_t)b * 3 + 2);
+    if (with_deg) {
+      v[3] += __ldcg(sv.degsum + (size_t)b * 2 + 0);
+      v[4] += __ldcg(sv.degsum + (size_t)b * 2 + 1);
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
+  for (int j = 0; j < 5; ++j) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
     if (lane == 0) s_tot[j][warp] = v[j];
   }
   __syncthreads();
   if (tid == 0) {
-    long long c[3] = {0, 0, 0};
-    for (int j = 0; j < 3; ++j)
+    long long c[5] = {0, 0, 0, 0, 0};
+    for (int j = 0; j < 5; ++j)
       for (int w = 0; w < kThreads / 32; ++w) c[j] += s_tot[j][w];
     ctrl->ticket = 0;
     ctrl->sir_count[0] = c[0]; ctrl->sir_count[1] = c[1]; ctrl->sir_count[2] = c[2];
+    if (with_deg) {
+      ctrl->sir_deg[0] = c[3]; ctrl->sir_deg[1] = c[4];
+      if (sv.auto_mode) ctrl->sir_mode = (3 * c[4] + 2 * (long long)md.t[0].n < 2 * c[3]) ? 1 : 0;
+    }
     const long long tsn = ctrl->time_step + 1;
     if ((tsn % md.collect_interval) == 0) {
       double* row = md.metrics + (size_t)ctrl->n_recorded * kMaxMetrics;
@@ -219,7 +232,7 @@ __global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, con
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  sir_tail(sv, md, sv.nrb);
+  sir_tail(sv, md, sv.nrb, false);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -235,6 +248,30 @@ __global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, con
 // ---------------------------------------------------------------------------------------
 constexpr int kSirHeavy = 2048;
 
+// CTA-level fold of the S/I/R counts and the S/I adjacency sizes into this CTA's partial rows
+__device__ __forceinline__ void sir_publish_partials(const SirDev& sv, int cS, int cI, int cR, long long dS, long long dI,
+                                                     int (*s_red)[kThreads / 32]) {
+  __shared__ long long s_deg[2][kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cS = warp_sum(cS); cI = warp_sum(cI); cR = warp_sum(cR);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dS += __shfl_xor_sync(0xffffffffu, dS, o);
+    dI += __shfl_xor_sync(0xffffffffu, dI, o);
+  }
+  if (lane == 0) { s_red[0][warp] = cS; s_red[1][warp] = cI; s_red[2][warp] = cR; s_deg[0][warp] = dS; s_deg[1][warp] = dI; }
+  __syncthreads();
+  if (tid < 3) {
+    long long v = 0;
+    for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
+    sv.partials[(size_t)blockIdx.x * 3 + tid] = v;
+  } else if (tid < 5) {
+    long long v = 0;
+    for (int w = 0; w < kThreads / 32; ++w) v += s_deg[tid - 3][w];
+    sv.degsum[(size_t)blockIdx.x * 2 + (tid - 3)] = v;
+  }
+}
+
 __device__ __forceinline__ void red_add_u32(unsigned int* p, unsigned int v) {
   asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -242,6 +279,7 @@ __device__ __forceinline__ void red_add_u32(unsigned int* p, unsigned int v) {
 __global__ void __launch_bounds__(kThreads) sir_push_kernel(const SirDev sv, const ModelDev md) {
   const int tid = threadIdx.x, lane = tid & 31;
   const Ctrl* ctrl = md.ctrl;
+  if (ctrl->sir_mode != 1) return;                 // this step runs in the pull direction
   const int cur = (int)(ctrl->time_step & 1);
   const unsigned int* inf = sv.infbits[cur];
   const long long n = md.t[0].n;
@@ -280,11 +318,13 @@ __global__ void __launch_bounds__(kThreads) sir_transition_kernel(const SirDev s
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   Ctrl* ctrl = md.ctrl;
+  if (ctrl->sir_mode != 1) return;                 // the pull kernel does its own transitions
   const TypeDev& t = md.t[0];
   const int cur = (int)(ctrl->time_step & 1), nxt = cur ^ 1;
   const uint32_t* kp = md.keys + (size_t)ctrl->step_in_run * (md.n_types + 1) * 2;
   const Key ck = {kp[0], kp[1]};
   const float gamma = t.p[1];
+  long long dS = 0, dI = 0;
   const signed char* __restrict__ st_cur = sv.state8[cur];
   signed char* __restrict__ st_nxt = sv.state8[nxt];
   unsigned int* __restrict__ k32 = sv.k32;
@@ -294,12 +334,12 @@ __global__ void __launch_bounds__(kThreads) sir_transition_kernel(const SirDev s
   constexpr int kTile = kThreads * kSirRowsPerThread;
   for (long long base = (long long)blockIdx.x * kTile; base < t.n; base += (long long)gridDim.x * kTile) {
     int s[kSirRowsPerThread];
-    unsigned int k[kSirRowsPerThread];
+    unsigned int k[kSirRowsPerThread], deg[kSirRowsPerThread];
 #pragma unroll
     for (int i = 0; i < kSirRowsPerThread; ++i) {       // all loads of the tile in flight first
       const long long r = base + i * kThreads + tid;
-      s[i] = 0; k[i] = 0;
-      if (r < t.n) { s[i] = st_cur[r]; k[i] = __ldcg(k32 + r); }
+      s[i] = 0; k[i] = 0; deg[i] = 0;
+      if (r < t.n) { s[i] = st_cur[r]; k[i] = __ldcg(k32 + r); deg[i] = sv.row_ptr[r + 1] - sv.row_ptr[r]; }
     }
 #pragma unroll
     for (int i = 0; i < kSirRowsPerThread; ++i) {
@@ -321,27 +361,109 @@ __global__ void __launch_bounds__(kThreads) sir_transition_kernel(const SirDev s
         }
         st_nxt[r] = (signed char)sn;
         cS += (sn == 0); cI += (sn == 1); cR += (sn == 2);
+        if (sn == 0) dS += deg[i];
+        if (sn == 1) dI += deg[i];
       }
       const unsigned int w = __ballot_sync(0xffffffffu, active && sn == 1);
       const long long rg = base + i * kThreads + warp * 32;
       if (lane == 0 && rg < t.n) sv.infbits[nxt][rg >> 5] = w;
     }
   }
-  cS = warp_sum(cS); cI = warp_sum(cI); cR = warp_sum(cR);
-  if (lane == 0) { s_red[0][warp] = cS; s_red[1][warp] = cI; s_red[2][warp] = cR; }
-  __syncthreads();
-  if (tid < 3) {
-    long long v = 0;
-    for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
-    sv.partials[(size_t)blockIdx.x * 3 + tid] = v;
-  }
+  sir_publish_partials(sv, cS, cI, cR, dS, dI, s_red);
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&ctrl->ticket, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  sir_tail(sv, md, (int)gridDim.x);
+  sir_tail(sv, md, (int)gridDim.x, true);
+}
+
+// ---------------------------------------------------------------------------------------
+// pull over the SUSCEPTIBLE rows only (fused step, no atomics): one warp per 32-row group, lane =
+// row.  Only susceptible agents need their infected-neighbour count, so only their adjacency is
+// read: lanes stride each susceptible row, one bitmap gather per entry, the row's count is the
+// popcount of the hit ballot.  Transitions, the new bitmap word and the partial counts follow in
+// the same warp.  Cost is proportional to the susceptible rows' adjacency -- the complement of the
+// push kernel's; the step's tail picks whichever is cheaper for the next step.
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, const ModelDev md) {
+  __shared__ int s_red[3][kThreads / 32];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31;
+  Ctrl* ctrl = md.ctrl;
+  if (ctrl->sir_mode != 0) return;
+  const TypeDev& t = md.t[0];
+  const long long n = t.n;
+  const int cur = (int)(ctrl->time_step & 1), nxt = cur ^ 1;
+  const uint32_t* kp = md.keys + (size_t)ctrl->step_in_run * (md.n_types + 1) * 2;
+  const Key ck = {kp[0], kp[1]};
+  const float gamma = t.p[1];
+  const unsigned int* __restrict__ inf = sv.infbits[cur];
+  const signed char* __restrict__ st_cur = sv.state8[cur];
+  signed char* __restrict__ st_nxt = sv.state8[nxt];
+  int cS = 0, cI = 0, cR = 0;
+  long long dS = 0, dI = 0;
+  const long long ngroups = (n + 31) >> 5;
+  const long long wstride = (long long)gridDim.x * (kThreads / 32);
+  for (long long g = (long long)blockIdx.x * (kThreads / 32) + (tid >> 5); g < ngroups; g += wstride) {
+    const long long r = (g << 5) + lane;
+    const bool active = r < n;
+    int s = 3;
+    unsigned int lo = 0, len = 0;
+    if (active) {
+      s = st_cur[r];
+      lo = sv.row_ptr[r];
+      len = sv.row_ptr[r + 1] - lo;
+    }
+    unsigned int k = 0;
+    unsigned int todo = __ballot_sync(0xffffffffu, active && s == 0 && len > 0);
+    while (todo) {
+      const int b = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const unsigned int blo = __shfl_sync(0xffffffffu, lo, b), blen = __shfl_sync(0xffffffffu, len, b);
+      unsigned int cnt = 0;
+      for (unsigned int e0 = 0; e0 < blen; e0 += 32) {
+        const unsigned int e = e0 + lane;
+        unsigned int bit = 0;
+        if (e < blen) {
+          const int c = __ldcs(sv.col + blo + e);
+          bit = (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, bit));
+      }
+      if (lane == b) k = cnt;
+    }
+    int sn = s;
+    if (active) {
+      const bool need = (s == 0 && k > 0) || s == 1;
+      if (need) {
+        const Key ak = split_child<MODE>(ck, (unsigned long long)(t.goff + r), (unsigned long long)t.gn);
+        const float u = bits_to_uniform(bits_scalar<MODE>(ak), 0.f, 1.f);
+        if (s == 0) {
+          const float p = 1.0f - __ldg(sv.escape + (k < (unsigned)kSirKCap ? k : (unsigned)kSirKCap));
+          if (u < p) sn = 1;
+        } else if (u < gamma) {
+          sn = 2;
+        }
+      }
+      st_nxt[r] = (signed char)sn;
+      cS += (sn == 0); cI += (sn == 1); cR += (sn == 2);
+      if (sn == 0) dS += len;
+      if (sn == 1) dI += len;
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, active && sn == 1);
+    if (lane == 0) sv.infbits[nxt][g] = w;
+  }
+  sir_publish_partials(sv, cS, cI, cR, dS, dI, s_red);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&ctrl->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  sir_tail(sv, md, (int)gridDim.x, true);
 }
 
 // API column 'state' int32[N]  <->  packed int8 + infected bitmap
