@@ -47,7 +47,8 @@ struct Ctrl {
   // SIR per-step counts
   long long sir_count[3];
   // SIR direction choice for the NEXT step (0 pull over susceptible rows, 1 push from infected rows)
-  int sir_mode;
+  int sir_mode;             // direction of the step being executed (latched by sir_begin_step_kernel)
+  int sir_mode_next;        // written by the step's tail
   long long sir_deg[2];     // adjacency entries of the susceptible / infected rows after the step
 };
 

@@ -842,6 +842,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     sv.auto_mode = m->sir_mode == 3;
     const int dev_mode = m->sir_mode == 2 ? 0 : 1;       // auto starts in the push direction
     CK(cudaMemcpy(&m->dev.ctrl->sir_mode, &dev_mode, sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&m->dev.ctrl->sir_mode_next, &dev_mode, sizeof(int), cudaMemcpyHostToDevice));
     const size_t max_ctas = (size_t)std::max<long long>(m->sir_tblocks, (long long)m->eng->sms * 8);
     if ((rc = dev_alloc(m, &sv.degsum, max_ctas * 2 + 2))) return rc;
   }
@@ -977,6 +978,10 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
         else sir_step_kernel<0><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
       } else {
         const int pgrid = m->eng->sms * 8;
+        if (m->sir_mode == 3) {
+          sir_begin_step_kernel<<<1, 32, 0, s>>>(m->dev.ctrl);
+          eng->launches += 1;
+        }
         if (m->sir_mode != 2) {          // push direction (self-gated on ctrl->sir_mode in auto mode)
           sir_push_kernel<<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
           if (part) sir_transition_kernel<1><<<m->sir_tblocks, kThreads, 0, s>>>(m->sv, m->dev);
@@ -1073,7 +1078,7 @@ static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
 }
 
 static int launches_per_step(jxb_model* m) {
-  if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 3 : (m->sir_mode == 1 ? 2 : 1);
+  if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 : (m->sir_mode == 1 ? 2 : 1);
   if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? 4 : 1);
   return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
 }

@@ -202,7 +202,16 @@ __device__ __forceinline__ void sir_tail(const SirDev& sv, const ModelDev& md, i
     ctrl->sir_count[0] = c[0]; ctrl->sir_count[1] = c[1]; ctrl->sir_count[2] = c[2];
     if (with_deg) {
       ctrl->sir_deg[0] = c[3]; ctrl->sir_deg[1] = c[4];
-      if (sv.auto_mode) ctrl->sir_mode = (3 * c[4] + 2 * (long long)md.t[0].n < 2 * c[3]) ? 1 : 0;
+      // cost model fitted on B200 at C3, in units of adjacency entries:
+      //   push ~ 7.5 n + 2.3 min(dI, n) + 0.95 max(dI - n, 0) + 0.3 dS   (L2 reductions + transition pass
+      //                                                                    + draws of the exposed S rows)
+      //   pull ~ 13 n + 0.8 dS                                            (bitmap gathers over the S rows)
+      if (sv.auto_mode) {
+        const long long nn = md.t[0].n, dS = c[3], dI = c[4];
+        const long long lhs = 11 * nn + 10 * dS;
+        const long long rhs = 46 * (dI < nn ? dI : nn) + 19 * (dI > nn ? dI - nn : 0);
+        ctrl->sir_mode_next = lhs < rhs ? 0 : 1;
+      }
     }
     const long long tsn = ctrl->time_step + 1;
     if ((tsn % md.collect_interval) == 0) {
@@ -247,6 +256,12 @@ __global__ void __launch_bounds__(kThreads) sir_step_kernel(const SirDev sv, con
 // CTA; all other rows are handled by one warp per 32-row group, lanes striding the row.
 // ---------------------------------------------------------------------------------------
 constexpr int kSirHeavy = 2048;
+
+// first kernel of every step: latch the direction picked by the previous step's tail, so that the
+// three self-gating kernels of ONE step all see the same decision
+__global__ void sir_begin_step_kernel(Ctrl* ctrl) {
+  if (threadIdx.x == 0) ctrl->sir_mode = ctrl->sir_mode_next;
+}
 
 // CTA-level fold of the S/I/R counts and the S/I adjacency sizes into this CTA's partial rows
 __device__ __forceinline__ void sir_publish_partials(const SirDev& sv, int cS, int cI, int cR, long long dS, long long dI,
@@ -418,22 +433,64 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
       len = sv.row_ptr[r + 1] - lo;
     }
     unsigned int k = 0;
-    unsigned int todo = __ballot_sync(0xffffffffu, active && s == 0 && len > 0);
-    while (todo) {
-      const int b = __ffs(todo) - 1;
-      todo &= todo - 1;
+    // long susceptible rows (hubs before they are infected): all 32 lanes stride the row
+    unsigned int big = __ballot_sync(0xffffffffu, active && s == 0 && len > 256u);
+    while (big) {
+      const int b = __ffs(big) - 1;
+      big &= big - 1;
       const unsigned int blo = __shfl_sync(0xffffffffu, lo, b), blen = __shfl_sync(0xffffffffu, len, b);
       unsigned int cnt = 0;
-      for (unsigned int e0 = 0; e0 < blen; e0 += 32) {
-        const unsigned int e = e0 + lane;
+      for (unsigned int e0 = 0; e0 < blen; e0 += 128) {          // 4 independent gathers per lane in flight
+        unsigned int bits = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned int e = e0 + j * 32 + lane;
+          if (e < blen) {
+            const int c = __ldcs(sv.col + blo + e);
+            bits += (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;
+          }
+        }
+        cnt += bits;
+      }
+      cnt = (unsigned int)warp_sum((int)cnt);
+      if (lane == b) k = cnt;
+    }
+    unsigned int todo = __ballot_sync(0xffffffffu, active && s == 0 && len > 0 && len <= 256u);
+    // four susceptible rows at a time, 8 lanes striding each (most susceptible rows are short): four
+    // independent gather chains per warp instead of one
+    const int sub = lane >> 3, sl = lane & 7;
+    while (todo) {
+      int rb[4];
+      unsigned int rest = todo;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        rb[q] = rest ? __ffs(rest) - 1 : -1;
+        rest &= rest - 1;                          // (0 & 0xffffffff stays 0)
+      }
+      todo = rest;
+      const int myb = sub == 0 ? rb[0] : (sub == 1 ? rb[1] : (sub == 2 ? rb[2] : rb[3]));
+      const unsigned int slo = __shfl_sync(0xffffffffu, lo, myb & 31);
+      unsigned int slen = __shfl_sync(0xffffffffu, len, myb & 31);
+      if (myb < 0) slen = 0;
+      unsigned int maxlen = slen;
+      maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
+      maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
+      unsigned int cnt = 0;
+      for (unsigned int e0 = 0; e0 < maxlen; e0 += 8) {
+        const unsigned int e = e0 + sl;
         unsigned int bit = 0;
-        if (e < blen) {
-          const int c = __ldcs(sv.col + blo + e);
+        if (e < slen) {
+          const int c = __ldcs(sv.col + slo + e);
           bit = (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;
         }
-        cnt += __popc(__ballot_sync(0xffffffffu, bit));
+        const unsigned int bal = __ballot_sync(0xffffffffu, bit);
+        cnt += __popc((bal >> (8 * sub)) & 0xFFu);
       }
-      if (lane == b) k = cnt;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned int cq = __shfl_sync(0xffffffffu, cnt, q * 8);
+        if (lane == rb[q]) k = cq;
+      }
     }
     int sn = s;
     if (active) {
