@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "rules.cuh"
 #include "schelling.cuh"
+#include "schelling_bits.cuh"
 #include "sir.cuh"
 #include "ensemble.cuh"
 
@@ -204,6 +205,8 @@ struct jxb_model {
   // Schelling
   bool has_grid = false; SchellingDev sd{}; long long pad = 0; float* d_ratio = nullptr;
   bool grid_built = false; bool sat_dirty = false; long long n_empty_cells = 0; int sch_blocks = 0;
+  // bit-sliced variant (row length a multiple of 1024): the planes are the live grid during a run
+  bool sch_bits = false; SchellingBitsDev sb{}; bool ct_stale = false;
   // SIR
   bool has_net = false; SirDev sv{}; bool net_built = false; long long nnz = 0;
   // SIR formulation (JXB_SIR_MODE): 0 "pull" = CSR ballot-segmented sweep of ALL edges, fused
@@ -490,6 +493,35 @@ extern "C" int jxb_model_create(jxb_engine* eng, const jxb_model_desc* d, jxb_mo
       if (const char* ev = getenv("JXB_SCH_BPS")) bps = std::max(1, std::min(occ, atoi(ev)));
       else bps = std::min(occ, 4);
       m->sch_blocks = (int)std::max<long long>(1, std::min<long long>((long long)eng->sms * bps, (sd.cells + 511) / 512));
+      const int strips = sd.H / 1024;
+      static const bool no_bits = getenv("JXB_SCH_NO_BITS") != nullptr;
+      if (!no_bits && sd.H % 1024 == 0 && (strips == 1 || strips == 2 || strips == 4 || strips == 8)) {
+        int occb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, schelling_bits_kernel<1>, kThreads, 0) == cudaSuccess && occb >= 1) {
+          m->sch_bits = true;
+          int bpsb = std::min(occb, 4);
+          if (const char* ev = getenv("JXB_SCH_BPS")) bpsb = std::max(1, std::min(occb, atoi(ev)));
+          // at least ~2 strip-rows per warp, all CTAs co-resident
+          m->sch_blocks = (int)std::max<long long>(1, std::min<long long>((long long)eng->sms * bpsb,
+                                                                          ((long long)sd.W * strips + 15) / 16));
+        } else {
+          cudaGetLastError();
+        }
+      }
+    }
+    if (m->sch_bits) {
+      SchellingBitsDev& sb = m->sb;
+      sb.wpr = sd.H / 32;
+      sb.spr = sd.H / 1024;
+      const size_t plane_words = (size_t)(sd.W + 2) * sb.wpr + 32;
+      unsigned int* p0 = nullptr; unsigned int* p1 = nullptr;
+      TRY(dev_alloc(m, &p0, plane_words));
+      TRY(dev_alloc(m, &p1, plane_words));
+      cudaMemsetAsync(p0, 0, plane_words * 4, eng->stream);
+      cudaMemsetAsync(p1, 0, plane_words * 4, eng->stream);
+      sb.occ = p0 + sb.wpr;
+      sb.t1 = p1 + sb.wpr;
+      TRY(dev_alloc(m, &sb.umask, (size_t)(sd.cells >> 5) + 32));
     }
     {
       BlkPart* bp = nullptr;
@@ -505,6 +537,7 @@ extern "C" int jxb_model_create(jxb_engine* eng, const jxb_model_desc* d, jxb_mo
       for (int sm = 0; sm <= o; ++sm)
         if (((float)sm / (float)o) >= thr) { need = sm; break; }
       sd.need_lut |= (unsigned long long)need << (4 * o);
+      for (int q = 0; q < 4; ++q) m->sb.need_sel[o][q] = ((need >> q) & 1) ? 0xFFFFFFFFu : 0u;
     }
     m->has_grid = true;
   }
@@ -713,6 +746,12 @@ extern "C" int jxb_model_grid_rebuild(jxb_model* m) {
   CK(cudaGetLastError());
   if (err == 1) return fail(JXB_ERR_INVALID, "an agent position lies outside the grid");
   if (err == 2) return fail(JXB_ERR_INVALID, "two agents share a grid cell");
+  if (m->sch_bits) {
+    planes_from_ct_kernel<<<m->eng->sms * 8, 256, 0, s>>>(m->sd, m->sb);
+    m->eng->launches++;
+    CK(cudaGetLastError());
+    m->ct_stale = false;
+  }
   m->grid_built = true;
   return JXB_OK;
 }
@@ -723,6 +762,11 @@ extern "C" int jxb_model_download_grid(jxb_model* m, int32_t* host, size_t bytes
   if (bytes != (size_t)m->sd.cells * 4) return fail(JXB_ERR_INVALID, "grid is %lld int32", m->sd.cells);
   CK(cudaSetDevice(m->eng->device));
   if (!m->grid_built) { int rc = jxb_model_grid_rebuild(m); if (rc) return rc; }
+  if (m->sch_bits && m->ct_stale) {
+    ct_from_planes_kernel<<<m->eng->sms * 8, 256, 0, m->eng->stream>>>(m->sd, m->sb);
+    m->eng->launches++;
+    m->ct_stale = false;
+  }
   int* tmp = nullptr;
   CK(cudaMalloc(&tmp, bytes));
   grid_export_kernel<<<m->eng->sms * 8, 256, 0, m->eng->stream>>>(m->sd, tmp);
@@ -1069,6 +1113,14 @@ static int build_graph(jxb_model* m, int chunk, cudaGraphExec_t* out) {
 // Schelling: the whole run is ONE cooperative launch (csrc/schelling.cuh)
 static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
   const bool fast = (m->sd.H % 16) == 0, part = m->desc.rng_mode == JXB_RNG_PARTITIONABLE;
+  if (m->sch_bits) {
+    void* args[] = {(void*)&m->sd, (void*)&m->sb, (void*)&m->dev, (void*)&steps};
+    const void* fn = part ? (const void*)schelling_bits_kernel<1> : (const void*)schelling_bits_kernel<0>;
+    CK(cudaLaunchCooperativeKernel(fn, dim3(m->sch_blocks), dim3(kThreads), args, 0, s));
+    m->ct_stale = true;
+    m->eng->launches += 1;
+    return JXB_OK;
+  }
   void* args[] = {(void*)&m->sd, (void*)&m->dev, (void*)&steps};
   const void* fn = fast ? (part ? (const void*)schelling_run_kernel<true, 1> : (const void*)schelling_run_kernel<true, 0>)
                         : (part ? (const void*)schelling_run_kernel<false, 1> : (const void*)schelling_run_kernel<false, 0>);
@@ -1095,7 +1147,7 @@ extern "C" int jxb_model_profile(jxb_model* m, double* seconds, int64_t* launche
   if (launches) *launches = m->prof_launches;
   if (name) {
     switch (m->desc.program) {
-      case JXB_PROGRAM_SCHELLING: *name = "schelling_run_kernel"; break;
+      case JXB_PROGRAM_SCHELLING: *name = m->sch_bits ? "schelling_bits_kernel" : "schelling_run_kernel"; break;
       case JXB_PROGRAM_ECONOMY: *name = "economy_step_kernel"; break;
       case JXB_PROGRAM_SIR:
         *name = m->sir_mode == 0 ? "sir_step_kernel" : (m->sir_mode == 1 ? "sir_push_kernel+sir_transition_kernel"

@@ -81,6 +81,32 @@ def test_schelling_full_size_vs_c_oracle():
     assert ps[-1] > 0.99 and ps[-1] == np.float32(st["satisfied"].mean())
 
 
+@pytest.mark.parametrize("g,n,periodic,thr", [(1024, 800_000, False, 0.5), (1024, 800_000, True, 0.5),
+                                              (2048, 3_000_000, True, 0.375), (1024, 1_000_000, False, 0.7),
+                                              (1024, 1024 * 1024 - 5, False, 0.5)])
+def test_schelling_bit_sliced_vs_c_oracle(mode, g, n, periodic, thr):
+    """Row lengths that are multiples of 1024 take the bit-sliced kernel (csrc/schelling_bits.cuh: 1, 2
+    strips per row here, 4 in the full-size test above): bit-exact against the C/OpenMP oracle over the
+    active phase, periodic and non-periodic, several thresholds, nearly full grid."""
+    from oracle import cfast
+    types, pos = schelling.initial_layout(g, n, 0.5, 7)
+    m = schelling.create_schelling_model(g, n, seed=7, types=types, positions=pos, periodic=periodic,
+                                         similarity_threshold=thr, config=jx.ModelConfig(seed=7, rng_mode=mode))
+    f = cfast.SchellingFast(g, types, pos, similarity_threshold=thr, periodic=periodic, seed=7, mode=mode)
+    for steps in (1, 6, 9):
+        r, fr = m.run(steps=steps), f.run(steps)
+        assert [int(v) for v in r["total_moves"]] == [int(v) for v in fr["total_moves"]], steps
+        assert np.array_equal(series(r, "percent_satisfied"), series(fr, "percent_satisfied"))
+        np.testing.assert_allclose(series(r, "segregation_index"), series(fr, "segregation_index"), rtol=1e-6)
+    st = m.agent_collections["agents"].states
+    assert np.array_equal(st["position"], f.pos)
+    assert np.array_equal(st["moves"], f.moves)
+    assert np.array_equal(st["satisfied"], f.satisfied.astype(bool))
+    assert np.array_equal(m._dev.download_grid().reshape(-1), f.grid)
+    ec = m._dev.download_empty_cells()
+    assert np.array_equal(ec[:, 0].astype(np.int64) * g + ec[:, 1], f.E)
+
+
 def test_market_full_size_properties():
     """C4-A at 45 M + 5 M agents: totals reported by the fused reductions equal host-side sums of the
     downloaded columns; savings identity holds per agent."""
