@@ -182,6 +182,10 @@ struct jxb_engine {
   int64_t launches = 0;
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // caching allocator: device blocks of destroyed models are kept and handed to the next model of
+  // a similar shape (cudaMalloc / cudaFree of ~0.5 GB of columns costs milliseconds per model)
+  std::vector<std::pair<void*, size_t>> pool;
+  size_t pool_bytes = 0;
   // peer-memory exchange (CUDA IPC over NVLink): own buffer + every rank's buffer as mapped here
   XchgBuf* xlocal = nullptr;
   XchgBuf* xpeer[kMaxPeers] = {};
@@ -194,13 +198,13 @@ struct jxb_model {
   const ProgramSpec* prog = nullptr;
   const RuleSpec* rules[JXB_MAX_TYPES] = {};
   ModelDev dev{};
-  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> allocs;
   Key rng{0, 0};
   bool initialized = false;
   bool collections_ready[JXB_MAX_TYPES] = {};
   long long time_step = 0;
   // per-run buffers
-  uint32_t* d_keys = nullptr; uint32_t* h_keys = nullptr; size_t keys_cap = 0;
+  uint32_t* d_keys = nullptr; std::vector<uint32_t> h_keys; size_t keys_cap = 0;
   double* d_metrics = nullptr; int* d_rec = nullptr; size_t rec_cap = 0;
   // Schelling
   bool has_grid = false; SchellingDev sd{}; long long pad = 0; float* d_ratio = nullptr;
@@ -225,11 +229,56 @@ struct jxb_model {
   int step_blocks = 0;
 };
 
+static size_t pool_cap_bytes() {
+  static const size_t cap = [] {
+    const char* ev = getenv("JXB_POOL_MB");
+    return (size_t)(ev ? atoll(ev) : 16384) << 20;
+  }();
+  return cap;
+}
+
+static cudaError_t pool_alloc(jxb_engine* eng, void** out, size_t bytes) {
+  bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+  int best = -1;
+  for (int i = 0; i < (int)eng->pool.size(); ++i) {
+    const size_t b = eng->pool[i].second;
+    if (b >= bytes && b <= bytes + bytes / 8 + (1u << 16) && (best < 0 || b < eng->pool[best].second)) best = i;
+  }
+  if (best >= 0) {
+    *out = eng->pool[best].first;
+    eng->pool_bytes -= eng->pool[best].second;
+    eng->pool.erase(eng->pool.begin() + best);
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess && !eng->pool.empty()) {          // give the cached blocks back and retry
+    cudaGetLastError();
+    for (auto& b : eng->pool) cudaFree(b.first);
+    eng->pool.clear();
+    eng->pool_bytes = 0;
+    e = cudaMalloc(out, bytes);
+  }
+  return e;
+}
+
+static void pool_free(jxb_engine* eng, void* p, size_t bytes) {
+  if (!p) return;
+  bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+  eng->pool.emplace_back(p, bytes);
+  eng->pool_bytes += bytes;
+  while (eng->pool_bytes > pool_cap_bytes() && !eng->pool.empty()) {
+    cudaFree(eng->pool.front().first);
+    eng->pool_bytes -= eng->pool.front().second;
+    eng->pool.erase(eng->pool.begin());
+  }
+}
+
 template <class T>
 static int dev_alloc(jxb_model* m, T** p, size_t count) {
   void* q = nullptr;
-  CK(cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 16)));
-  m->allocs.push_back(q);
+  const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+  CK(pool_alloc(m->eng, &q, bytes));
+  m->allocs.emplace_back(q, bytes);
   *p = (T*)q;
   return JXB_OK;
 }
@@ -262,6 +311,7 @@ extern "C" int jxb_engine_destroy(jxb_engine* eng) {
   for (int p = 0; p < kMaxPeers; ++p)
     if (eng->xpeer[p] && eng->xpeer[p] != eng->xlocal) cudaIpcCloseMemHandle(eng->xpeer[p]);
   if (eng->xlocal) cudaFree(eng->xlocal);
+  for (auto& b : eng->pool) cudaFree(b.first);
   cudaEventDestroy(eng->ev0);
   cudaEventDestroy(eng->ev1);
   cudaStreamDestroy(eng->stream);
@@ -572,11 +622,10 @@ extern "C" int jxb_model_destroy(jxb_model* m) {
   if (m->graph1) cudaGraphExecDestroy(m->graph1);
   if (m->graphK) cudaGraphExecDestroy(m->graphK);
   for (auto e : m->prof_events) cudaEventDestroy(e);
-  for (void* p : m->allocs) cudaFree(p);
-  if (m->d_keys) cudaFree(m->d_keys);
-  if (m->h_keys) cudaFreeHost(m->h_keys);
-  if (m->d_metrics) cudaFree(m->d_metrics);
-  if (m->d_rec) cudaFree(m->d_rec);
+  for (auto& a : m->allocs) pool_free(m->eng, a.first, a.second);
+  pool_free(m->eng, m->d_keys, m->keys_cap * 4);
+  pool_free(m->eng, m->d_metrics, m->rec_cap * kMaxMetrics * sizeof(double));
+  pool_free(m->eng, m->d_rec, m->rec_cap * sizeof(int));
   delete m;
   return JXB_OK;
 }
@@ -1178,16 +1227,17 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   const int C = m->desc.n_types, mode = m->desc.rng_mode, stride = (C + 1) * 2;
   // ---- key schedule of the whole run (model.py:156,164,183), host scalar work ----------
   if ((size_t)steps * stride > m->keys_cap) {
-    if (m->d_keys) cudaFree(m->d_keys);
-    if (m->h_keys) cudaFreeHost(m->h_keys);
+    CK(cudaStreamSynchronize(s));
+    pool_free(eng, m->d_keys, m->keys_cap * 4);
     m->keys_cap = (size_t)std::max(steps, 16) * stride;
-    CK(cudaMalloc(&m->d_keys, m->keys_cap * 4));
-    CK(cudaMallocHost(&m->h_keys, m->keys_cap * 4));
+    m->d_keys = nullptr;
+    CK(pool_alloc(eng, (void**)&m->d_keys, m->keys_cap * 4));
+    m->h_keys.resize(m->keys_cap);
   }
   for (int t = 0; t < steps; ++t) {
     Key step_key = split_child(mode, m->rng, 1, 2);
     m->rng = split_child(mode, m->rng, 0, 2);
-    uint32_t* row = m->h_keys + (size_t)t * stride;
+    uint32_t* row = m->h_keys.data() + (size_t)t * stride;
     for (int c = 0; c < C; ++c) {
       Key ck = split_child(mode, step_key, 1, 2);
       step_key = split_child(mode, step_key, 0, 2);
@@ -1197,18 +1247,20 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
     if (m->prog->has_env_fn) uk = split_child(mode, step_key, 1, 2);
     row[2 * C] = uk.a; row[2 * C + 1] = uk.b;
   }
-  if (steps) CK(cudaMemcpyAsync(m->d_keys, m->h_keys, (size_t)steps * stride * 4, cudaMemcpyHostToDevice, s));
+  if (steps) CK(cudaMemcpyAsync(m->d_keys, m->h_keys.data(), (size_t)steps * stride * 4, cudaMemcpyHostToDevice, s));
   m->dev.keys = m->d_keys;
 
   // ---- history ring ---------------------------------------------------------------------
   const long long t0 = m->time_step;
   const int n_rec = (int)((t0 + steps) / collect_interval - t0 / collect_interval);
   if ((size_t)n_rec + 1 > m->rec_cap) {
-    if (m->d_metrics) cudaFree(m->d_metrics);
-    if (m->d_rec) cudaFree(m->d_rec);
+    CK(cudaStreamSynchronize(s));
+    pool_free(eng, m->d_metrics, m->rec_cap * kMaxMetrics * sizeof(double));
+    pool_free(eng, m->d_rec, m->rec_cap * sizeof(int));
     m->rec_cap = (size_t)n_rec + 64;
-    CK(cudaMalloc(&m->d_metrics, m->rec_cap * kMaxMetrics * sizeof(double)));
-    CK(cudaMalloc(&m->d_rec, m->rec_cap * sizeof(int)));
+    m->d_metrics = nullptr; m->d_rec = nullptr;
+    CK(pool_alloc(eng, (void**)&m->d_metrics, m->rec_cap * kMaxMetrics * sizeof(double)));
+    CK(pool_alloc(eng, (void**)&m->d_rec, m->rec_cap * sizeof(int)));
   }
   m->dev.metrics = m->d_metrics;
   m->dev.record_steps = m->d_rec;

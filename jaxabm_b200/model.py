@@ -234,9 +234,21 @@ class Model:
         self.last_device_seconds = secs
         self._time_step += steps
         names = self._metric_names()
-        rows = [{"time_step": int(rec_steps[r]),
-                 "metrics": {name: self._cast(rec[r, k], dt) for k, (name, dt) in names}}
-                for r in range(len(rec_steps))]
+        # one vectorised cast per metric column (a list of NumPy scalars, like the reference's list of
+        # jnp scalars), then the rows
+        cols = []
+        for k, (name, dt) in names:
+            col = rec[:, k]
+            if dt == np.float64:
+                cols.append(col.tolist())
+            elif dt == np.int32:
+                cols.append(list(col.astype(np.int64).astype(np.int32)))
+            else:
+                cols.append(list(col.astype(dt)))
+        keys = [name for _, (name, _) in names]
+        ts = rec_steps.tolist()
+        rows = [{"time_step": ts[r], "metrics": dict(zip(keys, vals))}
+                for r, vals in enumerate(zip(*cols))] if cols else [{"time_step": t, "metrics": {}} for t in ts]
         self._pull_env()
         return rows
 
