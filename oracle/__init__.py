@@ -20,7 +20,8 @@ PARITY PINNING STATUS
 * threefry2x32 / ``PRNGKey`` / ``split`` / ``uniform``: pinned by the published
   Random123 + JAX known-answer vectors (``tests/golden/threefry_kat.json``).
 * Model loop, key schedule, step ordering: pinned by the reference's own
-  behavioural tests (ported in ``tests/test_reference_contract.py``) and by
+  behavioural tests (ported in ``tests/test_oracle.py::test_model_contract``,
+  ``::test_agent_collection_contract`` and ``tests/test_host.py::test_api_contract_without_device``) and by
   closed forms.
 * Floating trajectories of the workload rules and the Schelling / SIR rules:
   **parity unpinned** -- the reference holds no golden vectors for them
