@@ -48,32 +48,33 @@ __device__ __forceinline__ unsigned int maj3(unsigned int a, unsigned int b, uns
   return (a & b) | (a & c) | (b & c);
 }
 
-// row x of a plane (x may be -1 or W: the halo rows); j = word index inside the row.  fetch_row only
-// issues the loads (so that the next row can be in flight while the current one is evaluated),
-// finish_row does the shuffles and the horizontal sums.
+// row x of a plane (x may be -1 or W: the halo rows).  Every lane loads its own word and the words
+// left and right of it (indices jl / jr precomputed per lane, wrapped when periodic; lmask / rmask
+// zero the neighbour at a non-periodic row end) -- branch-free, no shuffles; the three loads of a
+// lane hit the same or the adjacent L2 sector.  fetch_row only issues the loads (so that the next
+// row is in flight while the current one is evaluated), finish_row forms the horizontal sums.
 struct RawRow {
-  unsigned int c, le, re;     // le / re: the word left of lane 0 / right of lane 31
+  unsigned int c, l, r;
 };
 
-__device__ __forceinline__ RawRow fetch_row(const unsigned int* plane, long long x, int j, int wpr, int periodic, int lane) {
+struct LaneCols {
+  int j, jl, jr;
+  unsigned int lmask, rmask;
+};
+
+__device__ __forceinline__ RawRow fetch_row(const unsigned int* plane, long long x, const LaneCols& lc, int wpr) {
   const unsigned int* row = plane + x * wpr;
   RawRow r;
-  r.c = __ldcg(row + j);
-  r.le = 0u;
-  r.re = 0u;
-  if (lane == 0) r.le = j > 0 ? __ldcg(row + j - 1) : (periodic ? __ldcg(row + wpr - 1) : 0u);
-  if (lane == 31) r.re = j + 1 < wpr ? __ldcg(row + j + 1) : (periodic ? __ldcg(row) : 0u);
+  r.c = __ldcg(row + lc.j);
+  r.l = __ldcg(row + lc.jl);
+  r.r = __ldcg(row + lc.jr);
   return r;
 }
 
-__device__ __forceinline__ RowSums finish_row(const RawRow& raw, int lane) {
+__device__ __forceinline__ RowSums finish_row(const RawRow& raw, const LaneCols& lc) {
   const unsigned int c = raw.c;
-  unsigned int l = __shfl_up_sync(0xffffffffu, c, 1);
-  unsigned int r = __shfl_down_sync(0xffffffffu, c, 1);
-  if (lane == 0) l = raw.le;
-  if (lane == 31) r = raw.re;
-  const unsigned int a = __funnelshift_l(l, c, 1);     // bit i <- cell i-1
-  const unsigned int b = __funnelshift_r(c, r, 1);     // bit i <- cell i+1
+  const unsigned int a = __funnelshift_l(raw.l & lc.lmask, c, 1);     // bit i <- cell i-1
+  const unsigned int b = __funnelshift_r(c, raw.r & lc.rmask, 1);     // bit i <- cell i+1
   RowSums s;
   s.c = c;
   s.m0 = a ^ b;
@@ -81,11 +82,6 @@ __device__ __forceinline__ RowSums finish_row(const RawRow& raw, int lane) {
   s.s0 = s.m0 ^ c;
   s.s1 = maj3(a, b, c);
   return s;
-}
-
-__device__ __forceinline__ RowSums load_row(const unsigned int* plane, long long x, int j, int wpr, int periodic,
-                                            int lane) {
-  return finish_row(fetch_row(plane, x, j, wpr, periodic, lane), lane);
 }
 
 // top(3-sum) + mid(2-sum) + bottom(3-sum) -> 4-bit bit-sliced count (0..8)
@@ -110,7 +106,7 @@ __device__ __forceinline__ unsigned int lt_step(unsigned int s, unsigned int k, 
 constexpr int kSegPairs = 13;
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 3) schelling_bits_kernel(const SchellingDev sd, const SchellingBitsDev sb,
+__global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const SchellingDev sd, const SchellingBitsDev sb,
                                                                   const ModelDev md, int steps) {
   __shared__ unsigned int s_u32[kThreads / 32];
   __shared__ unsigned long long s_u64[kThreads / 32];
@@ -130,7 +126,12 @@ __global__ void __launch_bounds__(kThreads, 3) schelling_bits_kernel(const Schel
   const long long R0 = (long long)W * b / B, R1 = (long long)W * (b + 1) / B;
   const int strip = warp % spr, sub = warp / spr;
   const long long rs = R0 + (R1 - R0) * sub / nsub, re = R0 + (R1 - R0) * (sub + 1) / nsub;
-  const int j = strip * 32 + lane;
+  LaneCols lc;
+  lc.j = strip * 32 + lane;
+  lc.jl = lc.j > 0 ? lc.j - 1 : (sd.periodic ? wpr - 1 : lc.j);
+  lc.jr = lc.j + 1 < wpr ? lc.j + 1 : (sd.periodic ? 0 : lc.j);
+  lc.lmask = (lc.j > 0 || sd.periodic) ? 0xFFFFFFFFu : 0u;
+  lc.rmask = (lc.j + 1 < wpr || sd.periodic) ? 0xFFFFFFFFu : 0u;
   const long long wbeg = R0 * wpr, wend = R1 * wpr;       // this CTA's words, in cell order
   const unsigned int e = sd.n_empty;
   const int step0 = ctrl->step_in_run;
@@ -150,73 +151,91 @@ __global__ void __launch_bounds__(kThreads, 3) schelling_bits_kernel(const Schel
 #pragma unroll
     for (int i = 0; i < kSegPairs; ++i) seg[i] = 0;
     if (rs < re) {
-      RowSums to = load_row(sb.occ, rs - 1, j, wpr, sd.periodic, lane), tt = load_row(sb.t1, rs - 1, j, wpr, sd.periodic, lane);
-      RowSums mo = load_row(sb.occ, rs, j, wpr, sd.periodic, lane), mt = load_row(sb.t1, rs, j, wpr, sd.periodic, lane);
-      RawRow ro = fetch_row(sb.occ, rs + 1, j, wpr, sd.periodic, lane), rt = fetch_row(sb.t1, rs + 1, j, wpr, sd.periodic, lane);
-      for (long long x = rs; x < re; ++x) {
-        const RowSums bo = finish_row(ro, lane);
-        const RowSums bt = finish_row(rt, lane);
-        if (x + 1 < re) {          // next row's loads in flight while this row is evaluated
-          ro = fetch_row(sb.occ, x + 2, j, wpr, sd.periodic, lane);
-          rt = fetch_row(sb.t1, x + 2, j, wpr, sd.periodic, lane);
-        }
-        unsigned int o[4], n[4];
-        add_rows(to, mo, bo, o);
-        add_rows(tt, mt, bt, n);
-        const unsigned int A = mo.c, T = mt.c;
-        // d = o - n  (n <= o per cell, so no final borrow)
-        unsigned int d[4], br;
-        d[0] = o[0] ^ n[0];
-        br = ~o[0] & n[0];
-        d[1] = o[1] ^ n[1] ^ br;
-        br = maj3(~o[1], n[1], br);
-        d[2] = o[2] ^ n[2] ^ br;
-        br = maj3(~o[2], n[2], br);
-        d[3] = o[3] ^ n[3] ^ br;
-        unsigned int same[4];
+      // rolling window of three rows per plane in R[0..2]: at step i the row above is R[i%3], the own
+      // row R[(i+1)%3], and the row below is loaded into R[(i+2)%3]; the loop is unrolled by three
+      // so that the rotation is a renaming, not register moves
+      RowSums Ro[3], Rt[3];
+      Ro[0] = finish_row(fetch_row(sb.occ, rs - 1, lc, wpr), lc);
+      Rt[0] = finish_row(fetch_row(sb.t1, rs - 1, lc, wpr), lc);
+      Ro[1] = finish_row(fetch_row(sb.occ, rs, lc, wpr), lc);
+      Rt[1] = finish_row(fetch_row(sb.t1, rs, lc, wpr), lc);
+      RawRow ro = fetch_row(sb.occ, rs + 1, lc, wpr), rt = fetch_row(sb.t1, rs + 1, lc, wpr);
+      for (long long x0 = rs; x0 < re; x0 += 3) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) same[q] = (T & n[q]) | (~T & d[q]);
-        // one-hot decode of o = 1..8
-        const unsigned int l00 = ~o[1] & ~o[0], l01 = ~o[1] & o[0], l10 = o[1] & ~o[0], l11 = o[1] & o[0];
-        const unsigned int h0 = ~o[3] & ~o[2], h1 = ~o[3] & o[2];
-        unsigned int is[9];
-        is[1] = h0 & l01; is[2] = h0 & l10; is[3] = h0 & l11;
-        is[4] = h1 & l00; is[5] = h1 & l01; is[6] = h1 & l10; is[7] = h1 & l11;
-        is[8] = o[3];
-        // need[o] of every cell as 4 bit-sliced bits, then unsat = agent & (same < need)
-        unsigned int K[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 3; ++i) {
+          const long long x = x0 + i;
+          if (x < re) {
+            const RowSums& to = Ro[i % 3];
+            const RowSums& tt = Rt[i % 3];
+            const RowSums& mo = Ro[(i + 1) % 3];
+            const RowSums& mt = Rt[(i + 1) % 3];
+            Ro[(i + 2) % 3] = finish_row(ro, lc);
+            Rt[(i + 2) % 3] = finish_row(rt, lc);
+            const RowSums& bo = Ro[(i + 2) % 3];
+            const RowSums& bt = Rt[(i + 2) % 3];
+            {                      // next row's loads in flight while this row is evaluated (row re+1 of the
+              const long long xn = x + 2 <= (long long)W ? x + 2 : (long long)W;   // last band is clamped to the halo)
+              ro = fetch_row(sb.occ, xn, lc, wpr);
+              rt = fetch_row(sb.t1, xn, lc, wpr);
+            }
+            unsigned int o[4], n[4];
+            add_rows(to, mo, bo, o);
+            add_rows(tt, mt, bt, n);
+            const unsigned int A = mo.c, T = mt.c;
+            // d = o - n  (n <= o per cell, so no final borrow)
+            unsigned int d[4], br;
+            d[0] = o[0] ^ n[0];
+            br = ~o[0] & n[0];
+            d[1] = o[1] ^ n[1] ^ br;
+            br = maj3(~o[1], n[1], br);
+            d[2] = o[2] ^ n[2] ^ br;
+            br = maj3(~o[2], n[2], br);
+            d[3] = o[3] ^ n[3] ^ br;
+            unsigned int same[4];
 #pragma unroll
-        for (int k = 1; k <= 8; ++k) {
+            for (int q = 0; q < 4; ++q) same[q] = (T & n[q]) | (~T & d[q]);
+            // one-hot decode of o = 1..8
+            const unsigned int l00 = ~o[1] & ~o[0], l01 = ~o[1] & o[0], l10 = o[1] & ~o[0], l11 = o[1] & o[0];
+            const unsigned int h0 = ~o[3] & ~o[2], h1 = ~o[3] & o[2];
+            unsigned int is[9];
+            is[1] = h0 & l01; is[2] = h0 & l10; is[3] = h0 & l11;
+            is[4] = h1 & l00; is[5] = h1 & l01; is[6] = h1 & l10; is[7] = h1 & l11;
+            is[8] = o[3];
+            // need[o] of every cell as 4 bit-sliced bits, then unsat = agent & (same < need)
+            unsigned int K[4] = {0, 0, 0, 0};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) K[q] |= is[k] & sb.need_sel[k][q];
+            for (int k = 1; k <= 8; ++k) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) K[q] |= is[k] & sb.need_sel[k][q];
+            }
+            unsigned int lt = ~same[0] & K[0];
+            lt = lt_step(same[1], K[1], lt);
+            lt = lt_step(same[2], K[2], lt);
+            lt = lt_step(same[3], K[3], lt);
+            const unsigned int unsat = A & lt;
+            sb.umask[x * wpr + lc.j] = unsat;
+            my_unsat += __popc(unsat);
+            my_occ += __popc(A & (o[0] | o[1] | o[2] | o[3]));
+            // segregation numerator: one popcount per distinct weight (840/o) << b
+            {
+              const unsigned int a1 = A & is[1], a2 = A & is[2], a3 = A & is[3], a4 = A & is[4];
+              const unsigned int a5 = A & is[5], a6 = A & is[6], a7 = A & is[7], a8 = A & is[8];
+              seg[0] += __popc((a1 & same[0]) | (a2 & same[1]) | (a4 & same[2]) | (a8 & same[3]));   // 840
+              seg[1] += __popc((a2 & same[0]) | (a4 & same[1]) | (a8 & same[2]));                     // 420
+              seg[2] += __popc((a4 & same[0]) | (a8 & same[1]));                                      // 210
+              seg[3] += __popc(a8 & same[0]);                                                         // 105
+              seg[4] += __popc((a3 & same[0]) | (a6 & same[1]));                                      // 280
+              seg[5] += __popc((a3 & same[1]) | (a6 & same[2]));                                      // 560
+              seg[6] += __popc(a6 & same[0]);                                                         // 140
+              seg[7] += __popc(a5 & same[0]);                                                         // 168
+              seg[8] += __popc(a5 & same[1]);                                                         // 336
+              seg[9] += __popc(a5 & same[2]);                                                         // 672
+              seg[10] += __popc(a7 & same[0]);                                                        // 120
+              seg[11] += __popc(a7 & same[1]);                                                        // 240
+              seg[12] += __popc(a7 & same[2]);                                                        // 480
+            }
+          }
         }
-        unsigned int lt = ~same[0] & K[0];
-        lt = lt_step(same[1], K[1], lt);
-        lt = lt_step(same[2], K[2], lt);
-        lt = lt_step(same[3], K[3], lt);
-        const unsigned int unsat = A & lt;
-        sb.umask[x * wpr + j] = unsat;
-        my_unsat += __popc(unsat);
-        my_occ += __popc(A & (o[0] | o[1] | o[2] | o[3]));
-        // segregation numerator: one popcount per distinct weight (840/o) << b
-        {
-          const unsigned int a1 = A & is[1], a2 = A & is[2], a3 = A & is[3], a4 = A & is[4];
-          const unsigned int a5 = A & is[5], a6 = A & is[6], a7 = A & is[7], a8 = A & is[8];
-          seg[0] += __popc((a1 & same[0]) | (a2 & same[1]) | (a4 & same[2]) | (a8 & same[3]));   // 840
-          seg[1] += __popc((a2 & same[0]) | (a4 & same[1]) | (a8 & same[2]));                     // 420
-          seg[2] += __popc((a4 & same[0]) | (a8 & same[1]));                                      // 210
-          seg[3] += __popc(a8 & same[0]);                                                         // 105
-          seg[4] += __popc((a3 & same[0]) | (a6 & same[1]));                                      // 280
-          seg[5] += __popc((a3 & same[1]) | (a6 & same[2]));                                      // 560
-          seg[6] += __popc(a6 & same[0]);                                                         // 140
-          seg[7] += __popc(a5 & same[0]);                                                         // 168
-          seg[8] += __popc(a5 & same[1]);                                                         // 336
-          seg[9] += __popc(a5 & same[2]);                                                         // 672
-          seg[10] += __popc(a7 & same[0]);                                                        // 120
-          seg[11] += __popc(a7 & same[1]);                                                        // 240
-          seg[12] += __popc(a7 & same[2]);                                                        // 480
-        }
-        to = mo; tt = mt; mo = bo; mt = bt;
       }
     }
     unsigned long long my_num = 0;
