@@ -205,14 +205,18 @@ class EconomyWorkload:
     kernel = "economy_step_kernel"
     l2_note = "no flush: per-step state traffic (3.3 GB) exceeds the 126 MB L2"
 
-    def __init__(self, rank, nh=49_000_000, nf=1_000_000):
-        self.nh, self.nf, self.seed = nh, nf, 42 + rank
+    def __init__(self, rank, nh=49_000_000, nf=1_000_000, world=1, shard=False):
+        self.nh, self.nf, self.seed = nh, nf, 42 + (0 if shard else rank)
+        self.shard = shard
         self.agents = nh + nf
 
     def fresh(self):
         import jaxabm_b200 as jx
         from jaxabm_b200.rules import economy
         m = economy.create_economy_model(self.nh, self.nf, config=jx.ModelConfig(seed=self.seed))
+        if self.shard:
+            from jaxabm_b200 import sharding
+            sharding.shard_model(m)
         m.initialize()
         return m
 
@@ -464,7 +468,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="schelling", choices=sorted(WORKLOADS))
-    ap.add_argument("--shard", action="store_true", help="market: split ONE population over the ranks")
+    ap.add_argument("--shard", action="store_true", help="market / economy: split ONE population over the ranks")
     ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -507,11 +511,13 @@ def main():
         wl = EnsembleWorkload(rank, world)
     elif args.workload == "market":
         wl = MarketWorkload(rank, world=world, shard=args.shard)
+    elif args.workload == "economy":
+        wl = EconomyWorkload(rank, world=world, shard=args.shard)
     else:
         wl = WORKLOADS[args.workload](rank)
     K = args.steps if args.steps is not None else wl.default_steps
     sampler = ClockSampler(local)
-    total_agents = wl.agents * (1 if (args.workload == "market" and args.shard) else world)
+    total_agents = wl.agents * (1 if (args.workload in ("market", "economy") and args.shard) else world)
     if args.workload == "ensemble":
         total_agents = wl.samples_total * wl.n
     extra = {}
@@ -570,7 +576,7 @@ def main():
                 del pm
         # ---- end to end through the public API with host buffers ------------------------------------------
         e2e = None
-        if not args.no_e2e and not (args.workload == "market" and args.shard):
+        if not args.no_e2e and not (args.workload in ("market", "economy") and args.shard):
             del model
             wl.e2e(min(K, 3))                      # warm-up of the same call
             sync_all()
@@ -610,7 +616,7 @@ def main():
     par = "single-gpu"
     if world > 1:
         par = (f"one population sharded over {world} gpus (per-step env partial-sum exchange)"
-               if (args.workload == "market" and args.shard) else
+               if (args.workload in ("market", "economy") and args.shard) else
                (f"replica blocks over {world} gpus" if args.workload == "ensemble" else f"replica-per-gpu x{world}"))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": max_s / K * 1e3, "higher_is_better": True,

@@ -59,8 +59,9 @@ struct Ctrl {
 // world_size flags in its own buffer and folds the rows in rank order -- one kernel does the
 // update, the reduction and the exchange; all ranks fold identical values in identical order.
 constexpr int kMaxPeers = 8;
+constexpr int kXchgRow = 16;        // doubles per exchanged row (>= kAcc and >= the economy's 15 sums)
 struct XchgBuf {
-  double row[2][kMaxPeers][kAcc];
+  double row[2][kMaxPeers][kXchgRow];
   unsigned int flag[2][kMaxPeers];
   unsigned int seq;       // sharded steps completed by this rank since the peers were attached
   unsigned int err;       // set when a peer's flag did not arrive within the spin budget
@@ -194,6 +195,60 @@ template <bool STREAM, class V>
 __device__ __forceinline__ void stv(V* p, V v) {
   if (STREAM) st_stream(p, v);
   else *p = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// in-kernel all-reduce of the totals row over NVLink peer memory (see XchgBuf, common.cuh).
+// Called by every thread of the LAST CTA of a rank's step kernel; tot = this rank's totals
+// (shared memory) on entry, the world totals on exit.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// tot[0..count): this rank's row on entry, the world totals on exit; entries [max_lo, max_hi) are
+// combined with max, the others with +.
+__device__ inline void peer_exchange(const ModelDev& md, double* tot /*smem*/, int count = kAcc, int max_lo = kFSum,
+                                     int max_hi = kFSum + kFMax) {
+  const int W = md.world_size, me = md.rank, tid = threadIdx.x;
+  XchgBuf* mine = md.xpeer[me];
+  const unsigned int seq = mine->seq + 1u;          // same value on every rank (SPMD exchange count)
+  const int par = (int)(seq & 1u);
+  // publish: warp p stores my row into rank p's buffer (remote stores), then the flag (release)
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int p = warp; p < W; p += (int)(blockDim.x >> 5)) {
+    XchgBuf* dst = md.xpeer[p];
+    if (lane < count) dst->row[par][me][lane] = tot[lane];
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) st_release_sys(&dst->flag[par][me], seq);
+  }
+  __syncthreads();
+  // wait for every rank's row of this exchange in MY buffer
+  if (tid < W) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&mine->flag[par][tid]) != seq) {
+      if (clock64() - t0 > (20ll << 30)) { mine->err = 1u; break; }    // ~10 s at 2 GHz: a peer is gone
+    }
+  }
+  __syncthreads();
+  if (tid < count) {
+    const bool is_max = (tid >= max_lo && tid < max_hi);
+    double r = __ldcv(&mine->row[par][0][tid]);
+    for (int p = 1; p < W; ++p) {
+      const double v = __ldcv(&mine->row[par][p][tid]);
+      r = is_max ? fmax(r, v) : r + v;
+    }
+    tot[tid] = r;
+  }
+  __syncthreads();
+  if (tid == 0) mine->seq = seq;
+  __syncthreads();
 }
 
 }  // namespace jxb

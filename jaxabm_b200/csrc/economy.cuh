@@ -443,6 +443,9 @@ __global__ void __launch_bounds__(kThreads) economy_step_kernel(const ModelDev m
     if (lane == 0) s_tot[i] = r;
   }
   __syncthreads();
+  // sharded population: sum the ranks' rows over NVLink peer memory (every rank then runs the same
+  // update_environment on identical totals)
+  if (md.world_size > 1) peer_exchange(md, s_tot, kEcoAcc, 0, 0);
   if (threadIdx.x == 0) {
     md.ctrl->ticket = 0;
     const Key uk = {kp[2 * md.n_types], kp[2 * md.n_types + 1]};
@@ -562,37 +565,43 @@ __global__ void __launch_bounds__(kThreads) gini_accumulate_kernel(const ModelDe
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  __shared__ double s_gt[2];
   if (warp == 0) {
     double a = 0, b = 0;
     for (int i = lane; i < (int)gridDim.x; i += 32) { a += __ldcg(ed.gini_partials + 2 * i); b += __ldcg(ed.gini_partials + 2 * i + 1); }
     a = warp_sum(a); b = warp_sum(b);
-    if (lane == 0) {
-      *ed.ticket2 = 0;
-      float gini = 0.0f;
-      if (hh_type >= 0 && n > 0) {
-        const float income_sum = (float)b, weighted = (float)a;
-        if (income_sum > 1e-6f) {
-          const float nf = (float)md.t[hh_type].gn;
-          gini = (2.0f * weighted) / (nf * income_sum) - (float)(((double)md.t[hh_type].gn + 1.0) / (double)md.t[hh_type].gn);
-        }
+    if (lane == 0) { s_gt[0] = a; s_gt[1] = b; *ed.ticket2 = 0; }
+  }
+  __syncthreads();
+  // sharded population: ranks hold the GLOBAL histogram (all-reduced before the scan), so their
+  // partial rank-weighted sums simply add up
+  if (md.world_size > 1) peer_exchange(md, s_gt, 2, 0, 0);
+  if (tid == 0) {
+    const double a = s_gt[0], b = s_gt[1];
+    float gini = 0.0f;
+    if (hh_type >= 0 && md.t[hh_type].gn > 0) {
+      const float income_sum = (float)b, weighted = (float)a;
+      if (income_sum > 1e-6f) {
+        const float nf = (float)md.t[hh_type].gn;
+        gini = (2.0f * weighted) / (nf * income_sum) - (float)(((double)md.t[hh_type].gn + 1.0) / (double)md.t[hh_type].gn);
       }
-      md.env[EE_GINI] = gini;
-      Ctrl* c = md.ctrl;
-      const long long t = c->time_step + 1;
-      if ((t % md.collect_interval) == 0) {
-        double m[kMaxMetrics];
-#pragma unroll
-        for (int i = 0; i < kMaxMetrics; ++i) m[i] = 0.0;
-        eco_compute_metrics(md.env, gini, m);
-        double* row = md.metrics + (size_t)c->n_recorded * kMaxMetrics;
-#pragma unroll
-        for (int i = 0; i < kMaxMetrics; ++i) row[i] = m[i];
-        md.record_steps[c->n_recorded] = (int)t;
-        c->n_recorded += 1;
-      }
-      c->time_step = t;
-      c->step_in_run += 1;
     }
+    md.env[EE_GINI] = gini;
+    Ctrl* c = md.ctrl;
+    const long long t = c->time_step + 1;
+    if ((t % md.collect_interval) == 0) {
+      double m[kMaxMetrics];
+#pragma unroll
+      for (int i = 0; i < kMaxMetrics; ++i) m[i] = 0.0;
+      eco_compute_metrics(md.env, gini, m);
+      double* row = md.metrics + (size_t)c->n_recorded * kMaxMetrics;
+#pragma unroll
+      for (int i = 0; i < kMaxMetrics; ++i) row[i] = m[i];
+      md.record_steps[c->n_recorded] = (int)t;
+      c->n_recorded += 1;
+    }
+    c->time_step = t;
+    c->step_in_run += 1;
   }
 }
 

@@ -593,7 +593,11 @@ extern "C" int jxb_model_create(jxb_engine* eng, const jxb_model_desc* d, jxb_mo
   }
   if (d->program == JXB_PROGRAM_SIR) m->has_net = true;
   if (d->program == JXB_PROGRAM_ECONOMY) {
-    if (md.world_size > 1) { jxb_model_destroy(m); return fail(JXB_ERR_UNSUPPORTED, "the economy program is not population-sharded (Gini needs a global rank)"); }
+    if (md.world_size > 1 && (md.exchange != 1 || !eng->nccl_comm)) {
+      jxb_model_destroy(m);
+      return fail(JXB_ERR_STATE, "a sharded economy needs BOTH the peer-memory exchange (env partial sums) and an NCCL "
+                                 "communicator (all-reduce of the Gini histogram); attach both");
+    }
     EcoDev& ed = m->eco;
     TRY(dev_alloc(m, &ed.partials, (size_t)std::max(m->step_blocks, 1) * kEcoAcc));
     TRY(dev_alloc(m, &ed.bin_count, (size_t)kGiniBins));
@@ -1107,6 +1111,12 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       }
       if (timed) cudaEventRecord(e1, s);
       const int hh = m->eco_hh;
+      if (hh >= 0 && m->dev.world_size > 1) {
+        // sharded population: the income histogram is the one real bulk exchange of this step (16 MB)
+        int r = g_nccl.AllReduce(m->eco.bin_count, m->eco.bin_count, (size_t)kGiniBins, /*ncclUint32*/ 3, /*ncclSum*/ 0,
+                                 eng->nccl_comm, s);
+        if (r) return fail(JXB_ERR_NCCL, "ncclAllReduce(histogram): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+      }
       if (hh >= 0) {
         gini_scan_sums_kernel<<<kGiniBins / kGiniScanTile, kThreads, 0, s>>>(m->eco.bin_count, m->eco.scan_sums);
         gini_scan_top_kernel<<<1, 1024, 0, s>>>(m->eco.scan_sums, kGiniBins / kGiniScanTile);
@@ -1272,7 +1282,8 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   }
   static const bool use_graph = getenv("JXB_NO_GRAPH") == nullptr;
   const bool persistent = m->desc.program == JXB_PROGRAM_SCHELLING;
-  const bool graphs = use_graph && !persistent && !m->profile && m->dev.exchange != 2 && steps > 0;
+  const bool graphs = use_graph && !persistent && !m->profile && m->dev.exchange != 2 && steps > 0 &&
+                      !(m->has_eco && m->dev.world_size > 1);   // NCCL call on the step path: launch eagerly
   if (graphs) {
     // kernel arguments (the ModelDev snapshot) are baked into a captured graph: rebuild the
     // two cached graphs (1 step, 32 steps) whenever a pointer or the interval changed

@@ -165,7 +165,7 @@ class Model:
             grid = (int(shape[0]), int(shape[1]), bool(self._env_state.get("grid_periodic", False)))
         rank, world = self._shard or (0, 1)
         if world > 1:
-            if program in ("schelling", "sir", "economy"):
+            if program in ("schelling", "sir"):
                 raise UnregisteredRuleError("grid / network programs are not population-sharded; run replicas")
             from .dist import shard_bounds
             for spec in specs:

@@ -39,22 +39,23 @@ def attach_peers() -> None:
     lib = nat.lib()
     use_nccl = os.environ.get("JXB_EXCHANGE", "") == "nccl"
     dev = dist._device_for_backend(td)
-    if use_nccl:
-        ident = np.zeros(128, dtype=np.uint8)
-        if rank == 0:
-            nat.check(lib.jxb_nccl_unique_id(nat.ptr(ident), ident.nbytes))
-        t = torch.from_numpy(ident).to(dev)
-        td.broadcast(t, src=0)
-        ident = t.cpu().numpy()
-        nat.check(lib.jxb_engine_attach_nccl(eng.handle, nat.ptr(ident), ident.nbytes, rank, world))
-    else:
+    # NCCL communicator of the engine: the comparison arm of the scalar exchange (JXB_EXCHANGE=nccl)
+    # and the bulk all-reduce of the economy's Gini histogram
+    ident = np.zeros(128, dtype=np.uint8)
+    if rank == 0:
+        nat.check(lib.jxb_nccl_unique_id(nat.ptr(ident), ident.nbytes))
+    t = torch.from_numpy(ident).to(dev)
+    td.broadcast(t, src=0)
+    ident = np.ascontiguousarray(t.cpu().numpy())
+    nat.check(lib.jxb_engine_attach_nccl(eng.handle, nat.ptr(ident), ident.nbytes, rank, world))
+    if not use_nccl:
         h = np.zeros(64, dtype=np.uint8)
         nat.check(lib.jxb_engine_p2p_export(eng.handle, nat.ptr(h), h.nbytes))
         parts = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
         td.all_gather(parts, torch.from_numpy(h).to(dev))
         table = np.ascontiguousarray(np.stack([p.cpu().numpy() for p in parts], axis=0))
         nat.check(lib.jxb_engine_p2p_attach(eng.handle, nat.ptr(table), 64, rank, world))
-        td.barrier()
+    td.barrier()
     _attached = True
 
 

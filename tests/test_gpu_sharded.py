@@ -55,6 +55,26 @@ def worker():
         cap_ref = ref.agent_collections["producers"].states["capital"][lo:hi]
         cap_sh = sh.agent_collections["producers"].states["capital"]
         assert np.allclose(cap_ref, cap_sh, rtol=1e-4), "capital trajectories diverged"
+    # ---- C4-B economy: 15 env partial sums through the in-kernel exchange + NCCL all-reduce of the
+    # Gini histogram; per-agent draws use global indices, so booleans are exact and floats agree to
+    # the fold-order rounding
+    if os.environ.get("JXB_EXCHANGE", "p2p") != "nccl":
+        from jaxabm_b200.rules import economy
+        nh, nf = 60_001, 1_503
+        for mode in (0, 1):
+            ref = economy.create_economy_model(nh, nf, config=jx.ModelConfig(seed=5, rng_mode=mode))
+            r0 = ref.run(steps=3)
+            sh = economy.create_economy_model(nh, nf, config=jx.ModelConfig(seed=5, rng_mode=mode))
+            sharding.shard_model(sh)
+            r1 = sh.run(steps=3)
+            for k in ("gdp", "wage_rate", "interest_rate", "unemployment", "inequality"):
+                a, b = np.array(r0[k], dtype=np.float64), np.array(r1[k], dtype=np.float64)
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-6), ("economy", mode, k, a, b)
+            lo, hi = dist.shard_bounds(nh, rank, world)
+            assert np.array_equal(ref.agent_collections["households"].states["employed"][lo:hi],
+                                  sh.agent_collections["households"].states["employed"])
+            assert np.allclose(ref.agent_collections["households"].states["cash"][lo:hi],
+                               sh.agent_collections["households"].states["cash"], rtol=1e-4)
     td.barrier()
     if rank == 0:
         print(f"sharded market OK on {world} GPUs (exchange={os.environ.get('JXB_EXCHANGE', 'p2p')})")
