@@ -281,3 +281,21 @@ def test_calibrator_evaluate_robust(mode):
     assert loss == pytest.approx(float(want), rel=1e-4)
     best = cal.calibrate(verbose=False)
     assert set(best) == {"propensity_to_consume"} and len(cal.loss_history) == 2
+
+
+def test_saltelli_sobol_through_the_ensemble_kernel(mode):
+    """True Sobol indices (SensitivityAnalysis.run_saltelli) on the growth model: avg_value depends on
+    growth_rate only, price_gap on adjustment_rate only -- one ensemble launch for all (P+2)n runs."""
+    from jaxabm_b200.analysis import SensitivityAnalysis
+    from jaxabm_b200.rules import growth
+
+    def factory(params=None, config=None):
+        config.rng_mode = mode
+        return growth.create_test_model(params=params, config=config, num_agents=256, initial_value=1.0)
+
+    sa = SensitivityAnalysis(factory, {"growth_rate": (0.05, 0.2), "adjustment_rate": (0.05, 0.3)},
+                             ["avg_value", "price_gap"], num_samples=8, seed=1)
+    idx = sa.run_saltelli(num_base=256, steps=20)
+    assert sa.last_device_seconds > 0.0
+    assert idx["avg_value"]["ST"]["growth_rate"] > 0.9 and idx["avg_value"]["ST"]["adjustment_rate"] < 0.02
+    assert idx["price_gap"]["ST"]["adjustment_rate"] > 0.9 and idx["price_gap"]["ST"]["growth_rate"] < 0.02

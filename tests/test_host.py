@@ -200,3 +200,23 @@ def test_synthetic_generators():
     assert np.array_equal(e, synthetic.scale_free_edges(5000, 4, 1))
     t, p = schelling.initial_layout(32, 700, 0.5, 3)
     assert len({(a, b) for a, b in p.tolist()}) == 700 and t.sum() == 350
+
+
+def test_saltelli_estimators_on_an_analytic_model():
+    """run_saltelli with a duck-typed host model (the ensemble factory protocol of analysis.py:128-145):
+    y = a + 2 b has S1 = ST = (1/5, 4/5) for independent uniform a, b on [0, 1]."""
+    from jaxabm_b200.analysis import SensitivityAnalysis
+
+    class Lin:
+        def __init__(self, params, config):
+            self.p = params
+
+        def run(self, steps=None):
+            return {"y": [self.p["a"] + 2.0 * self.p["b"]]}
+
+    sa = SensitivityAnalysis(lambda params, config: Lin(params, config), {"a": (0.0, 1.0), "b": (0.0, 1.0)}, ["y"],
+                             num_samples=16, seed=3)
+    idx = sa.run_saltelli(num_base=512)
+    assert sa.saltelli_design.shape == (512 * 4, 2)
+    assert idx["y"]["S1"]["a"] == pytest.approx(0.2, abs=0.04) and idx["y"]["S1"]["b"] == pytest.approx(0.8, abs=0.06)
+    assert idx["y"]["ST"]["a"] == pytest.approx(0.2, abs=0.03) and idx["y"]["ST"]["b"] == pytest.approx(0.8, abs=0.05)
