@@ -202,15 +202,14 @@ __device__ __forceinline__ void sir_tail(const SirDev& sv, const ModelDev& md, i
     ctrl->sir_count[0] = c[0]; ctrl->sir_count[1] = c[1]; ctrl->sir_count[2] = c[2];
     if (with_deg) {
       ctrl->sir_deg[0] = c[3]; ctrl->sir_deg[1] = c[4];
-      // cost model fitted on B200 at C3, in units of adjacency entries:
-      //   push ~ 7.5 n + 2.3 min(dI, n) + 0.95 max(dI - n, 0) + 0.3 dS   (L2 reductions + transition pass
-      //                                                                    + draws of the exposed S rows)
-      //   pull ~ 13 n + 0.8 dS                                            (bitmap gathers over the S rows)
+      // cost model fitted on B200 at C3, microseconds with dS, dI in millions of entries, n = 10 M:
+      //   push ~ 75 + 23 min(dI, 10) + 9.5 max(dI - 10, 0) + 3.0 dS   (L2 reductions + transition pass + the
+      //                                                                draws of the exposed S rows)
+      //   pull ~ 145 + 2.9 dS + 1.0 dI                                 (bitmap gathers over the S rows)
+      // => pull wins once the infected rows hold more than ~2 % of n*10 entries: 220 dI + dS > 50 n
       if (sv.auto_mode) {
         const long long nn = md.t[0].n, dS = c[3], dI = c[4];
-        const long long lhs = 11 * nn + 10 * dS;
-        const long long rhs = 46 * (dI < nn ? dI : nn) + 19 * (dI > nn ? dI - nn : 0);
-        ctrl->sir_mode_next = lhs < rhs ? 0 : 1;
+        ctrl->sir_mode_next = (220 * dI + dS > 50 * nn) ? 0 : 1;
       }
     }
     const long long tsn = ctrl->time_step + 1;
@@ -397,8 +396,8 @@ __global__ void __launch_bounds__(kThreads) sir_transition_kernel(const SirDev s
 // ---------------------------------------------------------------------------------------
 // pull over the SUSCEPTIBLE rows only (fused step, no atomics): one warp per 32-row group, lane =
 // row.  Only susceptible agents need their infected-neighbour count, so only their adjacency is
-// read: lanes stride each susceptible row, one bitmap gather per entry, the row's count is the
-// popcount of the hit ballot.  Transitions, the new bitmap word and the partial counts follow in
+// read: each lane walks its own susceptible row (long rows: all 32 lanes stride the row), one
+// bitmap gather per entry.  Transitions, the new bitmap word and the partial counts follow in
 // the same warp.  Cost is proportional to the susceptible rows' adjacency -- the complement of the
 // push kernel's; the step's tail picks whichever is cheaper for the next step.
 // ---------------------------------------------------------------------------------------
@@ -455,41 +454,20 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
       cnt = (unsigned int)warp_sum((int)cnt);
       if (lane == b) k = cnt;
     }
-    unsigned int todo = __ballot_sync(0xffffffffu, active && s == 0 && len > 0 && len <= 256u);
-    // four susceptible rows at a time, 8 lanes striding each (most susceptible rows are short): four
-    // independent gather chains per warp instead of one
-    const int sub = lane >> 3, sl = lane & 7;
-    while (todo) {
-      int rb[4];
-      unsigned int rest = todo;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        rb[q] = rest ? __ffs(rest) - 1 : -1;
-        rest &= rest - 1;                          // (0 & 0xffffffff stays 0)
+    // every other susceptible row: its own lane walks it (consecutive lanes own consecutive CSR
+    // segments, so a warp's loads fall into a few adjacent lines that L1 keeps across the
+    // iterations); two entries per iteration for memory-level parallelism
+    if (active && s == 0 && len > 0 && len <= 256u) {
+      const int* cp = sv.col + lo;
+      unsigned int e = 0;
+      for (; e + 2 <= len; e += 2) {
+        const int c0 = __ldg(cp + e), c1 = __ldg(cp + e + 1);
+        const unsigned int w0 = __ldg(inf + (c0 >> 5)), w1 = __ldg(inf + (c1 >> 5));
+        k += ((w0 >> (c0 & 31)) & 1u) + ((w1 >> (c1 & 31)) & 1u);
       }
-      todo = rest;
-      const int myb = sub == 0 ? rb[0] : (sub == 1 ? rb[1] : (sub == 2 ? rb[2] : rb[3]));
-      const unsigned int slo = __shfl_sync(0xffffffffu, lo, myb & 31);
-      unsigned int slen = __shfl_sync(0xffffffffu, len, myb & 31);
-      if (myb < 0) slen = 0;
-      unsigned int maxlen = slen;
-      maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 8));
-      maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, 16));
-      unsigned int cnt = 0;
-      for (unsigned int e0 = 0; e0 < maxlen; e0 += 8) {
-        const unsigned int e = e0 + sl;
-        unsigned int bit = 0;
-        if (e < slen) {
-          const int c = __ldcs(sv.col + slo + e);
-          bit = (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;
-        }
-        const unsigned int bal = __ballot_sync(0xffffffffu, bit);
-        cnt += __popc((bal >> (8 * sub)) & 0xFFu);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const unsigned int cq = __shfl_sync(0xffffffffu, cnt, q * 8);
-        if (lane == rb[q]) k = cq;
+      if (e < len) {
+        const int c0 = __ldg(cp + e);
+        k += (__ldg(inf + (c0 >> 5)) >> (c0 & 31)) & 1u;
       }
     }
     int sn = s;
