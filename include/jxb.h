@@ -176,6 +176,12 @@ int jxb_model_set_profile(jxb_model*, int enable);
 int jxb_model_profile(jxb_model*, double* dominant_kernel_seconds, int64_t* launches,
                       const char** kernel_name);
 
+/* Page-locked host blocks for results (AgentCollection.states reads): a download into such a block
+ * runs at PCIe speed without a staging copy.  Freed blocks are cached by size inside the library
+ * (cudaMallocHost of a 100 MB block costs tens of milliseconds).                                 */
+int jxb_host_alloc(size_t bytes, void** out);
+int jxb_host_free(void* p);
+
 /* ---- ensembles (jaxabm/analysis.py:113-157 and :434-476) --------------------------- */
 /* R independent replicas of `desc`; replica r overrides params by
  * param_slots/params[r][n_swept] (slot < 100: model param index; slot >= 100:

@@ -89,6 +89,8 @@ SIGNATURES = {
     "jxb_engine_attach_nccl": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int]),
     "jxb_engine_p2p_export": (C.c_int, [_P, _P, C.c_size_t]),
     "jxb_engine_p2p_attach": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int]),
+    "jxb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "jxb_host_free": (C.c_int, [_P]),
     "jxb_prng_split": (C.c_int, [C.c_int, _P, C.c_int, _P]),
     "jxb_prng_bits": (C.c_int, [C.c_int, _P, C.c_int64, _P]),
     "jxb_prng_uniform": (C.c_int, [C.c_int, _P, C.c_int64, C.c_float, C.c_float, _P]),
@@ -121,6 +123,38 @@ def check(rc: int) -> None:
 
 def ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class _PinnedBlock:
+    """Owner of one page-locked host block; NumPy arrays made from it keep it alive as their base."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        check(lib().jxb_host_alloc(max(int(nbytes), 1), C.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+        self.__array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr.value, False),
+                                    "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().jxb_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+PINNED_MIN_BYTES = 1 << 20
+
+
+def result_empty(shape, dtype) -> np.ndarray:
+    """Uninitialised host array for a device read-back: page-locked (cached by the library) when it
+    is at least 1 MB, plain NumPy memory otherwise."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    if n < PINNED_MIN_BYTES:
+        return np.empty(shape, dtype=dtype)
+    return np.asarray(_PinnedBlock(n)).view(dtype).reshape(shape)
 
 
 _engine = None

@@ -1375,6 +1375,56 @@ extern "C" int jxb_collection_update(jxb_model* m, int type, uint32_t k0, uint32
 }
 
 // ---------------------------------------------------------------------------------------
+// page-locked host blocks (cached by size)
+// ---------------------------------------------------------------------------------------
+#include <map>
+#include <mutex>
+static std::mutex g_host_mu;
+static std::multimap<size_t, void*> g_host_free;        // size -> cached block
+static std::map<void*, size_t> g_host_live;             // block -> size
+static size_t g_host_cached = 0;
+
+extern "C" int jxb_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(JXB_ERR_INVALID, "out is NULL");
+  bytes = (std::max<size_t>(bytes, 64) + 4095) & ~(size_t)4095;
+  std::lock_guard<std::mutex> lk(g_host_mu);
+  auto it = g_host_free.lower_bound(bytes);
+  if (it != g_host_free.end() && it->first <= bytes + bytes / 8 + (1u << 16)) {
+    *out = it->second;
+    g_host_live[it->second] = it->first;
+    g_host_cached -= it->first;
+    g_host_free.erase(it);
+    return JXB_OK;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    for (auto& kv : g_host_free) cudaFreeHost(kv.second);
+    g_host_free.clear();
+    g_host_cached = 0;
+    e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) return fail(JXB_ERR_CUDA, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+  }
+  g_host_live[p] = bytes;
+  *out = p;
+  return JXB_OK;
+}
+
+extern "C" int jxb_host_free(void* p) {
+  if (!p) return JXB_OK;
+  std::lock_guard<std::mutex> lk(g_host_mu);
+  auto it = g_host_live.find(p);
+  if (it == g_host_live.end()) return fail(JXB_ERR_INVALID, "not a block of jxb_host_alloc");
+  const size_t bytes = it->second;
+  g_host_live.erase(it);
+  if (g_host_cached + bytes > ((size_t)4 << 30)) { cudaFreeHost(p); return JXB_OK; }
+  g_host_free.emplace(bytes, p);
+  g_host_cached += bytes;
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // ensembles
 // ---------------------------------------------------------------------------------------
 extern "C" int jxb_ensemble_run(jxb_engine* eng, const jxb_model_desc* d, int R, int n_swept,

@@ -110,7 +110,7 @@ class DeviceModel:
         """Copy one state column to the host (into ``out`` -- e.g. a pinned buffer -- if given)."""
         shape, dt = self._shape(t, f)
         if out is None:
-            out = np.empty(shape, dtype=dt)
+            out = nat.result_empty(shape, dt)
         elif out.shape != shape or out.dtype != dt or not out.flags.c_contiguous:
             raise ValueError(f"out must be a C-contiguous {dt} array of shape {shape}")
         nat.check(self._lib.jxb_model_download(self.handle, t, f, nat.ptr(out), out.nbytes))
