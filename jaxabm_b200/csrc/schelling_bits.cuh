@@ -62,8 +62,8 @@ struct LaneCols {
   unsigned int lmask, rmask;
 };
 
-__device__ __forceinline__ RawRow fetch_row(const unsigned int* plane, long long x, const LaneCols& lc, int wpr) {
-  const unsigned int* row = plane + x * wpr;
+__device__ __forceinline__ RawRow fetch_row(const unsigned int* plane, int x, const LaneCols& lc, int wpr) {
+  const unsigned int* row = plane + x * wpr;       // 32-bit index math: (W + 2) * wpr words < 2^31
   RawRow r;
   r.c = __ldcg(row + lc.j);
   r.l = __ldcg(row + lc.jl);
@@ -123,16 +123,16 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
   const TypeDev& t = md.t[0];
   const int W = sd.W, H = sd.H, wpr = sb.wpr, spr = sb.spr, nsub = kWarps / spr;
   // rows owned by this CTA, and by this warp's sub-band inside them
-  const long long R0 = (long long)W * b / B, R1 = (long long)W * (b + 1) / B;
+  const int R0 = (int)((long long)W * b / B), R1 = (int)((long long)W * (b + 1) / B);
   const int strip = warp % spr, sub = warp / spr;
-  const long long rs = R0 + (R1 - R0) * sub / nsub, re = R0 + (R1 - R0) * (sub + 1) / nsub;
+  const int rs = R0 + (R1 - R0) * sub / nsub, re = R0 + (R1 - R0) * (sub + 1) / nsub;
   LaneCols lc;
   lc.j = strip * 32 + lane;
   lc.jl = lc.j > 0 ? lc.j - 1 : (sd.periodic ? wpr - 1 : lc.j);
   lc.jr = lc.j + 1 < wpr ? lc.j + 1 : (sd.periodic ? 0 : lc.j);
   lc.lmask = (lc.j > 0 || sd.periodic) ? 0xFFFFFFFFu : 0u;
   lc.rmask = (lc.j + 1 < wpr || sd.periodic) ? 0xFFFFFFFFu : 0u;
-  const long long wbeg = R0 * wpr, wend = R1 * wpr;       // this CTA's words, in cell order
+  const long long wbeg = (long long)R0 * wpr, wend = (long long)R1 * wpr;       // this CTA's words, in cell order
   const unsigned int e = sd.n_empty;
   const int step0 = ctrl->step_in_run;
   BlkPart* blk_part = (BlkPart*)sd.blk_part;
@@ -160,10 +160,10 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
       Ro[1] = finish_row(fetch_row(sb.occ, rs, lc, wpr), lc);
       Rt[1] = finish_row(fetch_row(sb.t1, rs, lc, wpr), lc);
       RawRow ro = fetch_row(sb.occ, rs + 1, lc, wpr), rt = fetch_row(sb.t1, rs + 1, lc, wpr);
-      for (long long x0 = rs; x0 < re; x0 += 3) {
+      for (int x0 = rs; x0 < re; x0 += 3) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          const long long x = x0 + i;
+          const int x = x0 + i;
           if (x < re) {
             const RowSums& to = Ro[i % 3];
             const RowSums& tt = Rt[i % 3];
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
             const RowSums& bo = Ro[(i + 2) % 3];
             const RowSums& bt = Rt[(i + 2) % 3];
             {                      // next row's loads in flight while this row is evaluated (row re+1 of the
-              const long long xn = x + 2 <= (long long)W ? x + 2 : (long long)W;   // last band is clamped to the halo)
+              const int xn = min(x + 2, W);   // last band is clamped to the halo)
               ro = fetch_row(sb.occ, xn, lc, wpr);
               rt = fetch_row(sb.t1, xn, lc, wpr);
             }
