@@ -125,36 +125,55 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
-// Block-level reduction of an Acc into `out[kAcc]` doubles (valid in thread 0).
-// Fixed shuffle tree + fixed warp order: bit-reproducible for a fixed launch shape.
+// Block-level reduction of an Acc into `out[kAcc]` doubles (valid in threads < kAcc).
+// Fixed shuffle tree + fixed warp order: bit-reproducible for a fixed launch shape.  `mask` selects
+// the accumulator slots the program actually consumes (the others are left at 0 / -inf): in the
+// ensemble kernel this reduction runs once per step, and a warp shuffle costs a cycle per warp.
 __device__ __forceinline__ void block_reduce_acc(const Acc& a, double* smem /*[warps][kAcc]*/,
-                                                 double* out) {
+                                                 double* out, unsigned int mask = 0xFFFFFFFFu) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
   for (int i = 0; i < kFSum; ++i) {
+    if (!((mask >> i) & 1u)) continue;
     float v = warp_sum(a.fsum[i]);
     if (lane == 0) smem[warp * kAcc + i] = (double)v;
   }
 #pragma unroll
   for (int i = 0; i < kFMax; ++i) {
+    if (!((mask >> (kFSum + i)) & 1u)) continue;
     float v = warp_max(a.fmax[i]);
     if (lane == 0) smem[warp * kAcc + kFSum + i] = (double)v;
   }
 #pragma unroll
   for (int i = 0; i < kISum; ++i) {
+    if (!((mask >> (kFSum + kFMax + i)) & 1u)) continue;
     int v = warp_sum(a.isum[i]);
     if (lane == 0) smem[warp * kAcc + kFSum + kFMax + i] = (double)v;
   }
   __syncthreads();
   if (threadIdx.x < kAcc) {
     const int i = threadIdx.x;
-    double r = smem[i];
     const bool is_max = (i >= kFSum && i < kFSum + kFMax);
-    for (int w = 1; w < nw; ++w) {
-      double v = smem[w * kAcc + i];
-      r = is_max ? fmax(r, v) : r + v;
+    double r = is_max ? -1.0 / 0.0 : 0.0;
+    if ((mask >> i) & 1u) {
+      r = smem[i];
+      for (int w = 1; w < nw; ++w) {
+        double v = smem[w * kAcc + i];
+        r = is_max ? fmax(r, v) : r + v;
+      }
     }
     out[i] = r;
+  }
+}
+
+// accumulator slots consumed by each program's env/metrics tail (csrc/rules.cuh::program_tail)
+__device__ __host__ __forceinline__ unsigned int program_acc_mask(int program) {
+  switch (program) {
+    case JXB_PROGRAM_RANDOM_WALK: return 1u | (1u << kFSum);        // sum and max of the distances
+    case JXB_PROGRAM_MARKET: return 0xFu;                            // consumption, production, utility, profit
+    case JXB_PROGRAM_GROWTH: return 1u;
+    case JXB_PROGRAM_COUNTER: return 1u;
+    default: return 0u;
   }
 }
 

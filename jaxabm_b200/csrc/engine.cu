@@ -1456,23 +1456,44 @@ extern "C" int jxb_ensemble_run(jxb_engine* eng, const jxb_model_desc* d, int R,
   }
   for (int k = 0; k < JXB_MAX_PARAMS; ++k) ed.mp[k] = k < d->n_params ? d->params[k] : 0.0;
   for (int k = 0; k < prog->n_env; ++k) ed.env0[k] = env_init ? env_init[k] : prog->env[k].dflt;
-  size_t off = 0;
-  for (int i = 0; i < d->n_types; ++i) {
-    fill_type_dev(d->types[i], ed.t[i]);
-    const RuleSpec* rs = find_rule(d->types[i].rule);
-    for (int f = 0; f < rs->nf; ++f) {
-      ed.t[i].f[f] = (void*)off;
-      size_t bytes = (size_t)(d->types[i].n_agents + 8) * rs->f[f].width * dtype_size(rs->f[f].dtype);
-      off += (bytes + 15) / 16 * 16;
+  // state layout of ONE CTA for a cluster of `cs` CTAs per replica: every collection is sliced by
+  // agent index (slice = multiple of 4 agents); pick the smallest cluster whose slice fits shared memory
+  auto layout = [&](int cs, long long* slice) -> size_t {
+    size_t off = 0;
+    for (int i = 0; i < d->n_types; ++i) {
+      const long long n = d->types[i].n_agents;
+      slice[i] = cs == 1 ? n : ((n + cs - 1) / cs + 3) / 4 * 4;
+      const RuleSpec* rs = find_rule(d->types[i].rule);
+      for (int f = 0; f < rs->nf; ++f) {
+        ed.t[i].f[f] = (void*)off;
+        size_t bytes = (size_t)(slice[i] + 8) * rs->f[f].width * dtype_size(rs->f[f].dtype);
+        off += (bytes + 15) / 16 * 16;
+      }
     }
+    return off;
+  };
+  for (int i = 0; i < d->n_types; ++i) fill_type_dev(d->types[i], ed.t[i]);
+  static const int max_cluster = getenv("JXB_ENS_MAX_CLUSTER") ? atoi(getenv("JXB_ENS_MAX_CLUSTER")) : 8;
+  int cs = 1;
+  size_t off = layout(1, ed.slice);
+  if (off > kEnsSmemBudget) {
+    for (int c = 2; c <= std::min(max_cluster, (int)kMaxPeers); c *= 2) {
+      long long sl[JXB_MAX_TYPES];
+      const size_t o = layout(c, sl);
+      if (o <= kEnsSmemBudget) { cs = c; off = o; for (int i = 0; i < d->n_types; ++i) ed.slice[i] = sl[i]; break; }
+    }
+    if (cs == 1) off = layout(1, ed.slice);     // nothing fits: per-CTA L2 scratch slot
   }
+  ed.cluster = cs;
   ed.state_bytes = off;
   ed.use_smem = off <= kEnsSmemBudget;
   int grid;
   size_t dyn = 0;
   if (ed.use_smem) {
     dyn = off;
-    grid = std::min(R, eng->sms * (off <= kEnsSmemBudget / 2 ? 2 : 1));
+    const int per_sm = (cs == 1 && off <= kEnsSmemBudget / 2) ? 2 : 1;
+    const int clusters = std::max(1, std::min(R, eng->sms * per_sm / cs));
+    grid = clusters * cs;
   } else {
     // keep all live replica slots inside L2 (~64 MB) when possible, at least one CTA per SM
     long long fit = (long long)((64ull << 20) / off);
@@ -1495,8 +1516,22 @@ extern "C" int jxb_ensemble_run(jxb_engine* eng, const jxb_model_desc* d, int R,
     else ECK(cudaFuncSetAttribute(ensemble_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   }
   ECK(cudaEventRecord(eng->ev0, s));
-  if (part) ensemble_kernel<1><<<grid, kEnsThreads, dyn, s>>>(ed);
-  else ensemble_kernel<0><<<grid, kEnsThreads, dyn, s>>>(ed);
+  if (cs > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kEnsThreads);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (part) ECK(cudaLaunchKernelEx(&cfg, ensemble_kernel<1>, ed));
+    else ECK(cudaLaunchKernelEx(&cfg, ensemble_kernel<0>, ed));
+  } else {
+    if (part) ensemble_kernel<1><<<grid, kEnsThreads, dyn, s>>>(ed);
+    else ensemble_kernel<0><<<grid, kEnsThreads, dyn, s>>>(ed);
+  }
   eng->launches++;
   ECK(cudaGetLastError());
   ECK(cudaEventRecord(eng->ev1, s));
