@@ -861,18 +861,47 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
   if (n_edges < 0 || n_edges >= (1ll << 31)) return fail(JXB_ERR_UNSUPPORTED, "edge count out of range");
   CK(cudaSetDevice(m->eng->device));
   const long long n = m->desc.types[0].n_agents;
-  // bin by source (counting sort); neighbour order inside a row is irrelevant to the rule
+  // bin by source on the device (counting sort: degree histogram, exclusive scan, cursor scatter);
+  // neighbour order inside a row is irrelevant to the rule
+  cudaStream_t st = m->eng->stream;
+  int rc;
+  unsigned int* d_rp = nullptr; int* d_col = nullptr;
+  if ((rc = dev_alloc(m, &d_rp, (size_t)n + 2))) return rc;
+  if ((rc = dev_alloc(m, &d_col, (size_t)std::max<int64_t>(n_edges, 1)))) return rc;
   std::vector<unsigned int> row_ptr((size_t)n + 1, 0);
-  for (int64_t e = 0; e < n_edges; ++e) {
-    const int s = edges[2 * e], d = edges[2 * e + 1];
-    if (s < 0 || s >= n || d < 0 || d >= n) return fail(JXB_ERR_INVALID, "edge %lld references agent outside [0,%lld)", (long long)e, n);
-    row_ptr[(size_t)s + 1]++;
-  }
-  for (long long i = 0; i < n; ++i) row_ptr[i + 1] += row_ptr[i];
-  std::vector<int> col((size_t)std::max<int64_t>(n_edges, 1));
   {
-    std::vector<unsigned int> cur(row_ptr.begin(), row_ptr.end() - 1);
-    for (int64_t e = 0; e < n_edges; ++e) col[cur[edges[2 * e]]++] = edges[2 * e + 1];
+    void* d_edges = nullptr; void* d_cursor = nullptr; void* d_sums = nullptr; void* d_flag = nullptr;
+    const int ntiles = (int)((n + kScanTile - 1) / kScanTile);
+    const size_t eb = (size_t)std::max<int64_t>(n_edges, 1) * 8, cb = ((size_t)n + 2) * 4, sb = ((size_t)ntiles + 2) * 4;
+    auto release = [&]() {
+      cudaStreamSynchronize(st);
+      pool_free(m->eng, d_edges, eb); pool_free(m->eng, d_cursor, cb); pool_free(m->eng, d_sums, sb); pool_free(m->eng, d_flag, 16);
+    };
+#define NCK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { release(); return fail(JXB_ERR_CUDA, \
+    "%s failed: %s", #call, cudaGetErrorString(_e)); } } while (0)
+    NCK(pool_alloc(m->eng, &d_edges, eb));
+    NCK(pool_alloc(m->eng, &d_cursor, cb));
+    NCK(pool_alloc(m->eng, &d_sums, sb));
+    NCK(pool_alloc(m->eng, &d_flag, 16));
+    NCK(cudaMemsetAsync(d_rp, 0, cb, st));
+    NCK(cudaMemsetAsync(d_flag, 0, 16, st));
+    if (n_edges) NCK(cudaMemcpyAsync(d_edges, edges, (size_t)n_edges * 8, cudaMemcpyHostToDevice, st));
+    const int g = m->eng->sms * 8;
+    csr_count_kernel<<<g, kThreads, 0, st>>>((const int2*)d_edges, n_edges, n, d_rp, (int*)d_flag);
+    scan_tile_sums_kernel<<<ntiles, kThreads, 0, st>>>(d_rp, n, (unsigned int*)d_sums);
+    scan_sums_kernel<<<1, 1024, 0, st>>>((unsigned int*)d_sums, ntiles);
+    scan_apply_kernel<<<ntiles, kThreads, 0, st>>>(d_rp, n, (const unsigned int*)d_sums, d_rp, (unsigned int*)d_cursor);
+    csr_fill_kernel<<<g, kThreads, 0, st>>>((const int2*)d_edges, n_edges, (unsigned int*)d_cursor, d_col);
+    m->eng->launches += 5;
+    int bad = 0;
+    NCK(cudaMemcpyAsync(&bad, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NCK(cudaMemcpyAsync(row_ptr.data(), d_rp, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    NCK(cudaStreamSynchronize(st));
+    NCK(cudaGetLastError());
+#undef NCK
+    release();
+    if (bad) return fail(JXB_ERR_INVALID, "an edge references an agent outside [0,%lld)", n);
+    if (row_ptr[n] != (unsigned int)n_edges) return fail(JXB_ERR_CUDA, "CSR build lost edges (%u of %lld)", row_ptr[n], (long long)n_edges);
   }
   // row blocks: whole 32-row groups, greedy up to kSirTile entries / 1024 rows
   std::vector<int> rb;
@@ -891,10 +920,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     r = end;
   }
   SirDev& sv = m->sv;
-  unsigned int* d_rp; int* d_col; int* d_rb; float* d_esc;
-  int rc;
-  if ((rc = dev_alloc(m, &d_rp, (size_t)n + 1))) return rc;
-  if ((rc = dev_alloc(m, &d_col, col.size()))) return rc;
+  int* d_rb; float* d_esc;
   if ((rc = dev_alloc(m, &d_rb, rb.size()))) return rc;
   if ((rc = dev_alloc(m, &d_esc, kSirKCap + 1))) return rc;
   for (int b = 0; b < 2; ++b) {
@@ -903,8 +929,6 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     cudaMemset(sv.state8[b], 0, (size_t)n + 32);
     cudaMemset(sv.infbits[b], 0, ((size_t)(n + 31) / 32 + 1) * 4);
   }
-  CK(cudaMemcpy(d_rp, row_ptr.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_col, col.data(), (size_t)n_edges * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_rb, rb.data(), rb.size() * 4, cudaMemcpyHostToDevice));
   {
     // escape[k] = (1-beta)^k as a float32 product chain (DESIGN.md "SIR rule")

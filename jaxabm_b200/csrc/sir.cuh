@@ -501,6 +501,105 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
   sir_tail(sv, md, (int)gridDim.x, true);
 }
 
+// ---------------------------------------------------------------------------------------
+// CSR construction on the device: env 'network_edges' int32[E,2] (jaxabm/agentpy.py:557) -> row_ptr /
+// col by counting sort on the source: degree histogram (L2 reductions), exclusive prefix scan,
+// scatter through per-row cursors.  The order of a row's neighbours is whatever the atomics make
+// it; every formulation above only counts, so results do not depend on it.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) csr_count_kernel(const int2* edges, long long n_edges, long long n,
+                                                             unsigned int* deg, int* err) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (long long)gridDim.x * blockDim.x) {
+    const int2 ed = __ldcs(edges + e);
+    if (ed.x < 0 || ed.x >= n || ed.y < 0 || ed.y >= n) { atomicExch(err, 1); continue; }
+    atomicAdd(deg + ed.x, 1u);
+  }
+}
+
+constexpr int kScanTile = kThreads * 16;
+
+// tile sums of v[0..n)
+__global__ void __launch_bounds__(kThreads) scan_tile_sums_kernel(const unsigned int* v, long long n, unsigned int* sums) {
+  __shared__ unsigned int s_w[kThreads / 32];
+  const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * 16;
+  unsigned int s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += base + j < n ? v[base + j] : 0u;
+  s = (unsigned int)warp_sum((int)s);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int tot = 0;
+    for (int w = 0; w < kThreads / 32; ++w) tot += s_w[w];
+    sums[blockIdx.x] = tot;
+  }
+}
+
+// in-place exclusive scan of the tile sums by ONE CTA (any count), total written to sums[count]
+__global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* sums, int count) {
+  __shared__ unsigned int s_w[32];
+  __shared__ unsigned int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < count; c0 += 1024) {
+    const int i = c0 + tid;
+    const unsigned int v = i < count ? sums[i] : 0u;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    unsigned int off = s_carry;
+    for (int w = 0; w < warp; ++w) off += s_w[w];
+    if (i < count) sums[i] = off + inc - v;
+    __syncthreads();
+    if (tid == 1023) s_carry = off + inc;
+    __syncthreads();
+  }
+  if (tid == 0) sums[count] = s_carry;
+}
+
+// out[i] = exclusive prefix of v (out may alias v); also copies the prefix into `copy` when given;
+// out[n] = total
+__global__ void __launch_bounds__(kThreads) scan_apply_kernel(const unsigned int* v, long long n, const unsigned int* sums,
+                                                              unsigned int* out, unsigned int* copy) {
+  __shared__ unsigned int s_w[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long base = (long long)blockIdx.x * kScanTile + (long long)tid * 16;
+  unsigned int c[16];
+  unsigned int s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { c[j] = base + j < n ? v[base + j] : 0u; s += c[j]; }
+  unsigned int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  unsigned int run = sums[blockIdx.x] + inc - s;
+  for (int w = 0; w < warp; ++w) run += s_w[w];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (base + j < n) { out[base + j] = run; if (copy) copy[base + j] = run; }
+    run += c[j];
+  }
+  if (blockIdx.x == gridDim.x - 1 && tid == kThreads - 1) out[n] = sums[gridDim.x];
+}
+
+__global__ void __launch_bounds__(kThreads) csr_fill_kernel(const int2* edges, long long n_edges, unsigned int* cursor, int* col) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (long long)gridDim.x * blockDim.x) {
+    const int2 ed = __ldcs(edges + e);
+    const unsigned int pos = atomicAdd(cursor + ed.x, 1u);
+    col[pos] = ed.y;
+  }
+}
+
 // API column 'state' int32[N]  <->  packed int8 + infected bitmap
 __global__ void sir_pack_kernel(const int* state, signed char* s8, unsigned int* bits, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
