@@ -12,7 +12,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/jxb.h"
@@ -1401,8 +1404,6 @@ extern "C" int jxb_collection_update(jxb_model* m, int type, uint32_t k0, uint32
 // ---------------------------------------------------------------------------------------
 // page-locked host blocks (cached by size)
 // ---------------------------------------------------------------------------------------
-#include <map>
-#include <mutex>
 static std::mutex g_host_mu;
 static std::multimap<size_t, void*> g_host_free;        // size -> cached block
 static std::map<void*, size_t> g_host_live;             // block -> size
