@@ -58,7 +58,8 @@ enum {
   JXB_RULE_SCHELLING = 8,       /* layout examples/models/schelling_model.py:26-31   */
   JXB_RULE_SIR = 9,             /* layout jaxabm/agentpy.py:557,574-582              */
   JXB_RULE_HOUSEHOLD = 10,      /* examples/models/advanced_economic_model.py:57-296 */
-  JXB_RULE_CONSUMER_FIRM = 11   /* examples/models/advanced_economic_model.py:299-581*/
+  JXB_RULE_CONSUMER_FIRM = 11,  /* examples/models/advanced_economic_model.py:299-581*/
+  JXB_RULE_TRACED = 12          /* user AgentType traced into a generated kernel (jxb_model_create_traced) */
 };
 
 /* Registered model programs: the update_state_fn + metrics_fn pair that runs inside
@@ -71,7 +72,8 @@ enum {
   JXB_PROGRAM_COUNTER = 4,      /* tests/unit/test_model.py:20-40                    */
   JXB_PROGRAM_SCHELLING = 5,    /* builder-authored rule, DESIGN.md                  */
   JXB_PROGRAM_SIR = 6,          /* builder-authored rule, DESIGN.md                  */
-  JXB_PROGRAM_ECONOMY = 7       /* examples/models/advanced_economic_model.py:1461-1905 */
+  JXB_PROGRAM_ECONOMY = 7,      /* examples/models/advanced_economic_model.py:1461-1905 */
+  JXB_PROGRAM_TRACED = 8        /* user update_state_fn / metrics_fn traced into the generated kernel's tail */
 };
 
 #define JXB_MAX_TYPES 4
@@ -128,6 +130,36 @@ int jxb_model_n_env(jxb_model*, int* out);
 int jxb_model_env_info(jxb_model*, int slot, const char** name, int* dtype);
 int jxb_model_n_metrics(jxb_model*, int* out);
 int jxb_model_metric_info(jxb_model*, int metric, const char** name, int* dtype);
+
+/* Traced models (jaxabm/agent.py:168-177 evaluates arbitrary user Python under jax.vmap; here the
+ * host shim traces it -- jaxabm_b200/trace.py -- into a CUDA source compiled for sm_100a).  The
+ * spec gives the state / env / metric layout the trace found and the two launcher entry points of
+ * the generated library:
+ *   int launch_init(const void* model_dev, int type, unsigned k0, unsigned k1, int rng_mode, int blocks, void* stream)
+ *   int launch_step(const void* model_dev, int rng_mode, int variant, void* stream)
+ * desc->program must be JXB_PROGRAM_TRACED and every collection's rule JXB_RULE_TRACED.  variant 0 is
+ * used for the first step after construction (env entries still have their Python types), the
+ * last variant for every later step.                                                        */
+#define JXB_MAX_FIELDS 20
+#define JXB_MAX_ENV 32
+typedef struct {
+  int32_t n_fields[JXB_MAX_TYPES];
+  const char* field_names[JXB_MAX_TYPES][JXB_MAX_FIELDS];
+  int32_t field_dtypes[JXB_MAX_TYPES][JXB_MAX_FIELDS];     /* 0 f32, 1 i32, 2 bool */
+  int32_t n_env;
+  const char* env_names[JXB_MAX_ENV];
+  int32_t env_dtypes[JXB_MAX_ENV];                         /* 0 f32, 1 i32, 2 bool, 3 f64 (Python float) */
+  double env_init[JXB_MAX_ENV];
+  int32_t n_metrics;
+  const char* metric_names[JXB_MAX_METRICS];
+  int32_t metric_dtypes[JXB_MAX_METRICS];
+  int32_t has_env_fn;
+  int32_t n_acc;                                           /* reduction slots per CTA partial row */
+  int32_t n_variants;
+  void* launch_init;
+  void* launch_step;
+} jxb_traced_spec;
+int jxb_model_create_traced(jxb_engine*, const jxb_model_desc*, const jxb_traced_spec*, jxb_model** out);
 
 /* AgentCollection._states access (jaxabm/agent.py:179-196), host <-> HBM.           */
 int jxb_model_upload(jxb_model*, int type, int field, const void* host, size_t bytes);

@@ -21,8 +21,8 @@ MAX_METRICS = 32
 RNG_LEGACY, RNG_PARTITIONABLE = 0, 1
 
 RULE = dict(random_walker=1, scaled_walker=2, consumer=3, producer=4, growth=5, increment=6,
-            wealth=7, schelling=8, sir=9, household=10, consumer_firm=11)
-PROGRAM = dict(none=0, random_walk=1, market=2, growth=3, counter=4, schelling=5, sir=6, economy=7)
+            wealth=7, schelling=8, sir=9, household=10, consumer_firm=11, traced=12)
+PROGRAM = dict(none=0, random_walk=1, market=2, growth=3, counter=4, schelling=5, sir=6, economy=7, traced=8)
 
 DTYPES = {0: np.float32, 1: np.int32, 2: np.bool_, 3: np.float64}
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     "jxb_engine_sm_count": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "jxb_engine_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "jxb_model_create": (C.c_int, [_P, C.POINTER(ModelDesc), C.POINTER(_P)]),
+    "jxb_model_create_traced": (C.c_int, [_P, C.POINTER(ModelDesc), _P, C.POINTER(_P)]),
     "jxb_model_destroy": (C.c_int, [_P]),
     "jxb_model_n_fields": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "jxb_model_field_info": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int),

@@ -221,6 +221,11 @@ struct jxb_model {
   // over the susceptible rows only; 3 "auto" (default) = direction-optimising, the step's tail picks
   // push or pull_s for the next step on the device
   int sir_mode = 3; int sir_tblocks = 0;
+  // traced model (jxb_model_create_traced): layout owned by the model, kernels in a generated library
+  bool traced = false; RuleSpec traced_rules[JXB_MAX_TYPES]; ProgramSpec traced_prog;
+  std::vector<std::string> traced_names; int traced_acc = 0, traced_variants = 1; bool traced_started = false;
+  int (*traced_init)(const void*, int, unsigned int, unsigned int, int, int, void*) = nullptr;
+  int (*traced_step)(const void*, int, int, void*) = nullptr;
   // economy (C4-B)
   bool has_eco = false; EcoDev eco{}; int eco_hh = -1;
   // graphs: cached executable graphs of `chunk` consecutive steps
@@ -412,19 +417,21 @@ static bool program_accepts(int program, int rule) {
   return false;
 }
 
-static int validate_desc(const jxb_model_desc* d) {
+static int validate_desc(const jxb_model_desc* d, bool traced = false) {
   if (!d) return fail(JXB_ERR_INVALID, "desc is NULL");
-  if (!find_program(d->program)) return fail(JXB_ERR_INVALID, "unknown program %d", d->program);
+  if (traced != (d->program == JXB_PROGRAM_TRACED))
+    return fail(JXB_ERR_INVALID, "JXB_PROGRAM_TRACED models are created with jxb_model_create_traced (and only those)");
+  if (!traced && !find_program(d->program)) return fail(JXB_ERR_INVALID, "unknown program %d", d->program);
   if (d->rng_mode != JXB_RNG_LEGACY && d->rng_mode != JXB_RNG_PARTITIONABLE)
     return fail(JXB_ERR_INVALID, "unknown rng_mode %d", d->rng_mode);
   if (d->n_types < 1 || d->n_types > JXB_MAX_TYPES)
     return fail(JXB_ERR_INVALID, "No agent collections added to model");   // model.py:125-126
   for (int i = 0; i < d->n_types; ++i) {
     const jxb_type_desc& t = d->types[i];
-    if (!find_rule(t.rule))
+    if (traced ? t.rule != JXB_RULE_TRACED : !find_rule(t.rule))
       return fail(JXB_ERR_INVALID, "collection %d: rule %d is not a registered agent rule", i, t.rule);
     if (t.n_agents <= 0) return fail(JXB_ERR_INVALID, "num_agents must be a positive integer");
-    if (!program_accepts(d->program, t.rule))
+    if (!traced && !program_accepts(d->program, t.rule))
       return fail(JXB_ERR_INVALID, "program %d does not accept rule %d", d->program, t.rule);
     if (t.global_n < t.n_agents || t.global_offset < 0 || t.global_offset + t.n_agents > t.global_n)
       return fail(JXB_ERR_INVALID, "collection %d: bad shard [%lld,+%lld) of %lld", i,
@@ -451,15 +458,51 @@ static void fill_type_dev(const jxb_type_desc& t, TypeDev& td) {
 
 static int plan_step_blocks(jxb_model* m);
 
+static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_traced_spec* ts, jxb_model** out);
+
 extern "C" int jxb_model_create(jxb_engine* eng, const jxb_model_desc* d, jxb_model** out) {
+  return model_create(eng, d, nullptr, out);
+}
+
+extern "C" int jxb_model_create_traced(jxb_engine* eng, const jxb_model_desc* d, const jxb_traced_spec* ts, jxb_model** out) {
+  if (!ts || !ts->launch_init || !ts->launch_step) return fail(JXB_ERR_INVALID, "traced spec / launchers missing");
+  if (ts->n_env < 0 || ts->n_env > kMaxEnv || ts->n_metrics < 0 || ts->n_metrics > kMaxMetrics || ts->n_acc < 1 ||
+      ts->n_acc > 64 || ts->n_variants < 1)
+    return fail(JXB_ERR_INVALID, "traced spec out of range (<= %d env entries, <= %d metrics, <= 64 reductions)", kMaxEnv, kMaxMetrics);
+  return model_create(eng, d, ts, out);
+}
+
+static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_traced_spec* ts, jxb_model** out) {
   if (!eng || !out) return fail(JXB_ERR_INVALID, "null argument");
-  int rc = validate_desc(d);
+  int rc = validate_desc(d, ts != nullptr);
   if (rc) return rc;
   CK(cudaSetDevice(eng->device));
   jxb_model* m = new jxb_model();
   m->eng = eng;
   m->desc = *d;
-  m->prog = find_program(d->program);
+  m->prog = ts ? nullptr : find_program(d->program);
+  if (ts) {
+    // the model owns its layout tables (names are copied: the caller's strings need not outlive the call)
+    m->traced = true;
+    m->traced_names.reserve(JXB_MAX_TYPES * JXB_MAX_FIELDS + kMaxEnv + kMaxMetrics);
+    auto keep = [&](const char* sname) { m->traced_names.emplace_back(sname ? sname : ""); return m->traced_names.back().c_str(); };
+    for (int i = 0; i < d->n_types; ++i) {
+      RuleSpec& r = m->traced_rules[i];
+      r.rule = JXB_RULE_TRACED;
+      r.nf = ts->n_fields[i];
+      if (r.nf < 1 || r.nf > kMaxFields) { delete m; return fail(JXB_ERR_INVALID, "collection %d: 1..%d fields", i, kMaxFields); }
+      for (int f = 0; f < r.nf; ++f) r.f[f] = FieldSpec{keep(ts->field_names[i][f]), ts->field_dtypes[i][f], 1};
+    }
+    ProgramSpec& p = m->traced_prog;
+    p.program = JXB_PROGRAM_TRACED; p.has_env_fn = ts->has_env_fn; p.n_env = ts->n_env; p.n_metrics = ts->n_metrics;
+    for (int k = 0; k < ts->n_env; ++k) p.env[k] = SlotSpec{keep(ts->env_names[k]), ts->env_dtypes[k], ts->env_init[k]};
+    for (int k = 0; k < ts->n_metrics; ++k) p.metrics[k] = SlotSpec{keep(ts->metric_names[k]), ts->metric_dtypes[k], 0.0};
+    m->prog = &p;
+    m->traced_acc = ts->n_acc;
+    m->traced_variants = ts->n_variants;
+    *(void**)&m->traced_init = ts->launch_init;
+    *(void**)&m->traced_step = ts->launch_step;
+  }
   ModelDev& md = m->dev;
   memset(&md, 0, sizeof(md));
   md.n_types = d->n_types;
@@ -491,7 +534,7 @@ extern "C" int jxb_model_create(jxb_engine* eng, const jxb_model_desc* d, jxb_mo
 #define TRY(x) do { rc = (x); if (rc) { jxb_model_destroy(m); return rc; } } while (0)
   for (int i = 0; i < d->n_types; ++i) {
     const jxb_type_desc& t = d->types[i];
-    m->rules[i] = find_rule(t.rule);
+    m->rules[i] = ts ? &m->traced_rules[i] : find_rule(t.rule);
     fill_type_dev(t, md.t[i]);
     for (int f = 0; f < m->rules[i]->nf; ++f) {
       const FieldSpec& fs = m->rules[i]->f[f];
@@ -516,7 +559,7 @@ extern "C" int jxb_model_create(jxb_engine* eng, const jxb_model_desc* d, jxb_mo
   cudaMemset(md.ctrl, 0, sizeof(Ctrl));
   TRY(dev_alloc(m, &md.allreduce_buf, kAcc));
   TRY(plan_step_blocks(m));
-  TRY(dev_alloc(m, &md.partials, (size_t)std::max(m->step_blocks, 1) * kAcc));
+  TRY(dev_alloc(m, &md.partials, (size_t)std::max(m->step_blocks, 1) * std::max(kAcc, m->traced_acc)));
 
   if (d->program == JXB_PROGRAM_SCHELLING) {
     SchellingDev& sd = m->sd;
@@ -1002,6 +1045,13 @@ static int sir_sync_to_api(jxb_model* m) {
 static int launch_init(jxb_model* m, int type, Key key) {
   const TypeDev& t = m->dev.t[type];
   int blocks = (int)std::min<long long>((t.n + 255) / 256, (long long)m->eng->sms * 16);
+  if (m->traced) {
+    const int r = m->traced_init(&m->dev, type, key.a, key.b, m->desc.rng_mode, blocks, (void*)m->eng->stream);
+    m->eng->launches++;
+    if (r) return fail(JXB_ERR_CUDA, "traced init kernel launch failed (%d)", r);
+    m->collections_ready[type] = true;
+    return JXB_OK;
+  }
   if (m->desc.rng_mode == JXB_RNG_PARTITIONABLE)
     init_kernel<1><<<blocks, 256, 0, m->eng->stream>>>(t, key);
   else
@@ -1122,6 +1172,15 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       eng->launches += 1;
       break;
     }
+    case JXB_PROGRAM_TRACED: {
+      if (timed) cudaEventRecord(e0, s);
+      const int variant = m->traced_started ? m->traced_variants - 1 : 0;
+      const int r = m->traced_step(&m->dev, m->desc.rng_mode, variant, (void*)s);
+      if (timed) cudaEventRecord(e1, s);
+      eng->launches += 1;
+      if (r) return fail(JXB_ERR_CUDA, "traced step kernel launch failed (%d)", r);
+      break;
+    }
     case JXB_PROGRAM_ECONOMY: {
       if (timed) cudaEventRecord(e0, s);
       for (int ti = 0; ti < m->desc.n_types; ++ti) {
@@ -1235,6 +1294,7 @@ extern "C" int jxb_model_profile(jxb_model* m, double* seconds, int64_t* launche
     switch (m->desc.program) {
       case JXB_PROGRAM_SCHELLING: *name = m->sch_bits ? "schelling_bits_kernel" : "schelling_run_kernel"; break;
       case JXB_PROGRAM_ECONOMY: *name = "economy_step_kernel"; break;
+      case JXB_PROGRAM_TRACED: *name = "jxc_step_kernel (traced)"; break;
       case JXB_PROGRAM_SIR:
         *name = m->sir_mode == 0 ? "sir_step_kernel" : (m->sir_mode == 1 ? "sir_push_kernel+sir_transition_kernel"
                 : (m->sir_mode == 2 ? "sir_pull_s_kernel" : "sir_push_kernel+sir_transition_kernel|sir_pull_s_kernel"));
@@ -1310,7 +1370,8 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   static const bool use_graph = getenv("JXB_NO_GRAPH") == nullptr;
   const bool persistent = m->desc.program == JXB_PROGRAM_SCHELLING;
   const bool graphs = use_graph && !persistent && !m->profile && m->dev.exchange != 2 && steps > 0 &&
-                      !(m->has_eco && m->dev.world_size > 1);   // NCCL call on the step path: launch eagerly
+                      !(m->has_eco && m->dev.world_size > 1) &&  // NCCL call on the step path: launch eagerly
+                      !(m->traced && !m->traced_started);        // first step of a traced model uses variant 0
   if (graphs) {
     // kernel arguments (the ModelDev snapshot) are baked into a captured graph: rebuild the
     // two cached graphs (1 step, 32 steps) whenever a pointer or the interval changed
@@ -1342,6 +1403,7 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
     for (int t = 0; t < steps; ++t) {
       int rc = enqueue_step(m, s, m->profile);
       if (rc) return rc;
+      m->traced_started = true;
     }
   }
   CK(cudaEventRecord(eng->ev1, s));
@@ -1384,8 +1446,8 @@ extern "C" int jxb_collection_update(jxb_model* m, int type, uint32_t k0, uint32
   NEED(m); NEED_TYPE(m, type);
   if (!m->collections_ready[type])
     return fail(JXB_ERR_STATE, "Agent collection not initialized. Call init() first.");   // agent.py:150-151
-  if (m->has_grid || m->has_net || m->has_eco)
-    return fail(JXB_ERR_UNSUPPORTED, "grid / network / economy collections step through Model.step only");
+  if (m->has_grid || m->has_net || m->has_eco || m->traced)
+    return fail(JXB_ERR_UNSUPPORTED, "grid / network / economy / traced collections step through Model.step only");
   CK(cudaSetDevice(m->eng->device));
   const TypeDev& t = m->dev.t[type];
   const int blocks = (int)std::max<long long>(1, std::min<long long>((t.n / kVec + kThreads - 1) / kThreads,

@@ -49,12 +49,17 @@ def make_desc(program: str, types: Sequence[TypeSpec], params: Sequence[float] =
 
 
 class DeviceModel:
-    def __init__(self, desc: nat.ModelDesc, engine: Optional[nat.Engine] = None):
+    def __init__(self, desc: nat.ModelDesc, engine: Optional[nat.Engine] = None, traced_spec=None, keep=None):
         self.engine = engine or nat.engine()
         self.desc = desc
         self.handle = C.c_void_p()
         self._lib = nat.lib()
-        nat.check(self._lib.jxb_model_create(self.engine.handle, C.byref(desc), C.byref(self.handle)))
+        self._keep = keep                 # the generated library of a traced model must outlive the handle
+        if traced_spec is not None:
+            nat.check(self._lib.jxb_model_create_traced(self.engine.handle, C.byref(desc), C.byref(traced_spec),
+                                                        C.byref(self.handle)))
+        else:
+            nat.check(self._lib.jxb_model_create(self.engine.handle, C.byref(desc), C.byref(self.handle)))
         self.n_types = desc.n_types
         self.fields: List[List[Tuple[str, np.dtype, int]]] = []
         for t in range(self.n_types):

@@ -123,9 +123,45 @@ class Model:
         return state
 
     # ---- initialisation --------------------------------------------------------------------
+    def _needs_tracing(self) -> bool:
+        """True when the agent types / model functions are plain user Python (no registered kernel)."""
+        regs = [getattr(c.agent_type, "jxb_rule", None) is not None for c in self._agent_collections.values()]
+        fns = [getattr(f, "jxb_program", None) is not None for f in (self._update_state_fn, self._metrics_fn)
+               if f is not None]
+        if all(regs) and all(fns):
+            return False
+        if any(regs) or any(fns):
+            raise UnregisteredRuleError(
+                "registered kernels and traced user rules cannot be mixed in one model: either every agent type / "
+                "model function is a registered one (jaxabm_b200.rules) or all of them are plain Python to be traced")
+        return True
+
+    def _initialize_traced(self) -> None:
+        """User Python -> generated sm_100a step kernel (jaxabm_b200/trace.py, jit.py)."""
+        from . import jit
+        if self._shard:
+            raise UnregisteredRuleError("traced models are not population-sharded yet")
+        spec, lib, variants, src = jit.build(self)
+        tm = variants[-1]
+        from .device import TypeSpec
+        specs = [TypeSpec("traced", t["n"]) for t in tm.types]
+        desc = make_desc("traced", specs, [], rng_mode=self.config.rng_mode)
+        self._dev = DeviceModel(desc, traced_spec=spec, keep=(lib, spec))
+        self._program = "traced"
+        self._traced_source = src
+        keys = jrandom.split(self._rng, len(self._agent_collections) + 1, desc.rng_mode)
+        self._dev.init(self._rng)
+        self._rng = keys[0]
+        for i, c in enumerate(self._agent_collections.values()):
+            c._attach(self._dev, i, self.config, keys[i + 1])
+        self._is_initialized = True
+        self._state = {"env": self._env_state.copy()}
+
     def initialize(self) -> None:                                           # model.py:118-144
         if not self._agent_collections:
             raise ValueError("No agent collections added to model")
+        if self._needs_tracing():
+            return self._initialize_traced()
         program = program_of(self._update_state_fn, self._metrics_fn)
         specs = [c.type_spec() for c in self._agent_collections.values()]
         wanted = PROGRAM_COLLECTIONS.get(program)

@@ -11,7 +11,12 @@ import numpy as np
 
 from . import _native as nat
 
-__all__ = ["PRNGKey", "split", "bits", "uniform", "randint", "permutation", "threefry2x32"]
+__all__ = ["PRNGKey", "split", "bits", "uniform", "normal", "randint", "permutation", "threefry2x32"]
+
+
+def _traced(key) -> bool:
+    from .trace import TrKey
+    return isinstance(key, TrKey)
 
 
 def _mode(mode):
@@ -37,6 +42,9 @@ def threefry2x32(key, ctr) -> np.ndarray:
 
 
 def split(key, num: int = 2, mode=None) -> np.ndarray:
+    if _traced(key):                      # inside a traced rule: symbolic children (jaxabm_b200/trace.py)
+        from .trace import key_split
+        return key_split(key, num)
     out = np.zeros((num, 2), dtype=np.uint32)
     nat.check(nat.lib().jxb_prng_split(_mode(mode), nat.ptr(_key(key)), int(num), nat.ptr(out)))
     return out
@@ -50,7 +58,18 @@ def bits(key, shape=(), mode=None) -> np.ndarray:
     return out.reshape(shape)
 
 
+def normal(key, shape=(), mode=None):
+    """``jax.random.normal`` -- traced rules only (host code of this package never draws normals)."""
+    if _traced(key):
+        from .trace import key_normal
+        return key_normal(key, shape)
+    raise NotImplementedError("random.normal is available inside traced rules only")
+
+
 def uniform(key, shape=(), minval=0.0, maxval=1.0, mode=None) -> np.ndarray:
+    if _traced(key):
+        from .trace import key_uniform
+        return key_uniform(key, shape, minval, maxval)
     shape = (shape,) if isinstance(shape, int) else tuple(shape)
     n = int(np.prod(shape)) if shape else 1
     out = np.zeros(n, dtype=np.float32)

@@ -1,0 +1,893 @@
+"""Rule tracer: arbitrary user ``AgentType.update`` / ``update_state_fn`` / ``metrics_fn`` bodies ->
+one fused sm_100a step kernel.
+
+The reference evaluates user Python under ``jax.vmap`` (``jaxabm/agent.py:168-177``): JAX traces the
+body into an expression graph and XLA compiles it.  This module does the same without JAX: the
+body is run ONCE on symbolic values (:class:`Tr`) that record every operation with JAX's
+x64-disabled dtype rules (weak Python scalars, ``bool < int32 < float32``), and the recorded graph is
+emitted as CUDA C++ -- the per-agent update of every collection, the reductions that the model
+functions ask for (``jnp.sum / mean / max / min`` over agent columns or expressions of them), and
+the scalar env / metrics tail -- in the same single-launch shape as the hand-written
+``step_kernel`` (``csrc/rules.cuh``).  ``nvcc`` compiles it for sm_100a into an in-tree shared
+library that ``libjxb`` calls through two launcher entry points.
+
+What can be traced: scalar (width-1) float32 / int32 / bool state fields; ``+ - * / ** //``-free
+arithmetic, comparisons, ``& | ~``, ``where / minimum / maximum / clip / abs / sqrt / exp / log /
+log1p / power / astype``; ``random.split / uniform / normal`` on the per-agent key and on the
+update key; reads of ``model_state['env'][...]`` and ``model_state['time_step']``.  Python control
+flow on traced values raises, exactly as it does under JAX.  Anything else raises
+:class:`TraceError` -- there is still no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+import struct
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+F32, I32, BOOL, WF, WI = "f32", "i32", "bool", "wf64", "wi32"   # WF / WI: weak Python float / int scalars
+_RANK = {BOOL: 0, WI: 1, I32: 1, WF: 2, F32: 2}
+
+
+class TraceError(TypeError):
+    """The rule uses something the tracer cannot turn into a kernel."""
+
+
+_counter = [0]
+
+
+def _next_id() -> int:
+    _counter[0] += 1
+    return _counter[0]
+
+
+class Tr:
+    """A traced value: an operation, its operands, a dtype and a scope ('a' per agent, 's' scalar)."""
+
+    __array_priority__ = 1000
+    __slots__ = ("op", "args", "dtype", "scope", "id", "attr")
+
+    def __init__(self, op: str, args: tuple, dtype: str, scope: str, attr: Any = None):
+        self.op, self.args, self.dtype, self.scope, self.attr = op, args, dtype, scope, attr
+        self.id = _next_id()
+
+    # -- Python protocol -------------------------------------------------------------------
+    def __bool__(self):
+        raise TraceError("the truth value of a traced array is not available at trace time (use jnp.where), "
+                         "as under jax.vmap")
+
+    def __float__(self):
+        raise TraceError("float() of a traced value is not available at trace time")
+
+    __int__ = __float__
+
+    def __repr__(self):
+        return f"Tr<{self.op}:{self.dtype}:{self.scope}#{self.id}>"
+
+    @property
+    def shape(self):
+        return ()
+
+    def astype(self, dt):
+        return astype(self, dt)
+
+    # arithmetic
+    def __add__(self, o): return binary("add", self, o)
+    def __radd__(self, o): return binary("add", o, self)
+    def __sub__(self, o): return binary("sub", self, o)
+    def __rsub__(self, o): return binary("sub", o, self)
+    def __mul__(self, o): return binary("mul", self, o)
+    def __rmul__(self, o): return binary("mul", o, self)
+    def __truediv__(self, o): return binary("div", self, o)
+    def __rtruediv__(self, o): return binary("div", o, self)
+    def __pow__(self, o): return power(self, o)
+    def __rpow__(self, o): return power(o, self)
+    def __neg__(self): return unary("neg", self)
+    def __pos__(self): return self
+    def __abs__(self): return unary("abs", self)
+    # comparisons
+    def __lt__(self, o): return compare("lt", self, o)
+    def __le__(self, o): return compare("le", self, o)
+    def __gt__(self, o): return compare("gt", self, o)
+    def __ge__(self, o): return compare("ge", self, o)
+    def __eq__(self, o): return compare("eq", self, o)      # noqa: E711
+    def __ne__(self, o): return compare("ne", self, o)
+    __hash__ = object.__hash__
+    # logic
+    def __and__(self, o): return logical("and", self, o)
+    def __rand__(self, o): return logical("and", o, self)
+    def __or__(self, o): return logical("or", self, o)
+    def __ror__(self, o): return logical("or", o, self)
+    def __xor__(self, o): return logical("xor", self, o)
+    def __invert__(self): return unary("not", self)
+
+
+class TrKey:
+    """A traced PRNG key: the per-agent key, the update key, or a child of ``split``."""
+    __slots__ = ("kind", "parent", "index", "num", "id")
+
+    def __init__(self, kind: str, parent: Optional["TrKey"] = None, index: int = 0, num: int = 0):
+        self.kind, self.parent, self.index, self.num = kind, parent, index, num
+        self.id = _next_id()
+
+    @property
+    def scope(self):
+        k = self
+        while k.parent is not None:
+            k = k.parent
+        return "a" if k.kind == "agent" else "s"
+
+
+# ---------------------------------------------------------------------------------------------
+# constructors
+# ---------------------------------------------------------------------------------------------
+def _const(v) -> Tr:
+    if isinstance(v, Tr):
+        return v
+    if isinstance(v, (bool, np.bool_)):
+        return Tr("const", (), BOOL, "s", bool(v))
+    if isinstance(v, (int, np.integer)):
+        if isinstance(v, np.integer):
+            return Tr("const", (), I32, "s", int(v))
+        return Tr("const", (), WI, "s", int(v))
+    if isinstance(v, (float, np.floating)):
+        if isinstance(v, np.float32):
+            return Tr("const", (), F32, "s", float(v))
+        return Tr("const", (), WF, "s", float(v))
+    if isinstance(v, np.ndarray) and v.ndim == 0:
+        return _const(v[()])
+    raise TraceError(f"cannot trace a value of type {type(v).__name__} (only scalars and scalar state fields)")
+
+
+def _scope(*xs: Tr) -> str:
+    return "a" if any(x.scope == "a" for x in xs) else "s"
+
+
+def _promote(a: Tr, b: Tr) -> str:
+    """JAX's x64-disabled result dtype of a binary arithmetic op (weak scalars adopt the other side)."""
+    da, db = a.dtype, b.dtype
+    wa, wb = da in (WF, WI), db in (WF, WI)
+    if wa and wb:
+        return WF if WF in (da, db) else WI
+    if wa or wb:
+        weak, strong = (da, db) if wa else (db, da)
+        if strong == F32:
+            return F32
+        if strong == I32:
+            return F32 if weak == WF else I32
+        return F32 if weak == WF else I32                      # bool (op) python scalar
+    if F32 in (da, db):
+        return F32
+    if I32 in (da, db):
+        return I32
+    return BOOL
+
+
+def _fold2(op: str, a: Tr, b: Tr):
+    """Python-scalar (op) Python-scalar is evaluated by Python in double precision, as in the reference."""
+    if a.op == "const" and b.op == "const" and a.dtype in (WF, WI) and b.dtype in (WF, WI):
+        x, y = a.attr, b.attr
+        if op == "div":
+            return None if y == 0 else _const(x / y)
+        if op in ("add", "sub", "mul"):
+            return _const(x + y if op == "add" else (x - y if op == "sub" else x * y))
+    return None
+
+
+def binary(op: str, a, b) -> Tr:
+    a, b = _const(a), _const(b)
+    f = _fold2(op, a, b)
+    if f is not None:
+        return f
+    dt = _promote(a, b)
+    if op == "div":
+        dt = WF if dt in (WI, WF) else F32                     # true division
+    if dt == BOOL:
+        dt = I32 if op in ("add", "sub", "mul") else dt
+    return Tr(op, (a, b), dt, _scope(a, b))
+
+
+def unary(op: str, a) -> Tr:
+    a = _const(a)
+    if op == "not":
+        if a.dtype != BOOL:
+            raise TraceError("~ is only traced on boolean values")
+        return Tr("not", (a,), BOOL, a.scope)
+    if a.op == "const" and a.dtype in (WF, WI):
+        return _const(-a.attr if op == "neg" else abs(a.attr))
+    return Tr(op, (a,), I32 if a.dtype == BOOL else a.dtype, a.scope)
+
+
+def compare(op: str, a, b) -> Tr:
+    a, b = _const(a), _const(b)
+    return Tr(op, (a, b), BOOL, _scope(a, b), _promote(a, b))
+
+
+def logical(op: str, a, b) -> Tr:
+    a, b = _const(a), _const(b)
+    if a.dtype != BOOL or b.dtype != BOOL:
+        raise TraceError("& | ^ are only traced on boolean values")
+    return Tr(op, (a, b), BOOL, _scope(a, b))
+
+
+def power(a, b) -> Tr:
+    a, b = _const(a), _const(b)
+    if b.op == "const" and b.dtype == WI and 0 <= b.attr <= 4:          # integer_pow: repeated multiplication
+        if b.attr == 0:
+            return binary("mul", a, 0) + 1
+        r = a
+        for _ in range(b.attr - 1):
+            r = binary("mul", r, a)
+        return r
+    if a.op == "const" and b.op == "const" and a.dtype in (WF, WI) and b.dtype in (WF, WI):
+        return _const(float(a.attr) ** float(b.attr))
+    dt = _promote(a, b)
+    return Tr("pow", (a, b), WF if dt in (WF, WI) else F32, _scope(a, b))
+
+
+def _math(op: str, a) -> Tr:
+    a = _const(a)
+    return Tr(op, (a,), F32, a.scope)
+
+
+def where(c, a, b) -> Tr:
+    c, a, b = _const(c), _const(a), _const(b)
+    if c.dtype != BOOL:
+        c = compare("ne", c, 0)
+    return Tr("where", (c, a, b), _promote(a, b), _scope(c, a, b))
+
+
+def minimum(a, b) -> Tr:
+    a, b = _const(a), _const(b)
+    return Tr("min", (a, b), _promote(a, b), _scope(a, b))
+
+
+def maximum(a, b) -> Tr:
+    a, b = _const(a), _const(b)
+    return Tr("max", (a, b), _promote(a, b), _scope(a, b))
+
+
+def clip(x, lo, hi) -> Tr:
+    return minimum(maximum(x, lo), hi)
+
+
+def astype(a, dt) -> Tr:
+    a = _const(a)
+    name = getattr(dt, "__name__", str(dt))
+    if dt in (float, np.float32, np.float64) or name in ("float", "float32", "float64"):
+        target = F32
+    elif dt in (int, np.int32, np.int64) or name in ("int", "int32", "int64"):
+        target = I32
+    elif dt in (bool, np.bool_) or name in ("bool", "bool_"):
+        target = BOOL
+    else:
+        raise TraceError(f"astype({dt!r}) is not traced")
+    if a.dtype == target:
+        return a
+    return Tr("cast", (a,), target, a.scope)
+
+
+class Column:
+    """``agent_states[name][field]`` inside update_state_fn / metrics_fn: the POST-update column of a
+    collection, usable inside ``jnp.sum / mean / max / min`` (alone or inside an expression)."""
+
+    def __init__(self, type_index: int, field_index: int, dtype: str, n: int):
+        self.tr = Tr("field", (), dtype, "a", (type_index, field_index))
+        self.n = n
+
+
+def _reduce(kind: str, x) -> Tr:
+    if isinstance(x, Column):
+        x = x.tr
+    x = _const(x)
+    if x.scope != "a":
+        return x
+    types = _types_of(x)
+    if len(types) != 1:
+        raise TraceError("a reduction must range over exactly one agent collection")
+    dt = x.dtype
+    if kind == "mean":
+        dt = F32
+    elif dt == BOOL:
+        dt = I32 if kind == "sum" else BOOL
+    return Tr("reduce", (x,), dt, "s", (kind, types.pop()))
+
+
+def _types_of(x: Tr, seen=None) -> set:
+    out = set()
+    stack = [x]
+    visited = set()
+    while stack:
+        v = stack.pop()
+        if v.id in visited:
+            continue
+        visited.add(v.id)
+        if v.op in ("field", "field_new"):
+            out.add(v.attr[0])
+        stack.extend(a for a in v.args if isinstance(a, Tr))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# the jnp-like namespace handed to user code (jaxabm_b200.numpy)
+# ---------------------------------------------------------------------------------------------
+class _Namespace:
+    float32, int32, bool_ = np.float32, np.int32, np.bool_
+    pi, e, inf, nan = math.pi, math.e, math.inf, math.nan
+
+    @staticmethod
+    def _col(x):
+        return x.tr if isinstance(x, Column) else x
+
+    def where(self, c, a, b): return where(self._col(c), self._col(a), self._col(b))
+    def minimum(self, a, b): return minimum(self._col(a), self._col(b))
+    def maximum(self, a, b): return maximum(self._col(a), self._col(b))
+    def clip(self, x, a_min=None, a_max=None):
+        x = self._col(x)
+        if a_min is not None:
+            x = maximum(x, a_min)
+        if a_max is not None:
+            x = minimum(x, a_max)
+        return x
+    def abs(self, x): return unary("abs", self._col(x))
+    absolute = abs
+    def sqrt(self, x): return _math("sqrt", self._col(x))
+    def exp(self, x): return _math("exp", self._col(x))
+    def log(self, x): return _math("log", self._col(x))
+    def log1p(self, x): return _math("log1p", self._col(x))
+    def tanh(self, x): return _math("tanh", self._col(x))
+    def power(self, a, b): return power(self._col(a), self._col(b))
+    def logical_and(self, a, b): return logical("and", self._col(a), self._col(b))
+    def logical_or(self, a, b): return logical("or", self._col(a), self._col(b))
+    def logical_not(self, a): return unary("not", self._col(a))
+    def sum(self, x): return _reduce("sum", x)
+    def mean(self, x): return _reduce("mean", x)
+    def max(self, x): return _reduce("max", x)
+    def min(self, x): return _reduce("min", x)
+    def asarray(self, x, dtype=None): return astype(_const(self._col(x)), dtype) if dtype is not None else _const(self._col(x))
+    array = asarray
+    def nan_to_num(self, x, nan=0.0):
+        x = _const(self._col(x))
+        return where(compare("ne", x, x), nan, x)
+
+
+numpy = _Namespace()
+
+
+# ---------------------------------------------------------------------------------------------
+# traced jax.random
+# ---------------------------------------------------------------------------------------------
+def key_split(key: TrKey, num: int = 2) -> List[TrKey]:
+    return [TrKey("split", key, i, int(num)) for i in range(int(num))]
+
+
+def key_uniform(key: TrKey, shape=(), minval=0.0, maxval=1.0) -> Tr:
+    if shape not in ((), None):
+        raise TraceError("only scalar random draws are traced")
+    if isinstance(minval, Tr) or isinstance(maxval, Tr):
+        raise TraceError("uniform(minval, maxval) bounds must be Python numbers")
+    return Tr("uniform", (), F32, key.scope, (key, float(minval), float(maxval)))
+
+
+def key_normal(key: TrKey, shape=()) -> Tr:
+    if shape not in ((), None):
+        raise TraceError("only scalar random draws are traced")
+    return Tr("normal", (), F32, key.scope, (key,))
+
+
+# ---------------------------------------------------------------------------------------------
+# code generation
+# ---------------------------------------------------------------------------------------------
+def _f32_lit(v: float) -> str:
+    if v != v:
+        return "__int_as_float(0x7fc00000)"
+    if v in (math.inf, -math.inf):
+        return ("" if v > 0 else "-") + "__int_as_float(0x7f800000)"
+    f = struct.unpack("f", struct.pack("f", v))[0]
+    return f"{f:.9g}f" if ("." in f"{f:.9g}" or "e" in f"{f:.9g}" or "n" in f"{f:.9g}") else f"{f:.9g}.0f"
+
+
+def _f64_lit(v: float) -> str:
+    if v != v:
+        return "(0.0/0.0)"
+    if v in (math.inf, -math.inf):
+        return ("" if v > 0 else "-") + "(1.0/0.0)"
+    s = repr(float(v))
+    return s if ("." in s or "e" in s) else s + ".0"
+
+
+_CT = {F32: "float", I32: "int", BOOL: "bool", WF: "double", WI: "int"}
+
+
+class Emitter:
+    """Emits the statements of an expression DAG once each (common sub-expressions are shared)."""
+
+    def __init__(self, leaf, mode_key: str):
+        self.lines: List[str] = []
+        self.names: Dict[int, str] = {}
+        self.key_names: Dict[int, str] = {}
+        self.leaf = leaf                   # callable(Tr) -> C expression for 'field' / 'env' / 'time' / 'reduce' leaves
+        self.mode_key = mode_key           # C expression of the root key for this scope
+
+    def cast(self, x: Tr, to: str) -> str:
+        s = self.ref(x)
+        if x.dtype == to or (x.dtype == WI and to == I32) or (x.dtype == I32 and to == WI):
+            return s
+        return f"(({_CT[to]}){s})"
+
+    def key(self, k: TrKey) -> str:
+        if k.id in self.key_names:
+            return self.key_names[k.id]
+        if k.parent is None:
+            name = self.mode_key
+        else:
+            name = f"k{k.id}"
+            self.lines.append(f"const Key {name} = split_child<MODE>({self.key(k.parent)}, {k.index}ull, {k.num}ull);")
+        self.key_names[k.id] = name
+        return name
+
+    def ref(self, x: Tr) -> str:
+        if x.id in self.names:
+            return self.names[x.id]
+        expr = self.expr(x)
+        if x.op == "const":
+            self.names[x.id] = expr
+            return expr
+        name = f"v{x.id}"
+        self.lines.append(f"const {_CT[x.dtype]} {name} = {expr};")
+        self.names[x.id] = name
+        return name
+
+    def expr(self, x: Tr) -> str:
+        op, dt = x.op, x.dtype
+        if op == "const":
+            if dt == BOOL:
+                return "true" if x.attr else "false"
+            if dt in (I32, WI):
+                return f"{int(x.attr)}"
+            return _f32_lit(x.attr) if dt == F32 else _f64_lit(x.attr)
+        if op in ("field", "field_new", "env", "time", "reduce"):
+            return self.leaf(x, self)
+        if op in ("add", "sub", "mul", "div"):
+            a, b = self.cast(x.args[0], dt), self.cast(x.args[1], dt)
+            return f"{a} {'+-*/'['add sub mul div'.split().index(op)]} {b}"
+        if op == "neg":
+            return f"-{self.cast(x.args[0], dt)}"
+        if op == "abs":
+            a = self.cast(x.args[0], dt)
+            return f"fabsf({a})" if dt == F32 else (f"fabs({a})" if dt == WF else f"abs({a})")
+        if op in ("lt", "le", "gt", "ge", "eq", "ne"):
+            ct = x.attr if x.attr != BOOL else I32
+            a, b = self.cast(x.args[0], ct), self.cast(x.args[1], ct)
+            return f"{a} {dict(lt='<', le='<=', gt='>', ge='>=', eq='==', ne='!=')[op]} {b}"
+        if op in ("and", "or", "xor"):
+            return f"{self.ref(x.args[0])} {dict(**{'and': '&&', 'or': '||', 'xor': '!='})[op]} {self.ref(x.args[1])}"
+        if op == "not":
+            return f"!{self.ref(x.args[0])}"
+        if op == "where":
+            return f"{self.ref(x.args[0])} ? {self.cast(x.args[1], dt)} : {self.cast(x.args[2], dt)}"
+        if op in ("min", "max"):
+            a, b = self.cast(x.args[0], dt), self.cast(x.args[1], dt)
+            if dt == F32:
+                return f"{'jmin' if op == 'min' else 'jmax'}({a}, {b})"
+            if dt == WF:
+                return f"(({a} != {a} || {b} != {b}) ? (0.0/0.0) : f{op}({a}, {b}))"
+            return f"{op}({a}, {b})"
+        if op == "pow":
+            return f"powf({self.cast(x.args[0], F32)}, {self.cast(x.args[1], F32)})" if dt == F32 else \
+                f"pow({self.cast(x.args[0], WF)}, {self.cast(x.args[1], WF)})"
+        if op in ("sqrt", "exp", "log", "log1p", "tanh"):
+            return f"{op}f({self.cast(x.args[0], F32)})"
+        if op == "cast":
+            a = x.args[0]
+            if dt == BOOL:
+                return f"{self.ref(a)} != 0"
+            return f"({_CT[dt]}){self.ref(a)}"
+        if op == "uniform":
+            k, lo, hi = x.attr
+            return f"bits_to_uniform(bits_scalar<MODE>({self.key(k)}), {_f32_lit(lo)}, {_f32_lit(hi)})"
+        if op == "normal":
+            return f"normal_scalar<MODE>({self.key(x.attr[0])})"
+        raise TraceError(f"no code generation for traced op {op!r}")
+
+
+def used_leaves(roots: Sequence[Tr], op: str) -> List[Tr]:
+    out, seen, stack = {}, set(), list(roots)
+    while stack:
+        v = stack.pop()
+        if v.id in seen:
+            continue
+        seen.add(v.id)
+        if v.op == op:
+            out[v.id] = v
+        stack.extend(a for a in v.args if isinstance(a, Tr))
+    return list(out.values())
+
+
+# ---------------------------------------------------------------------------------------------
+# tracing a whole model and emitting its step kernel
+# ---------------------------------------------------------------------------------------------
+_DT_CODE = {F32: 0, I32: 1, BOOL: 2, WF: 3, WI: 1}
+_STORE = {F32: F32, WF: F32, I32: I32, WI: I32, BOOL: BOOL}
+
+
+def _env_dtype_of(v) -> Optional[str]:
+    if isinstance(v, Tr):
+        return v.dtype
+    if isinstance(v, (bool, np.bool_)):
+        return BOOL
+    if isinstance(v, (int, np.integer)):
+        return WI if isinstance(v, int) else I32
+    if isinstance(v, np.float32):
+        return F32
+    if isinstance(v, (float, np.floating)):
+        return WF
+    if isinstance(v, np.ndarray) and v.ndim == 0:
+        return _env_dtype_of(v[()])
+    return None
+
+
+class TracedModel:
+    """Everything the code generator needs, for one env dtype signature (variant)."""
+
+    def __init__(self):
+        self.types: List[dict] = []        # {name, n, fields [(name, dtype)], init {field: Tr}, update {field: Tr}}
+        self.env_names: List[str] = []
+        self.env_dtypes: List[str] = []
+        self.env_out: Dict[str, Tr] = {}
+        self.metrics: List[Tuple[str, Tr]] = []
+        self.has_env_fn = False
+
+
+def trace_model(collections, env_state: dict, params: dict, update_state_fn, metrics_fn, config,
+                env_dtypes: Optional[Dict[str, str]] = None, slot_order: Optional[List[str]] = None) -> TracedModel:
+    """Run every user function once on symbolic values.  ``env_dtypes``: dtype of every scalar env
+    entry at the START of the traced step (None: the Python types of ``env_state``); entries named
+    there but absent from ``env_state`` are the ones an earlier step's update_state_fn added."""
+    tm = TracedModel()
+    scalars = {k: v for k, v in env_state.items() if _env_dtype_of(v) is not None}
+    dts = {k: _env_dtype_of(v) for k, v in scalars.items()}
+    visible = list(scalars)
+    if env_dtypes:
+        for k, v in env_dtypes.items():
+            if k not in dts:
+                visible.append(k)
+            dts[k] = v
+    tm.env_names = list(slot_order) if slot_order else list(visible)
+
+    def env_view():
+        d = dict(env_state)
+        for name in visible:
+            d[name] = Tr("env", (), dts[name], "s", tm.env_names.index(name))
+        return d
+
+    for ti, (cname, coll) in enumerate(collections.items()):
+        at = coll.agent_type
+        init = at.init_state(config, TrKey("agent"))
+        if not isinstance(init, dict) or not init:
+            raise TraceError(f"{type(at).__name__}.init_state must return a non-empty dict")
+        fields, init_tr = [], {}
+        for fname, v in init.items():
+            t = _const(v) if not isinstance(v, Tr) else v
+            fields.append((fname, _STORE[t.dtype]))
+            init_tr[fname] = t
+        state = {fname: Tr("field", (), dt, "a", (ti, fi)) for fi, (fname, dt) in enumerate(fields)}
+        model_state = {"time_step": Tr("time", (), WI, "s"), "env": env_view()}
+        out = at.update(dict(state), model_state, config, TrKey("agent"))
+        if not isinstance(out, dict) or set(out) != set(state):
+            raise TraceError(f"{type(at).__name__}.update must return the same state keys as init_state "
+                             f"({sorted(state)}), got {sorted(out) if isinstance(out, dict) else type(out).__name__}")
+        upd = {}
+        for fname, dt in fields:
+            v = _const(out[fname]) if not isinstance(out[fname], Tr) else out[fname]
+            if _STORE[v.dtype] != dt:
+                v = astype(v, {F32: float, I32: int, BOOL: bool}[dt])       # the column keeps its dtype
+            upd[fname] = v
+        tm.types.append({"name": cname, "n": coll.num_agents, "fields": fields, "init": init_tr, "update": upd,
+                         "state": state})
+    # agent_states[name][field]: the POST-update column of a collection (model.py:182-200 hands the new
+    # states to update_state_fn / metrics_fn); usable inside jnp.sum / mean / max / min
+    agent_states = {t["name"]: {fname: Tr("field_new", (), dt, "a", (ti, fi)) for fi, (fname, dt) in enumerate(t["fields"])}
+                    for ti, t in enumerate(tm.types)}
+    env_after = env_view()
+    if update_state_fn is not None:
+        tm.has_env_fn = True
+        new_env = update_state_fn(dict(env_after), agent_states, params, TrKey("update"))
+        if not isinstance(new_env, dict):
+            raise TraceError("update_state_fn must return the env dict")
+        for k, v in new_env.items():
+            old = env_after.get(k)
+            if v is old:
+                continue
+            if _env_dtype_of(v) is None:
+                if isinstance(old, Tr):
+                    raise TraceError(f"env entry {k!r} becomes non-scalar")
+                continue
+            if k not in tm.env_names:
+                tm.env_names.append(k)
+                dts[k] = _env_dtype_of(v)
+            tm.env_out[k] = _const(v) if not isinstance(v, Tr) else v
+        env_after = dict(new_env)
+        for name in visible:                                   # entries the fn dropped keep their leaf
+            env_after.setdefault(name, Tr("env", (), dts[name], "s", tm.env_names.index(name)))
+    if metrics_fn is not None:
+        met = metrics_fn(env_after, agent_states, params)
+        if not isinstance(met, dict):
+            raise TraceError("metrics_fn must return a dict")
+        for k, v in met.items():
+            if _env_dtype_of(v) is None:
+                raise TraceError(f"metric {k!r} is not a scalar")
+            tm.metrics.append((k, _const(v) if not isinstance(v, Tr) else v))
+    tm.env_dtypes = [dts.get(n, WF) for n in tm.env_names]
+    return tm
+
+
+def _acc_native(dt: str) -> str:
+    return {F32: "float", WF: "float", I32: "int", WI: "int", BOOL: "int"}[dt]
+
+
+def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
+    """CUDA C++ of the step kernel (one template instance per env-dtype variant) + the init kernel."""
+    tm0 = variants[0]
+    n_types = len(tm0.types)
+    out: List[str] = []
+    w = out.append
+    w('// generated by jaxabm_b200/trace.py -- do not edit\n#include "common.cuh"\n#include "economy.cuh"\nusing namespace jxb;\n')
+    # reductions are numbered per variant (different dtype signatures may trace different graphs)
+    meta = {"n_acc": 0, "n_variants": len(variants)}
+    for var, tm in enumerate(variants):
+        roots = list(tm.env_out.values()) + [v for _, v in tm.metrics]
+        reds = used_leaves(roots, "reduce")
+        meta["n_acc"] = max(meta["n_acc"], len(reds))
+        red_slot = {r.id: i for i, r in enumerate(reds)}
+        nacc = max(len(reds), 1)
+        # ---- per-type agent code --------------------------------------------------------------
+        for ti, t in enumerate(tm.types):
+            w(f"template <int MODE> __device__ __forceinline__ void jxc_agents_v{var}_t{ti}(const TypeDev& t, const double* env, "
+              f"long long time_step, Key ck, int lb, double* accd) {{")
+            my_reds = [r for r in reds if r.attr[1] == ti]
+            for r in my_reds:
+                kind, nat = r.attr[0], _acc_native(r.args[0].dtype)
+                init = "0" if kind in ("sum", "mean") else (
+                    ("-__int_as_float(0x7f800000)" if kind == "max" else "__int_as_float(0x7f800000)") if nat == "float"
+                    else ("-2147483647-1" if kind == "max" else "2147483647"))
+                w(f"  {nat} a{red_slot[r.id]} = {init};")
+            w("  const long long stride = (long long)t.block_count * blockDim.x;")
+            w("  for (long long i = (long long)lb * blockDim.x + threadIdx.x; i < t.n; i += stride) {")
+            w("    const Key ak = split_child<MODE>(ck, (unsigned long long)(t.goff + i), (unsigned long long)t.gn);")
+            fields = t["fields"]
+
+            def leaf(x, em, ti=ti, fields=fields, tm=tm):
+                if x.op == "field":
+                    tj, fj = x.attr
+                    if tj != ti:
+                        raise TraceError("reading another collection's state inside update is not traced")
+                    return f"f{fj}"
+                if x.op == "env":
+                    return _env_load(x, "env")
+                if x.op == "time":
+                    return "(int)time_step"
+                raise TraceError("reductions cannot be used inside a per-agent update")
+            em = Emitter(leaf, "ak")
+            upd_roots = [t["update"][fname] for fname, _ in fields]
+            used = {x.attr[1] for x in used_leaves(upd_roots + [r.args[0] for r in my_reds], "field") if x.attr[0] == ti}
+            new_names = {}
+            for fi, (fname, dt) in enumerate(fields):
+                new_names[fi] = em.cast(t["update"][fname], dt) if t["update"][fname].op != "field" or \
+                    t["update"][fname].attr != (ti, fi) else None
+            # reductions read the NEW columns
+            def leaf_new(x, em2, ti=ti, new_names=new_names):
+                if x.op == "field_new":
+                    tj, fj = x.attr
+                    return new_names[fj] if new_names[fj] is not None else f"f{fj}"
+                if x.op == "env":
+                    return _env_load(x, "env")
+                if x.op == "time":
+                    return "(int)time_step"
+                raise TraceError("unsupported leaf inside a reduction")
+            em2 = Emitter(leaf_new, "ak")
+            em2.names, em2.lines, em2.key_names = em.names, em.lines, em.key_names     # share the statement list
+            red_exprs = {}
+            for r in my_reds:
+                red_exprs[r.id] = em2.cast(r.args[0], {"float": F32, "int": I32}[_acc_native(r.args[0].dtype)])
+                for x in used_leaves([r.args[0]], "field_new"):
+                    if new_names[x.attr[1]] is None:
+                        used.add(x.attr[1])
+            for fi, (fname, dt) in enumerate(fields):
+                if fi in used:
+                    ct = {F32: "float", I32: "int", BOOL: "unsigned char"}[dt]
+                    w(f"    const {_CT[dt]} f{fi} = (({ct}*)t.f[{fi}])[i]{' != 0' if dt == BOOL else ''};")
+            for ln in em.lines:
+                w("    " + ln)
+            for fi, (fname, dt) in enumerate(fields):
+                if new_names[fi] is not None:
+                    ct = {F32: "float", I32: "int", BOOL: "unsigned char"}[dt]
+                    w(f"    (({ct}*)t.f[{fi}])[i] = {new_names[fi]}{' ? 1 : 0' if dt == BOOL else ''};")
+            for r in my_reds:
+                s, kind, nat = red_slot[r.id], r.attr[0], _acc_native(r.args[0].dtype)
+                e = red_exprs[r.id]
+                if kind in ("sum", "mean"):
+                    w(f"    a{s} += {e};")
+                elif nat == "float":
+                    w(f"    a{s} = {'jmax' if kind == 'max' else 'jmin'}(a{s}, {e});")
+                else:
+                    w(f"    a{s} = {kind}(a{s}, {e});")
+            w("  }")
+            for r in my_reds:
+                s, kind, nat = red_slot[r.id], r.attr[0], _acc_native(r.args[0].dtype)
+                if kind in ("sum", "mean"):
+                    w(f"  accd[{s}] = (double)warp_sum(a{s});")
+                elif nat == "float":
+                    w(f"  accd[{s}] = (double)warp_{kind}(a{s});" if kind == "max" else f"  accd[{s}] = -(double)warp_max(-a{s});")
+                else:
+                    w(f"  {{ int v = a{s}; for (int o = 16; o > 0; o >>= 1) v = {kind}(v, __shfl_xor_sync(0xffffffffu, v, o)); accd[{s}] = (double)v; }}")
+            w("}\n")
+        # ---- tail -----------------------------------------------------------------------------
+        w(f"template <int MODE> __device__ inline void jxc_tail_v{var}(const ModelDev& md, const double* tot, Key uk, double* m) {{")
+        w("  double* env = md.env;\n  const long long time_step = md.ctrl->time_step;")
+
+        def leaf_tail(x, em, tm=tm, red_slot=red_slot):
+            if x.op == "env":
+                return _env_load(x, "env")
+            if x.op == "time":
+                return "(int)time_step"
+            if x.op == "reduce":
+                kind, ti = x.attr
+                s = red_slot[x.id]
+                nat = _acc_native(x.args[0].dtype)
+                if kind == "mean":
+                    return f"((float)tot[{s}] / (float)md.t[{ti}].gn)"
+                if nat == "float":
+                    return f"(float)tot[{s}]"
+                return f"(int)tot[{s}]" if x.dtype != BOOL else f"(tot[{s}] != 0.0)"
+            raise TraceError("agent columns can only be used inside jnp.sum / mean / max / min in model functions")
+        em = Emitter(leaf_tail, "uk")
+        env_exprs = {k: em.ref(v) for k, v in tm.env_out.items()}
+        met_exprs = [(k, em.ref(v)) for k, v in tm.metrics]
+        for ln in em.lines:
+            w("  " + ln)
+        for k, e in env_exprs.items():
+            w(f"  env[{tm.env_names.index(k)}] = (double){e};")
+        for i, (k, e) in enumerate(met_exprs):
+            w(f"  m[{i}] = (double){e};")
+        w("}\n")
+    nacc = max(meta["n_acc"], 1)
+    meta["n_acc"] = nacc
+    # ---- kernels -----------------------------------------------------------------------------
+    w(f"constexpr int NACC = {nacc};")
+    w('''
+template <int MODE, int VAR>
+__global__ void __launch_bounds__(kThreads) jxc_step_kernel(const ModelDev md) {
+  __shared__ double s_red[(kThreads / 32) * NACC];
+  __shared__ double s_tot[NACC];
+  __shared__ int s_last;
+  int ti = 0;
+  for (int i = 1; i < md.n_types; ++i)
+    if ((int)blockIdx.x >= md.t[i].block_begin) ti = i;
+  const TypeDev& t = md.t[ti];
+  const int lb = blockIdx.x - t.block_begin;
+  const uint32_t* kp = md.keys + (size_t)md.ctrl->step_in_run * (md.n_types + 1) * 2;
+  const Key ck = {kp[2 * ti], kp[2 * ti + 1]};
+  const long long time_step = md.ctrl->time_step;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double accd[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) accd[i] = 0.0;
+  bool is_minmax[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) is_minmax[i] = false;''')
+    for var, tm in enumerate(variants):
+        w(f"  if (VAR == {var}) {{")
+        w("    switch (ti) {")
+        for ti in range(n_types):
+            w(f"      case {ti}: jxc_agents_v{var}_t{ti}<MODE>(t, md.env, time_step, ck, lb, accd); break;")
+        w("    }")
+        w("  }")
+    w('''  if (lane == 0)
+    for (int i = 0; i < NACC; ++i) s_red[warp * NACC + i] = accd[i];
+  __syncthreads();''')
+    # fold across warps / CTAs needs to know the combine op and owner type of every slot
+    for var, tm in enumerate(variants):
+        roots = list(tm.env_out.values()) + [v for _, v in tm.metrics]
+        reds = used_leaves(roots, "reduce")
+        kinds = ", ".join({"sum": "0", "mean": "0", "max": "1", "min": "2"}[r.attr[0]] for r in reds) or "0"
+        owners = ", ".join(str(r.attr[1]) for r in reds) or "0"
+        w(f"  const int kind_v{var}[NACC] = {{{kinds}}}; const int owner_v{var}[NACC] = {{{owners}}};")
+    w("  const int* kind = " + " : ".join([f"VAR == {v} ? kind_v{v}" for v in range(len(variants) - 1)] + [f"kind_v{len(variants) - 1}"]) + ";")
+    w("  const int* owner = " + " : ".join([f"VAR == {v} ? owner_v{v}" for v in range(len(variants) - 1)] + [f"owner_v{len(variants) - 1}"]) + ";")
+    w('''  // a CTA only contributes to the slots of its own collection; the others get the identity
+  if (threadIdx.x < NACC) {
+    const int i = threadIdx.x;
+    double r = kind[i] == 0 ? 0.0 : (kind[i] == 1 ? -1.0 / 0.0 : 1.0 / 0.0);
+    if (owner[i] == ti) {
+      r = s_red[i];
+      for (int w2 = 1; w2 < kThreads / 32; ++w2) {
+        const double v = s_red[w2 * NACC + i];
+        r = kind[i] == 0 ? r + v : (kind[i] == 1 ? fmax(r, v) : fmin(r, v));
+      }
+    }
+    md.partials[(size_t)blockIdx.x * NACC + i] = r;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&md.ctrl->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = warp; i < NACC; i += kThreads / 32) {
+    double r = kind[i] == 0 ? 0.0 : (kind[i] == 1 ? -1.0 / 0.0 : 1.0 / 0.0);
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
+      const double v = __ldcg(md.partials + (size_t)b * NACC + i);
+      r = kind[i] == 0 ? r + v : (kind[i] == 1 ? fmax(r, v) : fmin(r, v));
+    }
+    if (kind[i] == 0) r = warp_sum(r);
+    else if (kind[i] == 1) r = warp_max(r);
+    else r = -warp_max(-r);
+    if (lane == 0) s_tot[i] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Ctrl* c = md.ctrl;
+    c->ticket = 0;
+    const Key uk = {kp[2 * md.n_types], kp[2 * md.n_types + 1]};
+    double m[kMaxMetrics];
+#pragma unroll
+    for (int i = 0; i < kMaxMetrics; ++i) m[i] = 0.0;''')
+    for var in range(len(variants)):
+        w(f"    if (VAR == {var}) jxc_tail_v{var}<MODE>(md, s_tot, uk, m);")
+    w('''    const long long tn = c->time_step + 1;
+    if ((tn % md.collect_interval) == 0) {
+      double* row = md.metrics + (size_t)c->n_recorded * kMaxMetrics;
+#pragma unroll
+      for (int i = 0; i < kMaxMetrics; ++i) row[i] = m[i];
+      md.record_steps[c->n_recorded] = (int)tn;
+      c->n_recorded += 1;
+    }
+    c->time_step = tn;
+    c->step_in_run += 1;
+  }
+}
+''')
+    # ---- init kernel ----------------------------------------------------------------------------
+    for ti, t in enumerate(tm0.types):
+        w(f"template <int MODE> __global__ void __launch_bounds__(kThreads) jxc_init_kernel_t{ti}(const TypeDev t, Key key) {{")
+        w("  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {")
+        w("    const Key ak = split_child<MODE>(key, (unsigned long long)(t.goff + i), (unsigned long long)t.gn);")
+
+        def leaf_init(x, em):
+            raise TraceError("init_state can only use its key and Python constants")
+        em = Emitter(leaf_init, "ak")
+        vals = [(fi, dt, em.cast(t["init"][fname], dt)) for fi, (fname, dt) in enumerate(t["fields"])]
+        for ln in em.lines:
+            w("    " + ln)
+        for fi, dt, e in vals:
+            ct = {F32: "float", I32: "int", BOOL: "unsigned char"}[dt]
+            w(f"    (({ct}*)t.f[{fi}])[i] = {e}{' ? 1 : 0' if dt == BOOL else ''};")
+        w("  }\n}\n")
+    # ---- launchers ------------------------------------------------------------------------------
+    w('extern "C" int jxc_n_acc() { return NACC; }')
+    w(f'extern "C" int jxc_n_variants() {{ return {len(variants)}; }}')
+    w('extern "C" int jxc_launch_init(const ModelDev* md, int type, unsigned int k0, unsigned int k1, int rng_mode, int blocks, cudaStream_t s) {')
+    w("  const Key key{k0, k1};\n  switch (type) {")
+    for ti in range(n_types):
+        w(f"    case {ti}: if (rng_mode == 1) jxc_init_kernel_t{ti}<1><<<blocks, kThreads, 0, s>>>(md->t[{ti}], key); "
+          f"else jxc_init_kernel_t{ti}<0><<<blocks, kThreads, 0, s>>>(md->t[{ti}], key); break;")
+    w("    default: return -1;\n  }\n  return (int)cudaGetLastError();\n}")
+    w('extern "C" int jxc_launch_step(const ModelDev* md, int rng_mode, int variant, cudaStream_t s) {')
+    for var in range(len(variants)):
+        w(f"  if (variant == {var}) {{ if (rng_mode == 1) jxc_step_kernel<1, {var}><<<md->grid_blocks, kThreads, 0, s>>>(*md); "
+          f"else jxc_step_kernel<0, {var}><<<md->grid_blocks, kThreads, 0, s>>>(*md); }}")
+    w("  return (int)cudaGetLastError();\n}")
+    return "\n".join(out) + "\n", meta
+
+
+def _env_load(x: Tr, arr: str) -> str:
+    slot, dt = x.attr, x.dtype
+    if dt == WF:
+        return f"{arr}[{slot}]"
+    if dt == F32:
+        return f"(float){arr}[{slot}]"
+    if dt in (I32, WI):
+        return f"(int){arr}[{slot}]"
+    return f"({arr}[{slot}] != 0.0)"

@@ -220,3 +220,28 @@ def test_saltelli_estimators_on_an_analytic_model():
     assert sa.saltelli_design.shape == (512 * 4, 2)
     assert idx["y"]["S1"]["a"] == pytest.approx(0.2, abs=0.04) and idx["y"]["S1"]["b"] == pytest.approx(0.8, abs=0.06)
     assert idx["y"]["ST"]["a"] == pytest.approx(0.2, abs=0.03) and idx["y"]["ST"]["b"] == pytest.approx(0.8, abs=0.05)
+
+
+def test_rule_tracer_generates_and_compiles_a_kernel_without_a_gpu():
+    """Plain user code -> expression graph -> CUDA source -> sm_100a library (nvcc cross-compiles here);
+    dtype rules of the trace follow JAX's weak typing."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from jaxabm_b200 import jit, trace
+    from traced_models import build
+    m = build.device_noisy(1000, 1, 1)
+    variants = jit.trace_variants(m)
+    assert [v.env_dtypes for v in variants] == [["wf64", "wf64", "wi32"], ["f32", "f32", "wi32"]]
+    assert variants[-1].types[0]["fields"] == [("wealth", "f32"), ("active", "bool"), ("trades", "i32")]
+    src, meta = trace.generate_source(variants)
+    assert "normal_scalar<MODE>" in src and "jxc_step_kernel" in src and meta["n_variants"] == 2
+    lib = jit.compile_source(src)
+    assert lib.jxc_n_acc() == meta["n_acc"] >= 6 and lib.jxc_n_variants() == 2
+    # weak-type rules
+    x = trace.Tr("field", (), trace.I32, "a", (0, 0))
+    assert (x * 0.5).dtype == trace.F32 and (x * 2).dtype == trace.I32 and (x / 2).dtype == trace.F32
+    assert (x > 1).dtype == trace.BOOL and trace.where(x > 1, 1.0, 0.0).dtype == trace.WF
+    assert (trace._const(2.0) * 3).attr == 6.0                      # scalar (op) scalar folds in Python doubles
+    with pytest.raises(trace.TraceError):
+        bool(x > 1)
