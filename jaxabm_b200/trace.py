@@ -231,21 +231,27 @@ def _math(op: str, a) -> Tr:
     return Tr(op, (a,), F32, a.scope)
 
 
+def _array_dtype(dt: str) -> str:
+    """jnp functions return arrays: a Python-scalar result becomes (weak) float32 / int32, it does not
+    stay a double-precision Python number."""
+    return F32 if dt == WF else (I32 if dt == WI else dt)
+
+
 def where(c, a, b) -> Tr:
     c, a, b = _const(c), _const(a), _const(b)
     if c.dtype != BOOL:
         c = compare("ne", c, 0)
-    return Tr("where", (c, a, b), _promote(a, b), _scope(c, a, b))
+    return Tr("where", (c, a, b), _array_dtype(_promote(a, b)), _scope(c, a, b))
 
 
 def minimum(a, b) -> Tr:
     a, b = _const(a), _const(b)
-    return Tr("min", (a, b), _promote(a, b), _scope(a, b))
+    return Tr("min", (a, b), _array_dtype(_promote(a, b)), _scope(a, b))
 
 
 def maximum(a, b) -> Tr:
     a, b = _const(a), _const(b)
-    return Tr("max", (a, b), _promote(a, b), _scope(a, b))
+    return Tr("max", (a, b), _array_dtype(_promote(a, b)), _scope(a, b))
 
 
 def clip(x, lo, hi) -> Tr:
@@ -643,22 +649,14 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
         red_slot = {r.id: i for i, r in enumerate(reds)}
         nacc = max(len(reds), 1)
         # ---- per-type agent code --------------------------------------------------------------
+        # jxc_one_*: the traced update of ONE agent (inputs by value, new columns and accumulators by
+        # reference); jxc_agents_*: the streaming driver -- four agents per thread per iteration with
+        # one 16-byte (4-byte for bool) load / store per column, like the hand-written kernels.
         for ti, t in enumerate(tm.types):
-            w(f"template <int MODE> __device__ __forceinline__ void jxc_agents_v{var}_t{ti}(const TypeDev& t, const double* env, "
-              f"long long time_step, Key ck, int lb, double* accd) {{")
             my_reds = [r for r in reds if r.attr[1] == ti]
-            for r in my_reds:
-                kind, nat = r.attr[0], _acc_native(r.args[0].dtype)
-                init = "0" if kind in ("sum", "mean") else (
-                    ("-__int_as_float(0x7f800000)" if kind == "max" else "__int_as_float(0x7f800000)") if nat == "float"
-                    else ("-2147483647-1" if kind == "max" else "2147483647"))
-                w(f"  {nat} a{red_slot[r.id]} = {init};")
-            w("  const long long stride = (long long)t.block_count * blockDim.x;")
-            w("  for (long long i = (long long)lb * blockDim.x + threadIdx.x; i < t.n; i += stride) {")
-            w("    const Key ak = split_child<MODE>(ck, (unsigned long long)(t.goff + i), (unsigned long long)t.gn);")
             fields = t["fields"]
 
-            def leaf(x, em, ti=ti, fields=fields, tm=tm):
+            def leaf(x, em, ti=ti):
                 if x.op == "field":
                     tj, fj = x.attr
                     if tj != ti:
@@ -676,8 +674,8 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
             for fi, (fname, dt) in enumerate(fields):
                 new_names[fi] = em.cast(t["update"][fname], dt) if t["update"][fname].op != "field" or \
                     t["update"][fname].attr != (ti, fi) else None
-            # reductions read the NEW columns
-            def leaf_new(x, em2, ti=ti, new_names=new_names):
+
+            def leaf_new(x, em2, ti=ti, new_names=new_names):          # reductions read the NEW columns
                 if x.op == "field_new":
                     tj, fj = x.attr
                     return new_names[fj] if new_names[fj] is not None else f"f{fj}"
@@ -694,34 +692,82 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
                 for x in used_leaves([r.args[0]], "field_new"):
                     if new_names[x.attr[1]] is None:
                         used.add(x.attr[1])
-            for fi, (fname, dt) in enumerate(fields):
-                if fi in used:
-                    ct = {F32: "float", I32: "int", BOOL: "unsigned char"}[dt]
-                    w(f"    const {_CT[dt]} f{fi} = (({ct}*)t.f[{fi}])[i]{' != 0' if dt == BOOL else ''};")
+            loaded = [fi for fi in range(len(fields)) if fi in used]
+            stored = [fi for fi in range(len(fields)) if new_names[fi] is not None]
+            needs_key = any("ak" in ln for ln in em.lines)
+            sig_in = "".join(f", const {_CT[fields[fi][1]]} f{fi}" for fi in loaded)
+            sig_out = "".join(f", {_CT[fields[fi][1]]}& n{fi}" for fi in stored)
+            sig_acc = "".join(f", {_acc_native(r.args[0].dtype)}& a{red_slot[r.id]}" for r in my_reds)
+            w(f"template <int MODE> __device__ __forceinline__ void jxc_one_v{var}_t{ti}(const TypeDev& t, const double* env, "
+              f"long long time_step, Key ck, long long i{sig_in}{sig_out}{sig_acc}) {{")
+            if needs_key:
+                w("  const Key ak = split_child<MODE>(ck, (unsigned long long)(t.goff + i), (unsigned long long)t.gn);")
             for ln in em.lines:
-                w("    " + ln)
-            for fi, (fname, dt) in enumerate(fields):
-                if new_names[fi] is not None:
-                    ct = {F32: "float", I32: "int", BOOL: "unsigned char"}[dt]
-                    w(f"    (({ct}*)t.f[{fi}])[i] = {new_names[fi]}{' ? 1 : 0' if dt == BOOL else ''};")
+                w("  " + ln)
+            for fi in stored:
+                w(f"  n{fi} = {new_names[fi]};")
             for r in my_reds:
-                s, kind, nat = red_slot[r.id], r.attr[0], _acc_native(r.args[0].dtype)
+                sl, kind, nat = red_slot[r.id], r.attr[0], _acc_native(r.args[0].dtype)
                 e = red_exprs[r.id]
                 if kind in ("sum", "mean"):
-                    w(f"    a{s} += {e};")
+                    w(f"  a{sl} += {e};")
                 elif nat == "float":
-                    w(f"    a{s} = {'jmax' if kind == 'max' else 'jmin'}(a{s}, {e});")
+                    w(f"  a{sl} = {'jmax' if kind == 'max' else 'jmin'}(a{sl}, {e});")
                 else:
-                    w(f"    a{s} = {kind}(a{s}, {e});")
+                    w(f"  a{sl} = {kind}(a{sl}, {e});")
+            w("}\n")
+            # ---- driver ------------------------------------------------------------------------
+            VT = {F32: ("float4", "float"), I32: ("int4", "int"), BOOL: ("uchar4", "unsigned char")}
+            w(f"template <int MODE> __device__ __forceinline__ void jxc_agents_v{var}_t{ti}(const TypeDev& t, const double* env, "
+              f"long long time_step, Key ck, int lb, double* accd) {{")
+            for r in my_reds:
+                kind, nat = r.attr[0], _acc_native(r.args[0].dtype)
+                init = "0" if kind in ("sum", "mean") else (
+                    ("-__int_as_float(0x7f800000)" if kind == "max" else "__int_as_float(0x7f800000)") if nat == "float"
+                    else ("-2147483647-1" if kind == "max" else "2147483647"))
+                w(f"  {nat} a{red_slot[r.id]} = {init};")
+            acc_args = "".join(f", a{red_slot[r.id]}" for r in my_reds)
+            w("  const long long ngroups = t.n / 4, stride = (long long)t.block_count * blockDim.x;")
+            w("  for (long long g = (long long)lb * blockDim.x + threadIdx.x; g < ngroups; g += stride) {")
+            for fi in loaded:
+                vt, _ = VT[fields[fi][1]]
+                w(f"    const {vt} F{fi} = *(({vt}*)t.f[{fi}] + g);")
+            for fi in stored:
+                vt, _ = VT[fields[fi][1]]
+                w(f"    {vt} N{fi};")
+            for lane_i, comp in enumerate("xyzw"):
+                ins = "".join(f", F{fi}.{comp}{' != 0' if fields[fi][1] == BOOL else ''}" for fi in loaded)
+                for fi in stored:
+                    w(f"    {_CT[fields[fi][1]]} n{fi}_{comp};")
+                outs = "".join(f", n{fi}_{comp}" for fi in stored)
+                w(f"    jxc_one_v{var}_t{ti}<MODE>(t, env, time_step, ck, 4 * g + {lane_i}{ins}{outs}{acc_args});")
+                for fi in stored:
+                    w(f"    N{fi}.{comp} = n{fi}_{comp}{' ? 1 : 0' if fields[fi][1] == BOOL else ''};")
+            for fi in stored:
+                vt, _ = VT[fields[fi][1]]
+                w(f"    *(({vt}*)t.f[{fi}] + g) = N{fi};")
+            w("  }")
+            w("  for (long long i = ngroups * 4 + threadIdx.x; lb == 0 && i < t.n; i += blockDim.x) {   // tail agents")
+            for fi in loaded:
+                _, st = VT[fields[fi][1]]
+                w(f"    const {_CT[fields[fi][1]]} f{fi} = (({st}*)t.f[{fi}])[i]{' != 0' if fields[fi][1] == BOOL else ''};")
+            for fi in stored:
+                w(f"    {_CT[fields[fi][1]]} n{fi};")
+            ins = "".join(f", f{fi}" for fi in loaded)
+            outs = "".join(f", n{fi}" for fi in stored)
+            w(f"    jxc_one_v{var}_t{ti}<MODE>(t, env, time_step, ck, i{ins}{outs}{acc_args});")
+            for fi in stored:
+                _, st = VT[fields[fi][1]]
+                w(f"    (({st}*)t.f[{fi}])[i] = n{fi}{' ? 1 : 0' if fields[fi][1] == BOOL else ''};")
             w("  }")
             for r in my_reds:
-                s, kind, nat = red_slot[r.id], r.attr[0], _acc_native(r.args[0].dtype)
+                sl, kind, nat = red_slot[r.id], r.attr[0], _acc_native(r.args[0].dtype)
                 if kind in ("sum", "mean"):
-                    w(f"  accd[{s}] = (double)warp_sum(a{s});")
+                    w(f"  accd[{sl}] = (double)warp_sum(a{sl});")
                 elif nat == "float":
-                    w(f"  accd[{s}] = (double)warp_{kind}(a{s});" if kind == "max" else f"  accd[{s}] = -(double)warp_max(-a{s});")
+                    w(f"  accd[{sl}] = (double)warp_{kind}(a{sl});" if kind == "max" else f"  accd[{sl}] = -(double)warp_max(-a{sl});")
                 else:
-                    w(f"  {{ int v = a{s}; for (int o = 16; o > 0; o >>= 1) v = {kind}(v, __shfl_xor_sync(0xffffffffu, v, o)); accd[{s}] = (double)v; }}")
+                    w(f"  {{ int v = a{sl}; for (int o = 16; o > 0; o >>= 1) v = {kind}(v, __shfl_xor_sync(0xffffffffu, v, o)); accd[{sl}] = (double)v; }}")
             w("}\n")
         # ---- tail -----------------------------------------------------------------------------
         w(f"template <int MODE> __device__ inline void jxc_tail_v{var}(const ModelDev& md, const double* tot, Key uk, double* m) {{")

@@ -154,14 +154,14 @@ class _JNP:
 
     def minimum(self, a, b):
         dt = _target(a, b)
-        if dt is None:
-            return min(a, b)
+        if dt is None:                                   # jnp functions return (weak) float32 / int32 arrays
+            dt = f32 if isinstance(a, float) or isinstance(b, float) else i32
         return EArr(np.minimum(np.asarray(_val(a)).astype(dt), np.asarray(_val(b)).astype(dt)))
 
     def maximum(self, a, b):
         dt = _target(a, b)
         if dt is None:
-            return max(a, b)
+            dt = f32 if isinstance(a, float) or isinstance(b, float) else i32
         return EArr(np.maximum(np.asarray(_val(a)).astype(dt), np.asarray(_val(b)).astype(dt)))
 
     def clip(self, x, a_min=None, a_max=None):

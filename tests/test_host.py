@@ -241,7 +241,7 @@ def test_rule_tracer_generates_and_compiles_a_kernel_without_a_gpu():
     # weak-type rules
     x = trace.Tr("field", (), trace.I32, "a", (0, 0))
     assert (x * 0.5).dtype == trace.F32 and (x * 2).dtype == trace.I32 and (x / 2).dtype == trace.F32
-    assert (x > 1).dtype == trace.BOOL and trace.where(x > 1, 1.0, 0.0).dtype == trace.WF
+    assert (x > 1).dtype == trace.BOOL and trace.where(x > 1, 1.0, 0.0).dtype == trace.F32
     assert (trace._const(2.0) * 3).attr == 6.0                      # scalar (op) scalar folds in Python doubles
     with pytest.raises(trace.TraceError):
         bool(x > 1)
