@@ -158,6 +158,8 @@ typedef struct {
   int32_t n_variants;
   void* launch_init;
   void* launch_step;
+  int32_t n_consts;                                        /* float constants of the traced code ...      */
+  const double* consts;                                    /* ... uploaded once; the kernels read them     */
 } jxb_traced_spec;
 int jxb_model_create_traced(jxb_engine*, const jxb_model_desc*, const jxb_traced_spec*, jxb_model** out);
 

@@ -55,7 +55,9 @@ def rule_of(agent_type) -> str:
         name = getattr(agent_type, "__name__", type(agent_type).__name__)
         raise UnregisteredRuleError(
             f"agent type {name!r} has no registered CUDA rule (jxb_rule). Registered rules: "
-            f"{sorted(nat.RULE)}. See jaxabm_b200.rules; there is no CPU fallback.")
+            f"{sorted(nat.RULE)}. See jaxabm_b200.rules, or write the type as plain Python against "
+            "jaxabm_b200.numpy / jaxabm_b200.random and add it to a Model whose functions are plain Python too: "
+            "Model.initialize() then traces it into a generated kernel. There is no CPU fallback.")
     return rule
 
 

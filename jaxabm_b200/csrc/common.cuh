@@ -97,6 +97,8 @@ struct ModelDev {
   int rank;
   int exchange;           // 0 none, 1 in-kernel peer-memory exchange, 2 NCCL all-reduce + tail kernel
   XchgBuf* xpeer[kMaxPeers];   // every rank's buffer as mapped into this process (own = local)
+  const double* consts;   // traced models: the float constants of the user code (values, not code: one
+                          // compiled kernel serves every parameter set of a sweep)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -502,6 +502,7 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
     m->traced_variants = ts->n_variants;
     *(void**)&m->traced_init = ts->launch_init;
     *(void**)&m->traced_step = ts->launch_step;
+    if (ts->n_consts < 0 || ts->n_consts > 4096 || (ts->n_consts && !ts->consts)) { delete m; return fail(JXB_ERR_INVALID, "bad constant table"); }
   }
   ModelDev& md = m->dev;
   memset(&md, 0, sizeof(md));
@@ -557,6 +558,15 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
   }
   TRY(dev_alloc(m, &md.ctrl, 1));
   cudaMemset(md.ctrl, 0, sizeof(Ctrl));
+  if (ts) {
+    double* d_c = nullptr;
+    TRY(dev_alloc(m, &d_c, (size_t)std::max(ts->n_consts, 1)));
+    if (ts->n_consts && cudaMemcpy(d_c, ts->consts, (size_t)ts->n_consts * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+      jxb_model_destroy(m);
+      return fail(JXB_ERR_CUDA, "constant table upload failed");
+    }
+    md.consts = d_c;
+  }
   TRY(dev_alloc(m, &md.allreduce_buf, kAcc));
   TRY(plan_step_blocks(m));
   TRY(dev_alloc(m, &md.partials, (size_t)std::max(m->step_blocks, 1) * std::max(kAcc, m->traced_acc)));

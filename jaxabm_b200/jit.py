@@ -89,7 +89,8 @@ class TracedSpec(C.Structure):
                 ("n_metrics", C.c_int32), ("metric_names", C.c_char_p * nat.MAX_METRICS),
                 ("metric_dtypes", C.c_int32 * nat.MAX_METRICS),
                 ("has_env_fn", C.c_int32), ("n_acc", C.c_int32), ("n_variants", C.c_int32),
-                ("launch_init", C.c_void_p), ("launch_step", C.c_void_p)]
+                ("launch_init", C.c_void_p), ("launch_step", C.c_void_p),
+                ("n_consts", C.c_int32), ("consts", C.POINTER(C.c_double))]
 
 
 def build(model) -> Tuple[TracedSpec, C.CDLL, List[T.TracedModel], str]:
@@ -125,4 +126,8 @@ def build(model) -> Tuple[TracedSpec, C.CDLL, List[T.TracedModel], str]:
     spec.n_variants = int(lib.jxc_n_variants())
     spec.launch_init = C.cast(lib.jxc_launch_init, C.c_void_p)
     spec.launch_step = C.cast(lib.jxc_launch_step, C.c_void_p)
+    consts = (C.c_double * max(len(meta["consts"]), 1))(*meta["consts"])
+    spec.n_consts = len(meta["consts"])
+    spec.consts = C.cast(consts, C.POINTER(C.c_double))
+    spec._keep_consts = consts
     return spec, lib, variants, src

@@ -406,11 +406,16 @@ def _f64_lit(v: float) -> str:
 _CT = {F32: "float", I32: "int", BOOL: "bool", WF: "double", WI: "int"}
 
 
+_SEQ = [0]
+
+
 class Emitter:
     """Emits the statements of an expression DAG once each (common sub-expressions are shared)."""
 
-    def __init__(self, leaf, mode_key: str):
-        self.lines: List[str] = []
+    def __init__(self, leaf, mode_key: str, pool: Optional[List[float]] = None):
+        self.pool = pool                   # float constants go to a table (values) instead of into the code
+        self.seq = _SEQ                    # statement names are numbered in emission order, not by node id, so
+        self.lines: List[str] = []         # that two traces of the same code give byte-identical sources
         self.names: Dict[int, str] = {}
         self.key_names: Dict[int, str] = {}
         self.leaf = leaf                   # callable(Tr) -> C expression for 'field' / 'env' / 'time' / 'reduce' leaves
@@ -428,7 +433,8 @@ class Emitter:
         if k.parent is None:
             name = self.mode_key
         else:
-            name = f"k{k.id}"
+            self.seq[0] += 1
+            name = f"k{self.seq[0]}"
             self.lines.append(f"const Key {name} = split_child<MODE>({self.key(k.parent)}, {k.index}ull, {k.num}ull);")
         self.key_names[k.id] = name
         return name
@@ -440,7 +446,8 @@ class Emitter:
         if x.op == "const":
             self.names[x.id] = expr
             return expr
-        name = f"v{x.id}"
+        self.seq[0] += 1
+        name = f"v{self.seq[0]}"
         self.lines.append(f"const {_CT[x.dtype]} {name} = {expr};")
         self.names[x.id] = name
         return name
@@ -452,6 +459,9 @@ class Emitter:
                 return "true" if x.attr else "false"
             if dt in (I32, WI):
                 return f"{int(x.attr)}"
+            if self.pool is not None:
+                self.pool.append(float(x.attr))
+                return f"(float)cst[{len(self.pool) - 1}]" if dt == F32 else f"cst[{len(self.pool) - 1}]"
             return _f32_lit(x.attr) if dt == F32 else _f64_lit(x.attr)
         if op in ("field", "field_new", "env", "time", "reduce"):
             return self.leaf(x, self)
@@ -639,6 +649,9 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
     n_types = len(tm0.types)
     out: List[str] = []
     w = out.append
+    _SEQ[0] = 0
+    pool: List[float] = []               # float constants, in emission order (position-based: the SOURCE does
+                                         # not depend on their values, so a parameter sweep compiles once)
     w('// generated by jaxabm_b200/trace.py -- do not edit\n#include "common.cuh"\n#include "economy.cuh"\nusing namespace jxb;\n')
     # reductions are numbered per variant (different dtype signatures may trace different graphs)
     meta = {"n_acc": 0, "n_variants": len(variants)}
@@ -667,7 +680,7 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
                 if x.op == "time":
                     return "(int)time_step"
                 raise TraceError("reductions cannot be used inside a per-agent update")
-            em = Emitter(leaf, "ak")
+            em = Emitter(leaf, "ak", pool)
             upd_roots = [t["update"][fname] for fname, _ in fields]
             used = {x.attr[1] for x in used_leaves(upd_roots + [r.args[0] for r in my_reds], "field") if x.attr[0] == ti}
             new_names = {}
@@ -684,7 +697,7 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
                 if x.op == "time":
                     return "(int)time_step"
                 raise TraceError("unsupported leaf inside a reduction")
-            em2 = Emitter(leaf_new, "ak")
+            em2 = Emitter(leaf_new, "ak", pool)
             em2.names, em2.lines, em2.key_names = em.names, em.lines, em.key_names     # share the statement list
             red_exprs = {}
             for r in my_reds:
@@ -699,7 +712,7 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
             sig_out = "".join(f", {_CT[fields[fi][1]]}& n{fi}" for fi in stored)
             sig_acc = "".join(f", {_acc_native(r.args[0].dtype)}& a{red_slot[r.id]}" for r in my_reds)
             w(f"template <int MODE> __device__ __forceinline__ void jxc_one_v{var}_t{ti}(const TypeDev& t, const double* env, "
-              f"long long time_step, Key ck, long long i{sig_in}{sig_out}{sig_acc}) {{")
+              f"const double* __restrict__ cst, long long time_step, Key ck, long long i{sig_in}{sig_out}{sig_acc}) {{")
             if needs_key:
                 w("  const Key ak = split_child<MODE>(ck, (unsigned long long)(t.goff + i), (unsigned long long)t.gn);")
             for ln in em.lines:
@@ -719,7 +732,7 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
             # ---- driver ------------------------------------------------------------------------
             VT = {F32: ("float4", "float"), I32: ("int4", "int"), BOOL: ("uchar4", "unsigned char")}
             w(f"template <int MODE> __device__ __forceinline__ void jxc_agents_v{var}_t{ti}(const TypeDev& t, const double* env, "
-              f"long long time_step, Key ck, int lb, double* accd) {{")
+              f"const double* __restrict__ cst, long long time_step, Key ck, int lb, double* accd) {{")
             for r in my_reds:
                 kind, nat = r.attr[0], _acc_native(r.args[0].dtype)
                 init = "0" if kind in ("sum", "mean") else (
@@ -740,7 +753,7 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
                 for fi in stored:
                     w(f"    {_CT[fields[fi][1]]} n{fi}_{comp};")
                 outs = "".join(f", n{fi}_{comp}" for fi in stored)
-                w(f"    jxc_one_v{var}_t{ti}<MODE>(t, env, time_step, ck, 4 * g + {lane_i}{ins}{outs}{acc_args});")
+                w(f"    jxc_one_v{var}_t{ti}<MODE>(t, env, cst, time_step, ck, 4 * g + {lane_i}{ins}{outs}{acc_args});")
                 for fi in stored:
                     w(f"    N{fi}.{comp} = n{fi}_{comp}{' ? 1 : 0' if fields[fi][1] == BOOL else ''};")
             for fi in stored:
@@ -755,7 +768,7 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
                 w(f"    {_CT[fields[fi][1]]} n{fi};")
             ins = "".join(f", f{fi}" for fi in loaded)
             outs = "".join(f", n{fi}" for fi in stored)
-            w(f"    jxc_one_v{var}_t{ti}<MODE>(t, env, time_step, ck, i{ins}{outs}{acc_args});")
+            w(f"    jxc_one_v{var}_t{ti}<MODE>(t, env, cst, time_step, ck, i{ins}{outs}{acc_args});")
             for fi in stored:
                 _, st = VT[fields[fi][1]]
                 w(f"    (({st}*)t.f[{fi}])[i] = n{fi}{' ? 1 : 0' if fields[fi][1] == BOOL else ''};")
@@ -771,7 +784,7 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
             w("}\n")
         # ---- tail -----------------------------------------------------------------------------
         w(f"template <int MODE> __device__ inline void jxc_tail_v{var}(const ModelDev& md, const double* tot, Key uk, double* m) {{")
-        w("  double* env = md.env;\n  const long long time_step = md.ctrl->time_step;")
+        w("  double* env = md.env;\n  const double* __restrict__ cst = md.consts;\n  const long long time_step = md.ctrl->time_step;")
 
         def leaf_tail(x, em, tm=tm, red_slot=red_slot):
             if x.op == "env":
@@ -788,7 +801,7 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
                     return f"(float)tot[{s}]"
                 return f"(int)tot[{s}]" if x.dtype != BOOL else f"(tot[{s}] != 0.0)"
             raise TraceError("agent columns can only be used inside jnp.sum / mean / max / min in model functions")
-        em = Emitter(leaf_tail, "uk")
+        em = Emitter(leaf_tail, "uk", pool)
         env_exprs = {k: em.ref(v) for k, v in tm.env_out.items()}
         met_exprs = [(k, em.ref(v)) for k, v in tm.metrics]
         for ln in em.lines:
@@ -827,7 +840,7 @@ __global__ void __launch_bounds__(kThreads) jxc_step_kernel(const ModelDev md) {
         w(f"  if (VAR == {var}) {{")
         w("    switch (ti) {")
         for ti in range(n_types):
-            w(f"      case {ti}: jxc_agents_v{var}_t{ti}<MODE>(t, md.env, time_step, ck, lb, accd); break;")
+            w(f"      case {ti}: jxc_agents_v{var}_t{ti}<MODE>(t, md.env, md.consts, time_step, ck, lb, accd); break;")
         w("    }")
         w("  }")
     w('''  if (lane == 0)
@@ -897,13 +910,14 @@ __global__ void __launch_bounds__(kThreads) jxc_step_kernel(const ModelDev md) {
 ''')
     # ---- init kernel ----------------------------------------------------------------------------
     for ti, t in enumerate(tm0.types):
-        w(f"template <int MODE> __global__ void __launch_bounds__(kThreads) jxc_init_kernel_t{ti}(const TypeDev t, Key key) {{")
+        w(f"template <int MODE> __global__ void __launch_bounds__(kThreads) jxc_init_kernel_t{ti}(const TypeDev t, Key key, "
+          f"const double* __restrict__ cst) {{")
         w("  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {")
         w("    const Key ak = split_child<MODE>(key, (unsigned long long)(t.goff + i), (unsigned long long)t.gn);")
 
         def leaf_init(x, em):
             raise TraceError("init_state can only use its key and Python constants")
-        em = Emitter(leaf_init, "ak")
+        em = Emitter(leaf_init, "ak", pool)
         vals = [(fi, dt, em.cast(t["init"][fname], dt)) for fi, (fname, dt) in enumerate(t["fields"])]
         for ln in em.lines:
             w("    " + ln)
@@ -917,14 +931,15 @@ __global__ void __launch_bounds__(kThreads) jxc_step_kernel(const ModelDev md) {
     w('extern "C" int jxc_launch_init(const ModelDev* md, int type, unsigned int k0, unsigned int k1, int rng_mode, int blocks, cudaStream_t s) {')
     w("  const Key key{k0, k1};\n  switch (type) {")
     for ti in range(n_types):
-        w(f"    case {ti}: if (rng_mode == 1) jxc_init_kernel_t{ti}<1><<<blocks, kThreads, 0, s>>>(md->t[{ti}], key); "
-          f"else jxc_init_kernel_t{ti}<0><<<blocks, kThreads, 0, s>>>(md->t[{ti}], key); break;")
+        w(f"    case {ti}: if (rng_mode == 1) jxc_init_kernel_t{ti}<1><<<blocks, kThreads, 0, s>>>(md->t[{ti}], key, md->consts); "
+          f"else jxc_init_kernel_t{ti}<0><<<blocks, kThreads, 0, s>>>(md->t[{ti}], key, md->consts); break;")
     w("    default: return -1;\n  }\n  return (int)cudaGetLastError();\n}")
     w('extern "C" int jxc_launch_step(const ModelDev* md, int rng_mode, int variant, cudaStream_t s) {')
     for var in range(len(variants)):
         w(f"  if (variant == {var}) {{ if (rng_mode == 1) jxc_step_kernel<1, {var}><<<md->grid_blocks, kThreads, 0, s>>>(*md); "
           f"else jxc_step_kernel<0, {var}><<<md->grid_blocks, kThreads, 0, s>>>(*md); }}")
     w("  return (int)cudaGetLastError();\n}")
+    meta["consts"] = pool
     return "\n".join(out) + "\n", meta
 
 

@@ -82,3 +82,48 @@ def test_tracer_rejects_what_it_cannot_compile():
     m.add_agent_collection("a", AgentCollection(Branchy(), 10))
     with pytest.raises(trace.TraceError):
         m.initialize()
+
+
+def test_sensitivity_analysis_over_a_traced_factory(mode):
+    """SensitivityAnalysis.run with a factory of user-written (traced) models: the float constants live
+    in a table, so the sweep compiles ONE kernel and every sample only uploads its values; results
+    match the eager oracle sample by sample and move in the direction the reference's integration
+    test asserts (tests/integration/test_integration.py:338-348)."""
+    import jaxabm_b200.numpy as jnp
+    from jaxabm_b200 import jit, random
+    from jaxabm_b200.agent import AgentCollection, AgentType
+    from jaxabm_b200.analysis import SensitivityAnalysis
+    from jaxabm_b200.model import Model
+    from oracle import eager
+    from traced_models import market as um
+    Consumer, Producer, ums, cm = um.make(jnp, random, AgentType)
+
+    def factory(params=None, config=None):
+        config.rng_mode = mode
+        config.steps = 12
+        m = Model(params={"price_adjustment_rate": 0.1}, config=config, update_state_fn=ums, metrics_fn=cm)
+        m.add_agent_collection("consumers", AgentCollection(Consumer(propensity_to_consume=params["propensity_to_consume"]), 300))
+        m.add_agent_collection("producers", AgentCollection(Producer(productivity=params["productivity"]), 60))
+        for k, v in build.MARKET_ENV.items():
+            m.add_env_state(k, v)
+        return m
+
+    n_before = len(jit._loaded)
+    sa = SensitivityAnalysis(factory, {"propensity_to_consume": (0.6, 0.9), "productivity": (0.8, 1.5)}, ["gdp", "avg_utility"],
+                             num_samples=6, seed=2)
+    res = sa.run(verbose=False)
+    assert len(jit._loaded) - n_before <= 1                      # one compiled kernel for the whole sweep
+    oC, oP, oums, ocm = um.make(eager.jnp, eager.random, eager.AgentTypeBase)
+    for i in range(6):
+        p = {k: float(sa.samples[i, j]) for j, k in enumerate(("propensity_to_consume", "productivity"))}
+        o = ort.Model(params={"price_adjustment_rate": 0.1}, config=ort.ModelConfig(seed=i + 1000, steps=12, rng_mode=mode),
+                      update_state_fn=eager.wrap_model_fn(oums, mode), metrics_fn=eager.wrap_model_fn(ocm, mode, has_key=False))
+        o.add_agent_collection("consumers", ort.AgentCollection(eager.wrap_agent_type(oC(propensity_to_consume=p["propensity_to_consume"])), 300))
+        o.add_agent_collection("producers", ort.AgentCollection(eager.wrap_agent_type(oP(productivity=p["productivity"])), 60))
+        for k, v in build.MARKET_ENV.items():
+            o.add_env_state(k, v)
+        ro = o.run()
+        assert float(res["gdp"][i]) == pytest.approx(float(ro["gdp"][-1]), rel=1e-5)
+        assert float(res["avg_utility"][i]) == pytest.approx(float(ro["avg_utility"][-1]), rel=1e-5)
+    idx = sa.sobol_indices()
+    assert idx["gdp"]["productivity"] > idx["gdp"]["propensity_to_consume"]
