@@ -127,3 +127,119 @@ def test_sensitivity_analysis_over_a_traced_factory(mode):
         assert float(res["avg_utility"][i]) == pytest.approx(float(ro["avg_utility"][-1]), rel=1e-5)
     idx = sa.sobol_indices()
     assert idx["gdp"]["productivity"] > idx["gdp"]["propensity_to_consume"]
+
+
+def _random_rule(rng, jnp, depth=4):
+    """A random expression generator, replayed identically for both backends (same rng stream)."""
+    ops = ["add", "sub", "mul", "div", "where", "min", "max", "neg", "abs", "cmp", "const_f", "const_i", "field_x",
+           "field_k", "field_b", "sqrt", "log1p", "pow2", "astype_f", "astype_i", "env", "time"]
+
+    def gen(state, env, t, d, want=None):
+        choice = ops[rng.randint(len(ops))] if d > 0 else ["const_f", "const_i", "field_x", "field_k", "env"][rng.randint(5)]
+        if choice == "const_f":
+            return float(np.round(rng.uniform(-2, 2), 3))
+        if choice == "const_i":
+            return int(rng.randint(-3, 4))
+        if choice == "field_x":
+            return state["x"]
+        if choice == "field_k":
+            return state["k"]
+        if choice == "field_b":
+            return jnp.where(state["b"], gen(state, env, t, d - 1), gen(state, env, t, d - 1))
+        if choice == "env":
+            return env["scale"]
+        if choice == "time":
+            return t * 0.125
+        a = gen(state, env, t, d - 1)
+        if choice == "neg":
+            return -a
+        if choice == "abs":
+            return jnp.abs(a)
+        if choice == "sqrt":
+            return jnp.sqrt(jnp.abs(a) + 1.0)
+        if choice == "log1p":
+            return jnp.log1p(jnp.abs(a))
+        if choice == "pow2":
+            return a ** 2
+        if choice == "astype_f":
+            return (a * 1).astype(float) if hasattr(a * 1, "astype") else float(a)
+        if choice == "astype_i":
+            return jnp.clip(a, -1000, 1000).astype(int)
+        b = gen(state, env, t, d - 1)
+        if choice == "add":
+            return a + b
+        if choice == "sub":
+            return a - b
+        if choice == "mul":
+            return a * b
+        if choice == "div":
+            return a / (jnp.abs(b) + 1.5)
+        if choice == "min":
+            return jnp.minimum(a, b)
+        if choice == "max":
+            return jnp.maximum(a, b)
+        if choice == "cmp":
+            return jnp.where(a < b, a, b * 0.5)
+        if choice == "where":
+            return jnp.where(state["x"] > 0.25, a, b)
+        raise AssertionError(choice)
+    return gen
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_tracer_dtype_rules_on_random_expressions(mode, case):
+    """Random expression trees over float32 / int32 / bool columns, Python constants (weak), an env
+    scalar and time_step: the traced kernel and the eager NumPy oracle run the SAME generated user
+    code; float columns agree to rounding, integer / boolean columns exactly."""
+    import jaxabm_b200.numpy as djnp
+    from jaxabm_b200 import random as drandom
+    from jaxabm_b200.agent import AgentCollection, AgentType
+    from jaxabm_b200.model import Model
+    from oracle import eager
+
+    def make(jnp, random, Base):
+        class A(Base):
+            def init_state(self, cfg, key):
+                k1, k2, k3 = random.split(key, 3)
+                return {"x": random.uniform(k1, minval=-1.0, maxval=1.0), "k": (random.uniform(k2) * 7.0).astype(int),
+                        "b": random.uniform(k3) < 0.5}
+
+            def update(self, state, model_state, cfg, key):
+                rng = np.random.RandomState(100 + case)
+                gen = _random_rule(rng, jnp)
+                env, t = model_state["env"], model_state["time_step"]
+                x = jnp.clip(gen(state, env, t, 4) * 1.0, -50.0, 50.0)
+                k = jnp.clip(gen(state, env, t, 3), -20, 20)
+                b = gen(state, env, t, 3) > gen(state, env, t, 2)
+                return {"x": (x * 1.0).astype(float), "k": (k * 1).astype(int), "b": b}
+
+        def upd(env, agent_states, params, key):
+            a = agent_states["a"]
+            new = dict(env)
+            new["scale"] = jnp.clip(jnp.mean(a["x"]) * 0.5 + env["scale"] * 0.5, -3.0, 3.0)
+            return new
+
+        def met(env, agent_states, params):
+            a = agent_states["a"]
+            return {"sx": jnp.sum(a["x"]), "sk": jnp.sum(a["k"]), "nb": jnp.sum(a["b"]), "mx": jnp.max(a["x"]),
+                    "scale": env["scale"]}
+        return A, upd, met
+
+    n = 4099
+    A, upd, met = make(djnp, drandom, AgentType)
+    m = Model(config=jx.ModelConfig(seed=21 + case, rng_mode=mode), update_state_fn=upd, metrics_fn=met)
+    m.add_agent_collection("a", AgentCollection(A(), n))
+    m.add_env_state("scale", 0.75)
+    OA, oupd, omet = make(eager.jnp, eager.random, eager.AgentTypeBase)
+    o = ort.Model(config=ort.ModelConfig(seed=21 + case, rng_mode=mode), update_state_fn=eager.wrap_model_fn(oupd, mode),
+                  metrics_fn=eager.wrap_model_fn(omet, mode, has_key=False))
+    o.add_agent_collection("a", ort.AgentCollection(eager.wrap_agent_type(OA()), n))
+    o.add_env_state("scale", 0.75)
+    r, ro = m.run(steps=5), o.run(steps=5)
+    st, ost = m.agent_collections["a"].states, o.agent_collections["a"].states
+    assert np.array_equal(st["k"], ost["k"]), np.nonzero(st["k"] != ost["k"])[0][:5]
+    assert np.array_equal(st["b"], ost["b"])
+    assert np.allclose(st["x"], ost["x"], rtol=1e-4, atol=1e-5, equal_nan=True)
+    assert [int(v) for v in r["sk"]] == [int(v) for v in ro["sk"]] and [int(v) for v in r["nb"]] == [int(v) for v in ro["nb"]]
+    for k in ("sx", "mx", "scale"):
+        assert np.allclose(_series(r, k), _series(ro, k), rtol=1e-4, atol=1e-4), k
