@@ -43,11 +43,20 @@ def _signature(m: Model):
     return program, specs, mparams, shape
 
 
+def _traced(models: Sequence[Any]) -> bool:
+    try:
+        return all(isinstance(m, Model) and not m._is_initialized and m._needs_tracing() for m in models)
+    except Exception:
+        return False
+
+
 def batchable(models: Sequence[Any]) -> bool:
     if not models or not all(isinstance(m, Model) for m in models):
         return False
     if any(m._is_initialized for m in models):
         return False
+    if _traced(models):
+        return True
     try:
         sigs = [_signature(m) for m in models]
     except Exception:
@@ -126,11 +135,66 @@ def metric_layout(models: Sequence[Model]):
     return out
 
 
+def _run_traced(models: Sequence[Model], steps: int):
+    """Replica-parallel run of user-written (traced) models: every model is traced (cheap), all must
+    generate the same source -- they then differ only in their constant tables, env values and seeds --
+    and the generated library's ensemble kernel runs them all in one launch."""
+    import ctypes as C
+    from . import jit, trace as T
+    R = len(models)
+    lo, hi = dist.shard_range(R)
+    src0 = meta0 = variants0 = None
+    consts, env0 = [], []
+    for m in models:
+        variants = jit.trace_variants(m)
+        src, meta = T.generate_source(variants)
+        if src0 is None:
+            src0, meta0, variants0 = src, meta, variants
+        elif src != src0:
+            raise ValueError("the models of an ensemble must trace to the same kernel (same structure, same sizes)")
+        consts.append(meta["consts"])
+        tm = variants[-1]
+        row = np.zeros(32, dtype=np.float64)
+        for k, name in enumerate(tm.env_names):
+            v = m._env_state.get(name, 0.0)
+            row[k] = float(v) if T._env_dtype_of(v) is not None else 0.0
+        env0.append(row)
+    lib = jit.compile_source(src0)
+    tm = variants0[-1]
+    n_agents = (C.c_longlong * 4)(*([t["n"] for t in tm.types] + [0] * (4 - len(tm.types))))
+    nc = len(meta0["consts"])
+    cst = np.ascontiguousarray(np.array(consts, dtype=np.float64).reshape(R, max(nc, 0)))
+    envs = np.ascontiguousarray(np.stack(env0, axis=0))
+    seeds = np.array([int(m.config.seed) & 0xFFFFFFFF for m in models], dtype=np.uint32)
+    local = np.zeros((hi - lo, nat.MAX_METRICS), dtype=np.float64)
+    secs = C.c_double(0.0)
+    if hi > lo:
+        lib.jxc_ensemble_run.restype = C.c_int
+        rc = lib.jxc_ensemble_run(C.c_int(nat.engine().device), C.c_int(hi - lo), C.c_int(int(steps)), n_agents,
+                                  nat.ptr(np.ascontiguousarray(cst[lo:hi])), C.c_int(nc),
+                                  nat.ptr(np.ascontiguousarray(envs[lo:hi])), nat.ptr(np.ascontiguousarray(seeds[lo:hi])),
+                                  C.c_int(1 if tm.has_env_fn else 0), C.c_int(int(models[0].config.rng_mode
+                                                                                 if models[0].config.rng_mode is not None
+                                                                                 else nat.default_rng_mode())),
+                                  nat.ptr(local), C.byref(secs))
+        if rc != 0:
+            raise nat.JxbError(rc, "traced ensemble launch failed")
+    full = dist.gather_rows(local, R)
+    out = {}
+    for k, (name, v) in enumerate(tm.metrics):
+        dt = {T.F32: np.float32, T.I32: np.int32, T.WI: np.int32, T.BOOL: np.bool_}.get(v.dtype, np.float64)
+        col = full[:, k]
+        out[name] = col if dt == np.float64 else col.astype(dt)
+    return out, dist.max_over_ranks(secs.value)
+
+
 def run_last_metrics(models: Sequence[Model], steps: Optional[int] = None):
     """Final value of every metric for every model -> (dict name -> array[R], device_seconds).
 
     Sharded over ranks when torch.distributed is initialised with world_size > 1."""
     steps = models[0].config.steps if steps is None else steps
+    if _traced(models):
+        return _run_traced(models, steps)
     desc, slots, params, seeds, env0 = plan(models)
     layout = metric_layout(models)
     R = len(models)

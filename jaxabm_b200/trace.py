@@ -652,7 +652,7 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
     _SEQ[0] = 0
     pool: List[float] = []               # float constants, in emission order (position-based: the SOURCE does
                                          # not depend on their values, so a parameter sweep compiles once)
-    w('// generated by jaxabm_b200/trace.py -- do not edit\n#include "common.cuh"\n#include "economy.cuh"\nusing namespace jxb;\n')
+    w('// generated by jaxabm_b200/trace.py -- do not edit\n#include <string.h>\n#include "common.cuh"\n#include "economy.cuh"\nusing namespace jxb;\n')
     # reductions are numbered per variant (different dtype signatures may trace different graphs)
     meta = {"n_acc": 0, "n_variants": len(variants)}
     for var, tm in enumerate(variants):
@@ -908,23 +908,27 @@ __global__ void __launch_bounds__(kThreads) jxc_step_kernel(const ModelDev md) {
   }
 }
 ''')
-    # ---- init kernel ----------------------------------------------------------------------------
+    # ---- init (AgentCollection.init, agent.py:92-130) -------------------------------------------
     for ti, t in enumerate(tm0.types):
-        w(f"template <int MODE> __global__ void __launch_bounds__(kThreads) jxc_init_kernel_t{ti}(const TypeDev t, Key key, "
-          f"const double* __restrict__ cst) {{")
-        w("  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {")
-        w("    const Key ak = split_child<MODE>(key, (unsigned long long)(t.goff + i), (unsigned long long)t.gn);")
+        w(f"template <int MODE> __device__ __forceinline__ void jxc_init_one_t{ti}(const TypeDev& t, Key key, "
+          f"const double* __restrict__ cst, long long i) {{")
+        w("  const Key ak = split_child<MODE>(key, (unsigned long long)(t.goff + i), (unsigned long long)t.gn);")
 
         def leaf_init(x, em):
             raise TraceError("init_state can only use its key and Python constants")
         em = Emitter(leaf_init, "ak", pool)
         vals = [(fi, dt, em.cast(t["init"][fname], dt)) for fi, (fname, dt) in enumerate(t["fields"])]
         for ln in em.lines:
-            w("    " + ln)
+            w("  " + ln)
         for fi, dt, e in vals:
             ct = {F32: "float", I32: "int", BOOL: "unsigned char"}[dt]
-            w(f"    (({ct}*)t.f[{fi}])[i] = {e}{' ? 1 : 0' if dt == BOOL else ''};")
-        w("  }\n}\n")
+            w(f"  (({ct}*)t.f[{fi}])[i] = {e}{' ? 1 : 0' if dt == BOOL else ''};")
+        w("}")
+        w(f"template <int MODE> __global__ void __launch_bounds__(kThreads) jxc_init_kernel_t{ti}(const TypeDev t, Key key, "
+          f"const double* __restrict__ cst) {{")
+        w("  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x)")
+        w(f"    jxc_init_one_t{ti}<MODE>(t, key, cst, i);")
+        w("}\n")
     # ---- launchers ------------------------------------------------------------------------------
     w('extern "C" int jxc_n_acc() { return NACC; }')
     w(f'extern "C" int jxc_n_variants() {{ return {len(variants)}; }}')
@@ -939,6 +943,168 @@ __global__ void __launch_bounds__(kThreads) jxc_step_kernel(const ModelDev md) {
         w(f"  if (variant == {var}) {{ if (rng_mode == 1) jxc_step_kernel<1, {var}><<<md->grid_blocks, kThreads, 0, s>>>(*md); "
           f"else jxc_step_kernel<0, {var}><<<md->grid_blocks, kThreads, 0, s>>>(*md); }}")
     w("  return (int)cudaGetLastError();\n}")
+    # ---- replica-parallel ensemble of the traced model (analysis.py:113-157, :434-476) ----------------
+    kinds_last = ", ".join({"sum": "0", "mean": "0", "max": "1", "min": "2"}[r.attr[0]] for r in
+                           used_leaves(list(variants[-1].env_out.values()) + [v for _, v in variants[-1].metrics], "reduce")) or "0"
+    kinds_first = ", ".join({"sum": "0", "mean": "0", "max": "1", "min": "2"}[r.attr[0]] for r in
+                            used_leaves(list(variants[0].env_out.values()) + [v for _, v in variants[0].metrics], "reduce")) or "0"
+    field_sizes = [[{F32: 4, I32: 4, BOOL: 1}[dt] for _, dt in t["fields"]] for t in tm0.types]
+    w(f"constexpr int kEnsTypes = {n_types};")
+    w("constexpr int kEnsThreads2 = 1024;")
+    w("struct JxcEns { int R, steps, n_consts, has_env_fn, use_smem; const double* consts; const double* env0; const unsigned int* seeds; "
+      "double* out; unsigned char* scratch; size_t state_bytes; long long n[JXB_MAX_TYPES]; size_t foff[JXB_MAX_TYPES][kMaxFields]; };")
+    w("""
+// One CTA owns one replica at a time and runs its whole life in shared memory (or an L2-resident slot):
+// initialize from PRNGKey(seed), then `steps` x (traced agent updates -> reduction -> traced env/metrics
+// tail), with the key schedule of model.py:129-130,156,164,183 derived in the kernel.
+template <int MODE>
+__global__ void __launch_bounds__(kEnsThreads2) jxc_ensemble_kernel(const JxcEns e) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  __shared__ ModelDev md;
+  __shared__ Ctrl ctrl;
+  __shared__ double env[kMaxEnv];
+  __shared__ double s_red[(kEnsThreads2 / 32) * NACC];
+  __shared__ double s_tot[NACC];
+  __shared__ double metrics[kMaxMetrics];
+  __shared__ Key s_keys[JXB_MAX_TYPES + 2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned char* base = e.use_smem ? dsm : e.scratch + (size_t)blockIdx.x * e.state_bytes;
+  for (int r = blockIdx.x; r < e.R; r += gridDim.x) {
+    const double* cst = e.consts + (size_t)r * e.n_consts;
+    if (tid == 0) {
+      md.n_types = kEnsTypes; md.collect_interval = 1; md.world_size = 1; md.env = env; md.ctrl = &ctrl; md.consts = cst;
+      for (int i = 0; i < kEnsTypes; ++i) {
+        md.t[i].n = e.n[i]; md.t[i].goff = 0; md.t[i].gn = e.n[i]; md.t[i].block_begin = 0; md.t[i].block_count = 1;
+        for (int f = 0; f < kMaxFields; ++f) md.t[i].f[f] = base + e.foff[i][f];
+      }
+      for (int k = 0; k < kMaxEnv; ++k) env[k] = e.env0[(size_t)r * kMaxEnv + k];
+      for (int k = 0; k < kMaxMetrics; ++k) metrics[k] = 0.0;
+      ctrl.time_step = 0;
+      const Key root{0u, e.seeds[r]};
+      s_keys[JXB_MAX_TYPES + 1] = split_child<MODE>(root, 0ull, (unsigned long long)(kEnsTypes + 1));     // model _rng
+      for (int i = 0; i < kEnsTypes; ++i) s_keys[i] = split_child<MODE>(root, (unsigned long long)(i + 1), (unsigned long long)(kEnsTypes + 1));
+    }
+    __syncthreads();""")
+    for ti in range(n_types):
+        w(f"    for (long long i = tid; i < md.t[{ti}].n; i += blockDim.x) jxc_init_one_t{ti}<MODE>(md.t[{ti}], s_keys[{ti}], cst, i);")
+    w("""    __syncthreads();
+    for (int step = 0; step < e.steps; ++step) {
+      if (tid == 0) {                       // model.py:156,164,183
+        Key rng = s_keys[JXB_MAX_TYPES + 1];
+        Key step_key = split_child<MODE>(rng, 1ull, 2ull);
+        s_keys[JXB_MAX_TYPES + 1] = split_child<MODE>(rng, 0ull, 2ull);
+        for (int i = 0; i < kEnsTypes; ++i) {
+          s_keys[i] = split_child<MODE>(step_key, 1ull, 2ull);
+          step_key = split_child<MODE>(step_key, 0ull, 2ull);
+        }
+        s_keys[JXB_MAX_TYPES] = e.has_env_fn ? split_child<MODE>(step_key, 1ull, 2ull) : Key{0u, 0u};
+      }
+      __syncthreads();
+      double accd[NACC];
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) accd[i] = 0.0;
+      const long long time_step = ctrl.time_step;
+      const bool first = step == 0;""")
+    nv = len(variants)
+    for ti in range(n_types):
+        if nv > 1:
+            w(f"      if (first) jxc_agents_v0_t{ti}<MODE>(md.t[{ti}], env, cst, time_step, s_keys[{ti}], 0, accd);")
+            w(f"      else jxc_agents_v{nv - 1}_t{ti}<MODE>(md.t[{ti}], env, cst, time_step, s_keys[{ti}], 0, accd);")
+        else:
+            w(f"      jxc_agents_v0_t{ti}<MODE>(md.t[{ti}], env, cst, time_step, s_keys[{ti}], 0, accd);")
+    w(f"      const int kind0[NACC] = {{{kinds_first}}}; const int kind1[NACC] = {{{kinds_last}}};")
+    w("""      const int* kind = first ? kind0 : kind1;
+      if (lane == 0)
+        for (int i = 0; i < NACC; ++i) s_red[warp * NACC + i] = accd[i];
+      __syncthreads();
+      if (tid < NACC) {
+        double rr = s_red[tid];
+        for (int w2 = 1; w2 < kEnsThreads2 / 32; ++w2) {
+          const double v = s_red[w2 * NACC + tid];
+          rr = kind[tid] == 0 ? rr + v : (kind[tid] == 1 ? fmax(rr, v) : fmin(rr, v));
+        }
+        s_tot[tid] = rr;
+      }
+      __syncthreads();
+      if (tid == 0) {""")
+    if nv > 1:
+        w(f"        if (first) jxc_tail_v0<MODE>(md, s_tot, s_keys[JXB_MAX_TYPES], metrics); else jxc_tail_v{nv - 1}<MODE>(md, s_tot, s_keys[JXB_MAX_TYPES], metrics);")
+    else:
+        w("        jxc_tail_v0<MODE>(md, s_tot, s_keys[JXB_MAX_TYPES], metrics);")
+    w("""        ctrl.time_step += 1;
+      }
+      __syncthreads();
+    }
+    if (tid < kMaxMetrics) e.out[(size_t)r * kMaxMetrics + tid] = metrics[tid];
+    __syncthreads();
+  }
+}
+""")
+    sizes_init = "{" + ", ".join("{" + ", ".join(str(x) for x in fs) + "}" for fs in field_sizes) + "}"
+    nf_init = "{" + ", ".join(str(len(fs)) for fs in field_sizes) + "}"
+    w(f"static const int kFieldSize[kEnsTypes][kMaxFields] = {sizes_init};")
+    w(f"static const int kNumFields[kEnsTypes] = {nf_init};")
+    w("""
+// Self-contained ensemble entry point: R replicas, replica r uses the constant table consts[r][n_consts], the
+// env values env0[r][kMaxEnv] and PRNGKey(seeds[r]); last_metrics[r][kMaxMetrics] receives results[m][-1].
+extern "C" int jxc_ensemble_run(int device, int R, int steps, const long long* n_agents, const double* consts, int n_consts,
+                                const double* env0, const unsigned int* seeds, int has_env_fn, int rng_mode,
+                                double* last_metrics, double* device_seconds) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  JxcEns e;
+  memset(&e, 0, sizeof(e));
+  e.R = R; e.steps = steps; e.n_consts = n_consts; e.has_env_fn = has_env_fn;
+  size_t off = 0;
+  for (int i = 0; i < kEnsTypes; ++i) {
+    e.n[i] = n_agents[i];
+    for (int f = 0; f < kNumFields[i]; ++f) {
+      e.foff[i][f] = off;
+      off += (((size_t)n_agents[i] + 8) * kFieldSize[i][f] + 15) / 16 * 16;
+    }
+  }
+  e.state_bytes = off;
+  e.use_smem = off <= 200 * 1024;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -2;
+  int grid = e.use_smem ? (R < prop.multiProcessorCount ? R : prop.multiProcessorCount)
+                        : (R < 2 * prop.multiProcessorCount ? R : 2 * prop.multiProcessorCount);
+  double *d_c = nullptr, *d_e = nullptr, *d_o = nullptr; unsigned int* d_s = nullptr; unsigned char* d_scr = nullptr;
+  cudaEvent_t e0, e1;
+  int rc = 0;
+#define JCK(x) do { if ((x) != cudaSuccess) { rc = -3; goto done; } } while (0)
+  JCK(cudaMalloc(&d_c, (size_t)R * (n_consts > 0 ? n_consts : 1) * sizeof(double)));
+  JCK(cudaMalloc(&d_e, (size_t)R * kMaxEnv * sizeof(double)));
+  JCK(cudaMalloc(&d_o, (size_t)R * kMaxMetrics * sizeof(double)));
+  JCK(cudaMalloc(&d_s, (size_t)R * sizeof(unsigned int)));
+  if (!e.use_smem) JCK(cudaMalloc(&d_scr, (size_t)grid * off));
+  if (n_consts) JCK(cudaMemcpy(d_c, consts, (size_t)R * n_consts * sizeof(double), cudaMemcpyHostToDevice));
+  JCK(cudaMemcpy(d_e, env0, (size_t)R * kMaxEnv * sizeof(double), cudaMemcpyHostToDevice));
+  JCK(cudaMemcpy(d_s, seeds, (size_t)R * sizeof(unsigned int), cudaMemcpyHostToDevice));
+  e.consts = d_c; e.env0 = d_e; e.seeds = d_s; e.out = d_o; e.scratch = d_scr;
+  {
+    const size_t dyn = e.use_smem ? off : 0;
+    if (dyn > 48 * 1024) {
+      JCK(cudaFuncSetAttribute(jxc_ensemble_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      JCK(cudaFuncSetAttribute(jxc_ensemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    }
+    JCK(cudaEventCreate(&e0)); JCK(cudaEventCreate(&e1));
+    JCK(cudaEventRecord(e0, 0));
+    if (rng_mode == 1) jxc_ensemble_kernel<1><<<grid, kEnsThreads2, dyn>>>(e);
+    else jxc_ensemble_kernel<0><<<grid, kEnsThreads2, dyn>>>(e);
+    JCK(cudaGetLastError());
+    JCK(cudaEventRecord(e1, 0));
+    JCK(cudaMemcpy(last_metrics, d_o, (size_t)R * kMaxMetrics * sizeof(double), cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    JCK(cudaEventElapsedTime(&ms, e0, e1));
+    if (device_seconds) *device_seconds = ms * 1e-3;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+done:
+#undef JCK
+  cudaFree(d_c); cudaFree(d_e); cudaFree(d_o); cudaFree(d_s); cudaFree(d_scr);
+  return rc;
+}
+""")
     meta["consts"] = pool
     return "\n".join(out) + "\n", meta
 

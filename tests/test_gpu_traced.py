@@ -243,3 +243,34 @@ def test_tracer_dtype_rules_on_random_expressions(mode, case):
     assert [int(v) for v in r["sk"]] == [int(v) for v in ro["sk"]] and [int(v) for v in r["nb"]] == [int(v) for v in ro["nb"]]
     for k in ("sx", "mx", "scale"):
         assert np.allclose(_series(r, k), _series(ro, k), rtol=1e-4, atol=1e-4), k
+
+
+def test_traced_ensemble_matches_single_runs(mode):
+    """Replica-parallel ensemble kernel of a traced model (generated with the step kernel): its in-kernel
+    key schedule (model.py:129-130,156,164,183), per-replica env values and seeds must reproduce the
+    individual device runs and the eager oracle."""
+    from jaxabm_b200 import ensemble
+    from traced_models import build as b
+    seeds = [5, 6, 7, 1234]
+    vols = [0.02, 0.03, 0.01, 0.05]
+    models = []
+    for s, v in zip(seeds, vols):
+        m = b.device_noisy(3001, s, mode)
+        m.add_env_state("volatility", v)
+        m.config.steps = 9
+        models.append(m)
+    assert ensemble.batchable(models)
+    last, secs = ensemble.run_last_metrics(models, steps=9)
+    assert secs > 0.0
+    for i, (s, v) in enumerate(zip(seeds, vols)):
+        single = b.device_noisy(3001, s, mode)
+        single.add_env_state("volatility", v)
+        r = single.run(steps=9)
+        o = b.oracle_noisy(3001, s, mode)
+        o.add_env_state("volatility", v)
+        ro = o.run(steps=9)
+        for k in ("n_active", "total_trades", "steps_done"):
+            assert int(last[k][i]) == int(r[k][-1]) == int(ro[k][-1]), (k, i)
+        for k in ("mean_wealth", "max_wealth", "volatility", "participation", "rich_share"):
+            assert float(last[k][i]) == pytest.approx(float(r[k][-1]), rel=2e-5, abs=1e-6), (k, i)
+            assert float(last[k][i]) == pytest.approx(float(ro[k][-1]), rel=5e-5, abs=1e-6), (k, i)
