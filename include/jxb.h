@@ -246,6 +246,19 @@ int jxb_engine_p2p_export(jxb_engine*, void* handle_out, size_t bytes);
 int jxb_engine_p2p_attach(jxb_engine*, const void* handles, size_t bytes_each, int rank,
                           int world_size);
 
+/* ---- ONE grid split into row bands over the GPUs of a box (Grid) ------ */
+/* jaxabm/agentpy.py:480-527 keeps one env['grid'] for all agents; here rank r of desc.world_size owns
+ * the rows [row_begin, row_end) (consecutive bands in rank order, at most ceil(W / world) rows each)
+ * and every rank holds the whole per-agent columns.  export allocates this rank's receive area and
+ * returns its CUDA IPC handle (JXB_IPC_HANDLE_BYTES); the host shim all-gathers the handles and
+ * attach maps the peers' areas (one process per rank; the ranks may share a device).  After that jxb_model_run
+ * steps the band with no host round trip: the unsatisfied agents' records are stored straight into
+ * every peer's area over NVLink by the compaction kernel (no NCCL call on the step path).
+ * Downloads of a shard return ITS view; the host combines the ranks: 'position' max (-1 = agent is
+ * not in my band), 'satisfied' min, 'moves' sum, 'type' any; env grid rows [row_begin, row_end).     */
+int jxb_model_grid_shard_export(jxb_model*, int row_begin, int row_end, void* handle_out, size_t bytes);
+int jxb_model_grid_shard_attach(jxb_model*, const void* handles, size_t bytes_each, int n_ranks);
+
 /* ---- host-only scalar key algebra (jax.random on the reference's host path) -------- */
 /* jax.random.split(key, n) -> out[n][2] (jaxabm/model.py:129,156; analysis.py:438).  */
 int jxb_prng_split(int rng_mode, const uint32_t key[2], int n, uint32_t* out);

@@ -90,6 +90,8 @@ SIGNATURES = {
     "jxb_engine_attach_nccl": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int]),
     "jxb_engine_p2p_export": (C.c_int, [_P, _P, C.c_size_t]),
     "jxb_engine_p2p_attach": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int]),
+    "jxb_model_grid_shard_export": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_size_t]),
+    "jxb_model_grid_shard_attach": (C.c_int, [_P, _P, C.c_size_t, C.c_int]),
     "jxb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "jxb_host_free": (C.c_int, [_P]),
     "jxb_prng_split": (C.c_int, [C.c_int, _P, C.c_int, _P]),

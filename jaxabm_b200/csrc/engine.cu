@@ -23,6 +23,7 @@
 #include "rules.cuh"
 #include "schelling.cuh"
 #include "schelling_bits.cuh"
+#include "grid_shard.cuh"
 #include "sir.cuh"
 #include "ensemble.cuh"
 
@@ -214,6 +215,9 @@ struct jxb_model {
   bool grid_built = false; bool sat_dirty = false; long long n_empty_cells = 0; int sch_blocks = 0;
   // bit-sliced variant (row length a multiple of 1024): the planes are the live grid during a run
   bool sch_bits = false; SchellingBitsDev sb{}; bool ct_stale = false;
+  // row-band decomposition over the GPUs of a box (csrc/grid_shard.cuh): receive area + peers' areas
+  bool grid_sharded = false; bool gs_attached = false; GridShardDev gs{}; unsigned char* gs_area = nullptr;
+  size_t gs_area_bytes = 0; void* gs_opened[kMaxPeers] = {}; int gs_move_blocks = 0;
   // SIR
   bool has_net = false; SirDev sv{}; bool net_built = false; long long nnz = 0;
   // SIR formulation (JXB_SIR_MODE): 0 "pull" = CSR ballot-segmented sweep of ALL edges, fused
@@ -513,7 +517,7 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
   md.world_size = d->world_size > 1 ? d->world_size : 1;
   md.rank = d->rank;
   md.exchange = 0;
-  if (md.world_size > 1) {
+  if (md.world_size > 1 && d->program != JXB_PROGRAM_SCHELLING) {   // a sharded grid has its own receive areas
     static const bool force_nccl = getenv("JXB_EXCHANGE") && !strcmp(getenv("JXB_EXCHANGE"), "nccl");
     if (eng->p2p && !force_nccl) {
       if (eng->world != md.world_size || eng->rank != md.rank) {
@@ -615,6 +619,16 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
         }
       }
     }
+    if (md.world_size > 1) {
+      // row bands over the ranks: always the bit-plane layout (any row length that fills whole words)
+      if (sd.H % 32 != 0) { jxb_model_destroy(m); return fail(JXB_ERR_UNSUPPORTED, "a sharded Grid needs a row length that is a multiple of 32 cells"); }
+      if (md.world_size > kMaxPeers || md.rank < 0 || md.rank >= md.world_size || sd.W < md.world_size) {
+        jxb_model_destroy(m);
+        return fail(JXB_ERR_INVALID, "cannot split %d grid rows over rank %d of %d (at most %d ranks)", sd.W, md.rank, md.world_size, kMaxPeers);
+      }
+      m->sch_bits = true;
+      m->grid_sharded = true;
+    }
     if (m->sch_bits) {
       SchellingBitsDev& sb = m->sb;
       sb.wpr = sd.H / 32;
@@ -683,6 +697,9 @@ extern "C" int jxb_model_destroy(jxb_model* m) {
   if (m->graphK) cudaGraphExecDestroy(m->graphK);
   for (auto e : m->prof_events) cudaEventDestroy(e);
   for (auto& a : m->allocs) pool_free(m->eng, a.first, a.second);
+  for (int p = 0; p < kMaxPeers; ++p)
+    if (m->gs_opened[p]) cudaIpcCloseMemHandle(m->gs_opened[p]);
+  if (m->gs_area) cudaFree(m->gs_area);
   pool_free(m->eng, m->d_keys, m->keys_cap * 4);
   pool_free(m->eng, m->d_metrics, m->rec_cap * kMaxMetrics * sizeof(double));
   pool_free(m->eng, m->d_rec, m->rec_cap * sizeof(int));
@@ -756,7 +773,7 @@ extern "C" int jxb_model_upload(jxb_model* m, int type, int field, const void* h
   CK(cudaMemcpyAsync(m->dev.t[type].f[field], host, bytes, cudaMemcpyHostToDevice, m->eng->stream));
   CK(cudaStreamSynchronize(m->eng->stream));
   if (m->has_net) return sir_sync_from_api(m);
-  if (m->has_grid && (field == 0 || field == 1)) m->grid_built = false;
+  if (m->has_grid && (field == 0 || field == 1 || (field == 3 && m->grid_sharded))) m->grid_built = false;
   if (m->has_grid && field == 2) m->sat_dirty = false;
   return JXB_OK;
 }
@@ -767,8 +784,18 @@ extern "C" int jxb_model_download(jxb_model* m, int type, int field, void* host,
   CK(cudaSetDevice(m->eng->device));
   if (m->has_net) { rc = sir_sync_to_api(m); if (rc) return rc; }
   if (m->has_grid && field == 2 && m->sat_dirty) { rc = schelling_export_satisfied(m); if (rc) return rc; }
+  if (m->grid_sharded && field == 1 && m->grid_built) {
+    // this rank's view: the agents sitting in its band, -1 for everybody else (host: max over ranks)
+    CK(cudaMemsetAsync(m->dev.t[0].f[1], 0xFF, bytes, m->eng->stream));
+    grid_shard_export_position_kernel<<<m->eng->sms * 8, 256, 0, m->eng->stream>>>(m->sd, m->gs, (int2*)m->dev.t[0].f[1]);
+    m->eng->launches++;
+    CK(cudaGetLastError());
+  }
   CK(cudaMemcpyAsync(host, m->dev.t[type].f[field], bytes, cudaMemcpyDeviceToHost, m->eng->stream));
   CK(cudaStreamSynchronize(m->eng->stream));
+  // 'moves' of a sharded Grid is a sum over ranks; until the first rebuild splits the uploaded values by
+  // band, every rank still holds the caller's whole column: only rank 0 reports it
+  if (m->grid_sharded && field == 3 && !m->grid_built && m->dev.rank != 0) memset(host, 0, bytes);
   return JXB_OK;
 }
 
@@ -832,10 +859,13 @@ extern "C" int jxb_model_time_step(jxb_model* m, int64_t* out) {
 extern "C" int jxb_model_grid_rebuild(jxb_model* m) {
   NEED(m);
   if (!m->has_grid) return fail(JXB_ERR_STATE, "model has no Grid");
+  if (m->grid_sharded && !m->gs_attached)
+    return fail(JXB_ERR_STATE, "sharded Grid: call jxb_model_grid_shard_export / jxb_model_grid_shard_attach first");
   CK(cudaSetDevice(m->eng->device));
   cudaStream_t s = m->eng->stream;
   int* d_err = nullptr;
-  CK(cudaMalloc(&d_err, (2 + (size_t)m->sd.ntiles) * sizeof(int)));
+  const size_t err_bytes = (2 + (size_t)m->sd.ntiles) * sizeof(int);
+  CK(pool_alloc(m->eng, (void**)&d_err, err_bytes));     // pooled: cudaFree would synchronise the whole device
   CK(cudaMemsetAsync(d_err, 0, 2 * sizeof(int), s));
   const int blocks = m->eng->sms * 8;
   grid_clear_kernel<<<blocks, 256, 0, s>>>(m->sd, m->pad);
@@ -850,7 +880,7 @@ extern "C" int jxb_model_grid_rebuild(jxb_model* m) {
   CK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&n_empty, d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  cudaFree(d_err);
+  pool_free(m->eng, d_err, err_bytes);
   if (!err && n_empty != m->sd.n_empty) err = 2;
   CK(cudaGetLastError());
   if (err == 1) return fail(JXB_ERR_INVALID, "an agent position lies outside the grid");
@@ -860,6 +890,12 @@ extern "C" int jxb_model_grid_rebuild(jxb_model* m) {
     m->eng->launches++;
     CK(cudaGetLastError());
     m->ct_stale = false;
+  }
+  if (m->grid_sharded) {
+    grid_shard_own_moves_kernel<<<blocks, 256, 0, s>>>(m->gs, (const int2*)m->dev.t[0].f[1], (int*)m->dev.t[0].f[3],
+                                                       m->desc.types[0].n_agents);
+    m->eng->launches++;
+    CK(cudaGetLastError());
   }
   m->grid_built = true;
   return JXB_OK;
@@ -897,11 +933,71 @@ extern "C" int jxb_model_download_empty_cells(jxb_model* m, int32_t* host, size_
   return JXB_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Grid row-band sharding (csrc/grid_shard.cuh)
+// ---------------------------------------------------------------------------------------
+extern "C" int jxb_model_grid_shard_export(jxb_model* m, int row_begin, int row_end, void* handle_out, size_t bytes) {
+  NEED(m);
+  if (!m->grid_sharded) return fail(JXB_ERR_STATE, "model is not a sharded Grid (desc.world_size > 1 with a Schelling program)");
+  if (!handle_out || bytes < sizeof(cudaIpcMemHandle_t))
+    return fail(JXB_ERR_INVALID, "need %zu bytes for the IPC handle", sizeof(cudaIpcMemHandle_t));
+  const int G = m->dev.world_size, W = m->sd.W, H = m->sd.H;
+  const int max_rows = (W + G - 1) / G;
+  if (row_begin < 0 || row_end > W || row_end <= row_begin || row_end - row_begin > max_rows)
+    return fail(JXB_ERR_INVALID, "band [%d,%d) of %d rows: every rank owns 1..%d consecutive rows", row_begin, row_end, W, max_rows);
+  CK(cudaSetDevice(m->eng->device));
+  GridShardDev& gs = m->gs;
+  gs.rank = m->dev.rank; gs.world = G; gs.X0 = row_begin; gs.X1 = row_end;
+  gs.cap = (unsigned long long)std::min<long long>(m->desc.types[0].n_agents, (long long)max_rows * H);
+  if (!m->gs_area) {
+    m->gs_area_bytes = sizeof(GridXchgHdr) + (size_t)2 * G * gs.cap * sizeof(uint2);
+    CK(cudaMalloc((void**)&m->gs_area, m->gs_area_bytes));      // its own allocation: IPC handles name whole allocations
+    CK(cudaMemset(m->gs_area, 0, sizeof(GridXchgHdr)));
+    int rc;
+    if ((rc = dev_alloc(m, &gs.info, 1))) return rc;
+    CK(cudaMemset(gs.info, 0, sizeof(GridStepInfo)));
+    const int nrows = row_end - row_begin, strips = (m->sb.wpr + 31) / 32;
+    // same split for every band size this model can get: ~2 strip-rows per warp, at most 2 CTAs per SM
+    gs.blocks = (int)std::max<long long>(1, std::min<long long>(std::min<long long>((long long)m->eng->sms * 2, nrows),
+                                                                ((long long)nrows * strips + 15) / 16));
+    if ((rc = dev_alloc(m, &gs.part, (size_t)gs.blocks))) return rc;
+    m->gs_move_blocks = m->eng->sms * 4;
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, m->gs_area));
+  memset(handle_out, 0, bytes);
+  memcpy(handle_out, &h, sizeof(h));
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_grid_shard_attach(jxb_model* m, const void* handles, size_t bytes_each, int n_ranks) {
+  NEED(m);
+  if (!m->grid_sharded || !m->gs_area) return fail(JXB_ERR_STATE, "call jxb_model_grid_shard_export first");
+  if (!handles || n_ranks != m->dev.world_size) return fail(JXB_ERR_INVALID, "need the handles of all %d ranks", m->dev.world_size);
+  if (bytes_each < sizeof(cudaIpcMemHandle_t)) return fail(JXB_ERR_INVALID, "handle entries too small");
+  CK(cudaSetDevice(m->eng->device));
+  for (int p = 0; p < n_ranks; ++p) {
+    if (p == m->dev.rank) { m->gs.peer[p] = m->gs_area; m->gs.self = m->gs_area; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)p * bytes_each, sizeof(h));
+    void* q = nullptr;
+    CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    m->gs_opened[p] = q;
+    m->gs.peer[p] = (unsigned char*)q;
+  }
+  m->gs_attached = true;
+  // kernel arguments are baked into cached graphs
+  if (m->graph1) { cudaGraphExecDestroy(m->graph1); m->graph1 = nullptr; }
+  if (m->graphK) { cudaGraphExecDestroy(m->graphK); m->graphK = nullptr; }
+  return JXB_OK;
+}
+
 static int schelling_export_satisfied(jxb_model* m) {
   cudaStream_t s = m->eng->stream;
   unsigned char* sat = (unsigned char*)m->dev.t[0].f[2];
   CK(cudaMemsetAsync(sat, 1, (size_t)m->desc.types[0].n_agents, s));
-  satisfied_export_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->sd, m->dev.ctrl, sat);
+  if (m->grid_sharded) grid_shard_export_satisfied_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->gs, sat);   // host: min over ranks
+  else satisfied_export_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->sd, m->dev.ctrl, sat);
   m->eng->launches++;
   CK(cudaGetLastError());
   m->sat_dirty = false;
@@ -1182,6 +1278,18 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       eng->launches += 1;
       break;
     }
+    case JXB_PROGRAM_SCHELLING: {     // row-band shard of a grid (the single-GPU run is one persistent launch)
+      if (!m->grid_sharded || !m->gs_attached) return fail(JXB_ERR_STATE, "sharded Grid step without attached peers");
+      if (timed) cudaEventRecord(e0, s);
+      grid_shard_sweep_kernel<<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs);
+      if (timed) cudaEventRecord(e1, s);
+      grid_shard_publish_kernel<<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
+      grid_shard_wait_kernel<<<1, 32, 0, s>>>(m->sd, m->gs, m->dev);
+      if (part) grid_shard_move_kernel<1><<<m->gs_move_blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
+      else grid_shard_move_kernel<0><<<m->gs_move_blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
+      eng->launches += 4;
+      break;
+    }
     case JXB_PROGRAM_TRACED: {
       if (timed) cudaEventRecord(e0, s);
       const int variant = m->traced_started ? m->traced_variants - 1 : 0;
@@ -1285,6 +1393,7 @@ static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
 }
 
 static int launches_per_step(jxb_model* m) {
+  if (m->grid_sharded) return 4;
   if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 : (m->sir_mode == 1 ? 2 : 1);
   if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? 4 : 1);
   return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
@@ -1302,7 +1411,7 @@ extern "C" int jxb_model_profile(jxb_model* m, double* seconds, int64_t* launche
   if (launches) *launches = m->prof_launches;
   if (name) {
     switch (m->desc.program) {
-      case JXB_PROGRAM_SCHELLING: *name = m->sch_bits ? "schelling_bits_kernel" : "schelling_run_kernel"; break;
+      case JXB_PROGRAM_SCHELLING: *name = m->grid_sharded ? "grid_shard_sweep_kernel" : (m->sch_bits ? "schelling_bits_kernel" : "schelling_run_kernel"); break;
       case JXB_PROGRAM_ECONOMY: *name = "economy_step_kernel"; break;
       case JXB_PROGRAM_TRACED: *name = "jxc_step_kernel (traced)"; break;
       case JXB_PROGRAM_SIR:
@@ -1378,7 +1487,7 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
     CK(cudaMemcpyAsync(&m->dev.ctrl->step_in_run, zeros, sizeof(zeros), cudaMemcpyHostToDevice, s));
   }
   static const bool use_graph = getenv("JXB_NO_GRAPH") == nullptr;
-  const bool persistent = m->desc.program == JXB_PROGRAM_SCHELLING;
+  const bool persistent = m->desc.program == JXB_PROGRAM_SCHELLING && !m->grid_sharded;
   const bool graphs = use_graph && !persistent && !m->profile && m->dev.exchange != 2 && steps > 0 &&
                       !(m->has_eco && m->dev.world_size > 1) &&  // NCCL call on the step path: launch eagerly
                       !(m->traced && !m->traced_started);        // first step of a traced model uses variant 0
@@ -1443,6 +1552,12 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   }
   m->time_step = t0 + steps;
   if (m->has_grid && steps > 0) m->sat_dirty = true;
+  if (m->grid_sharded) {
+    if (steps > 0) m->ct_stale = true;
+    unsigned int gerr = 0;
+    CK(cudaMemcpy(&gerr, &((GridXchgHdr*)m->gs_area)->err, sizeof(gerr), cudaMemcpyDeviceToHost));
+    if (gerr) return fail(JXB_ERR_NCCL, "sharded Grid: a rank did not publish its band within the spin budget");
+  }
   if (m->dev.exchange == 1) {
     unsigned int xerr = 0;
     CK(cudaMemcpy(&xerr, &eng->xlocal->err, sizeof(xerr), cudaMemcpyDeviceToHost));

@@ -105,6 +105,70 @@ __device__ __forceinline__ unsigned int lt_step(unsigned int s, unsigned int k, 
 // cell sets, so classes with the same weight share one mask and one popcount: 13 distinct weights.
 constexpr int kSegPairs = 13;
 
+// one output row: the 32 cells of a lane's word from the horizontal sums of the rows above (t*), own
+// (m*) and below (b*) of both planes.  Returns the unsatisfied-agent mask; adds the cells with an
+// occupied neighbour to my_occ and the segregation numerator classes to seg.
+__device__ __forceinline__ unsigned int eval_row(const RowSums& to, const RowSums& tt, const RowSums& mo,
+                                                 const RowSums& mt, const RowSums& bo, const RowSums& bt,
+                                                 const SchellingBitsDev& sb, unsigned int& my_occ,
+                                                 unsigned int (&seg)[kSegPairs]) {
+  unsigned int o[4], n[4];
+  add_rows(to, mo, bo, o);
+  add_rows(tt, mt, bt, n);
+  const unsigned int A = mo.c, T = mt.c;
+  // d = o - n  (n <= o per cell, so no final borrow)
+  unsigned int d[4], br;
+  d[0] = o[0] ^ n[0];
+  br = ~o[0] & n[0];
+  d[1] = o[1] ^ n[1] ^ br;
+  br = maj3(~o[1], n[1], br);
+  d[2] = o[2] ^ n[2] ^ br;
+  br = maj3(~o[2], n[2], br);
+  d[3] = o[3] ^ n[3] ^ br;
+  unsigned int same[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) same[q] = (T & n[q]) | (~T & d[q]);
+  // one-hot decode of o = 1..8
+  const unsigned int l00 = ~o[1] & ~o[0], l01 = ~o[1] & o[0], l10 = o[1] & ~o[0], l11 = o[1] & o[0];
+  const unsigned int h0 = ~o[3] & ~o[2], h1 = ~o[3] & o[2];
+  unsigned int is[9];
+  is[1] = h0 & l01; is[2] = h0 & l10; is[3] = h0 & l11;
+  is[4] = h1 & l00; is[5] = h1 & l01; is[6] = h1 & l10; is[7] = h1 & l11;
+  is[8] = o[3];
+  // need[o] of every cell as 4 bit-sliced bits, then unsat = agent & (same < need)
+  unsigned int K[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 1; k <= 8; ++k) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) K[q] |= is[k] & sb.need_sel[k][q];
+  }
+  unsigned int lt = ~same[0] & K[0];
+  lt = lt_step(same[1], K[1], lt);
+  lt = lt_step(same[2], K[2], lt);
+  lt = lt_step(same[3], K[3], lt);
+  const unsigned int unsat = A & lt;
+  my_occ += __popc(A & (o[0] | o[1] | o[2] | o[3]));
+  // segregation numerator: one popcount per distinct weight (840/o) << b
+  {
+    const unsigned int a1 = A & is[1], a2 = A & is[2], a3 = A & is[3], a4 = A & is[4];
+    const unsigned int a5 = A & is[5], a6 = A & is[6], a7 = A & is[7], a8 = A & is[8];
+    seg[0] += __popc((a1 & same[0]) | (a2 & same[1]) | (a4 & same[2]) | (a8 & same[3]));   // 840
+    seg[1] += __popc((a2 & same[0]) | (a4 & same[1]) | (a8 & same[2]));                     // 420
+    seg[2] += __popc((a4 & same[0]) | (a8 & same[1]));                                      // 210
+    seg[3] += __popc(a8 & same[0]);                                                         // 105
+    seg[4] += __popc((a3 & same[0]) | (a6 & same[1]));                                      // 280
+    seg[5] += __popc((a3 & same[1]) | (a6 & same[2]));                                      // 560
+    seg[6] += __popc(a6 & same[0]);                                                         // 140
+    seg[7] += __popc(a5 & same[0]);                                                         // 168
+    seg[8] += __popc(a5 & same[1]);                                                         // 336
+    seg[9] += __popc(a5 & same[2]);                                                         // 672
+    seg[10] += __popc(a7 & same[0]);                                                        // 120
+    seg[11] += __popc(a7 & same[1]);                                                        // 240
+    seg[12] += __popc(a7 & same[2]);                                                        // 480
+  }
+  return unsat;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const SchellingDev sd, const SchellingBitsDev sb,
                                                                   const ModelDev md, int steps) {
@@ -178,62 +242,9 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
               ro = fetch_row(sb.occ, xn, lc, wpr);
               rt = fetch_row(sb.t1, xn, lc, wpr);
             }
-            unsigned int o[4], n[4];
-            add_rows(to, mo, bo, o);
-            add_rows(tt, mt, bt, n);
-            const unsigned int A = mo.c, T = mt.c;
-            // d = o - n  (n <= o per cell, so no final borrow)
-            unsigned int d[4], br;
-            d[0] = o[0] ^ n[0];
-            br = ~o[0] & n[0];
-            d[1] = o[1] ^ n[1] ^ br;
-            br = maj3(~o[1], n[1], br);
-            d[2] = o[2] ^ n[2] ^ br;
-            br = maj3(~o[2], n[2], br);
-            d[3] = o[3] ^ n[3] ^ br;
-            unsigned int same[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) same[q] = (T & n[q]) | (~T & d[q]);
-            // one-hot decode of o = 1..8
-            const unsigned int l00 = ~o[1] & ~o[0], l01 = ~o[1] & o[0], l10 = o[1] & ~o[0], l11 = o[1] & o[0];
-            const unsigned int h0 = ~o[3] & ~o[2], h1 = ~o[3] & o[2];
-            unsigned int is[9];
-            is[1] = h0 & l01; is[2] = h0 & l10; is[3] = h0 & l11;
-            is[4] = h1 & l00; is[5] = h1 & l01; is[6] = h1 & l10; is[7] = h1 & l11;
-            is[8] = o[3];
-            // need[o] of every cell as 4 bit-sliced bits, then unsat = agent & (same < need)
-            unsigned int K[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int k = 1; k <= 8; ++k) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) K[q] |= is[k] & sb.need_sel[k][q];
-            }
-            unsigned int lt = ~same[0] & K[0];
-            lt = lt_step(same[1], K[1], lt);
-            lt = lt_step(same[2], K[2], lt);
-            lt = lt_step(same[3], K[3], lt);
-            const unsigned int unsat = A & lt;
+            const unsigned int unsat = eval_row(to, tt, mo, mt, bo, bt, sb, my_occ, seg);
             sb.umask[x * wpr + lc.j] = unsat;
             my_unsat += __popc(unsat);
-            my_occ += __popc(A & (o[0] | o[1] | o[2] | o[3]));
-            // segregation numerator: one popcount per distinct weight (840/o) << b
-            {
-              const unsigned int a1 = A & is[1], a2 = A & is[2], a3 = A & is[3], a4 = A & is[4];
-              const unsigned int a5 = A & is[5], a6 = A & is[6], a7 = A & is[7], a8 = A & is[8];
-              seg[0] += __popc((a1 & same[0]) | (a2 & same[1]) | (a4 & same[2]) | (a8 & same[3]));   // 840
-              seg[1] += __popc((a2 & same[0]) | (a4 & same[1]) | (a8 & same[2]));                     // 420
-              seg[2] += __popc((a4 & same[0]) | (a8 & same[1]));                                      // 210
-              seg[3] += __popc(a8 & same[0]);                                                         // 105
-              seg[4] += __popc((a3 & same[0]) | (a6 & same[1]));                                      // 280
-              seg[5] += __popc((a3 & same[1]) | (a6 & same[2]));                                      // 560
-              seg[6] += __popc(a6 & same[0]);                                                         // 140
-              seg[7] += __popc(a5 & same[0]);                                                         // 168
-              seg[8] += __popc(a5 & same[1]);                                                         // 336
-              seg[9] += __popc(a5 & same[2]);                                                         // 672
-              seg[10] += __popc(a7 & same[0]);                                                        // 120
-              seg[11] += __popc(a7 & same[1]);                                                        // 240
-              seg[12] += __popc(a7 & same[2]);                                                        // 480
-            }
           }
         }
       }

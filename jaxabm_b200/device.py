@@ -55,6 +55,8 @@ class DeviceModel:
         self.handle = C.c_void_p()
         self._lib = nat.lib()
         self._keep = keep                 # the generated library of a traced model must outlive the handle
+        self.group = None                 # host-side rank group of a row-band sharded Grid
+        self.band = None                  # (row_begin, row_end) of this rank
         if traced_spec is not None:
             nat.check(self._lib.jxb_model_create_traced(self.engine.handle, C.byref(desc), C.byref(traced_spec),
                                                         C.byref(self.handle)))
@@ -111,15 +113,34 @@ class DeviceModel:
         n = self.n_agents(t)
         return ((n,) if w == 1 else (n, w)), dt
 
-    def download(self, t: int, f: int, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """Copy one state column to the host (into ``out`` -- e.g. a pinned buffer -- if given)."""
+    # how the ranks' views of a sharded Grid's columns combine (include/jxb.h, grid sharding)
+    GRID_COMBINE = {"position": "max", "satisfied": "min", "moves": "sum"}
+
+    def download(self, t: int, f: int, out: Optional[np.ndarray] = None, combine: bool = True) -> np.ndarray:
+        """Copy one state column to the host (into ``out`` -- e.g. a pinned buffer -- if given).  On a
+        row-band sharded Grid this is a collective call that returns the whole population's column
+        (``combine=False``: this rank's view only)."""
         shape, dt = self._shape(t, f)
         if out is None:
             out = nat.result_empty(shape, dt)
         elif out.shape != shape or out.dtype != dt or not out.flags.c_contiguous:
             raise ValueError(f"out must be a C-contiguous {dt} array of shape {shape}")
         nat.check(self._lib.jxb_model_download(self.handle, t, f, nat.ptr(out), out.nbytes))
+        op = self.GRID_COMBINE.get(self.fields[t][f][0]) if (self.group is not None and combine) else None
+        if op is not None:
+            out[...] = self.group.all_reduce(out, op)
         return out
+
+    def grid_shard_setup(self, group) -> None:
+        """Row band of this rank + receive areas of all ranks (``jxb_model_grid_shard_export/attach``)."""
+        from .dist import shard_bounds
+        lo, hi = shard_bounds(int(self.desc.grid_w), group.rank, group.world)
+        handle = np.zeros(64, dtype=np.uint8)
+        nat.check(self._lib.jxb_model_grid_shard_export(self.handle, lo, hi, nat.ptr(handle), handle.nbytes))
+        table = np.ascontiguousarray(group.all_gather_bytes(handle))
+        nat.check(self._lib.jxb_model_grid_shard_attach(self.handle, nat.ptr(table), table.shape[1], group.world))
+        group.barrier()
+        self.group, self.band = group, (lo, hi)
 
     def upload(self, t: int, f: int, value) -> None:
         shape, dt = self._shape(t, f)
@@ -161,6 +182,11 @@ class DeviceModel:
     def download_grid(self) -> np.ndarray:
         out = np.empty((self.desc.grid_w, self.desc.grid_h), dtype=np.int32)
         nat.check(self._lib.jxb_model_download_grid(self.handle, nat.ptr(out), out.nbytes))
+        if self.group is not None:         # every rank contributes its own rows (cells are >= -1)
+            lo, hi = self.band
+            out[:lo] = -2
+            out[hi:] = -2
+            out = self.group.all_reduce(out, "max")
         return out
 
     def download_empty_cells(self) -> np.ndarray:

@@ -85,6 +85,7 @@ class Model:
         self._dev: Optional[DeviceModel] = None
         self._program: Optional[str] = None
         self._shard = None            # (rank, world) when split across GPUs (sharding.shard_model)
+        self._shard_group = None      # how the ranks talk on the host (sharding.DistGroup)
         self.last_device_seconds = 0.0
 
     # ---- construction ---------------------------------------------------------------------
@@ -200,9 +201,9 @@ class Model:
                 raise ValueError("Schelling needs a Grid: env state 'grid_shape' is missing")
             grid = (int(shape[0]), int(shape[1]), bool(self._env_state.get("grid_periodic", False)))
         rank, world = self._shard or (0, 1)
-        if world > 1:
-            if program in ("schelling", "sir"):
-                raise UnregisteredRuleError("grid / network programs are not population-sharded; run replicas")
+        if world > 1 and program == "sir":
+            raise UnregisteredRuleError("network programs are not population-sharded; run replicas")
+        if world > 1 and program != "schelling":   # a Grid splits by row bands; every rank keeps the agent columns
             from .dist import shard_bounds
             for spec in specs:
                 lo, hi = shard_bounds(spec.n_agents, rank, world)
@@ -213,6 +214,8 @@ class Model:
                          world_size=world, rank=rank)
         self._dev = DeviceModel(desc)
         self._program = program
+        if world > 1 and program == "schelling":
+            self._dev.grid_shard_setup(self._shard_group)
         for name, value in list(self._env_state.items()):
             self._push_env(name, value)
         # keys = split(_rng, C+1); _rng = keys[0]; collection i <- keys[i+1]     (model.py:129-137)

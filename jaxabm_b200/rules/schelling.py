@@ -82,8 +82,12 @@ class SchellingModel(FacadeModel):
 
 
 def create_schelling_model(grid_size=20, n_agents=300, ratio=0.5, similarity_threshold=0.5, periodic=False,
-                           seed=42, config: ModelConfig = None, types=None, positions=None) -> Model:
-    """Core-protocol construction; returns an *initialized* model with the layout uploaded."""
+                           seed=42, config: ModelConfig = None, types=None, positions=None,
+                           shard=False) -> Model:
+    """Core-protocol construction; returns an *initialized* model with the layout uploaded.
+
+    ``shard=True`` splits the ONE grid into row bands over the ranks of the ``torch.distributed``
+    world (``csrc/grid_shard.cuh``); every rank passes the same full layout."""
     if config is None:
         config = ModelConfig(seed=seed)
     if types is None or positions is None:
@@ -97,6 +101,9 @@ def create_schelling_model(grid_size=20, n_agents=300, ratio=0.5, similarity_thr
     model.add_env_state("segregation_index", 0.0)
     model.add_env_state("percent_satisfied", 0.0)
     model.add_env_state("total_moves", 0)
+    if shard:
+        from .. import sharding
+        sharding.shard_model(model)
     model.initialize()
     coll.states["type"] = types
     coll.states["position"] = positions

@@ -11,6 +11,16 @@ the step path.  ``JXB_EXCHANGE=nccl`` selects the NCCL all-reduce arm instead (c
 Per-agent keys use the GLOBAL agent index (``split(key, N_global)[global_offset + i]``), so a
 sharded run reproduces the unsharded model's state bit for bit; the reduction order differs
 (per-rank partials folded in rank order), so float32 env trajectories agree to rounding.
+
+Grids (C2, SURVEY.md 8(e) "Grid: row blocks + halo") split by ROW BANDS: rank r owns the rows
+``shard_bounds(W, r, world)`` of the one ``env['grid']``; the per-step exchange (the unsatisfied
+agents' records + three integer counts) is written straight into every peer's receive area over
+NVLink by the compaction kernel (``csrc/grid_shard.cuh``).  :func:`shard_model` on a Schelling model
+selects it; state reads combine the ranks' views (``position`` max, ``satisfied`` min, ``moves``
+sum) and are collective calls.  Results are bit-identical to the single-GPU run.  The ranks of a
+sharded Grid may share one device (``JXB_DEVICE=0`` for every rank, ``gloo`` process group): CUDA
+IPC and the spin waits work across processes on the same GPU, which is how the parity tests cover
+the whole path where only one GPU is visible.
 """
 from __future__ import annotations
 
@@ -59,13 +69,52 @@ def attach_peers() -> None:
     _attached = True
 
 
+class DistGroup:
+    """The ranks of the ``torch.distributed`` process group (one process per GPU)."""
+    def __init__(self):
+        td = dist._td()
+        if td is None or td.get_world_size() == 1:
+            raise RuntimeError("population sharding needs torch.distributed initialised with world_size > 1")
+        self._td = td
+        self.rank, self.world = td.get_rank(), td.get_world_size()
+
+    def all_gather_bytes(self, b: np.ndarray) -> np.ndarray:
+        """uint8[n] of every rank -> uint8[world, n]."""
+        import torch
+        dev = dist._device_for_backend(self._td)
+        mine = torch.from_numpy(np.ascontiguousarray(b, dtype=np.uint8)).to(dev)
+        parts = [torch.zeros_like(mine) for _ in range(self.world)]
+        self._td.all_gather(parts, mine)
+        return np.stack([p.cpu().numpy() for p in parts], axis=0)
+
+    def all_reduce(self, a: np.ndarray, op: str) -> np.ndarray:
+        import torch
+        td = self._td
+        dev = dist._device_for_backend(td)
+        src = np.ascontiguousarray(a)
+        view = src.view(np.uint8) if src.dtype == np.bool_ else src
+        t = torch.from_numpy(view).to(dev)
+        td.all_reduce(t, op={"max": td.ReduceOp.MAX, "min": td.ReduceOp.MIN, "sum": td.ReduceOp.SUM}[op])
+        out = t.cpu().numpy()
+        return out.view(np.bool_) if src.dtype == np.bool_ else out
+
+    def barrier(self) -> None:
+        self._td.barrier()
+
+
 def shard_model(model) -> None:
     """Mark an un-initialised core ``Model`` as sharded over the ranks of the process group:
-    ``initialize()`` then allocates only this rank's index range of every collection."""
+    ``initialize()`` then allocates only this rank's index range of every collection (well-mixed
+    populations) or this rank's row band of the Grid (Schelling)."""
     if model._is_initialized:
         raise RuntimeError("shard_model must be called before Model.initialize()")
-    attach_peers()
-    model._shard = dist.rank_world()
+    from .model import program_of
+    is_grid = program_of(model._update_state_fn, model._metrics_fn) == "schelling" and not model._needs_tracing()
+    if not is_grid:
+        attach_peers()            # engine-level exchange buffer + NCCL communicator of the well-mixed programs
+    group = DistGroup()
+    model._shard = (group.rank, group.world)
+    model._shard_group = group
 
 
 def local_range(n: int):
