@@ -12,7 +12,9 @@ move as well as the converged tail), default K = 1000 = the configured run lengt
 every rank runs an independent replica of the workload on its own GPU (ensemble sharding, no
 data-path collective): scaling = "weak", value = sum of agent-steps over ranks / max device time
 over ranks.  `--workload market --shard` instead splits ONE population across the ranks (strong
-scaling, per-step cross-rank reduction of the env partial sums).
+scaling, per-step cross-rank reduction of the env partial sums); `--workload schelling --shard
+[--grid G --agents N]` splits ONE grid into row bands over the ranks (strong scaling, the
+unsatisfied agents' records exchanged over NVLink peer memory every step).
 """
 from __future__ import annotations
 
@@ -64,9 +66,14 @@ class SchellingWorkload:
                "(agents SoA + cell_agent + U/E lists, ~350 MB) exceeds the 126 MB L2; the bit-plane "
                "grid (4 MB) is L2-resident by design")
 
-    def __init__(self, rank, grid=4096, n=13_000_000):
+    def __init__(self, rank, grid=4096, n=13_000_000, shard=False):
         from jaxabm_b200.rules import schelling
-        self.grid, self.n, self.seed = grid, n, 42 + rank
+        self.grid, self.n, self.seed, self.shard = grid, n, 42 + (0 if shard else rank), shard
+        self.name = f"schelling_{grid}x{grid}_{n / 1e6:.3g}M" if (grid, n) != (4096, 13_000_000) else self.name
+        if shard:
+            self.kernel = "grid_shard_sweep_kernel"
+            self.l2_note = ("no flush; 4 launches per step and rank (band sweep, compaction + peer stores, flag wait, "
+                            "movers); the band's bit planes are L2-resident, the active-phase working set is not")
         self.types, self.positions = schelling.initial_layout(grid, n, 0.5, self.seed)
         self.agents = n
         self._pins = None
@@ -75,7 +82,8 @@ class SchellingWorkload:
         import jaxabm_b200 as jx
         from jaxabm_b200.rules import schelling
         m = schelling.create_schelling_model(self.grid, self.n, seed=self.seed, types=self.types,
-                                             positions=self.positions, config=jx.ModelConfig(seed=self.seed))
+                                             positions=self.positions, config=jx.ModelConfig(seed=self.seed),
+                                             shard=self.shard)
         m._dev.grid_rebuild()                       # cell binning of the uploaded layout (untimed setup)
         return m
 
@@ -468,7 +476,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="schelling", choices=sorted(WORKLOADS))
-    ap.add_argument("--shard", action="store_true", help="market / economy: split ONE population over the ranks")
+    ap.add_argument("--shard", action="store_true",
+                    help="market / economy: split ONE population over the ranks; schelling: ONE grid in row bands")
+    ap.add_argument("--grid", type=int, default=4096, help="schelling: grid side")
+    ap.add_argument("--agents", type=int, default=None, help="schelling: agents (default 77.5 %% fill)")
     ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -513,11 +524,15 @@ def main():
         wl = MarketWorkload(rank, world=world, shard=args.shard)
     elif args.workload == "economy":
         wl = EconomyWorkload(rank, world=world, shard=args.shard)
+    elif args.workload == "schelling":
+        n_ag = args.agents if args.agents is not None else (13_000_000 if args.grid == 4096 else int(args.grid * args.grid * 0.775))
+        wl = SchellingWorkload(rank, grid=args.grid, n=n_ag, shard=args.shard and world > 1)
     else:
         wl = WORKLOADS[args.workload](rank)
+    sharded = args.shard and world > 1 and args.workload in ("market", "economy", "schelling")
     K = args.steps if args.steps is not None else wl.default_steps
     sampler = ClockSampler(local)
-    total_agents = wl.agents * (1 if (args.workload in ("market", "economy") and args.shard) else world)
+    total_agents = wl.agents * (1 if sharded else world)
     if args.workload == "ensemble":
         total_agents = wl.samples_total * wl.n
     extra = {}
@@ -564,7 +579,7 @@ def main():
         clocks = sampler.stop() if rank == 0 else None
         max_s = max_over_ranks(dev_s)
         # ---- dominant kernel: its own CUDA-event time -------------------------------------------------
-        if args.workload == "schelling":
+        if args.workload == "schelling" and not sharded:
             ksecs, klaunches = dev_s, 1            # the persistent kernel IS the timed region (one launch)
         else:
             pm = model if wl.stationary else wl.fresh()
@@ -576,7 +591,7 @@ def main():
                 del pm
         # ---- end to end through the public API with host buffers ------------------------------------------
         e2e = None
-        if not args.no_e2e and not (args.workload in ("market", "economy") and args.shard):
+        if not args.no_e2e and not sharded:
             del model
             wl.e2e(min(K, 3))                      # warm-up of the same call
             sync_all()
@@ -587,8 +602,9 @@ def main():
 
     value = total_agents * K / max_s
     peak, peak_kind = load_peak()
-    api_b = wl.api_bytes(res, K) / max(klaunches, 1)
-    eng_b = wl.engine_bytes(res, K) / max(klaunches, 1)
+    band = world if (sharded and args.workload == "schelling") else 1     # a rank's launch covers its row band only
+    api_b = wl.api_bytes(res, K) / max(klaunches, 1) / band
+    eng_b = wl.engine_bytes(res, K) / max(klaunches, 1) / band
     per_launch = ksecs / max(klaunches, 1)
     traffic = load_traffic(args.workload)
     roofline = {"bound": "hbm", "kernel": wl.kernel, "achieved": api_b / per_launch / 1e9, "peak": peak,
@@ -603,6 +619,9 @@ def main():
                 "note": "achieved/frac use SURVEY.md 8(d) algorithmic bytes in the reference's API dtypes; "
                         "engine_layout uses the bytes the packed HBM layout actually has to move "
                         "(frac > 1 on the API figure means the engine moves fewer bytes than the reference layout implies)"}
+    if world > 1:
+        td.barrier()
+        td.destroy_process_group()
     if rank != 0:
         return
     cpu = None
@@ -615,12 +634,13 @@ def main():
             cpu = None
     par = "single-gpu"
     if world > 1:
-        par = (f"one population sharded over {world} gpus (per-step env partial-sum exchange)"
-               if (args.workload in ("market", "economy") and args.shard) else
+        par = (f"one grid in {world} row bands, one per gpu (per-step records of the unsatisfied agents over NVLink peer memory)"
+               if (sharded and args.workload == "schelling") else
+               f"one population sharded over {world} gpus (per-step env partial-sum exchange)" if sharded else
                (f"replica blocks over {world} gpus" if args.workload == "ensemble" else f"replica-per-gpu x{world}"))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": max_s / K * 1e3, "higher_is_better": True,
-            "scaling": "strong" if (args.workload in ("ensemble",) or args.shard) else "weak",
+            "scaling": "strong" if (args.workload in ("ensemble",) or sharded) else "weak",
             "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
             "config": {"workload": wl.name, "agents_per_gpu": wl.agents, "parallelism": par, "l2": wl.l2_note,
                        "timed_region": ("K steps from the seeded initial state (fresh model after the warm-up model)"

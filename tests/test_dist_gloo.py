@@ -47,8 +47,25 @@ def _worker(rank, world, port, q):
             return out, 0.5 + rank
         ensemble.ensemble_run = fake_launch
         last, secs = ensemble.run_last_metrics(models, steps=5)
+        # host side of a row-band sharded Grid (sharding.DistGroup): handle table + the combines of the
+        # ranks' views of the per-agent columns (position max, satisfied min, moves sum)
+        from jaxabm_b200 import sharding
+        from jaxabm_b200.device import DeviceModel
+        g = sharding.DistGroup()
+        table = g.all_gather_bytes(np.full(64, rank + 1, dtype=np.uint8))
+        assert table.shape == (world, 64) and [int(r[0]) for r in table] == [1, 2]
+        pos = np.full((5, 2), -1, dtype=np.int32)
+        pos[rank::2] = rank + 10                               # every agent sits in exactly one band
+        sat = np.ones(5, dtype=np.bool_)
+        sat[rank] = False
+        moves = np.arange(5, dtype=np.int32) * (rank + 1)
+        assert DeviceModel.GRID_COMBINE == {"position": "max", "satisfied": "min", "moves": "sum"}
+        combined = (g.all_reduce(pos, "max").tolist(), g.all_reduce(sat, "min").tolist(), g.all_reduce(moves, "sum").tolist())
+        assert g.all_reduce(sat, "min").dtype == np.bool_
+        assert dist.shard_bounds(4096, rank, world) == ((0, 2048) if rank == 0 else (2048, 4096))
         dist.barrier()
-        q.put((rank, (lo, hi), full[:, 0].tolist(), full[:, 1].tolist(), t, s, calls, last["avg_value"].tolist(), secs))
+        q.put((rank, (lo, hi), full[:, 0].tolist(), full[:, 1].tolist(), t, s, calls, last["avg_value"].tolist(), secs,
+               combined))
     finally:
         td.destroy_process_group()
 
@@ -64,7 +81,9 @@ def test_two_rank_sharding_and_gather():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, b0, f0, o0, t0, s0, c0, l0, e0), (r1, b1, f1, o1, t1, s1, c1, l1, e1) = out
+    (r0, b0, f0, o0, t0, s0, c0, l0, e0, g0), (r1, b1, f1, o1, t1, s1, c1, l1, e1, g1) = out
+    assert g0 == g1 == ([[10, 10], [11, 11], [10, 10], [11, 11], [10, 10]], [False, False, True, True, True],
+                        [0, 3, 6, 9, 12])
     assert b0 == (0, 6) and b1 == (6, 11)
     assert f0 == f1 == [10.0 * i for i in range(11)]
     assert o0 == [0.0] * 6 + [1.0] * 5
