@@ -259,6 +259,21 @@ int jxb_engine_p2p_attach(jxb_engine*, const void* handles, size_t bytes_each, i
 int jxb_model_grid_shard_export(jxb_model*, int row_begin, int row_end, void* handle_out, size_t bytes);
 int jxb_model_grid_shard_attach(jxb_model*, const void* handles, size_t bytes_each, int n_ranks);
 
+/* ---- ONE network split by node ranges over the GPUs of a box (Network) - */
+/* jaxabm/agentpy.py:545-582 keeps one env['network_edges'] for all agents; here rank r owns the agents
+ * [global_offset, global_offset + n_agents) of types[0] (boundaries at multiples of 32) and passes
+ * jxb_model_set_network only the edges whose SOURCE it owns, sources re-based to local rows, targets
+ * left as global ids.  Every rank holds the two global "is infected" bitmaps inside an IPC-shared
+ * receive area; export / attach map the peers' areas (as for the grid), sync hands this rank's slice
+ * of the freshly packed bitmap to every peer (call it after init / an upload of 'state', then barrier).
+ * jxb_model_run then steps the rank's rows in the pull direction: the aggregation kernel stores the
+ * new bitmap word of each 32-row group straight into every rank's copy over NVLink and releases a
+ * step flag; a one-warp wait kernel folds the ranks' exact S/I/R counts.  'state' reads return this
+ * rank's slice.                                                                                          */
+int jxb_model_net_shard_export(jxb_model*, void* handle_out, size_t bytes);
+int jxb_model_net_shard_attach(jxb_model*, const void* handles, size_t bytes_each, int n_ranks);
+int jxb_model_net_shard_sync(jxb_model*);
+
 /* ---- host-only scalar key algebra (jax.random on the reference's host path) -------- */
 /* jax.random.split(key, n) -> out[n][2] (jaxabm/model.py:129,156; analysis.py:438).  */
 int jxb_prng_split(int rng_mode, const uint32_t key[2], int n, uint32_t* out);

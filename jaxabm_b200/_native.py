@@ -92,6 +92,9 @@ SIGNATURES = {
     "jxb_engine_p2p_attach": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int]),
     "jxb_model_grid_shard_export": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_size_t]),
     "jxb_model_grid_shard_attach": (C.c_int, [_P, _P, C.c_size_t, C.c_int]),
+    "jxb_model_net_shard_export": (C.c_int, [_P, _P, C.c_size_t]),
+    "jxb_model_net_shard_attach": (C.c_int, [_P, _P, C.c_size_t, C.c_int]),
+    "jxb_model_net_shard_sync": (C.c_int, [_P]),
     "jxb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "jxb_host_free": (C.c_int, [_P]),
     "jxb_prng_split": (C.c_int, [C.c_int, _P, C.c_int, _P]),

@@ -220,6 +220,9 @@ struct jxb_model {
   size_t gs_area_bytes = 0; void* gs_opened[kMaxPeers] = {}; int gs_move_blocks = 0;
   // SIR
   bool has_net = false; SirDev sv{}; bool net_built = false; long long nnz = 0;
+  // node-range sharding of the network over ranks (csrc/sir.cuh): IPC-shared area [hdr | bitmap 0 | bitmap 1]
+  bool net_sharded = false; bool ns_attached = false; unsigned char* ns_area = nullptr; size_t ns_area_bytes = 0;
+  void* ns_opened[kMaxPeers] = {};
   // SIR formulation (JXB_SIR_MODE): 0 "pull" = CSR ballot-segmented sweep of ALL edges, fused
   // transitions; 1 "push" = infected rows scatter-add into k32 + transition kernel; 2 "pull_s" = pull
   // over the susceptible rows only; 3 "auto" (default) = direction-optimising, the step's tail picks
@@ -517,7 +520,17 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
   md.world_size = d->world_size > 1 ? d->world_size : 1;
   md.rank = d->rank;
   md.exchange = 0;
-  if (md.world_size > 1 && d->program != JXB_PROGRAM_SCHELLING) {   // a sharded grid has its own receive areas
+  if (md.world_size > 1 && d->program == JXB_PROGRAM_SIR) {
+    const jxb_type_desc& t0 = d->types[0];
+    if (md.world_size > kMaxPeers || md.rank < 0 || md.rank >= md.world_size || (t0.global_offset % 32) != 0 ||
+        (t0.global_offset + t0.n_agents != t0.global_n && (t0.n_agents % 32) != 0)) {
+      delete m;
+      return fail(JXB_ERR_INVALID, "a sharded Network splits the agents at multiples of 32 over at most %d ranks", kMaxPeers);
+    }
+    m->net_sharded = true;
+  }
+  // a sharded grid / network has its own receive areas
+  if (md.world_size > 1 && d->program != JXB_PROGRAM_SCHELLING && d->program != JXB_PROGRAM_SIR) {
     static const bool force_nccl = getenv("JXB_EXCHANGE") && !strcmp(getenv("JXB_EXCHANGE"), "nccl");
     if (eng->p2p && !force_nccl) {
       if (eng->world != md.world_size || eng->rank != md.rank) {
@@ -700,6 +713,9 @@ extern "C" int jxb_model_destroy(jxb_model* m) {
   for (int p = 0; p < kMaxPeers; ++p)
     if (m->gs_opened[p]) cudaIpcCloseMemHandle(m->gs_opened[p]);
   if (m->gs_area) cudaFree(m->gs_area);
+  for (int p = 0; p < kMaxPeers; ++p)
+    if (m->ns_opened[p]) cudaIpcCloseMemHandle(m->ns_opened[p]);
+  if (m->ns_area) cudaFree(m->ns_area);
   pool_free(m->eng, m->d_keys, m->keys_cap * 4);
   pool_free(m->eng, m->d_metrics, m->rec_cap * kMaxMetrics * sizeof(double));
   pool_free(m->eng, m->d_rec, m->rec_cap * sizeof(int));
@@ -1039,7 +1055,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     NCK(cudaMemsetAsync(d_flag, 0, 16, st));
     if (n_edges) NCK(cudaMemcpyAsync(d_edges, edges, (size_t)n_edges * 8, cudaMemcpyHostToDevice, st));
     const int g = m->eng->sms * 8;
-    csr_count_kernel<<<g, kThreads, 0, st>>>((const int2*)d_edges, n_edges, n, d_rp, (int*)d_flag);
+    csr_count_kernel<<<g, kThreads, 0, st>>>((const int2*)d_edges, n_edges, n, (long long)m->desc.types[0].global_n, d_rp, (int*)d_flag);
     scan_tile_sums_kernel<<<ntiles, kThreads, 0, st>>>(d_rp, n, (unsigned int*)d_sums);
     scan_sums_kernel<<<1, 1024, 0, st>>>((unsigned int*)d_sums, ntiles);
     scan_apply_kernel<<<ntiles, kThreads, 0, st>>>(d_rp, n, (const unsigned int*)d_sums, d_rp, (unsigned int*)d_cursor);
@@ -1052,7 +1068,8 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     NCK(cudaGetLastError());
 #undef NCK
     release();
-    if (bad) return fail(JXB_ERR_INVALID, "an edge references an agent outside [0,%lld)", n);
+    if (bad) return fail(JXB_ERR_INVALID, "an edge references an agent outside [0,%lld) (sources are local rows, targets global ids)",
+                         (long long)m->desc.types[0].global_n);
     if (row_ptr[n] != (unsigned int)n_edges) return fail(JXB_ERR_CUDA, "CSR build lost edges (%u of %lld)", row_ptr[n], (long long)n_edges);
   }
   // row blocks: whole 32-row groups, greedy up to kSirTile entries / 1024 rows
@@ -1075,11 +1092,31 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
   int* d_rb; float* d_esc;
   if ((rc = dev_alloc(m, &d_rb, rb.size()))) return rc;
   if ((rc = dev_alloc(m, &d_esc, kSirKCap + 1))) return rc;
+  if (m->net_sharded) {
+    // the two GLOBAL bitmaps live in one IPC-shareable allocation behind the exchange header
+    const long long gn = m->desc.types[0].global_n;
+    const size_t words = (size_t)(gn + 31) / 32 + 1;
+    sv.bits_stride = (words * 4 + 255) & ~(size_t)255;
+    if (!m->ns_area) {
+      m->ns_area_bytes = sizeof(SirXchgHdr) + 2 * sv.bits_stride;
+      CK(cudaMalloc((void**)&m->ns_area, m->ns_area_bytes));
+    }
+    CK(cudaMemset(m->ns_area, 0, m->ns_area_bytes));
+    sv.world = m->dev.world_size; sv.rank = m->dev.rank;
+    sv.gw0 = (unsigned int)(m->desc.types[0].global_offset / 32);
+    sv.gwords = (unsigned int)((n + 31) / 32);
+    sv.self = m->ns_area;
+    sv.peer[sv.rank] = m->ns_area;
+  }
   for (int b = 0; b < 2; ++b) {
     if ((rc = dev_alloc(m, &sv.state8[b], (size_t)n + 32))) return rc;
-    if ((rc = dev_alloc(m, &sv.infbits[b], (size_t)(n + 31) / 32 + 1))) return rc;
     cudaMemset(sv.state8[b], 0, (size_t)n + 32);
-    cudaMemset(sv.infbits[b], 0, ((size_t)(n + 31) / 32 + 1) * 4);
+    if (m->net_sharded) {
+      sv.infbits[b] = (unsigned int*)(m->ns_area + sizeof(SirXchgHdr) + (size_t)b * sv.bits_stride);
+    } else {
+      if ((rc = dev_alloc(m, &sv.infbits[b], (size_t)(n + 31) / 32 + 1))) return rc;
+      cudaMemset(sv.infbits[b], 0, ((size_t)(n + 31) / 32 + 1) * 4);
+    }
   }
   CK(cudaMemcpy(d_rb, rb.data(), rb.size() * 4, cudaMemcpyHostToDevice));
   {
@@ -1112,6 +1149,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     if (mode && !strcmp(mode, "pull")) m->sir_mode = 0;
     else if (mode && !strcmp(mode, "push")) m->sir_mode = 1;
     else if (mode && !strcmp(mode, "pull_s")) m->sir_mode = 2;
+    if (m->net_sharded) m->sir_mode = 2;     // a rank only holds its own rows: pull over them (a push would scatter remotely)
     sv.auto_mode = m->sir_mode == 3;
     const int dev_mode = m->sir_mode == 2 ? 0 : 1;       // auto starts in the push direction
     CK(cudaMemcpy(&m->dev.ctrl->sir_mode, &dev_mode, sizeof(int), cudaMemcpyHostToDevice));
@@ -1122,13 +1160,64 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
   return sir_sync_from_api(m);
 }
 
+// ---------------------------------------------------------------------------------------
+// Network node-range sharding (csrc/sir.cuh)
+// ---------------------------------------------------------------------------------------
+extern "C" int jxb_model_net_shard_export(jxb_model* m, void* handle_out, size_t bytes) {
+  NEED(m);
+  if (!m->net_sharded || !m->net_built || !m->ns_area)
+    return fail(JXB_ERR_STATE, "not a sharded Network model with its network set (desc.world_size > 1, jxb_model_set_network)");
+  if (!handle_out || bytes < sizeof(cudaIpcMemHandle_t))
+    return fail(JXB_ERR_INVALID, "need %zu bytes for the IPC handle", sizeof(cudaIpcMemHandle_t));
+  CK(cudaSetDevice(m->eng->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, m->ns_area));
+  memset(handle_out, 0, bytes);
+  memcpy(handle_out, &h, sizeof(h));
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_net_shard_attach(jxb_model* m, const void* handles, size_t bytes_each, int n_ranks) {
+  NEED(m);
+  if (!m->net_sharded || !m->ns_area) return fail(JXB_ERR_STATE, "call jxb_model_net_shard_export first");
+  if (!handles || n_ranks != m->dev.world_size || bytes_each < sizeof(cudaIpcMemHandle_t))
+    return fail(JXB_ERR_INVALID, "need the IPC handles of all %d ranks", m->dev.world_size);
+  CK(cudaSetDevice(m->eng->device));
+  for (int p = 0; p < n_ranks; ++p) {
+    if (p == m->dev.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)p * bytes_each, sizeof(h));
+    void* q = nullptr;
+    CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    m->ns_opened[p] = q;
+    m->sv.peer[p] = (unsigned char*)q;
+  }
+  m->ns_attached = true;
+  if (m->graph1) { cudaGraphExecDestroy(m->graph1); m->graph1 = nullptr; }
+  if (m->graphK) { cudaGraphExecDestroy(m->graphK); m->graphK = nullptr; }
+  return JXB_OK;
+}
+
+// hand my slice of the current infected bitmap to every peer (after init / an upload of 'state'); the host
+// shim barriers afterwards, so that every rank's copy is whole before anybody steps
+extern "C" int jxb_model_net_shard_sync(jxb_model* m) {
+  NEED(m);
+  if (!m->net_sharded || !m->ns_attached) return fail(JXB_ERR_STATE, "sharded Network: export / attach the peers first");
+  CK(cudaSetDevice(m->eng->device));
+  sir_shard_sync_kernel<<<m->eng->sms * 2, 256, 0, m->eng->stream>>>(m->sv, (int)(m->time_step & 1));
+  m->eng->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(m->eng->stream));
+  return JXB_OK;
+}
+
 static int sir_sync_from_api(jxb_model* m) {
   if (!m->net_built) return JXB_OK;
   const long long n = m->desc.types[0].n_agents;
   const int cur = (int)(m->time_step & 1);
   const int blocks = (int)((n + 255) / 256);
   sir_pack_kernel<<<blocks, 256, 0, m->eng->stream>>>((const int*)m->dev.t[0].f[0], m->sv.state8[cur],
-                                                      m->sv.infbits[cur], n);
+                                                      m->sv.infbits[cur] + (m->net_sharded ? m->sv.gw0 : 0u), n);
   m->eng->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(m->eng->stream));
@@ -1252,6 +1341,18 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
   }
   switch (m->desc.program) {
     case JXB_PROGRAM_SIR: {
+      if (m->net_sharded) {
+        // node-range shard: pull over my rows (new bitmap words stored into every rank's copy) + flag wait
+        if (!m->ns_attached) return fail(JXB_ERR_STATE, "sharded Network step without attached peers");
+        const int pgrid = m->eng->sms * 8;
+        if (timed) cudaEventRecord(e0, s);
+        if (part) sir_pull_s_kernel<1, true><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
+        else sir_pull_s_kernel<0, true><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
+        if (timed) cudaEventRecord(e1, s);
+        sir_shard_wait_kernel<<<1, 32, 0, s>>>(m->sv, m->dev);
+        eng->launches += 2;
+        break;
+      }
       if (timed) cudaEventRecord(e0, s);
       if (m->sir_mode == 0) {
         if (part) sir_step_kernel<1><<<m->sv.nrb, kThreads, 0, s>>>(m->sv, m->dev);
@@ -1394,6 +1495,7 @@ static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
 
 static int launches_per_step(jxb_model* m) {
   if (m->grid_sharded) return 4;
+  if (m->net_sharded) return 2;
   if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 : (m->sir_mode == 1 ? 2 : 1);
   if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? 4 : 1);
   return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
@@ -1552,6 +1654,11 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   }
   m->time_step = t0 + steps;
   if (m->has_grid && steps > 0) m->sat_dirty = true;
+  if (m->net_sharded) {
+    unsigned int nerr = 0;
+    CK(cudaMemcpy(&nerr, &((SirXchgHdr*)m->ns_area)->err, sizeof(nerr), cudaMemcpyDeviceToHost));
+    if (nerr) return fail(JXB_ERR_NCCL, "sharded Network: a rank did not publish its step within the spin budget");
+  }
   if (m->grid_sharded) {
     if (steps > 0) m->ct_stale = true;
     unsigned int gerr = 0;

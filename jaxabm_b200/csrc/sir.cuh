@@ -39,7 +39,35 @@ struct SirDev {
   int n_heavy;
   long long* degsum;       // [CTAs][2] adjacency entries of the new susceptible / infected rows per CTA
   int auto_mode;           // 1: the step's tail picks push or pull for the next step (direction-optimising)
+  // node-range sharding over ranks (one process per GPU): this rank owns rows [goff, goff + n) of the global
+  // population; infbits[] are GLOBAL bitmaps inside an IPC-shared receive area [SirXchgHdr | bits0 | bits1], and
+  // the pull kernel stores the new words of its rows straight into every rank's copy
+  int world, rank;
+  unsigned int gw0;              // global bitmap word of local row group 0 (goff / 32)
+  unsigned int gwords;           // my bitmap words (ceil(n / 32))
+  unsigned long long bits_stride;   // bytes from bits0 to bits1 inside an area
+  unsigned char* peer[kMaxPeers];   // every rank's area as mapped here (own = local)
+  unsigned char* self;
 };
+
+struct SirXchgHdr {
+  unsigned int flag[2][kMaxPeers];        // step tag of rank p's last published step of this parity
+  unsigned int cnt[2][kMaxPeers][4];      // rank p's S / I / R counts after that step
+  unsigned int err;
+  unsigned int pad[128 - 2 * kMaxPeers - 8 * kMaxPeers - 1];
+};
+static_assert(sizeof(SirXchgHdr) == 512, "receive-area header is 512 bytes");
+
+__device__ __forceinline__ unsigned char* sir_peer(const SirDev& sv, int p) {
+  unsigned char* r = sv.peer[0];
+#pragma unroll
+  for (int i = 1; i < kMaxPeers; ++i)
+    if (p == i) r = sv.peer[i];
+  return r;
+}
+__device__ __forceinline__ unsigned int* sir_peer_bits(const SirDev& sv, unsigned char* base, int buf) {
+  return (unsigned int*)(base + sizeof(SirXchgHdr) + (size_t)buf * sv.bits_stride);
+}
 
 // ---------------------------------------------------------------------------------------
 // infected-bit gather policies.
@@ -401,13 +429,13 @@ __global__ void __launch_bounds__(kThreads) sir_transition_kernel(const SirDev s
 // the same warp.  Cost is proportional to the susceptible rows' adjacency -- the complement of the
 // push kernel's; the step's tail picks whichever is cheaper for the next step.
 // ---------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool SHARD = false>
 __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, const ModelDev md) {
   __shared__ int s_red[3][kThreads / 32];
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31;
   Ctrl* ctrl = md.ctrl;
-  if (ctrl->sir_mode != 0) return;
+  if (!SHARD && ctrl->sir_mode != 0) return;
   const TypeDev& t = md.t[0];
   const long long n = t.n;
   const int cur = (int)(ctrl->time_step & 1), nxt = cur ^ 1;
@@ -489,16 +517,98 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
       if (sn == 1) dI += len;
     }
     const unsigned int w = __ballot_sync(0xffffffffu, active && sn == 1);
-    if (lane == 0) sv.infbits[nxt][g] = w;
+    if (SHARD) {
+      // the new word of this 32-row group goes straight into EVERY rank's next bitmap (remote stores over
+      // NVLink): the aggregation kernel is also the all-gather of the state slices
+      if (lane < sv.world) sir_peer_bits(sv, sir_peer(sv, lane), nxt)[sv.gw0 + g] = w;
+    } else {
+      if (lane == 0) sv.infbits[nxt][g] = w;
+    }
   }
   sir_publish_partials(sv, cS, cI, cR, dS, dI, s_red);
-  __threadfence();
+  if (SHARD) __threadfence_system(); else __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&ctrl->ticket, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
-  sir_tail(sv, md, (int)gridDim.x, true);
+  if (!SHARD) {
+    __threadfence();
+    sir_tail(sv, md, (int)gridDim.x, true);
+    return;
+  }
+  // sharded: fold this rank's exact counts, hand them to every rank and release the step's flag; the
+  // wait kernel that follows folds the ranks and writes the metrics row
+  __threadfence_system();
+  __shared__ long long s_cnt[3];
+  if (tid < 3) {
+    long long v = 0;
+    for (int b = 0; b < (int)gridDim.x; ++b) v += __ldcg(sv.partials + (size_t)b * 3 + tid);
+    s_cnt[tid] = v;
+  }
+  __syncthreads();
+  const unsigned int tag = (unsigned int)(ctrl->time_step + 1);
+  const unsigned int par = tag & 1u;
+  if (tid < sv.world) {
+    SirXchgHdr* h = (SirXchgHdr*)sir_peer(sv, tid);
+    h->cnt[par][sv.rank][0] = (unsigned int)s_cnt[0];
+    h->cnt[par][sv.rank][1] = (unsigned int)s_cnt[1];
+    h->cnt[par][sv.rank][2] = (unsigned int)s_cnt[2];
+    __threadfence_system();
+    st_release_sys(&h->flag[par][sv.rank], tag);
+  }
+  if (tid == 0) ctrl->ticket = 0;
+}
+
+// sharded step, second launch: wait for every rank's flag of this step (their bitmap slices and counts are
+// then in my area), fold the counts in rank order and write the metrics row (what sir_tail does on one GPU)
+__global__ void __launch_bounds__(32) sir_shard_wait_kernel(const SirDev sv, const ModelDev md) {
+  const int lane = threadIdx.x;
+  Ctrl* ctrl = md.ctrl;
+  const unsigned int tag = (unsigned int)(ctrl->time_step + 1);
+  const unsigned int par = tag & 1u;
+  SirXchgHdr* h = (SirXchgHdr*)sv.self;
+  long long c0 = 0, c1 = 0, c2 = 0;
+  if (lane < sv.world) {
+    if (!*(volatile unsigned int*)&h->err) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys(&h->flag[par][lane]) != tag) {
+        if (clock64() - t0 > (20ll << 30)) { h->err = 1u; break; }     // ~10 s: a peer is gone
+      }
+    }
+    c0 = __ldcv(&h->cnt[par][lane][0]);
+    c1 = __ldcv(&h->cnt[par][lane][1]);
+    c2 = __ldcv(&h->cnt[par][lane][2]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+  }
+  if (lane == 0) {
+    ctrl->sir_count[0] = c0; ctrl->sir_count[1] = c1; ctrl->sir_count[2] = c2;
+    const long long tsn = ctrl->time_step + 1;
+    if ((tsn % md.collect_interval) == 0) {
+      double* row = md.metrics + (size_t)ctrl->n_recorded * kMaxMetrics;
+      row[0] = (double)c0; row[1] = (double)c1; row[2] = (double)c2;
+      md.record_steps[ctrl->n_recorded] = (int)tsn;
+      ctrl->n_recorded += 1;
+    }
+    ctrl->time_step = tsn;
+    ctrl->step_in_run += 1;
+  }
+}
+
+// after the API column was (re)packed: copy my slice of the current bitmap into every peer's copy
+// (setup path; the host barriers afterwards)
+__global__ void sir_shard_sync_kernel(const SirDev sv, int cur) {
+  const unsigned int* mine = sir_peer_bits(sv, sv.self, cur) + sv.gw0;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < sv.gwords; i += gridDim.x * blockDim.x) {
+    const unsigned int w = mine[i];
+    for (int p = 0; p < sv.world; ++p)
+      if (p != sv.rank) sir_peer_bits(sv, sir_peer(sv, p), cur)[sv.gw0 + i] = w;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -508,10 +618,10 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
 // it; every formulation above only counts, so results do not depend on it.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) csr_count_kernel(const int2* edges, long long n_edges, long long n,
-                                                             unsigned int* deg, int* err) {
+                                                             long long n_cols, unsigned int* deg, int* err) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (long long)gridDim.x * blockDim.x) {
     const int2 ed = __ldcs(edges + e);
-    if (ed.x < 0 || ed.x >= n || ed.y < 0 || ed.y >= n) { atomicExch(err, 1); continue; }
+    if (ed.x < 0 || ed.x >= n || ed.y < 0 || ed.y >= n_cols) { atomicExch(err, 1); continue; }
     atomicAdd(deg + ed.x, 1u);
   }
 }
@@ -606,7 +716,7 @@ __global__ void sir_pack_kernel(const int* state, signed char* s8, unsigned int*
   int s = 0;
   if (i < n) { s = state[i]; s8[i] = (signed char)s; }
   const unsigned int w = __ballot_sync(0xffffffffu, i < n && s == 1);
-  if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = w;
+  if ((threadIdx.x & 31) == 0 && i < n) bits[i >> 5] = w;      // bits = word of local row 0 (sharded: + goff / 32)
 }
 
 __global__ void sir_unpack_kernel(const signed char* s8, int* state, long long n) {

@@ -57,6 +57,7 @@ class DeviceModel:
         self._keep = keep                 # the generated library of a traced model must outlive the handle
         self.group = None                 # host-side rank group of a row-band sharded Grid
         self.band = None                  # (row_begin, row_end) of this rank
+        self.net_group = None             # host-side rank group of a node-range sharded Network
         if traced_spec is not None:
             nat.check(self._lib.jxb_model_create_traced(self.engine.handle, C.byref(desc), C.byref(traced_spec),
                                                         C.byref(self.handle)))
@@ -142,10 +143,26 @@ class DeviceModel:
         group.barrier()
         self.group, self.band = group, (lo, hi)
 
+    def net_shard_setup(self, group) -> None:
+        """Receive areas (global infected bitmaps) of all ranks (``jxb_model_net_shard_export/attach``)."""
+        handle = np.zeros(64, dtype=np.uint8)
+        nat.check(self._lib.jxb_model_net_shard_export(self.handle, nat.ptr(handle), handle.nbytes))
+        table = np.ascontiguousarray(group.all_gather_bytes(handle))
+        nat.check(self._lib.jxb_model_net_shard_attach(self.handle, nat.ptr(table), table.shape[1], group.world))
+        group.barrier()
+        self.net_group = group
+
+    def net_shard_sync(self) -> None:
+        """Collective: every rank hands its slice of the packed infected bitmap to all peers."""
+        nat.check(self._lib.jxb_model_net_shard_sync(self.handle))
+        self.net_group.barrier()
+
     def upload(self, t: int, f: int, value) -> None:
         shape, dt = self._shape(t, f)
         a = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), shape))
         nat.check(self._lib.jxb_model_upload(self.handle, t, f, nat.ptr(a), a.nbytes))
+        if self.net_group is not None:
+            self.net_shard_sync()
 
     def fill(self, t: int, f: int, value) -> None:
         _, dt, w = self.fields[t][f]
@@ -175,6 +192,8 @@ class DeviceModel:
     def set_network(self, edges) -> None:
         e = np.ascontiguousarray(np.asarray(edges, dtype=np.int32).reshape(-1, 2))
         nat.check(self._lib.jxb_model_set_network(self.handle, nat.ptr(e), e.shape[0]))
+        if self.net_group is not None:         # the areas were rebuilt: redistribute the bitmap slices
+            self.net_shard_sync()
 
     def grid_rebuild(self) -> None:
         nat.check(self._lib.jxb_model_grid_rebuild(self.handle))

@@ -86,6 +86,7 @@ class Model:
         self._program: Optional[str] = None
         self._shard = None            # (rank, world) when split across GPUs (sharding.shard_model)
         self._shard_group = None      # how the ranks talk on the host (sharding.DistGroup)
+        self._node_range = None       # (lo, hi) agents of this rank when a Network is split by node ranges
         self.last_device_seconds = 0.0
 
     # ---- construction ---------------------------------------------------------------------
@@ -111,6 +112,13 @@ class Model:
                     dev.set_env(s, v)
             return
         if name == "network_edges" and self._program == "sir":
+            if getattr(self, "_node_range", None) is not None:
+                # this rank's rows only: sources re-based to local rows, targets stay global ids
+                lo, hi = self._node_range
+                e = np.asarray(value, dtype=np.int32).reshape(-1, 2)
+                e = e[(e[:, 0] >= lo) & (e[:, 0] < hi)].copy()
+                e[:, 0] -= lo
+                value = e
             dev.set_network(value)
             return
         s = dev.env_index(name)
@@ -201,9 +209,19 @@ class Model:
                 raise ValueError("Schelling needs a Grid: env state 'grid_shape' is missing")
             grid = (int(shape[0]), int(shape[1]), bool(self._env_state.get("grid_periodic", False)))
         rank, world = self._shard or (0, 1)
+        self._node_range = None
         if world > 1 and program == "sir":
-            raise UnregisteredRuleError("network programs are not population-sharded; run replicas")
-        if world > 1 and program != "schelling":   # a Grid splits by row bands; every rank keeps the agent columns
+            # a Network splits by node ranges at multiples of 32 (whole words of the infected bitmap)
+            from .dist import shard_bounds
+            spec = specs[0]
+            n_all = spec.n_agents
+            g_lo, g_hi = shard_bounds((n_all + 31) // 32, rank, world)
+            lo, hi = g_lo * 32, min(g_hi * 32, n_all)
+            if hi <= lo:
+                raise ValueError(f"a network of {n_all} agents cannot be split over {world} ranks")
+            spec.global_n, spec.global_offset, spec.n_agents = n_all, lo, hi - lo
+            self._node_range = (lo, hi)
+        elif world > 1 and program != "schelling":   # a Grid splits by row bands; every rank keeps the agent columns
             from .dist import shard_bounds
             for spec in specs:
                 lo, hi = shard_bounds(spec.n_agents, rank, world)
@@ -218,9 +236,15 @@ class Model:
             self._dev.grid_shard_setup(self._shard_group)
         for name, value in list(self._env_state.items()):
             self._push_env(name, value)
+        if self._node_range is not None:
+            if "network_edges" not in self._env_state:
+                raise ValueError("a sharded Network model needs env state 'network_edges' before initialize()")
+            self._dev.net_shard_setup(self._shard_group)
         # keys = split(_rng, C+1); _rng = keys[0]; collection i <- keys[i+1]     (model.py:129-137)
         keys = jrandom.split(self._rng, len(self._agent_collections) + 1, desc.rng_mode)
         self._dev.init(self._rng)
+        if self._node_range is not None:
+            self._dev.net_shard_sync()             # every rank's bitmap copy whole before anybody steps
         self._rng = keys[0]
         for i, c in enumerate(self._agent_collections.values()):
             c._attach(self._dev, i, self.config, keys[i + 1])

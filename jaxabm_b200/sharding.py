@@ -17,8 +17,15 @@ Grids (C2, SURVEY.md 8(e) "Grid: row blocks + halo") split by ROW BANDS: rank r 
 agents' records + three integer counts) is written straight into every peer's receive area over
 NVLink by the compaction kernel (``csrc/grid_shard.cuh``).  :func:`shard_model` on a Schelling model
 selects it; state reads combine the ranks' views (``position`` max, ``satisfied`` min, ``moves``
-sum) and are collective calls.  Results are bit-identical to the single-GPU run.  The ranks of a
-sharded Grid may share one device (``JXB_DEVICE=0`` for every rank, ``gloo`` process group): CUDA
+sum) and are collective calls.  Results are bit-identical to the single-GPU run.
+
+Networks (C3, SURVEY.md 8(e) "Network: 1-D node partition, replicated bit-packed state") split by NODE
+RANGES at multiples of 32: rank r holds the CSR rows, the ``state`` slice and the draws of its agents
+and a copy of the global "is infected" bitmap; the pull kernel stores the new bitmap word of every
+32-row group straight into all ranks' copies (``csrc/sir.cuh``), so the neighbour aggregation is also
+the all-gather of the state slices.  ``states['state']`` returns the rank's slice; the S/I/R counts
+are exact integers folded in rank order, so the metric rows and states equal the single-GPU run's.  The ranks of a
+sharded Grid / Network may share one device (``JXB_DEVICE=0`` for every rank, ``gloo`` process group): CUDA
 IPC and the spin waits work across processes on the same GPU, which is how the parity tests cover
 the whole path where only one GPU is visible.
 """
@@ -105,12 +112,14 @@ class DistGroup:
 def shard_model(model) -> None:
     """Mark an un-initialised core ``Model`` as sharded over the ranks of the process group:
     ``initialize()`` then allocates only this rank's index range of every collection (well-mixed
-    populations) or this rank's row band of the Grid (Schelling)."""
+    populations), this rank's row band of the Grid (Schelling) or its node range of the Network (SIR)."""
     if model._is_initialized:
         raise RuntimeError("shard_model must be called before Model.initialize()")
     from .model import program_of
-    is_grid = program_of(model._update_state_fn, model._metrics_fn) == "schelling" and not model._needs_tracing()
-    if not is_grid:
+    # a Grid (row bands) and a Network (node ranges) bring their own peer-mapped receive areas
+    own_areas = (program_of(model._update_state_fn, model._metrics_fn) in ("schelling", "sir")
+                 and not model._needs_tracing())
+    if not own_areas:
         attach_peers()            # engine-level exchange buffer + NCCL communicator of the well-mixed programs
     group = DistGroup()
     model._shard = (group.rank, group.world)
