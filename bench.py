@@ -14,7 +14,8 @@ data-path collective): scaling = "weak", value = sum of agent-steps over ranks /
 over ranks.  `--workload market --shard` instead splits ONE population across the ranks (strong
 scaling, per-step cross-rank reduction of the env partial sums); `--workload schelling --shard
 [--grid G --agents N]` splits ONE grid into row bands over the ranks (strong scaling, the
-unsatisfied agents' records exchanged over NVLink peer memory every step).
+unsatisfied agents' records exchanged over NVLink peer memory every step); `--workload sir --shard`
+splits ONE network by node ranges (the infected bitmap's new words stored into every rank's copy).
 """
 from __future__ import annotations
 
@@ -303,9 +304,11 @@ class SirWorkload:
     kernel = "sir_step_kernel"
     l2_note = "no flush: adjacency (400 MB) is streamed every step and exceeds the 126 MB L2"
 
-    def __init__(self, rank, n=10_000_000, m=5):
+    def __init__(self, rank, n=10_000_000, m=5, shard=False):
         from jaxabm_b200 import synthetic
-        self.n, self.seed = n, 42 + rank
+        self.n, self.seed, self.shard = n, 42 + (0 if shard else rank), shard
+        if shard:
+            self.kernel = "sir_pull_s_kernel"
         self.edges = synthetic.scale_free_edges(n, m, self.seed)
         self.nnz = int(self.edges.shape[0])
         self.agents = n
@@ -315,6 +318,9 @@ class SirWorkload:
         from jaxabm_b200.rules import sir
         m = sir.create_sir_model(self.n, self.edges, beta=0.05, gamma=0.1, initial_infected=0.01,
                                  seed=self.seed, config=jx.ModelConfig(seed=self.seed))
+        if self.shard:
+            from jaxabm_b200 import sharding
+            sharding.shard_model(m)
         m.initialize()
         return m
 
@@ -527,9 +533,11 @@ def main():
     elif args.workload == "schelling":
         n_ag = args.agents if args.agents is not None else (13_000_000 if args.grid == 4096 else int(args.grid * args.grid * 0.775))
         wl = SchellingWorkload(rank, grid=args.grid, n=n_ag, shard=args.shard and world > 1)
+    elif args.workload == "sir":
+        wl = SirWorkload(rank, shard=args.shard and world > 1)
     else:
         wl = WORKLOADS[args.workload](rank)
-    sharded = args.shard and world > 1 and args.workload in ("market", "economy", "schelling")
+    sharded = args.shard and world > 1 and args.workload in ("market", "economy", "schelling", "sir")
     K = args.steps if args.steps is not None else wl.default_steps
     sampler = ClockSampler(local)
     total_agents = wl.agents * (1 if sharded else world)
@@ -602,7 +610,7 @@ def main():
 
     value = total_agents * K / max_s
     peak, peak_kind = load_peak()
-    band = world if (sharded and args.workload == "schelling") else 1     # a rank's launch covers its row band only
+    band = world if (sharded and args.workload in ("schelling", "sir")) else 1     # a rank's launch covers its band / node range only
     api_b = wl.api_bytes(res, K) / max(klaunches, 1) / band
     eng_b = wl.engine_bytes(res, K) / max(klaunches, 1) / band
     per_launch = ksecs / max(klaunches, 1)
@@ -636,6 +644,8 @@ def main():
     if world > 1:
         par = (f"one grid in {world} row bands, one per gpu (per-step records of the unsatisfied agents over NVLink peer memory)"
                if (sharded and args.workload == "schelling") else
+               f"one network in {world} node ranges, one per gpu (new infected-bitmap words stored into every rank's copy over NVLink peer memory)"
+               if (sharded and args.workload == "sir") else
                f"one population sharded over {world} gpus (per-step env partial-sum exchange)" if sharded else
                (f"replica blocks over {world} gpus" if args.workload == "ensemble" else f"replica-per-gpu x{world}"))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,

@@ -540,10 +540,25 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
   // wait kernel that follows folds the ranks and writes the metrics row
   __threadfence_system();
   __shared__ long long s_cnt[3];
-  if (tid < 3) {
-    long long v = 0;
-    for (int b = 0; b < (int)gridDim.x; ++b) v += __ldcg(sv.partials + (size_t)b * 3 + tid);
-    s_cnt[tid] = v;
+  __shared__ long long s_w[3][kThreads / 32];
+  {
+    long long v[3] = {0, 0, 0};
+    for (int b = tid; b < (int)gridDim.x; b += kThreads) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v[j] += __ldcg(sv.partials + (size_t)b * 3 + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+      if (lane == 0) s_w[j][tid >> 5] = v[j];
+    }
+    __syncthreads();
+    if (tid < 3) {
+      long long c = 0;
+      for (int w = 0; w < kThreads / 32; ++w) c += s_w[tid][w];
+      s_cnt[tid] = c;
+    }
   }
   __syncthreads();
   const unsigned int tag = (unsigned int)(ctrl->time_step + 1);

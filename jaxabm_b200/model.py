@@ -215,8 +215,9 @@ class Model:
             from .dist import shard_bounds
             spec = specs[0]
             n_all = spec.n_agents
-            g_lo, g_hi = shard_bounds((n_all + 31) // 32, rank, world)
-            lo, hi = g_lo * 32, min(g_hi * 32, n_all)
+            from .sharding import network_cuts
+            cuts = network_cuts(n_all, self._env_state.get("network_edges"), world)
+            lo, hi = cuts[rank], cuts[rank + 1]
             if hi <= lo:
                 raise ValueError(f"a network of {n_all} agents cannot be split over {world} ranks")
             spec.global_n, spec.global_offset, spec.n_agents = n_all, lo, hi - lo

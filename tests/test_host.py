@@ -245,3 +245,23 @@ def test_rule_tracer_generates_and_compiles_a_kernel_without_a_gpu():
     assert (trace._const(2.0) * 3).attr == 6.0                      # scalar (op) scalar folds in Python doubles
     with pytest.raises(trace.TraceError):
         bool(x > 1)
+
+
+def test_network_cuts_balance_the_adjacency():
+    """Node-range boundaries of a sharded Network (sharding.network_cuts): multiples of 32, every rank
+    non-empty, adjacency (+ a per-row cost) balanced; falls back to an even split without edges."""
+    from jaxabm_b200 import sharding, synthetic
+    n = 50_000
+    e = synthetic.scale_free_edges(n, 5, 3)
+    deg = np.bincount(e[:, 0], minlength=n)
+    for world in (2, 3, 8):
+        c = sharding.network_cuts(n, e, world, balance="entries")
+        assert sharding.network_cuts(n, e, world)[1] == (((n + 31) // 32 + world - 1) // world) * 32       # default: even split
+        assert c[0] == 0 and c[-1] == n and len(c) == world + 1
+        assert all(b > a for a, b in zip(c, c[1:])) and all(x % 32 == 0 for x in c[:-1])
+        cost = [int(deg[a:b].sum()) + 4 * (b - a) for a, b in zip(c, c[1:])]
+        assert max(cost) < 1.1 * (sum(cost) / world), (world, cost)
+        even = [int(deg[a:b].sum()) for a, b in zip(range(0, n, n // world), range(n // world, n + 1, n // world))]
+        assert max(even) > 1.25 * (sum(even) / world)          # what the balancing is for: hubs sit at low indices
+    assert sharding.network_cuts(100, None, 2) == [0, 64, 100]
+    assert sharding.network_cuts(70, e[:0], 3) == [0, 32, 64, 70]
