@@ -587,10 +587,13 @@ def main():
         clocks = sampler.stop() if rank == 0 else None
         max_s = max_over_ranks(dev_s)
         # ---- dominant kernel: its own CUDA-event time -------------------------------------------------
-        if args.workload == "schelling" and not sharded:
+        if args.workload == "schelling" and not sharded and model._dev.profile()[2] != "grid_shard_sweep_kernel":
             ksecs, klaunches = dev_s, 1            # the persistent kernel IS the timed region (one launch)
+            wl.kernel = model._dev.profile()[2]
         else:
             pm = model if wl.stationary else wl.fresh()
+            if args.workload == "schelling":
+                wl.kernel = pm._dev.profile()[2]   # band kernels: whole-grid band on one GPU, or one band per rank
             pm._dev.set_profile(True)              # events around every launch, no graph
             res = pm.run(steps=K)
             ksecs, klaunches, _ = pm._dev.profile()

@@ -464,6 +464,7 @@ static void fill_type_dev(const jxb_type_desc& t, TypeDev& td) {
 }
 
 static int plan_step_blocks(jxb_model* m);
+static int grid_shard_prepare(jxb_model* m, int row_begin, int row_end);
 
 static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_traced_spec* ts, jxb_model** out);
 
@@ -641,6 +642,14 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
       }
       m->sch_bits = true;
       m->grid_sharded = true;
+    } else if (sd.H % 32 == 0) {
+      // ONE GPU: the band kernels (4 launches per step, whole grid = one band) also serve the large
+      // grids whose rows are outside the persistent bit-sliced kernel's shapes (not a multiple of 1024
+      // cells, or more than 8192) -- ~2x the byte/LUT kernel there; small grids stay on the persistent
+      // kernels (one launch for the whole run).  JXB_GRID_BANDS=1 / 0 forces / forbids it.
+      const char* ev = getenv("JXB_GRID_BANDS");
+      const bool want = ev ? atoi(ev) != 0 : (!m->sch_bits && sd.cells >= (1ll << 24));
+      if (want) { m->sch_bits = true; m->grid_sharded = true; }
     }
     if (m->sch_bits) {
       SchellingBitsDev& sb = m->sb;
@@ -673,6 +682,10 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
       for (int q = 0; q < 4; ++q) m->sb.need_sel[o][q] = ((need >> q) & 1) ? 0xFFFFFFFFu : 0u;
     }
     m->has_grid = true;
+    if (m->grid_sharded && md.world_size == 1) {     // single band: no peers to map
+      TRY(grid_shard_prepare(m, 0, sd.W));
+      m->gs_attached = true;
+    }
   }
   if (d->program == JXB_PROGRAM_SIR) m->has_net = true;
   if (d->program == JXB_PROGRAM_ECONOMY) {
@@ -952,11 +965,8 @@ extern "C" int jxb_model_download_empty_cells(jxb_model* m, int32_t* host, size_
 // ---------------------------------------------------------------------------------------
 // Grid row-band sharding (csrc/grid_shard.cuh)
 // ---------------------------------------------------------------------------------------
-extern "C" int jxb_model_grid_shard_export(jxb_model* m, int row_begin, int row_end, void* handle_out, size_t bytes) {
-  NEED(m);
-  if (!m->grid_sharded) return fail(JXB_ERR_STATE, "model is not a sharded Grid (desc.world_size > 1 with a Schelling program)");
-  if (!handle_out || bytes < sizeof(cudaIpcMemHandle_t))
-    return fail(JXB_ERR_INVALID, "need %zu bytes for the IPC handle", sizeof(cudaIpcMemHandle_t));
+// band of this rank + its receive area, step-info block and per-CTA partials (idempotent)
+static int grid_shard_prepare(jxb_model* m, int row_begin, int row_end) {
   const int G = m->dev.world_size, W = m->sd.W, H = m->sd.H;
   const int max_rows = (W + G - 1) / G;
   if (row_begin < 0 || row_end > W || row_end <= row_begin || row_end - row_begin > max_rows)
@@ -973,12 +983,29 @@ extern "C" int jxb_model_grid_shard_export(jxb_model* m, int row_begin, int row_
     if ((rc = dev_alloc(m, &gs.info, 1))) return rc;
     CK(cudaMemset(gs.info, 0, sizeof(GridStepInfo)));
     const int nrows = row_end - row_begin, strips = (m->sb.wpr + 31) / 32;
-    // same split for every band size this model can get: ~2 strip-rows per warp, at most 2 CTAs per SM
+    // ~2 strip-rows per warp, at most 2 CTAs per SM, at least one row per CTA
     gs.blocks = (int)std::max<long long>(1, std::min<long long>(std::min<long long>((long long)m->eng->sms * 2, nrows),
                                                                 ((long long)nrows * strips + 15) / 16));
     if ((rc = dev_alloc(m, &gs.part, (size_t)gs.blocks))) return rc;
-    m->gs_move_blocks = m->eng->sms * 4;
+    // the mover walk is latency-bound random access (ncu: long-scoreboard stalls, 4 % issue utilisation, 49 %
+    // occupancy at 4 CTAs per SM -- the measured configuration; JXB_GS_MOVE_BPS tries more resident CTAs)
+    int mv_bps = 4;
+    if (const char* ev = getenv("JXB_GS_MOVE_BPS")) mv_bps = std::max(1, std::min(8, atoi(ev)));
+    m->gs_move_blocks = m->eng->sms * mv_bps;
   }
+  gs.peer[gs.rank] = m->gs_area;
+  gs.self = m->gs_area;
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_grid_shard_export(jxb_model* m, int row_begin, int row_end, void* handle_out, size_t bytes) {
+  NEED(m);
+  if (!m->grid_sharded || m->dev.world_size < 2)
+    return fail(JXB_ERR_STATE, "model is not a sharded Grid (desc.world_size > 1 with a Schelling program)");
+  if (!handle_out || bytes < sizeof(cudaIpcMemHandle_t))
+    return fail(JXB_ERR_INVALID, "need %zu bytes for the IPC handle", sizeof(cudaIpcMemHandle_t));
+  int rc = grid_shard_prepare(m, row_begin, row_end);
+  if (rc) return rc;
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, m->gs_area));
   memset(handle_out, 0, bytes);
@@ -993,7 +1020,7 @@ extern "C" int jxb_model_grid_shard_attach(jxb_model* m, const void* handles, si
   if (bytes_each < sizeof(cudaIpcMemHandle_t)) return fail(JXB_ERR_INVALID, "handle entries too small");
   CK(cudaSetDevice(m->eng->device));
   for (int p = 0; p < n_ranks; ++p) {
-    if (p == m->dev.rank) { m->gs.peer[p] = m->gs_area; m->gs.self = m->gs_area; continue; }
+    if (p == m->dev.rank) continue;
     cudaIpcMemHandle_t h;
     memcpy(&h, (const char*)handles + (size_t)p * bytes_each, sizeof(h));
     void* q = nullptr;
@@ -1151,6 +1178,8 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     else if (mode && !strcmp(mode, "pull_s")) m->sir_mode = 2;
     if (m->net_sharded) m->sir_mode = 2;     // a rank only holds its own rows: pull over them (a push would scatter remotely)
     sv.auto_mode = m->sir_mode == 3;
+    sv.big_len = 256u;
+    if (const char* ev = getenv("JXB_SIR_BIG")) sv.big_len = (unsigned int)std::max(1, atoi(ev));
     const int dev_mode = m->sir_mode == 2 ? 0 : 1;       // auto starts in the push direction
     CK(cudaMemcpy(&m->dev.ctrl->sir_mode, &dev_mode, sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(&m->dev.ctrl->sir_mode_next, &dev_mode, sizeof(int), cudaMemcpyHostToDevice));

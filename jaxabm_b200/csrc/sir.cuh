@@ -39,6 +39,7 @@ struct SirDev {
   int n_heavy;
   long long* degsum;       // [CTAs][2] adjacency entries of the new susceptible / infected rows per CTA
   int auto_mode;           // 1: the step's tail picks push or pull for the next step (direction-optimising)
+  unsigned int big_len;    // pull over S rows: rows longer than this are walked by the whole warp, shorter ones by their own lane
   // node-range sharding over ranks (one process per GPU): this rank owns rows [goff, goff + n) of the global
   // population; infbits[] are GLOBAL bitmaps inside an IPC-shared receive area [SirXchgHdr | bits0 | bits1], and
   // the pull kernel stores the new words of its rows straight into every rank's copy
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
     }
     unsigned int k = 0;
     // long susceptible rows (hubs before they are infected): all 32 lanes stride the row
-    unsigned int big = __ballot_sync(0xffffffffu, active && s == 0 && len > 256u);
+    unsigned int big = __ballot_sync(0xffffffffu, active && s == 0 && len > sv.big_len);
     while (big) {
       const int b = __ffs(big) - 1;
       big &= big - 1;
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
     // every other susceptible row: its own lane walks it (consecutive lanes own consecutive CSR
     // segments, so a warp's loads fall into a few adjacent lines that L1 keeps across the
     // iterations); two entries per iteration for memory-level parallelism
-    if (active && s == 0 && len > 0 && len <= 256u) {
+    if (active && s == 0 && len > 0 && len <= sv.big_len) {
       const int* cp = sv.col + lo;
       unsigned int e = 0;
       for (; e + 2 <= len; e += 2) {

@@ -131,6 +131,35 @@ def test_grid_row_bands_two_gpus():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("grid,n,periodic,steps", [(64, 3300, False, 10), (96, 7000, True, 12), (1024, 800_000, False, 30),
+                                                   (4128, 13_000_000, False, 25)])
+def test_single_gpu_band_mode_matches_persistent_kernels(grid, n, periodic, steps, mode, monkeypatch):
+    """On ONE GPU the band kernels (whole grid = one band, 4 launches per step) serve the large grids outside the
+    persistent bit-sliced kernel's shapes; they must reproduce the persistent kernels bit for bit.  4128 x 4128
+    (>= 2^24 cells, rows not a multiple of 1024) selects them by default."""
+    import jaxabm_b200 as jx
+    from jaxabm_b200.rules import schelling
+
+    def run(bands):
+        monkeypatch.setenv("JXB_GRID_BANDS", bands)
+        m = schelling.create_schelling_model(grid, n, seed=5, periodic=periodic, similarity_threshold=0.6,
+                                             config=jx.ModelConfig(seed=9, rng_mode=mode))
+        snap = _snapshot(m, m.run(steps=steps)), _snapshot(m, m.run(steps=4)), m._dev.profile()[2]
+        del m
+        return snap
+    a1, a2, ka = run("0")
+    b1, b2, kb = run("1")
+    assert ka in ("schelling_bits_kernel", "schelling_run_kernel") and kb == "grid_shard_sweep_kernel"
+    _assert_same(a1, b1, "first run")
+    _assert_same(a2, b2, "second run")
+    if grid == 4128:
+        monkeypatch.delenv("JXB_GRID_BANDS")
+        m = schelling.create_schelling_model(grid, n, seed=5, periodic=periodic, similarity_threshold=0.6,
+                                             config=jx.ModelConfig(seed=9, rng_mode=mode))
+        assert m._dev.profile()[2] == "grid_shard_sweep_kernel"       # the default for this shape
+
+
+@pytest.mark.gpu
 def test_grid_shard_rejects_bad_shapes():
     from jaxabm_b200 import _native as nat
     from jaxabm_b200.device import DeviceModel, TypeSpec, make_desc

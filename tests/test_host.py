@@ -46,6 +46,9 @@ def test_host_prng_matches_oracle_and_kats(mode):
     assert jr.threefry2x32([0x13198A2E, 0x03707344], [0x243F6A88, 0x85A308D3]).tolist() == [0xC4923A9C, 0x483DF7A0]
     assert jr.split(jr.PRNGKey(0), 2, 0).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
     assert jr.split(jr.PRNGKey(0), 2, 1).tolist() == [[1797259609, 2579123966], [928981903, 3453687069]]
+    # values printed in JAX's documentation (tests/golden/threefry_kat.json)
+    assert float(jr.uniform(jr.PRNGKey(0), (), 0.0, 1.0, 0)) == pytest.approx(0.41845703, abs=1e-8)
+    assert float(jr.uniform(jr.PRNGKey(0), (), 0.0, 1.0, 1)) == pytest.approx(0.947667, abs=5e-7)
     for seed in (0, 42, 12345):
         k = jr.PRNGKey(seed)
         assert np.array_equal(k, jl.PRNGKey(seed))

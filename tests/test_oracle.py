@@ -40,6 +40,18 @@ def test_jax_published_values(kat):
     assert int(jl.random_bits(jl.PRNGKey(0), (), jl.PARTITIONABLE)) == _u32(kat["bits_prngkey0_partitionable"])
 
 
+def test_jax_documented_draws(kat):
+    """Outputs printed in JAX's documentation, float32 to the printed digits: they pin the bits -> uniform
+    mapping of both stream layouts and the whole normal path (uniform on (-1, 1) + XLA's float32 erf_inv)."""
+    f32 = lambda v: float(np.float32(v))
+    assert f32(jl.normal(jl.PRNGKey(0), (1,), jl.LEGACY)[0]) == f32(kat["normal_prngkey0_shape1_legacy_docs"])
+    sub = jl.split(jl.PRNGKey(0), 2, jl.LEGACY)[1]
+    assert f32(jl.normal(sub, (1,), jl.LEGACY)[0]) == f32(kat["normal_after_first_split_of_prngkey0_shape1_legacy_docs"])
+    assert f32(jl.normal(jl.PRNGKey(42), (), jl.LEGACY)) == f32(kat["normal_prngkey42_legacy_docs"])
+    assert f32(jl.uniform(jl.PRNGKey(0), (), mode=jl.PARTITIONABLE)) == pytest.approx(kat["uniform_prngkey0_partitionable_docs"], abs=5e-7)
+    assert f32(jl.normal(jl.PRNGKey(42), (), jl.PARTITIONABLE)) == f32(kat["normal_prngkey42_partitionable_docs"])
+
+
 def test_prng_structure(mode):
     key = jl.PRNGKey(7)
     # batched helpers agree with the scalar definitions
