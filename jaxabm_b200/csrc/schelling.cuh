@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kThreads) schelling_run_kernel(const Schelling
           if (src >= cells - H) sd.ct[(long long)src - cells] = (signed char)-1;
         }
         ((int2*)t.f[1])[a] = make_int2((int)(dst / sd.H), (int)(dst % sd.H));
-        ((int*)t.f[3])[a] += 1;
+        atomicAdd((int*)t.f[3] + a, 1);   // fire-and-forget L2 reduction: no load to wait for (ncu: 37 % of the mover stalls)
       }
     }
     grid.sync();

@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
             if (s_ >= sd.cells - H) { atomicAnd(sb.occ + (long long)(s_ >> 5) - words, ~sbit); if (ty) atomicAnd(sb.t1 + (long long)(s_ >> 5) - words, ~sbit); }
           }
           ((int2*)t.f[1])[a] = make_int2((int)(d_ / sd.H), (int)(d_ % sd.H));
-          ((int*)t.f[3])[a] += 1;
+          atomicAdd((int*)t.f[3] + a, 1);   // fire-and-forget L2 reduction: no load to wait for (ncu: 37 % of the mover stalls)
         }
       }
     }
