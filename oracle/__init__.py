@@ -17,8 +17,9 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 
 PARITY PINNING STATUS
 ---------------------
-* threefry2x32 / ``PRNGKey`` / ``split`` / ``uniform``: pinned by the published
-  Random123 + JAX known-answer vectors (``tests/golden/threefry_kat.json``).
+* threefry2x32 / ``PRNGKey`` / ``split`` / ``uniform`` / ``normal`` (both stream layouts): pinned by
+  the published Random123 vectors and by the draws JAX's own documentation prints
+  (``tests/golden/threefry_kat.json``; ``tests/test_oracle.py::test_jax_documented_draws``).
 * Model loop, key schedule, step ordering: pinned by the reference's own
   behavioural tests (ported in ``tests/test_oracle.py::test_model_contract``,
   ``::test_agent_collection_contract`` and ``tests/test_host.py::test_api_contract_without_device``) and by
@@ -26,4 +27,6 @@ PARITY PINNING STATUS
 * Floating trajectories of the workload rules and the Schelling / SIR rules:
   **parity unpinned** -- the reference holds no golden vectors for them
    and JAX cannot be run here to generate any.
+* ``oracle/sharded.py`` restates the multi-GPU decompositions (grid row bands, network node ranges)
+  rank by rank; ``tests/test_oracle_sharded.py`` pins them on the plain oracle.
 """
