@@ -31,7 +31,6 @@ the whole path where only one GPU is visible.
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 
 import numpy as np

@@ -1,11 +1,9 @@
 """Sweep of the pull kernel's lane-serial / warp-cooperative row-length threshold (JXB_SIR_BIG) at C3."""
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np
 import jaxabm_b200 as jx
 from jaxabm_b200 import synthetic
 from jaxabm_b200.rules import sir

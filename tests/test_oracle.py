@@ -50,6 +50,14 @@ def test_jax_documented_draws(kat):
     assert f32(jl.normal(jl.PRNGKey(42), (), jl.LEGACY)) == f32(kat["normal_prngkey42_legacy_docs"])
     assert f32(jl.uniform(jl.PRNGKey(0), (), mode=jl.PARTITIONABLE)) == pytest.approx(kat["uniform_prngkey0_partitionable_docs"], abs=5e-7)
     assert f32(jl.normal(jl.PRNGKey(42), (), jl.PARTITIONABLE)) == f32(kat["normal_prngkey42_partitionable_docs"])
+    # the tutorial's chained draws: split -> draw from the subkey -> carry the new key (the schedule of model.py:156)
+    assert jl.split(jl.PRNGKey(42), 2, jl.LEGACY).tolist() == kat["split_prngkey42_legacy_docs"]
+    for mode, name in ((jl.LEGACY, "legacy"), (jl.PARTITIONABLE, "partitionable")):
+        key, got = jl.PRNGKey(42), []
+        for _ in range(3):
+            key, sub = jl.split(key, 2, mode)
+            got.append(float(jl.normal(sub, (), mode)))
+        assert got == kat[f"tutorial_chained_normal_draws_prngkey42_{name}_docs"]
 
 
 def test_prng_structure(mode):
