@@ -472,34 +472,55 @@ class Parameter:
         raise ValueError(f"Unknown distribution: {self.distribution}")
 
 
-class Sample:
-    """``agentpy.py:1210-1260``: n joint samples of a parameter dict."""
+def _as_param_dict(parameters) -> Dict[str, Any]:
+    """The reference passes ``List[Parameter]`` (``agentpy.py:1230,1294,1404``); a ``{name: Parameter | fixed
+    value}`` dict is accepted as well."""
+    if isinstance(parameters, dict):
+        return dict(parameters)
+    return {p.name: p for p in parameters}
 
-    def __init__(self, parameters: Dict[str, Any], n: int = 10, seed: Optional[int] = None):
-        self.parameters, self.n, self.seed = parameters, n, seed
-        self.samples: List[Dict[str, Any]] = []
-        cols = {}
-        for i, (name, p) in enumerate(parameters.items()):
-            cols[name] = p.sample(n, None if seed is None else seed + i) if isinstance(p, Parameter) else [p] * n
-        for j in range(n):
-            self.samples.append({k: (v[j].item() if hasattr(v[j], "item") else v[j]) for k, v in cols.items()})
+
+class Sample:
+    """``agentpy.py:1210-1260``: ``Sample(parameters, n_samples)`` draws ``n_samples`` values per parameter;
+    ``sample[i]`` is the i-th parameter set, ``len(sample)`` the number of sets."""
+
+    def __init__(self, parameters, n_samples: int = 10, seed: Optional[int] = None, n: Optional[int] = None):
+        if n is not None:
+            n_samples = n
+        self.parameters, self.n_samples, self.n, self.seed = parameters, n_samples, n_samples, seed
+        self._samples: Dict[str, Any] = {}
+        for i, (name, p) in enumerate(_as_param_dict(parameters).items()):
+            if isinstance(p, Parameter):
+                self._samples[name] = p.sample(n_samples, None if seed is None else seed + i)
+            else:
+                self._samples[name] = [p] * n_samples
+        self.samples: List[Dict[str, Any]] = [self[j] for j in range(n_samples)]
+
+    def __getitem__(self, index: int) -> Dict[str, Any]:                      # agentpy.py:1247-1259
+        out = {}
+        for name, v in self._samples.items():
+            x = v[index]
+            out[name] = x.item() if hasattr(x, "item") else x
+        return out
 
     def __iter__(self):
         return iter(self.samples)
 
-    def __len__(self):
-        return self.n
+    def __len__(self):                                                        # agentpy.py:1261-1267
+        return self.n_samples
 
 
 class SensitivityAnalyzer:
     """``agentpy.py:1263-1380``: adapter onto :class:`jaxabm_b200.analysis.SensitivityAnalysis`."""
 
-    def __init__(self, model_class, parameters: Dict[str, Any], n_samples: int = 10,
+    def __init__(self, model_class, parameters, n_samples: int = 10,
                  metrics: Optional[List[str]] = None, seed: int = 0):
         self.model_class, self.parameters, self.n_samples = model_class, parameters, n_samples
         self.metrics, self.seed = metrics or [], seed
-        self.fixed = {k: v for k, v in parameters.items() if not isinstance(v, Parameter)}
-        self.ranges = {k: v.bounds for k, v in parameters.items() if isinstance(v, Parameter) and v.bounds}
+        pd = _as_param_dict(parameters)
+        self.fixed = {k: v for k, v in pd.items() if not isinstance(v, Parameter)}
+        self.ranges = {k: v.bounds for k, v in pd.items() if isinstance(v, Parameter) and v.bounds}
+        self.sample = Sample(parameters, n_samples, seed=seed)                # agentpy.py:1311
         self._sa = None
 
     def _factory(self, params=None, config=None):
@@ -525,13 +546,14 @@ class SensitivityAnalyzer:
 class ModelCalibrator:
     """``agentpy.py:1383-1485``: adapter onto :class:`jaxabm_b200.analysis.ModelCalibrator`."""
 
-    def __init__(self, model_class, parameters: Dict[str, Any], target_metrics: Dict[str, float],
+    def __init__(self, model_class, parameters, target_metrics: Dict[str, float],
                  metrics_weights: Optional[Dict[str, float]] = None, learning_rate: float = 0.01,
                  max_iterations: int = 20, method: str = "gradient", seed: int = 0):
         self.model_class, self.parameters, self.target_metrics = model_class, parameters, target_metrics
         self.metrics_weights, self.learning_rate = metrics_weights, learning_rate
         self.max_iterations, self.method, self.seed = max_iterations, method, seed
-        self.fixed = {k: v for k, v in parameters.items() if not isinstance(v, Parameter)}
+        self._pd = _as_param_dict(parameters)
+        self.fixed = {k: v for k, v in self._pd.items() if not isinstance(v, Parameter)}
 
     def _factory(self, params=None, config=None):
         p = {**self.fixed, **(params or {})}
@@ -542,8 +564,8 @@ class ModelCalibrator:
     def run(self, verbose: bool = False):
         from .analysis import ModelCalibrator as Core
         init = {k: (v.value if v.value is not None else sum(v.bounds) / 2)
-                for k, v in self.parameters.items() if isinstance(v, Parameter)}
-        bounds = {k: v.bounds for k, v in self.parameters.items() if isinstance(v, Parameter) and v.bounds}
+                for k, v in self._pd.items() if isinstance(v, Parameter)}
+        bounds = {k: v.bounds for k, v in self._pd.items() if isinstance(v, Parameter) and v.bounds}
         core = Core(self._factory, init, self.target_metrics, param_bounds=bounds,
                     metrics_weights=self.metrics_weights, learning_rate=self.learning_rate,
                     max_iterations=self.max_iterations, method=self.method, seed=self.seed)   # ValueError for 'gradient'

@@ -156,6 +156,15 @@ def test_facade_host_objects():
     p = jx.Parameter("a", bounds=(0.0, 1.0))
     s = jx.Sample({"a": p, "b": 3}, n=4, seed=1)
     assert len(s) == 4 and all(0 <= x["a"] <= 1 and x["b"] == 3 for x in s)
+    # the reference's own call forms (agentpy.py:1230,1247-1267,1294-1311): a list of Parameters, n_samples, indexing
+    p2 = jx.Parameter("growth", (0.01, 0.1))
+    s2 = jx.Sample([p, p2], n_samples=5)
+    assert len(s2) == 5 and s2.n_samples == 5 and set(s2[3]) == {"a", "growth"} and 0.01 <= s2[3]["growth"] <= 0.1
+    assert len(s2._samples["a"]) == 5 and s2.parameters[1] is p2
+    an2 = jx.SensitivityAnalyzer(random_walk.RandomWalkModel, [p, p2], n_samples=3, metrics=["mean_distance"])
+    assert an2.ranges == {"a": (0.0, 1.0), "growth": (0.01, 0.1)} and len(an2.sample) == 3 and an2.fixed == {}
+    cal = jx.ModelCalibrator(random_walk.RandomWalkModel, [p2], {"mean_distance": 0.1})
+    assert cal._pd == {"growth": p2} and cal.fixed == {}
     with pytest.raises(AttributeError):
         an = jx.SensitivityAnalyzer(random_walk.RandomWalkModel, {"n_agents": p}, n_samples=2)
         an._sa = object.__new__(jx.SensitivityAnalysis)
