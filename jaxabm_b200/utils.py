@@ -58,12 +58,30 @@ def standardize_metrics(metrics: Dict[str, Any]) -> Dict[str, float]:
     return out
 
 
-def run_parallel_simulations(model_factory: Callable, param_sets: List[Dict[str, Any]], seeds=None,
-                             steps=None) -> List[Dict[str, Any]]:
-    """``jaxabm/utils.py:128-175`` -- but actually batched: homogeneous engine models are
-    dispatched as one ensemble launch (``jaxabm_b200.ensemble``)."""
+def run_parallel_simulations(model_factory: Callable, param_sets: List[Dict[str, Any]], num_runs: int = 1,
+                             seed_offset: int = 0, seeds=None, steps=None) -> List[Dict[str, Any]]:
+    """``jaxabm/utils.py:128-175``: every parameter set is run ``num_runs`` times with the seeds
+    ``seed_offset + i * num_runs + j``; each results dict also carries ``'params'`` and ``'seed'``, and a run
+    that raises is reported and skipped.  (The reference's loop is serial despite its name; here each
+    run is one device-resident time loop.)  ``seeds`` (one per parameter set) and ``steps`` are
+    extensions: explicit seeds replace the schedule, ``steps`` overrides ``config.steps``."""
     from .core import ModelConfig
-    from .ensemble import run_models
-    seeds = list(seeds) if seeds is not None else list(range(len(param_sets)))
-    models = [model_factory(params=p, config=ModelConfig(seed=s)) for p, s in zip(param_sets, seeds)]
-    return run_models(models, steps=steps, full_history=True)
+    plan = []
+    for i, params in enumerate(param_sets):
+        if seeds is not None:
+            plan.append((i, 0, params, list(seeds)[i]))
+        else:
+            plan.extend((i, j, params, seed_offset + i * num_runs + j) for j in range(num_runs))
+    runs = 1 if seeds is not None else num_runs
+    all_results = []
+    for i, j, params, seed in plan:
+        print(f"Running simulation {i+1}/{len(param_sets)}, run {j+1}/{runs}, seed={seed}")
+        try:
+            model = model_factory(params=params, config=ModelConfig(seed=seed))
+            results = model.run(steps) if steps is not None else model.run()
+            results["params"] = params
+            results["seed"] = seed
+            all_results.append(results)
+        except Exception as e:                     # noqa: BLE001 - as in the reference (utils.py:173-174)
+            print(f"Error in simulation {i+1}/{len(param_sets)}, run {j+1}/{runs}: {e}")
+    return all_results

@@ -277,3 +277,24 @@ def test_network_cuts_balance_the_adjacency():
         assert max(even) > 1.25 * (sum(even) / world)          # what the balancing is for: hubs sit at low indices
     assert sharding.network_cuts(100, None, 2) == [0, 64, 100]
     assert sharding.network_cuts(70, e[:0], 3) == [0, 32, 64, 70]
+
+
+def test_run_parallel_simulations_follows_the_reference_schedule(capsys):
+    """jaxabm/utils.py:128-175: seeds seed_offset + i * num_runs + j, 'params' / 'seed' added to every results
+    dict, a failing run is reported and skipped."""
+    class Fake:
+        def __init__(self, params, config):
+            self.p, self.c = params, config
+
+        def run(self, steps=None):
+            if self.p.get("boom"):
+                raise RuntimeError("x")
+            return {"step": [steps or 1], "v": [self.p["a"] * 10 + self.c.seed]}
+
+    r = jx.run_parallel_simulations(lambda params, config: Fake(params, config),
+                                    [{"a": 1}, {"a": 2, "boom": 1}, {"a": 3}], num_runs=2, seed_offset=100)
+    assert [(x["seed"], x["v"], x["params"]["a"]) for x in r] == [(100, [110], 1), (101, [111], 1), (104, [134], 3), (105, [135], 3)]
+    out = capsys.readouterr().out
+    assert "Running simulation 2/3, run 2/2, seed=103" in out and "Error in simulation 2/3, run 1/2: x" in out
+    r = jx.run_parallel_simulations(lambda params, config: Fake(params, config), [{"a": 1}, {"a": 3}], seeds=[7, 9], steps=4)
+    assert [(x["seed"], x["step"]) for x in r] == [(7, [4]), (9, [4])]
