@@ -292,7 +292,18 @@ class WalkWorkload:
         return wall, 0, d2h + K * 7 * 8, "create + initialize on device, Model.run(K), download all 4 state columns"
 
     def cpu_run(self, steps):
-        raise NotImplementedError
+        """1/4 population sample on the C/OpenMP oracle (time scaled x4); uniform starts and velocities of the
+        scaled variant's ranges (the walker update draws nothing, so the stream is irrelevant to its cost)."""
+        from oracle import cfast
+        n = self.n // 4
+        rng = np.random.RandomState(self.seed)
+        f = cfast.WalkFast(rng.uniform(0, 1, (n, 2)).astype(np.float32), rng.uniform(-0.01, 0.01, (n, 2)).astype(np.float32))
+        f.run(1)
+        t0 = time.perf_counter()
+        f.run(steps)
+        secs = (time.perf_counter() - t0) * 4.0
+        return secs, cfast.num_threads(), (f"{steps} steps on a 1/4 population sample ({n} walkers, time scaled x4) "
+                                            "on the C/OpenMP oracle")
 
 
 class SirWorkload:
@@ -343,7 +354,13 @@ class SirWorkload:
                                                                "initialize, Model.run(K), download 'state'")
 
     def cpu_run(self, steps):
-        raise NotImplementedError
+        """The first `steps` full-size steps of the same seeded epidemic on the C/OpenMP oracle."""
+        from oracle import cfast
+        f = cfast.SirFast(self.n, self.edges, beta=0.05, gamma=0.1, initial_infected=0.01, seed=self.seed, mode=1)
+        t0 = time.perf_counter()
+        f.run(steps)
+        return (time.perf_counter() - t0, cfast.num_threads(),
+                f"first {steps} full-size steps of {self.name} (same seeded network and start) on the C/OpenMP oracle")
 
 
 class EnsembleWorkload:

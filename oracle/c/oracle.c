@@ -257,3 +257,66 @@ void orc_market_step(int64_t nc, float* savings, float* consumption, float* util
   *sum_utility = su;
   *sum_profit = sp;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * One SIR step (DESIGN.md "SIR rule"; oracle/rules.py::SIRAgent.update_batch): synchronous on the
+ * pre-step snapshot `st`, k = infected neighbours in the CSR, u = uniform(split(coll_key, N)[i])
+ * (jaxabm/agent.py:156), S -> I iff u < 1 - q[min(k, 4095)], I -> R iff u < gamma.
+ * counts[3] = S / I / R after the step.
+ * ------------------------------------------------------------------------------------------ */
+void orc_sir_step(int mode, const uint32_t coll_key[2], int64_t n, const int64_t* row_ptr, const int32_t* col,
+                  const int32_t* st, int32_t* out, const float* q, float gamma, int64_t counts[3]) {
+  int64_t cS = 0, cI = 0, cR = 0;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : cS, cI, cR)
+  for (int64_t i = 0; i < n; ++i) {
+    int s = st[i];
+    int64_t k = 0;
+    if (s == 0)
+      for (int64_t e = row_ptr[i]; e < row_ptr[i + 1]; ++e) k += (st[col[e]] == 1);
+    if ((s == 0 && k > 0) || s == 1) {
+      uint32_t ak[2];
+      split_child(mode, coll_key, (uint64_t)i, (uint64_t)n, ak);
+      const float u = bits_to_unit(bits_elem(mode, ak, 0, 1));
+      if (s == 0) {
+        const float p = 1.0f - q[k < 4095 ? k : 4095];
+        if (u < p) s = 1;
+      } else if (u < gamma) {
+        s = 2;
+      }
+    }
+    out[i] = s;
+    cS += (s == 0); cI += (s == 1); cR += (s == 2);
+  }
+  counts[0] = cS; counts[1] = cI; counts[2] = cR;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One random-walker step (examples/basic_example.py:33-69; oracle/rules.py::RandomWalker.step_batch)
+ * + the distance metrics of :141-182 on the NEW positions: sum and max of ||pos - 0.5||_2 (float32).
+ * ------------------------------------------------------------------------------------------ */
+void orc_walk_step(int64_t n, float* pos, float* vel, int32_t* color, int32_t* steps_taken, float lo, float hi,
+                   double* sum_dist, float* max_dist) {
+  double sd = 0.0;
+  float md = 0.0f;
+#pragma omp parallel for schedule(static) reduction(+ : sd) reduction(max : md)
+  for (int64_t i = 0; i < n; ++i) {
+    int any = 0;
+    float c[2];
+    for (int a = 0; a < 2; ++a) {
+      float p = pos[2 * i + a] + vel[2 * i + a];
+      const int b = (p <= lo) || (p >= hi);
+      vel[2 * i + a] = vel[2 * i + a] * (float)(1 - 2 * b);
+      p = fminf(fmaxf(p, lo), hi);
+      pos[2 * i + a] = p;
+      any |= b;
+      c[a] = p - 0.5f;
+    }
+    if (any) color[i] = 1 - color[i];
+    steps_taken[i] += 1;
+    const float d = sqrtf(c[0] * c[0] + c[1] * c[1]);
+    sd += (double)d;
+    md = d > md ? d : md;
+  }
+  *sum_dist = sd;
+  *max_dist = md;
+}

@@ -33,6 +33,10 @@ def lib():
         L.orc_market_step.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                       C.c_float, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_sir_step.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_float, C.c_void_p]
+        L.orc_walk_step.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                    C.POINTER(C.c_double), C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -136,4 +140,61 @@ class MarketFast:
             out["unemployment"].append(np.float32(self.env[2]))
             out["avg_utility"].append(np.float32(su.value / max(self.nc, 1)))
             out["avg_profit"].append(np.float32(sp.value / max(self.np_, 1)))
+        return out
+
+
+class SirFast:
+    """SIR on a network (C3) on the C oracle: same inputs and outputs as
+    ``oracle.rules.create_sir_model(...).run(steps)`` (no env function: the key schedule of
+    ``model.py:156,164`` only)."""
+
+    def __init__(self, n, edges, beta=0.05, gamma=0.1, initial_infected=0.01, seed=42, mode=1):
+        from .rules import edges_to_csr, sir_escape_table
+        self.n, self.mode, self.gamma = int(n), mode, np.float32(gamma)
+        rp, col = edges_to_csr(self.n, edges)
+        self.row_ptr = np.ascontiguousarray(rp, dtype=np.int64)
+        self.col = np.ascontiguousarray(col, dtype=np.int32)
+        self.q = np.ascontiguousarray(sir_escape_table(beta), dtype=np.float32)
+        init_keys, _, _, rng = key_schedule(seed, 1, False, 0, mode)
+        u = jl.uniform_scalar_batched(jl.split(init_keys[0], self.n, mode), mode=mode)
+        self.state = np.ascontiguousarray((u < np.float32(initial_infected)).astype(np.int32))
+        self._next = np.empty_like(self.state)
+        self._rng = rng
+
+    def run(self, steps: int):
+        coll = np.zeros((steps, 1, 2), dtype=np.uint32)
+        upd = np.zeros((steps, 2), dtype=np.uint32)
+        lib().orc_key_schedule(self.mode, _p(self._rng), 1, 0, steps, _p(coll), _p(upd))
+        out = {"count_S": [], "count_I": [], "count_R": []}
+        counts = np.zeros(3, dtype=np.int64)
+        for t in range(steps):
+            ck = np.ascontiguousarray(coll[t, 0])
+            lib().orc_sir_step(self.mode, _p(ck), self.n, _p(self.row_ptr), _p(self.col), _p(self.state), _p(self._next),
+                               _p(self.q), C.c_float(self.gamma), _p(counts))
+            self.state, self._next = self._next, self.state
+            for k, c in zip(("count_S", "count_I", "count_R"), counts):
+                out[k].append(np.int32(c))
+        return out
+
+
+class WalkFast:
+    """Random walkers (C1, ``examples/basic_example.py:33-69,141-182``) on the C oracle, from given
+    ``position`` / ``velocity`` columns (the scaled bench variant draws them per agent)."""
+
+    def __init__(self, position, velocity, bounds=(0.0, 1.0)):
+        self.pos = np.ascontiguousarray(position, dtype=np.float32).copy()
+        self.vel = np.ascontiguousarray(velocity, dtype=np.float32).copy()
+        self.n = self.pos.shape[0]
+        self.color = np.zeros(self.n, dtype=np.int32)
+        self.steps_taken = np.zeros(self.n, dtype=np.int32)
+        self.lo, self.hi = np.float32(bounds[0]), np.float32(bounds[1])
+
+    def run(self, steps: int):
+        out = {"mean_distance": [], "max_distance": []}
+        sd, md = C.c_double(), C.c_float()
+        for _ in range(steps):
+            lib().orc_walk_step(self.n, _p(self.pos), _p(self.vel), _p(self.color), _p(self.steps_taken),
+                                C.c_float(self.lo), C.c_float(self.hi), C.byref(sd), C.byref(md))
+            out["mean_distance"].append(np.float32(sd.value / self.n))
+            out["max_distance"].append(np.float32(md.value))
         return out

@@ -245,3 +245,34 @@ def test_c_oracle_key_schedule(mode):
     b = cfast.key_schedule(5, 2, True, 6, mode)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_c_oracle_sir_and_walk_match_the_numpy_oracle(mode):
+    """oracle/c: orc_sir_step / orc_walk_step (bench.py's cpu_baseline for --workload sir / walk) against the
+    NumPy restatement: integer states exact, float32 walker columns exact, mean distance to summation order."""
+    from jaxabm_b200 import synthetic
+    n = 2500
+    edges = synthetic.scale_free_edges(n, 3, 5)
+    om = orules.create_sir_model(n, edges, beta=0.1, gamma=0.1, initial_infected=0.02, seed=2,
+                                config=ort.ModelConfig(seed=2, rng_mode=mode))
+    r = om.run(steps=12)
+    f = cfast.SirFast(n, edges, beta=0.1, gamma=0.1, initial_infected=0.02, seed=2, mode=mode)
+    fr = f.run(12)
+    for k in ("count_S", "count_I", "count_R"):
+        assert [int(v) for v in r[k]] == [int(v) for v in fr[k]]
+    assert np.array_equal(f.state, np.asarray(om.agent_collections["agents"].states["state"]))
+    # walkers: the scaled variant's keyed start, 40 steps (many bounces at |v| <= 0.01 near the walls)
+    w = orules.ScaledRandomWalker()
+    keys = jl.split(jl.PRNGKey(9), 4000, mode)
+    s = w.init_batch(ort.ModelConfig(seed=9, rng_mode=mode), keys)
+    s = {"position": s["position"], "velocity": s["velocity"] * np.float32(8.0),
+         "color": np.zeros(4000, np.int32), "steps_taken": np.zeros(4000, np.int32)}
+    fw = cfast.WalkFast(s["position"], s["velocity"])
+    out = fw.run(40)
+    for _ in range(40):
+        s = w.step_batch(s, {"env": {"bounds": np.array([0.0, 1.0], dtype=np.float32)}})
+    assert np.array_equal(fw.pos, s["position"]) and np.array_equal(fw.vel, s["velocity"])
+    assert np.array_equal(fw.color, s["color"]) and np.array_equal(fw.steps_taken, s["steps_taken"]) and fw.color.sum() > 100
+    d = orules.walker_distances(s["position"])
+    assert float(out["max_distance"][-1]) == float(d.max())
+    assert float(out["mean_distance"][-1]) == pytest.approx(float(d.mean(dtype=np.float64)), rel=1e-6)
