@@ -520,7 +520,7 @@ def edges_to_csr(n, edges):
     order = np.argsort(edges[:, 0], kind="stable")
     col = edges[order, 1].astype(i32)
     row_ptr = np.zeros(n + 1, dtype=np.int64)
-    np.add.at(row_ptr, edges[:, 0] + 1, 1)
+    row_ptr[1:] = np.bincount(edges[:, 0], minlength=n)[:n]
     return np.cumsum(row_ptr).astype(np.int64), col
 
 
