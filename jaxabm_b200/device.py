@@ -153,7 +153,10 @@ class DeviceModel:
         self.net_group = group
 
     def net_shard_sync(self) -> None:
-        """Collective: every rank hands its slice of the packed infected bitmap to all peers."""
+        """Collective: every rank hands its slice of the packed infected bitmap to all peers.  Barriers on both
+        sides: nobody writes into a peer's area while that peer may still be rebuilding it (set_network clears
+        the area), and nobody steps before every copy is whole."""
+        self.net_group.barrier()
         nat.check(self._lib.jxb_model_net_shard_sync(self.handle))
         self.net_group.barrier()
 
