@@ -194,6 +194,10 @@ struct jxb_engine {
   XchgBuf* xlocal = nullptr;
   XchgBuf* xpeer[kMaxPeers] = {};
   bool p2p = false;
+  // receive areas of destroyed sharded models: an allocation whose IPC handle was exported must not be freed
+  // while a peer process may still have it mapped, and the peers close their mappings whenever THEY destroy
+  // their model -- so the areas are only released with the engine
+  std::vector<void*> retired_areas;
 };
 
 struct jxb_model {
@@ -326,6 +330,7 @@ extern "C" int jxb_engine_destroy(jxb_engine* eng) {
   for (int p = 0; p < kMaxPeers; ++p)
     if (eng->xpeer[p] && eng->xpeer[p] != eng->xlocal) cudaIpcCloseMemHandle(eng->xpeer[p]);
   if (eng->xlocal) cudaFree(eng->xlocal);
+  for (void* a : eng->retired_areas) cudaFree(a);
   for (auto& b : eng->pool) cudaFree(b.first);
   cudaEventDestroy(eng->ev0);
   cudaEventDestroy(eng->ev1);
@@ -725,10 +730,11 @@ extern "C" int jxb_model_destroy(jxb_model* m) {
   for (auto& a : m->allocs) pool_free(m->eng, a.first, a.second);
   for (int p = 0; p < kMaxPeers; ++p)
     if (m->gs_opened[p]) cudaIpcCloseMemHandle(m->gs_opened[p]);
-  if (m->gs_area) cudaFree(m->gs_area);
   for (int p = 0; p < kMaxPeers; ++p)
     if (m->ns_opened[p]) cudaIpcCloseMemHandle(m->ns_opened[p]);
-  if (m->ns_area) cudaFree(m->ns_area);
+  // exported areas outlive the model (see jxb_engine::retired_areas); a single-band grid never exported its area
+  if (m->gs_area) { if (m->dev.world_size > 1) m->eng->retired_areas.push_back(m->gs_area); else cudaFree(m->gs_area); }
+  if (m->ns_area) m->eng->retired_areas.push_back(m->ns_area);
   pool_free(m->eng, m->d_keys, m->keys_cap * 4);
   pool_free(m->eng, m->d_metrics, m->rec_cap * kMaxMetrics * sizeof(double));
   pool_free(m->eng, m->d_rec, m->rec_cap * sizeof(int));
