@@ -113,12 +113,8 @@ class Model:
             return
         if name == "network_edges" and self._program == "sir":
             if getattr(self, "_node_range", None) is not None:
-                # this rank's rows only: sources re-based to local rows, targets stay global ids
-                lo, hi = self._node_range
-                e = np.asarray(value, dtype=np.int32).reshape(-1, 2)
-                e = e[(e[:, 0] >= lo) & (e[:, 0] < hi)].copy()
-                e[:, 0] -= lo
-                value = e
+                from .sharding import local_edges
+                value = local_edges(value, *self._node_range)
             dev.set_network(value)
             return
         s = dev.env_index(name)

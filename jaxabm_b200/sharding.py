@@ -149,6 +149,16 @@ def network_cuts(n: int, edges, world: int, row_cost: int = 4, balance: str = No
     return cuts + [n]
 
 
+def local_edges(edges, lo: int, hi: int) -> np.ndarray:
+    """The rows of ``env['network_edges']`` (``jaxabm/agentpy.py:557``) a node range owns: edges whose SOURCE lies
+    in ``[lo, hi)``, sources re-based to local rows, targets left as global ids (what
+    ``jxb_model_set_network`` takes on a sharded Network)."""
+    e = np.asarray(edges, dtype=np.int32).reshape(-1, 2)
+    e = e[(e[:, 0] >= lo) & (e[:, 0] < hi)].copy()
+    e[:, 0] -= lo
+    return e
+
+
 def local_range(n: int):
     r, w = dist.rank_world()
     return dist.shard_bounds(n, r, w)

@@ -166,12 +166,14 @@ def schelling_bands_run(grid_size, types, positions, world, steps, seed_key, mod
     return {"type": types, "position": pos, "satisfied": sat, "moves": moves}, rows, ranks[0].E
 
 
-def sir_node_ranges_run(n, edges, cuts, steps, seed_key, mode, beta=0.05, gamma=0.1, initial_infected=0.01):
+def sir_node_ranges_run(n, edges, cuts, steps, seed_key, mode, beta=0.05, gamma=0.1, initial_infected=0.01,
+                        local_edges=None):
     """SIR (``oracle/rules.py::SIRAgent``) computed range by range: rank r holds the CSR of the edges whose
     SOURCE lies in ``[cuts[r], cuts[r+1])`` (sources re-based to local rows, targets global ids -- the filter of
     ``jaxabm_b200/model.py::_push_env``), its slice of ``state``, the draws of its agents by GLOBAL index
     (``split(key, N)[lo:hi]``, ``jaxabm/agent.py:115,156``) and a copy of the global infected bitmap that is
-    reassembled from the ranks' slices after every step.  -> (final state, [(S, I, R)] per step)."""
+    reassembled from the ranks' slices after every step.  ``local_edges`` lets a test substitute the product's
+    own edge filter (``jaxabm_b200.sharding.local_edges``).  -> (final state, [(S, I, R)] per step)."""
     from .rules import SIR_KCAP, edges_to_csr, sir_escape_table
     edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
     q = sir_escape_table(beta)
@@ -181,8 +183,10 @@ def sir_node_ranges_run(n, edges, cuts, steps, seed_key, mode, beta=0.05, gamma=
     agent_keys = jl.split(keys[1], n, mode)
     local = []
     for lo, hi in zip(cuts[:-1], cuts[1:]):
-        mine = edges[(edges[:, 0] >= lo) & (edges[:, 0] < hi)].copy()
-        mine[:, 0] -= lo
+        mine = edges[(edges[:, 0] >= lo) & (edges[:, 0] < hi)].copy() if local_edges is None else \
+            np.asarray(local_edges(edges, lo, hi), dtype=np.int64)
+        if local_edges is None:
+            mine[:, 0] -= lo
         row_ptr, col = edges_to_csr(hi - lo, mine)
         u0 = jl.uniform_scalar_batched(agent_keys[lo:hi], mode=mode)
         local.append({"lo": lo, "hi": hi, "row_ptr": row_ptr, "col": col.astype(np.int64),

@@ -54,7 +54,8 @@ def test_sir_node_ranges_equal_the_single_network(world, mode):
     for balance in ("nodes", "entries"):
         cuts = sharding.network_cuts(n, edges, world, balance=balance)          # the product's own cuts
         state, rows = sharded.sir_node_ranges_run(n, edges, cuts, steps, jl.PRNGKey(2), mode, beta=0.1, gamma=0.1,
-                                                  initial_infected=0.02)
+                                                  initial_infected=0.02,
+                                                  local_edges=sharding.local_edges if balance == "nodes" else None)
         assert np.array_equal(state, np.asarray(om.agent_collections["agents"].states["state"])), (world, balance)
         assert [r[0] for r in rows] == [int(v) for v in ores["count_S"]]
         assert [r[1] for r in rows] == [int(v) for v in ores["count_I"]]
