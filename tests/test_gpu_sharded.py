@@ -2,7 +2,7 @@
 must reproduce the single-GPU model -- per-agent state bit for bit (keys use the global agent
 index), env/metric trajectories to float32 rounding (partials are folded in a different order).
 
-Run by ``tests/run_sharded.sh`` / the gpurun command in DESIGN.md:
+Run directly under torchrun on a box with >= 2 GPUs (``gpurun --gpus 2``):
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
       tests/test_gpu_sharded.py
 Also collected by pytest (-m gpu): the test spawns the 2-rank job itself when >= 2 GPUs are visible.
