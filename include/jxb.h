@@ -4,7 +4,7 @@
  * The reference (a11to1n3/JaxABM) is pure Python on JAX and has no FFI of its own
  * (SURVEY.md F1); this header therefore *defines* the boundary.  Every entry point
  * names the reference interface it stands in for (path:line under /root/reference).
- * The host side (jaxabm_b200/*.py) keeps the reference's Python API verbatim and
+ * The host side (the jaxabm_b200 Python package) keeps the reference's Python API verbatim and
  * binds these symbols with ctypes (see INTEGRATION.md for the stub a maintainer of
  * the reference would add).
  *

@@ -298,3 +298,19 @@ def test_run_parallel_simulations_follows_the_reference_schedule(capsys):
     assert "Running simulation 2/3, run 2/2, seed=103" in out and "Error in simulation 2/3, run 1/2: x" in out
     r = jx.run_parallel_simulations(lambda params, config: Fake(params, config), [{"a": 1}, {"a": 3}], seeds=[7, 9], steps=4)
     assert [(x["seed"], x["step"]) for x in r] == [(7, [4]), (9, [4])]
+
+
+def test_header_is_plain_c():
+    """include/jxb.h is the drop-in boundary: it must compile as C99 on its own, without warnings."""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write('#include "jxb.h"\nint main(void) { return JXB_VERSION == 100 ? 0 : 1; }\n')
+    out = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                          "-I", os.path.join(ROOT, "include"), f.name], capture_output=True, text=True)
+    os.unlink(f.name)
+    assert out.returncode == 0, out.stderr
