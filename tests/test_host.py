@@ -314,3 +314,20 @@ def test_header_is_plain_c():
                           "-I", os.path.join(ROOT, "include"), f.name], capture_output=True, text=True)
     os.unlink(f.name)
     assert out.returncode == 0, out.stderr
+
+
+def test_c_program_links_against_the_library(tmp_path):
+    """tests/abi/abi_smoke.c: the C ABI used from C -- host key algebra works, device calls fail loudly without a GPU."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    libdir = os.path.join(ROOT, "jaxabm_b200", "csrc")
+    exe = str(tmp_path / "abi_smoke")
+    build = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                            os.path.join(ROOT, "tests", "abi", "abi_smoke.c"), "-o", exe, "-L", libdir, "-ljxb",
+                            f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0 and "abi ok" in run.stdout, (run.returncode, run.stdout, run.stderr)
