@@ -155,3 +155,21 @@ def test_sir_large_graph_properties():
     assert ((S + I + R) == n).all() and (np.diff(S) <= 0).all() and (np.diff(R) >= 0).all() and I.max() > I[0]
     for k in ("count_S", "count_I", "count_R"):
         assert np.array_equal(series(out[0], k), series(out[1], k))
+
+
+def test_sir_large_graph_vs_c_oracle(mode):
+    """C3-shaped input (scale-free, 2 M nodes / 20 M adjacency entries, hubs of > 2048 entries: the heavy-row and
+    long-row paths of both directions) bit for bit against the C/OpenMP oracle (``oracle/c::orc_sir_step``, itself
+    pinned on the NumPy restatement in tests/test_oracle.py)."""
+    from oracle import cfast
+    n, steps = 2_000_000, 25
+    edges = synthetic.scale_free_edges(n, 5, 42)
+    m = sir.create_sir_model(n, edges, beta=0.05, gamma=0.1, initial_infected=0.01, seed=42,
+                             config=jx.ModelConfig(seed=42, rng_mode=mode))
+    r = m.run(steps=steps)
+    f = cfast.SirFast(n, edges, beta=0.05, gamma=0.1, initial_infected=0.01, seed=42, mode=mode)
+    fr = f.run(steps)
+    for k in ("count_S", "count_I", "count_R"):
+        assert np.array_equal(series(r, k), series(fr, k)), k
+    assert np.array_equal(np.asarray(m.agent_collections["agents"].states["state"]), f.state)
+    assert np.bincount(edges[:, 0]).max() > 2048
