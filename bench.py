@@ -251,7 +251,19 @@ class EconomyWorkload:
                                            "download households' income/savings/employed + the metrics history")
 
     def cpu_run(self, steps):
-        raise NotImplementedError
+        """1/49 population sample on the NumPy restatement (single thread; time scaled x49): the C/OpenMP oracle
+        does not carry the economy rules."""
+        from oracle import economy as oe, runtime as ort
+        steps = min(steps, 5)
+        nh, nf = self.nh // 49, self.nf // 49
+        m = oe.create_economy_model(nh, nf, config=ort.ModelConfig(seed=self.seed, rng_mode=1))
+        m.initialize()
+        t0 = time.perf_counter()
+        m.run(steps=steps)
+        secs = (time.perf_counter() - t0) * 49.0
+        self._cpu_steps = steps
+        return secs, 1, (f"{steps} steps on a 1/49 population sample ({nh} households + {nf} firms, time scaled x49) "
+                         "on the single-threaded NumPy restatement")
 
 
 class WalkWorkload:
@@ -481,6 +493,7 @@ def reference_arm(args, rank, world):
     if args.warmup:
         wl.cpu_run(1)
     secs, threads, what = wl.cpu_run(cpu_steps)
+    cpu_steps = getattr(wl, "_cpu_steps", cpu_steps)
     value = wl.agents * cpu_steps / secs
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": cpu_steps, "warmup": min(args.warmup, 1), "ms_per_step": secs / cpu_steps * 1e3,
@@ -656,7 +669,8 @@ def main():
     if world == 1 and not args.no_cpu:
         try:
             secs, threads, what = wl.cpu_run(args.cpu_steps)
-            cpu = {"value": wl.agents * args.cpu_steps / secs, "unit": UNIT, "cores": threads, "kind": "port",
+            cpu_steps = getattr(wl, "_cpu_steps", args.cpu_steps)
+            cpu = {"value": wl.agents * cpu_steps / secs, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{what} ({secs:.1f} s)"}
         except NotImplementedError:
             cpu = None
