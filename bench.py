@@ -410,7 +410,21 @@ class EnsembleWorkload:
     engine_bytes = api_bytes
 
     def cpu_run(self, steps):
-        raise NotImplementedError
+        """16 of the replicas, each a whole serial run of the NumPy restatement (what the reference's sweep loop does,
+        analysis.py:113-157), time scaled to all replicas of this rank."""
+        from oracle import rules as orules, runtime as ort
+        rng = np.random.RandomState(0)
+        g = rng.uniform(0.05, 0.2, self.samples_total)
+        a = rng.uniform(0.05, 0.3, self.samples_total)
+        sample = 16
+        t0 = time.perf_counter()
+        for i in range(sample):
+            m = orules.create_test_model(params={"growth_rate": float(g[i]), "adjustment_rate": float(a[i])},
+                                         config=ort.ModelConfig(seed=i + 1000, steps=steps), num_agents=self.n)
+            m.run()
+        secs = (time.perf_counter() - t0) * ((self.hi - self.lo) / sample)
+        return secs, 1, (f"{sample} of the {self.hi - self.lo} replicas x {steps} steps as serial runs of the single-threaded "
+                         "NumPy restatement (time scaled to all replicas)")
 
 
 WORKLOADS = {"schelling": SchellingWorkload, "market": MarketWorkload, "walk": WalkWorkload, "sir": SirWorkload,
