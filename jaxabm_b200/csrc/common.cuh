@@ -59,7 +59,11 @@ struct Ctrl {
 // world_size flags in its own buffer and folds the rows in rank order -- one kernel does the
 // update, the reduction and the exchange; all ranks fold identical values in identical order.
 constexpr int kMaxPeers = 8;
-constexpr int kXchgRow = 16;        // doubles per exchanged row (>= kAcc and >= the economy's 15 sums)
+constexpr int kXchgRow = 20;        // doubles per exchanged row (>= kAcc and >= the economy's 15 sums + its bin range)
+// a rank's exchange allocation is [XchgBuf | pad to kXchgHistOffset | income histogram u32[2^22]]: the sharded
+// economy's Gini needs the GLOBAL income histogram, which every rank sums from its peers' local histograms
+// straight out of this region (csrc/economy.cuh::gini_gather_kernel)
+constexpr size_t kXchgHistOffset = 4096;
 struct XchgBuf {
   double row[2][kMaxPeers][kXchgRow];
   unsigned int flag[2][kMaxPeers];
@@ -223,6 +227,8 @@ __device__ __forceinline__ void stv(V* p, V v) {
 // Called by every thread of the LAST CTA of a rank's step kernel; tot = this rank's totals
 // (shared memory) on entry, the world totals on exit.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int* xchg_hist(XchgBuf* b) { return (unsigned int*)((unsigned char*)b + kXchgHistOffset); }
+
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

@@ -35,14 +35,18 @@ enum {
 
 constexpr int kEcoF = 14;             // float sums
 constexpr int kEcoAcc = kEcoF + 1;    // + employed count
+constexpr int kEcoRow = kEcoAcc + 2;  // + the populated range of the income histogram: max bin, -(min bin) (both fold with max)
 constexpr int kGiniBits = 22;
 constexpr int kGiniBins = 1 << kGiniBits;
 constexpr int kGiniScanTile = 4096;   // bins per scan CTA
 
 struct EcoDev {
-  double* partials;          // [grid][kEcoAcc]
-  unsigned int* bin_count;   // [kGiniBins]
+  double* partials;          // [grid][kEcoRow]
+  unsigned int* hist;        // [kGiniBins] where THIS rank's households count their incomes: bin_count itself on one
+                             // GPU; the histogram region of the rank's exchange allocation when the population is sharded
+  unsigned int* bin_count;   // [kGiniBins] counts of the WHOLE population (sharded: summed from the ranks' hist by gini_gather_kernel)
   unsigned int* bin_base;    // [kGiniBins] exclusive prefix of the counts
+  int* tile_range;           // [2] first / last scan tile holding an income of this step (written by the step's tail)
   unsigned int* scan_sums;   // [kGiniBins / kGiniScanTile]
   double* gini_partials;     // [gini grid][2]
   unsigned int* ticket2;     // election ticket of the Gini accumulate kernel
@@ -184,7 +188,8 @@ __device__ __forceinline__ unsigned int gini_bin(float x);
 
 template <int MODE>
 __device__ __forceinline__ void rule_household(const TypeDev& t, const double* env, Key ck, int lb, float* fs,
-                                               int& employed_count, unsigned int* bin_count) {
+                                               int& employed_count, unsigned int* bin_count, unsigned int& bin_lo,
+                                               unsigned int& bin_hi) {
   const EcoEnvView v = eco_env_view(env);
   const float init_inc = t.p[1];
   const float two_init_inc = (float)(2.0 * (double)t.p[1]);
@@ -212,7 +217,9 @@ __device__ __forceinline__ void rule_household(const TypeDev& t, const double* e
     employed_count += h.employed ? 1 : 0;
     // Gini histogram of the NEW incomes (metrics are computed on the post-update state): a
     // fire-and-forget L2 reduction whose latency hides behind the streaming loads
-    atomicAdd(bin_count + gini_bin(h.income), 1u);
+    const unsigned int bin = gini_bin(h.income);
+    bin_lo = min(bin_lo, bin); bin_hi = max(bin_hi, bin);
+    atomicAdd(bin_count + bin, 1u);
   }
 }
 
@@ -401,8 +408,8 @@ __device__ inline void eco_compute_metrics(const double* env, float gini, double
 template <int MODE, int RULE>
 __global__ void __launch_bounds__(kThreads) economy_step_kernel(const ModelDev md, const EcoDev ed, int ti,
                                                                 int row_offset, int total_ctas) {
-  __shared__ double s_red[(kThreads / 32) * kEcoAcc];
-  __shared__ double s_tot[kEcoAcc];
+  __shared__ double s_red[(kThreads / 32) * kEcoRow];
+  __shared__ double s_tot[kEcoRow];
   __shared__ int s_last;
   const TypeDev& t = md.t[ti];
   const int lb = blockIdx.x;
@@ -412,23 +419,28 @@ __global__ void __launch_bounds__(kThreads) economy_step_kernel(const ModelDev m
 #pragma unroll
   for (int i = 0; i < kEcoF; ++i) fs[i] = 0.f;
   int emp = 0;
-  if (RULE == JXB_RULE_HOUSEHOLD) rule_household<MODE>(t, md.env, ck, lb, fs, emp, ed.bin_count);
+  unsigned int bin_lo = kGiniBins, bin_hi = 0;        // empty range: hi < lo
+  if (RULE == JXB_RULE_HOUSEHOLD) rule_household<MODE>(t, md.env, ck, lb, fs, emp, ed.hist, bin_lo, bin_hi);
   else rule_firm<MODE>(t, md.env, ck, lb, fs);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < kEcoF; ++i) {
     const float w = warp_sum(fs[i]);
-    if (lane == 0) s_red[warp * kEcoAcc + i] = (double)w;
+    if (lane == 0) s_red[warp * kEcoRow + i] = (double)w;
   }
   {
     const int w = warp_sum(emp);
-    if (lane == 0) s_red[warp * kEcoAcc + kEcoF] = (double)w;
+    if (lane == 0) s_red[warp * kEcoRow + kEcoF] = (double)w;
+    // the range as two maxima: the highest bin, and minus the lowest one
+    const double hi = warp_max((double)bin_hi), nlo = warp_max(-(double)bin_lo);
+    if (lane == 0) { s_red[warp * kEcoRow + kEcoAcc] = hi; s_red[warp * kEcoRow + kEcoAcc + 1] = nlo; }
   }
   __syncthreads();
-  if (threadIdx.x < kEcoAcc) {
-    double r = 0.0;
-    for (int w = 0; w < kThreads / 32; ++w) r += s_red[w * kEcoAcc + threadIdx.x];
-    ed.partials[(size_t)(row_offset + blockIdx.x) * kEcoAcc + threadIdx.x] = r;
+  if (threadIdx.x < kEcoRow) {
+    const bool is_max = threadIdx.x >= kEcoAcc;
+    double r = s_red[threadIdx.x];
+    for (int w = 1; w < kThreads / 32; ++w) { const double v = s_red[w * kEcoRow + threadIdx.x]; r = is_max ? fmax(r, v) : r + v; }
+    ed.partials[(size_t)(row_offset + blockIdx.x) * kEcoRow + threadIdx.x] = r;
   }
   __threadfence();
   __syncthreads();
@@ -436,20 +448,27 @@ __global__ void __launch_bounds__(kThreads) economy_step_kernel(const ModelDev m
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int i = warp; i < kEcoAcc; i += kThreads / 32) {
-    double r = 0.0;
-    for (int b = lane; b < total_ctas; b += 32) r += __ldcg(ed.partials + (size_t)b * kEcoAcc + i);
-    r = warp_sum(r);
+  for (int i = warp; i < kEcoRow; i += kThreads / 32) {
+    const bool is_max = i >= kEcoAcc;
+    double r = is_max ? -1.0 / 0.0 : 0.0;
+    for (int b = lane; b < total_ctas; b += 32) { const double v = __ldcg(ed.partials + (size_t)b * kEcoRow + i); r = is_max ? fmax(r, v) : r + v; }
+    r = is_max ? warp_max(r) : warp_sum(r);
     if (lane == 0) s_tot[i] = r;
   }
   __syncthreads();
-  // sharded population: sum the ranks' rows over NVLink peer memory (every rank then runs the same
-  // update_environment on identical totals)
-  if (md.world_size > 1) peer_exchange(md, s_tot, kEcoAcc, 0, 0);
+  // sharded population: fold the ranks' rows over NVLink peer memory (every rank then runs the same
+  // update_environment on identical totals).  Its flags also order the histograms: every household of every
+  // rank has counted its income into its rank's histogram before any rank leaves this exchange.
+  if (md.world_size > 1) peer_exchange(md, s_tot, kEcoRow, kEcoAcc, kEcoRow);
   if (threadIdx.x == 0) {
     md.ctrl->ticket = 0;
     const Key uk = {kp[2 * md.n_types], kp[2 * md.n_types + 1]};
     eco_update_environment<MODE>(md, s_tot, md.env, uk);
+    // scan tiles that hold an income of this step (the whole population's): all the Gini kernels skip the rest
+    const double hi = s_tot[kEcoAcc], lo = -s_tot[kEcoAcc + 1];
+    const bool any = hi >= lo;
+    ed.tile_range[0] = any ? (int)lo / kGiniScanTile : 1;
+    ed.tile_range[1] = any ? (int)hi / kGiniScanTile : 0;
   }
 }
 
@@ -465,9 +484,41 @@ __device__ __forceinline__ unsigned int gini_bin(float x) {
   return b >> (32 - kGiniBits);
 }
 
-// exclusive scan of the bin counts: per-tile sums, scan of the sums, per-tile rescan
-__global__ void __launch_bounds__(kThreads) gini_scan_sums_kernel(const unsigned int* bin_count, unsigned int* sums) {
+// sharded population: the counts of the whole population = sum over the ranks' histograms, read straight out of
+// the peers' exchange allocations (CUDA IPC / NVLink peer loads; every rank does the whole fold over the populated
+// tiles -- a few hundred KB per peer).  One CTA per scan tile.
+__global__ void __launch_bounds__(kThreads) gini_gather_kernel(const ModelDev md, const EcoDev ed) {
+  const int tile = blockIdx.x;
+  if (tile < ed.tile_range[0] || tile > ed.tile_range[1]) return;
+  const size_t base = (size_t)tile * kGiniScanTile + (size_t)threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int p = 0; p < md.world_size; ++p) {
+      const uint4 v = __ldcv((const uint4*)(xchg_hist(md.xpeer[p]) + base) + j);     // never from a stale L1 line
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    ((uint4*)(ed.bin_count + base))[j] = acc;
+  }
+}
+
+// this rank's histogram back to zero over the populated tiles (16 MB memset -> a few hundred KB).  Sharded: runs
+// after gini_accumulate_kernel, whose tail exchange every rank only leaves once all ranks have gathered.
+__global__ void __launch_bounds__(kThreads) gini_clear_kernel(const EcoDev ed) {
+  const int tile = blockIdx.x;
+  if (tile < ed.tile_range[0] || tile > ed.tile_range[1]) return;
+  uint4* p = (uint4*)(ed.hist + (size_t)tile * kGiniScanTile) + threadIdx.x * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) p[j] = make_uint4(0, 0, 0, 0);
+}
+
+// exclusive scan of the bin counts: per-tile sums, scan of the sums, per-tile rescan (populated tiles only)
+__global__ void __launch_bounds__(kThreads) gini_scan_sums_kernel(const EcoDev ed, const unsigned int* bin_count, unsigned int* sums) {
   __shared__ unsigned int s_w[kThreads / 32];
+  if ((int)blockIdx.x < ed.tile_range[0] || (int)blockIdx.x > ed.tile_range[1]) {
+    if (threadIdx.x == 0) sums[blockIdx.x] = 0u;
+    return;
+  }
   const uint4* p = (const uint4*)(bin_count + (size_t)blockIdx.x * kGiniScanTile) + threadIdx.x * 4;
   unsigned int s = 0;
 #pragma unroll
@@ -499,9 +550,10 @@ __global__ void __launch_bounds__(1024) gini_scan_top_kernel(unsigned int* sums,
   if (tid < n) sums[tid] = off + inc - v;
 }
 
-__global__ void __launch_bounds__(kThreads) gini_scan_apply_kernel(const unsigned int* bin_count, const unsigned int* sums,
+__global__ void __launch_bounds__(kThreads) gini_scan_apply_kernel(const EcoDev ed, const unsigned int* bin_count, const unsigned int* sums,
                                                                    unsigned int* bin_base) {
   __shared__ unsigned int s_w[kThreads / 32];
+  if ((int)blockIdx.x < ed.tile_range[0] || (int)blockIdx.x > ed.tile_range[1]) return;    // no income looks these bins up
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t base = (size_t)blockIdx.x * kGiniScanTile + (size_t)tid * 16;
   unsigned int c[16];
@@ -573,8 +625,8 @@ __global__ void __launch_bounds__(kThreads) gini_accumulate_kernel(const ModelDe
     if (lane == 0) { s_gt[0] = a; s_gt[1] = b; *ed.ticket2 = 0; }
   }
   __syncthreads();
-  // sharded population: ranks hold the GLOBAL histogram (all-reduced before the scan), so their
-  // partial rank-weighted sums simply add up
+  // sharded population: ranks hold the GLOBAL histogram (gini_gather_kernel), so their partial rank-weighted
+  // sums simply add up
   if (md.world_size > 1) peer_exchange(md, s_gt, 2, 0, 0);
   if (tid == 0) {
     const double a = s_gt[0], b = s_gt[1];

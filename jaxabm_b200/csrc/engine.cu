@@ -194,10 +194,12 @@ struct jxb_engine {
   XchgBuf* xlocal = nullptr;
   XchgBuf* xpeer[kMaxPeers] = {};
   bool p2p = false;
+  const void* hist_owner = nullptr;     // the sharded economy model currently counting into xlocal's histogram region
   // receive areas of destroyed sharded models: an allocation whose IPC handle was exported must not be freed
   // while a peer process may still have it mapped, and the peers close their mappings whenever THEY destroy
-  // their model -- so the areas are only released with the engine
-  std::vector<void*> retired_areas;
+  // their model -- so the areas are only released with the engine; until then they are handed to the next
+  // sharded model that needs an area of the same size (take_retired_area)
+  std::vector<std::pair<void*, size_t>> retired_areas;
 };
 
 struct jxb_model {
@@ -207,6 +209,7 @@ struct jxb_model {
   const RuleSpec* rules[JXB_MAX_TYPES] = {};
   ModelDev dev{};
   std::vector<std::pair<void*, size_t>> allocs;
+  std::vector<std::pair<void*, size_t>> net_allocs;     // CSR + SIR buffers of the current network (released on rebuild)
   Key rng{0, 0};
   bool initialized = false;
   bool collections_ready[JXB_MAX_TYPES] = {};
@@ -293,13 +296,25 @@ static void pool_free(jxb_engine* eng, void* p, size_t bytes) {
 }
 
 template <class T>
-static int dev_alloc(jxb_model* m, T** p, size_t count) {
+static int dev_alloc(jxb_model* m, T** p, size_t count, std::vector<std::pair<void*, size_t>>* list = nullptr) {
   void* q = nullptr;
   const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
   CK(pool_alloc(m->eng, &q, bytes));
-  m->allocs.emplace_back(q, bytes);
+  (list ? *list : m->allocs).emplace_back(q, bytes);
   *p = (T*)q;
   return JXB_OK;
+}
+
+// receive areas whose IPC handle was exported: recycled by exact size for the next sharded model of the same
+// shape (bench loops, sweeps and test suites create and destroy many), never freed before the engine goes
+static void* take_retired_area(jxb_engine* eng, size_t bytes) {
+  for (size_t i = 0; i < eng->retired_areas.size(); ++i)
+    if (eng->retired_areas[i].second == bytes) {
+      void* p = eng->retired_areas[i].first;
+      eng->retired_areas.erase(eng->retired_areas.begin() + i);
+      return p;
+    }
+  return nullptr;
 }
 
 extern "C" int jxb_engine_create(int device, jxb_engine** out) {
@@ -330,7 +345,7 @@ extern "C" int jxb_engine_destroy(jxb_engine* eng) {
   for (int p = 0; p < kMaxPeers; ++p)
     if (eng->xpeer[p] && eng->xpeer[p] != eng->xlocal) cudaIpcCloseMemHandle(eng->xpeer[p]);
   if (eng->xlocal) cudaFree(eng->xlocal);
-  for (void* a : eng->retired_areas) cudaFree(a);
+  for (auto& a : eng->retired_areas) cudaFree(a.first);
   for (auto& b : eng->pool) cudaFree(b.first);
   cudaEventDestroy(eng->ev0);
   cudaEventDestroy(eng->ev1);
@@ -381,8 +396,11 @@ extern "C" int jxb_engine_p2p_export(jxb_engine* eng, void* handle_out, size_t b
     return fail(JXB_ERR_INVALID, "need %zu bytes for the IPC handle", sizeof(cudaIpcMemHandle_t));
   CK(cudaSetDevice(eng->device));
   if (!eng->xlocal) {
-    CK(cudaMalloc((void**)&eng->xlocal, sizeof(XchgBuf)));
-    CK(cudaMemset(eng->xlocal, 0, sizeof(XchgBuf)));
+    // [XchgBuf | pad | income histogram of the sharded economy's Gini] -- one allocation, one IPC handle
+    static_assert(sizeof(XchgBuf) <= kXchgHistOffset, "XchgBuf must fit in front of the histogram region");
+    const size_t bytes = kXchgHistOffset + (size_t)kGiniBins * sizeof(unsigned int);
+    CK(cudaMalloc((void**)&eng->xlocal, bytes));
+    CK(cudaMemset(eng->xlocal, 0, bytes));
   }
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, eng->xlocal));
@@ -694,14 +712,31 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
   }
   if (d->program == JXB_PROGRAM_SIR) m->has_net = true;
   if (d->program == JXB_PROGRAM_ECONOMY) {
-    if (md.world_size > 1 && (md.exchange != 1 || !eng->nccl_comm)) {
+    if (md.world_size > 1 && md.exchange != 1) {
       jxb_model_destroy(m);
-      return fail(JXB_ERR_STATE, "a sharded economy needs BOTH the peer-memory exchange (env partial sums) and an NCCL "
-                                 "communicator (all-reduce of the Gini histogram); attach both");
+      return fail(JXB_ERR_STATE, "a sharded economy runs on the peer-memory exchange (env partial sums and the ranks' income "
+                                 "histograms); attach it with jxb_engine_p2p_export / jxb_engine_p2p_attach");
+    }
+    if (md.world_size > 1 && eng->hist_owner) {
+      jxb_model_destroy(m);
+      return fail(JXB_ERR_STATE, "one sharded economy model at a time per engine (its income histogram lives in the engine's "
+                                 "exchange allocation); destroy the previous one first");
     }
     EcoDev& ed = m->eco;
-    TRY(dev_alloc(m, &ed.partials, (size_t)std::max(m->step_blocks, 1) * kEcoAcc));
+    TRY(dev_alloc(m, &ed.partials, (size_t)std::max(m->step_blocks, 1) * kEcoRow));
     TRY(dev_alloc(m, &ed.bin_count, (size_t)kGiniBins));
+    TRY(dev_alloc(m, &ed.tile_range, 2));
+    {
+      const int empty[2] = {1, 0};
+      cudaMemcpyAsync(ed.tile_range, empty, sizeof(empty), cudaMemcpyHostToDevice, eng->stream);
+    }
+    if (md.world_size > 1) {
+      ed.hist = (unsigned int*)((unsigned char*)eng->xlocal + kXchgHistOffset);
+      cudaMemsetAsync(ed.hist, 0, (size_t)kGiniBins * 4, eng->stream);
+      eng->hist_owner = m;
+    } else {
+      ed.hist = ed.bin_count;
+    }
     TRY(dev_alloc(m, &ed.bin_base, (size_t)kGiniBins));
     TRY(dev_alloc(m, &ed.scan_sums, (size_t)kGiniBins / kGiniScanTile));
     TRY(dev_alloc(m, &ed.ticket2, 4));
@@ -733,8 +768,10 @@ extern "C" int jxb_model_destroy(jxb_model* m) {
   for (int p = 0; p < kMaxPeers; ++p)
     if (m->ns_opened[p]) cudaIpcCloseMemHandle(m->ns_opened[p]);
   // exported areas outlive the model (see jxb_engine::retired_areas); a single-band grid never exported its area
-  if (m->gs_area) { if (m->dev.world_size > 1) m->eng->retired_areas.push_back(m->gs_area); else cudaFree(m->gs_area); }
-  if (m->ns_area) m->eng->retired_areas.push_back(m->ns_area);
+  if (m->gs_area) { if (m->dev.world_size > 1) m->eng->retired_areas.emplace_back(m->gs_area, m->gs_area_bytes); else cudaFree(m->gs_area); }
+  if (m->ns_area) m->eng->retired_areas.emplace_back(m->ns_area, m->ns_area_bytes);
+  for (auto& a : m->net_allocs) pool_free(m->eng, a.first, a.second);
+  if (m->eng->hist_owner == m) m->eng->hist_owner = nullptr;
   pool_free(m->eng, m->d_keys, m->keys_cap * 4);
   pool_free(m->eng, m->d_metrics, m->rec_cap * kMaxMetrics * sizeof(double));
   pool_free(m->eng, m->d_rec, m->rec_cap * sizeof(int));
@@ -983,8 +1020,12 @@ static int grid_shard_prepare(jxb_model* m, int row_begin, int row_end) {
   gs.cap = (unsigned long long)std::min<long long>(m->desc.types[0].n_agents, (long long)max_rows * H);
   if (!m->gs_area) {
     m->gs_area_bytes = sizeof(GridXchgHdr) + (size_t)2 * G * gs.cap * sizeof(uint2);
-    CK(cudaMalloc((void**)&m->gs_area, m->gs_area_bytes));      // its own allocation: IPC handles name whole allocations
+    m->gs_area = G > 1 ? (unsigned char*)take_retired_area(m->eng, m->gs_area_bytes) : nullptr;
+    if (!m->gs_area) CK(cudaMalloc((void**)&m->gs_area, m->gs_area_bytes));      // its own allocation: IPC handles name whole allocations
+    // flags / counts of a recycled area hold the step tags of its previous model: clear them before the handle
+    // leaves this call (the peers only store into the area after the attach barrier that follows)
     CK(cudaMemset(m->gs_area, 0, sizeof(GridXchgHdr)));
+    CK(cudaDeviceSynchronize());
     int rc;
     if ((rc = dev_alloc(m, &gs.info, 1))) return rc;
     CK(cudaMemset(gs.info, 0, sizeof(GridStepInfo)));
@@ -1066,9 +1107,20 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
   // neighbour order inside a row is irrelevant to the rule
   cudaStream_t st = m->eng->stream;
   int rc;
+  if (!m->net_allocs.empty()) {
+    // rebuild (Model.add_env_state('network_edges') after initialize(), Network.add_edge): the previous CSR,
+    // state and counter buffers go back to the pool; their pointers are baked into the cached step graphs
+    CK(cudaStreamSynchronize(st));
+    if (m->graph1) { cudaGraphExecDestroy(m->graph1); m->graph1 = nullptr; }
+    if (m->graphK) { cudaGraphExecDestroy(m->graphK); m->graphK = nullptr; }
+    for (auto& a : m->net_allocs) pool_free(m->eng, a.first, a.second);
+  if (m->eng->hist_owner == m) m->eng->hist_owner = nullptr;
+    m->net_allocs.clear();
+    m->net_built = false;
+  }
   unsigned int* d_rp = nullptr; int* d_col = nullptr;
-  if ((rc = dev_alloc(m, &d_rp, (size_t)n + 2))) return rc;
-  if ((rc = dev_alloc(m, &d_col, (size_t)std::max<int64_t>(n_edges, 1)))) return rc;
+  if ((rc = dev_alloc(m, &d_rp, (size_t)n + 2, &m->net_allocs))) return rc;
+  if ((rc = dev_alloc(m, &d_col, (size_t)std::max<int64_t>(n_edges, 1), &m->net_allocs))) return rc;
   std::vector<unsigned int> row_ptr((size_t)n + 1, 0);
   {
     void* d_edges = nullptr; void* d_cursor = nullptr; void* d_sums = nullptr; void* d_flag = nullptr;
@@ -1092,7 +1144,8 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     scan_tile_sums_kernel<<<ntiles, kThreads, 0, st>>>(d_rp, n, (unsigned int*)d_sums);
     scan_sums_kernel<<<1, 1024, 0, st>>>((unsigned int*)d_sums, ntiles);
     scan_apply_kernel<<<ntiles, kThreads, 0, st>>>(d_rp, n, (const unsigned int*)d_sums, d_rp, (unsigned int*)d_cursor);
-    csr_fill_kernel<<<g, kThreads, 0, st>>>((const int2*)d_edges, n_edges, (unsigned int*)d_cursor, d_col);
+    csr_fill_kernel<<<g, kThreads, 0, st>>>((const int2*)d_edges, n_edges, n, (long long)m->desc.types[0].global_n,
+                                            (unsigned int*)d_cursor, d_col);
     m->eng->launches += 5;
     int bad = 0;
     NCK(cudaMemcpyAsync(&bad, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1123,8 +1176,8 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
   }
   SirDev& sv = m->sv;
   int* d_rb; float* d_esc;
-  if ((rc = dev_alloc(m, &d_rb, rb.size()))) return rc;
-  if ((rc = dev_alloc(m, &d_esc, kSirKCap + 1))) return rc;
+  if ((rc = dev_alloc(m, &d_rb, rb.size(), &m->net_allocs))) return rc;
+  if ((rc = dev_alloc(m, &d_esc, kSirKCap + 1, &m->net_allocs))) return rc;
   if (m->net_sharded) {
     // the two GLOBAL bitmaps live in one IPC-shareable allocation behind the exchange header
     const long long gn = m->desc.types[0].global_n;
@@ -1132,9 +1185,11 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     sv.bits_stride = (words * 4 + 255) & ~(size_t)255;
     if (!m->ns_area) {
       m->ns_area_bytes = sizeof(SirXchgHdr) + 2 * sv.bits_stride;
-      CK(cudaMalloc((void**)&m->ns_area, m->ns_area_bytes));
+      m->ns_area = (unsigned char*)take_retired_area(m->eng, m->ns_area_bytes);
+      if (!m->ns_area) CK(cudaMalloc((void**)&m->ns_area, m->ns_area_bytes));
     }
     CK(cudaMemset(m->ns_area, 0, m->ns_area_bytes));
+    CK(cudaDeviceSynchronize());
     sv.world = m->dev.world_size; sv.rank = m->dev.rank;
     sv.gw0 = (unsigned int)(m->desc.types[0].global_offset / 32);
     sv.gwords = (unsigned int)((n + 31) / 32);
@@ -1142,12 +1197,12 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     sv.peer[sv.rank] = m->ns_area;
   }
   for (int b = 0; b < 2; ++b) {
-    if ((rc = dev_alloc(m, &sv.state8[b], (size_t)n + 32))) return rc;
+    if ((rc = dev_alloc(m, &sv.state8[b], (size_t)n + 32, &m->net_allocs))) return rc;
     cudaMemset(sv.state8[b], 0, (size_t)n + 32);
     if (m->net_sharded) {
       sv.infbits[b] = (unsigned int*)(m->ns_area + sizeof(SirXchgHdr) + (size_t)b * sv.bits_stride);
     } else {
-      if ((rc = dev_alloc(m, &sv.infbits[b], (size_t)(n + 31) / 32 + 1))) return rc;
+      if ((rc = dev_alloc(m, &sv.infbits[b], (size_t)(n + 31) / 32 + 1, &m->net_allocs))) return rc;
       cudaMemset(sv.infbits[b], 0, ((size_t)(n + 31) / 32 + 1) * 4);
     }
   }
@@ -1161,7 +1216,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     CK(cudaMemcpy(d_esc, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
   }
   sv.row_ptr = d_rp; sv.col = d_col; sv.rb = d_rb; sv.nrb = (int)rb.size() - 1; sv.escape = d_esc;
-  if ((rc = dev_alloc(m, &sv.partials, (size_t)std::max<long long>(std::max<long long>(sv.nrb, (long long)m->eng->sms * 8), (n + kThreads * kSirRowsPerThread - 1) / (kThreads * kSirRowsPerThread)) * 3 + 3))) return rc;
+  if ((rc = dev_alloc(m, &sv.partials, (size_t)std::max<long long>(std::max<long long>(sv.nrb, (long long)m->eng->sms * 8), (n + kThreads * kSirRowsPerThread - 1) / (kThreads * kSirRowsPerThread)) * 3 + 3, &m->net_allocs))) return rc;
   m->nnz = n_edges;
   m->net_built = true;
   {
@@ -1170,9 +1225,9 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     for (long long i = 0; i < n; ++i)
       if (row_ptr[i + 1] - row_ptr[i] > (unsigned)kSirHeavy) heavy.push_back((int)i);
     int* d_heavy = nullptr;
-    if ((rc = dev_alloc(m, &d_heavy, heavy.size() + 1))) return rc;
+    if ((rc = dev_alloc(m, &d_heavy, heavy.size() + 1, &m->net_allocs))) return rc;
     if (!heavy.empty()) CK(cudaMemcpy(d_heavy, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice));
-    if ((rc = dev_alloc(m, &sv.k32, (size_t)n + 32))) return rc;
+    if ((rc = dev_alloc(m, &sv.k32, (size_t)n + 32, &m->net_allocs))) return rc;
     CK(cudaMemset(sv.k32, 0, ((size_t)n + 32) * 4));
     sv.heavy = d_heavy;
     sv.n_heavy = (int)heavy.size();
@@ -1190,7 +1245,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     CK(cudaMemcpy(&m->dev.ctrl->sir_mode, &dev_mode, sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(&m->dev.ctrl->sir_mode_next, &dev_mode, sizeof(int), cudaMemcpyHostToDevice));
     const size_t max_ctas = (size_t)std::max<long long>(m->sir_tblocks, (long long)m->eng->sms * 8);
-    if ((rc = dev_alloc(m, &sv.degsum, max_ctas * 2 + 2))) return rc;
+    if ((rc = dev_alloc(m, &sv.degsum, max_ctas * 2 + 2, &m->net_allocs))) return rc;
   }
   return sir_sync_from_api(m);
 }
@@ -1451,22 +1506,26 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       }
       if (timed) cudaEventRecord(e1, s);
       const int hh = m->eco_hh;
+      const int tiles = kGiniBins / kGiniScanTile;
       if (hh >= 0 && m->dev.world_size > 1) {
-        // sharded population: the income histogram is the one real bulk exchange of this step (16 MB)
-        int r = g_nccl.AllReduce(m->eco.bin_count, m->eco.bin_count, (size_t)kGiniBins, /*ncclUint32*/ 3, /*ncclSum*/ 0,
-                                 eng->nccl_comm, s);
-        if (r) return fail(JXB_ERR_NCCL, "ncclAllReduce(histogram): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+        // sharded population: the whole population's income counts = the sum of the ranks' histograms, read out of
+        // the peers' exchange allocations (the step kernels' exchange ordered them); no NCCL call on the step path
+        gini_gather_kernel<<<tiles, kThreads, 0, s>>>(m->dev, m->eco);
+        eng->launches += 1;
       }
       if (hh >= 0) {
-        gini_scan_sums_kernel<<<kGiniBins / kGiniScanTile, kThreads, 0, s>>>(m->eco.bin_count, m->eco.scan_sums);
-        gini_scan_top_kernel<<<1, 1024, 0, s>>>(m->eco.scan_sums, kGiniBins / kGiniScanTile);
-        gini_scan_apply_kernel<<<kGiniBins / kGiniScanTile, kThreads, 0, s>>>(m->eco.bin_count, m->eco.scan_sums, m->eco.bin_base);
+        gini_scan_sums_kernel<<<tiles, kThreads, 0, s>>>(m->eco, m->eco.bin_count, m->eco.scan_sums);
+        gini_scan_top_kernel<<<1, 1024, 0, s>>>(m->eco.scan_sums, tiles);
+        gini_scan_apply_kernel<<<tiles, kThreads, 0, s>>>(m->eco, m->eco.bin_count, m->eco.scan_sums, m->eco.bin_base);
         eng->launches += 3;
       }
       gini_accumulate_kernel<<<hh >= 0 ? m->eco.gini_blocks : 1, kThreads, 0, s>>>(m->dev, m->eco, hh);
       eng->launches += 1;
-      // bins back to zero for the next step's histogram (16 MB memset node)
-      if (hh >= 0) CK(cudaMemsetAsync(m->eco.bin_count, 0, (size_t)kGiniBins * 4, s));
+      // this rank's bins back to zero for the next step's histogram (populated tiles only)
+      if (hh >= 0) {
+        gini_clear_kernel<<<tiles, kThreads, 0, s>>>(m->eco);
+        eng->launches += 1;
+      }
       break;
     }
     default: {
@@ -1532,7 +1591,7 @@ static int launches_per_step(jxb_model* m) {
   if (m->grid_sharded) return 4;
   if (m->net_sharded) return 2;
   if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 : (m->sir_mode == 1 ? 2 : 1);
-  if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? 4 : 1);
+  if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? (m->dev.world_size > 1 ? 6 : 5) : 1);
   return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
 }
 
@@ -1626,7 +1685,6 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   static const bool use_graph = getenv("JXB_NO_GRAPH") == nullptr;
   const bool persistent = m->desc.program == JXB_PROGRAM_SCHELLING && !m->grid_sharded;
   const bool graphs = use_graph && !persistent && !m->profile && m->dev.exchange != 2 && steps > 0 &&
-                      !(m->has_eco && m->dev.world_size > 1) &&  // NCCL call on the step path: launch eagerly
                       !(m->traced && !m->traced_started);        // first step of a traced model uses variant 0
   if (graphs) {
     // kernel arguments (the ModelDev snapshot) are baked into a captured graph: rebuild the
@@ -1827,20 +1885,27 @@ extern "C" int jxb_ensemble_run(jxb_engine* eng, const jxb_model_desc* d, int R,
     return off;
   };
   for (int i = 0; i < d->n_types; ++i) fill_type_dev(d->types[i], ed.t[i]);
-  static const int max_cluster = getenv("JXB_ENS_MAX_CLUSTER") ? atoi(getenv("JXB_ENS_MAX_CLUSTER")) : 8;
+  // JXB_ENS_MAX_CLUSTER / JXB_ENS_MIN_CLUSTER bound the cluster size (read per call: the parity tests force
+  // every shape -- 1, 2, 4, 8 CTAs per replica and the L2-scratch path -- on the same replicas);
+  // JXB_ENS_FORCE_SCRATCH=1 puts the state into the per-CTA L2 slot even when it would fit shared memory
+  const int max_cluster = getenv("JXB_ENS_MAX_CLUSTER") ? atoi(getenv("JXB_ENS_MAX_CLUSTER")) : 8;
+  const int min_cluster = getenv("JXB_ENS_MIN_CLUSTER") ? std::max(1, atoi(getenv("JXB_ENS_MIN_CLUSTER"))) : 1;
+  const bool force_scratch = getenv("JXB_ENS_FORCE_SCRATCH") && atoi(getenv("JXB_ENS_FORCE_SCRATCH")) != 0;
   int cs = 1;
   size_t off = layout(1, ed.slice);
-  if (off > kEnsSmemBudget) {
+  if ((off > kEnsSmemBudget || min_cluster > 1) && !force_scratch) {
+    bool found = false;
     for (int c = 2; c <= std::min(max_cluster, (int)kMaxPeers); c *= 2) {
+      if (c < min_cluster) continue;
       long long sl[JXB_MAX_TYPES];
       const size_t o = layout(c, sl);
-      if (o <= kEnsSmemBudget) { cs = c; off = o; for (int i = 0; i < d->n_types; ++i) ed.slice[i] = sl[i]; break; }
+      if (o <= kEnsSmemBudget) { cs = c; off = o; found = true; for (int i = 0; i < d->n_types; ++i) ed.slice[i] = sl[i]; break; }
     }
-    if (cs == 1) off = layout(1, ed.slice);     // nothing fits: per-CTA L2 scratch slot
+    if (!found) off = layout(1, ed.slice);     // nothing fits: per-CTA L2 scratch slot
   }
   ed.cluster = cs;
   ed.state_bytes = off;
-  ed.use_smem = off <= kEnsSmemBudget;
+  ed.use_smem = off <= kEnsSmemBudget && !force_scratch;
   int grid;
   size_t dyn = 0;
   if (ed.use_smem) {

@@ -718,9 +718,12 @@ __global__ void __launch_bounds__(kThreads) scan_apply_kernel(const unsigned int
   if (blockIdx.x == gridDim.x - 1 && tid == kThreads - 1) out[n] = sums[gridDim.x];
 }
 
-__global__ void __launch_bounds__(kThreads) csr_fill_kernel(const int2* edges, long long n_edges, unsigned int* cursor, int* col) {
+// (the same range test as csr_count_kernel: an edge it flagged and skipped must not be scattered either)
+__global__ void __launch_bounds__(kThreads) csr_fill_kernel(const int2* edges, long long n_edges, long long n, long long n_cols,
+                                                            unsigned int* cursor, int* col) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (long long)gridDim.x * blockDim.x) {
     const int2 ed = __ldcs(edges + e);
+    if (ed.x < 0 || ed.x >= n || ed.y < 0 || ed.y >= n_cols) continue;
     const unsigned int pos = atomicAdd(cursor + ed.x, 1u);
     col[pos] = ed.y;
   }

@@ -31,22 +31,49 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: traced rules are compiled at model build time")
 
 
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+_abi_salt: Optional[str] = None
+
+
+def _abi() -> str:
+    """Everything besides the generated source that decides the binary and its ABI towards libjxb: the headers the
+    source includes (ModelDev is passed by value), the public header, the flags and the library version."""
+    global _abi_salt
+    if _abi_salt is None:
+        h = hashlib.sha1()
+        for name in sorted(os.listdir(CSRC)):
+            if name.endswith(".cuh"):
+                with open(os.path.join(CSRC, name), "rb") as f:
+                    h.update(name.encode() + b"\0" + f.read())
+        with open(os.path.join(os.path.dirname(_HERE), "include", "jxb.h"), "rb") as f:
+            h.update(f.read())
+        h.update(" ".join(NVCC_FLAGS).encode())
+        h.update(str(nat.lib().jxb_version()).encode())
+        _abi_salt = h.hexdigest()
+    return _abi_salt
+
+
 def compile_source(src: str) -> C.CDLL:
-    h = hashlib.sha1(src.encode()).hexdigest()[:16]
+    h = hashlib.sha1((_abi() + "\0" + src).encode()).hexdigest()[:16]
     if h in _loaded:
         return _loaded[h]
     os.makedirs(JIT_DIR, exist_ok=True)
     so = os.path.join(JIT_DIR, f"jxc_{h}.so")
     if not os.path.exists(so):
-        cu = os.path.join(JIT_DIR, f"jxc_{h}.cu")
+        # per-process temporaries + one atomic rename: the ranks of a sharded traced ensemble all compile the
+        # same source at the same time
+        tag = f"{h}.{os.getpid()}"
+        cu = os.path.join(JIT_DIR, f"jxc_{tag}.tmp.cu")
+        tmp = os.path.join(JIT_DIR, f"jxc_{tag}.tmp.so")
         with open(cu, "w") as f:
             f.write(src)
-        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-               "-Xcompiler", "-fPIC", "-shared", "-I", CSRC, cu, "-o", so + ".tmp"]
+        cmd = [_nvcc(), *NVCC_FLAGS, "-I", CSRC, cu, "-o", tmp]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise T.TraceError("the generated kernel did not compile (this is a tracer bug):\n" + r.stderr[-3000:])
-        os.replace(so + ".tmp", so)
+        os.replace(cu, os.path.join(JIT_DIR, f"jxc_{h}.cu"))
+        os.replace(tmp, so)
     lib = C.CDLL(so)
     _loaded[h] = lib
     return lib

@@ -87,6 +87,7 @@ class Model:
         self._shard = None            # (rank, world) when split across GPUs (sharding.shard_model)
         self._shard_group = None      # how the ranks talk on the host (sharding.DistGroup)
         self._node_range = None       # (lo, hi) agents of this rank when a Network is split by node ranges
+        self._pending_network = None  # env['network_edges'] set after initialize(), not yet binned into CSR
         self.last_device_seconds = 0.0
 
     # ---- construction ---------------------------------------------------------------------
@@ -112,14 +113,27 @@ class Model:
                     dev.set_env(s, v)
             return
         if name == "network_edges" and self._program == "sir":
-            if getattr(self, "_node_range", None) is not None:
-                from .sharding import local_edges
-                value = local_edges(value, *self._node_range)
-            dev.set_network(value)
+            if self._is_initialized:
+                # edits after initialize() (Network.add_edge calls add_env_state once or twice per edge,
+                # agentpy.py:574-582) are batched on the host: ONE CSR rebuild before the next step
+                self._pending_network = value
+                return
+            self._set_network(value)
             return
         s = dev.env_index(name)
         if s is not None and np.ndim(value) == 0:
             dev.set_env(s, value)
+
+    def _set_network(self, value: Any) -> None:
+        if getattr(self, "_node_range", None) is not None:
+            from .sharding import local_edges
+            value = local_edges(value, *self._node_range)
+        self._dev.set_network(value)
+
+    def _flush_network(self) -> None:
+        pending, self._pending_network = self._pending_network, None
+        if pending is not None:
+            self._set_network(pending)
 
     def model_state(self) -> Dict[str, Any]:                                # model.py:101-116
         state = {"time_step": self._time_step, "env": self._env_state}
@@ -290,6 +304,7 @@ class Model:
 
     def _advance(self, steps: int, collect_interval: int) -> List[Dict[str, Any]]:
         """Run `steps` steps on the device; return the history rows they produced."""
+        self._flush_network()
         rec_steps, rec, secs = self._dev.run(steps, collect_interval)
         self.last_device_seconds = secs
         self._time_step += steps

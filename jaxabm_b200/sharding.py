@@ -57,13 +57,18 @@ def attach_peers() -> None:
     dev = dist._device_for_backend(td)
     # NCCL communicator of the engine: the comparison arm of the scalar exchange (JXB_EXCHANGE=nccl)
     # and the bulk all-reduce of the economy's Gini histogram
-    ident = np.zeros(128, dtype=np.uint8)
-    if rank == 0:
-        nat.check(lib.jxb_nccl_unique_id(nat.ptr(ident), ident.nbytes))
-    t = torch.from_numpy(ident).to(dev)
-    td.broadcast(t, src=0)
-    ident = np.ascontiguousarray(t.cpu().numpy())
-    nat.check(lib.jxb_engine_attach_nccl(eng.handle, nat.ptr(ident), ident.nbytes, rank, world))
+    # (only with one GPU per rank: NCCL refuses two ranks on one device; ranks that time-share a GPU -- the
+    # single-GPU parity tests, gloo process group -- run on the peer-memory exchange alone)
+    if td.get_backend() == "nccl":
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            nat.check(lib.jxb_nccl_unique_id(nat.ptr(ident), ident.nbytes))
+        t = torch.from_numpy(ident).to(dev)
+        td.broadcast(t, src=0)
+        ident = np.ascontiguousarray(t.cpu().numpy())
+        nat.check(lib.jxb_engine_attach_nccl(eng.handle, nat.ptr(ident), ident.nbytes, rank, world))
+    elif use_nccl:
+        raise RuntimeError("JXB_EXCHANGE=nccl needs the nccl process group (one GPU per rank)")
     if not use_nccl:
         h = np.zeros(64, dtype=np.uint8)
         nat.check(lib.jxb_engine_p2p_export(eng.handle, nat.ptr(h), h.nbytes))

@@ -213,13 +213,21 @@ def logical(op: str, a, b) -> Tr:
 
 def power(a, b) -> Tr:
     a, b = _const(a), _const(b)
-    if b.op == "const" and b.dtype == WI and 0 <= b.attr <= 4:          # integer_pow: repeated multiplication
-        if b.attr == 0:
-            return binary("mul", a, 0) + 1
-        r = a
-        for _ in range(b.attr - 1):
-            r = binary("mul", r, a)
-        return r
+    if b.op == "const" and b.dtype == WI and 0 <= b.attr <= 64:
+        # lax.integer_pow: square-and-multiply (x**4 = (x*x)*(x*x), x**3 = (x*x)*x ... the order decides the
+        # float32 rounding); x**0 is the constant 1 of the operand's dtype, also for inf / nan inputs
+        n = int(b.attr)
+        if n == 0:
+            dt = a.dtype if a.dtype in (F32, WF, I32, WI) else I32
+            return Tr("const", (), dt, "s", 1.0 if dt in (F32, WF) else 1)
+        acc, base = None, a
+        while n > 0:
+            if n & 1:
+                acc = base if acc is None else binary("mul", acc, base)
+            n >>= 1
+            if n > 0:
+                base = binary("mul", base, base)
+        return acc
     if a.op == "const" and b.op == "const" and a.dtype in (WF, WI) and b.dtype in (WF, WI):
         return _const(float(a.attr) ** float(b.attr))
     dt = _promote(a, b)

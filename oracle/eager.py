@@ -126,13 +126,22 @@ def _cmp(fn, a, b):
 
 
 def _pow(a, b):
-    if _is_py(b) and isinstance(b, int) and not isinstance(b, bool) and 0 <= b <= 4:       # integer_pow
+    if _is_py(b) and isinstance(b, int) and not isinstance(b, bool) and 0 <= b <= 64:
+        # lax.integer_pow (jax/_src/lax/lax.py _integer_pow_jvp / the XLA lowering): square-and-multiply,
+        # x**4 = (x*x)*(x*x); x**0 = ones_like(x), also for inf / nan
         if b == 0:
-            return a * 0 + 1
-        r = a
-        for _ in range(b - 1):
-            r = r * a
-        return r
+            if _is_py(a):
+                return 1.0 if isinstance(a, float) else 1
+            v = np.asarray(_val(a))
+            return EArr(np.ones_like(v))
+        acc, base, n = None, a, b
+        while n > 0:
+            if n & 1:
+                acc = base if acc is None else acc * base
+            n >>= 1
+            if n > 0:
+                base = base * base
+        return acc
     if _is_py(a) and _is_py(b):
         return float(a) ** float(b)
     with np.errstate(all="ignore"):

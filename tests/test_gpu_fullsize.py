@@ -49,24 +49,27 @@ def test_against_frozen_fixtures(mode):
 
 
 def test_schelling_full_size_vs_c_oracle():
-    """C2 at full size (4096^2, 13 M agents): bit-exact against the C/OpenMP oracle for the first
-    steps (where ~3.7 M agents move per step), then conservation invariants after a longer run."""
+    """C2 at full size (4096^2, 13 M agents): bit-exact against the C/OpenMP oracle over the first 64
+    steps (~3.7 M agents move in step 1), then conservation invariants after 60 more."""
     from oracle import cfast
     G, N = 4096, 13_000_000
     types, pos = schelling.initial_layout(G, N, 0.5, 42)
     m = schelling.create_schelling_model(G, N, seed=42, types=types, positions=pos, config=jx.ModelConfig(seed=42, rng_mode=1))
     f = cfast.SchellingFast(G, types, pos, seed=42, mode=1)
-    r, fr = m.run(steps=4), f.run(4)
-    assert [int(v) for v in r["total_moves"]] == [int(v) for v in fr["total_moves"]]
-    assert np.array_equal(series(r, "percent_satisfied"), series(fr, "percent_satisfied"))
-    np.testing.assert_allclose(series(r, "segregation_index"), series(fr, "segregation_index"), rtol=1e-6)
-    st = m.agent_collections["agents"].states
-    assert np.array_equal(st["position"], f.pos)
-    assert np.array_equal(st["moves"], f.moves)
-    assert np.array_equal(st["satisfied"], f.satisfied.astype(bool))
-    assert np.array_equal(m._dev.download_grid().reshape(-1), f.grid)
-    ec = m._dev.download_empty_cells()
-    assert np.array_equal(ec[:, 0].astype(np.int64) * G + ec[:, 1], f.E)
+    # 4 + 60 steps in two run() calls (state and _time_step persist), every metric row and the whole state
+    # compared bit for bit after each: the active phase (millions of movers per step) and its decay
+    for steps in (4, 60):
+        r, fr = m.run(steps=steps), f.run(steps)
+        assert [int(v) for v in r["total_moves"]] == [int(v) for v in fr["total_moves"]]
+        assert np.array_equal(series(r, "percent_satisfied"), series(fr, "percent_satisfied"))
+        np.testing.assert_allclose(series(r, "segregation_index"), series(fr, "segregation_index"), rtol=1e-6)
+        st = m.agent_collections["agents"].states
+        assert np.array_equal(st["position"], f.pos)
+        assert np.array_equal(st["moves"], f.moves)
+        assert np.array_equal(st["satisfied"], f.satisfied.astype(bool))
+        assert np.array_equal(m._dev.download_grid().reshape(-1), f.grid)
+        ec = m._dev.download_empty_cells()
+        assert np.array_equal(ec[:, 0].astype(np.int64) * G + ec[:, 1], f.E)
     r2 = m.run(steps=60)
     st = m.agent_collections["agents"].states
     p = st["position"].astype(np.int64)
@@ -173,3 +176,32 @@ def test_sir_large_graph_vs_c_oracle(mode):
         assert np.array_equal(series(r, k), series(fr, k)), k
     assert np.array_equal(np.asarray(m.agent_collections["agents"].states["state"]), f.state)
     assert np.bincount(edges[:, 0]).max() > 2048
+
+
+def test_sir_full_size_vs_c_oracle():
+    """C3 at ITS OWN size -- 10 M agents, ~100 M adjacency entries (BASELINE.json configs[2]): counts of every step and
+    the final state bit for bit against the C/OpenMP oracle, in the default direction-optimising mode (push while few
+    rows are infected, then pull over the susceptible rows) and in the full ballot-segmented pull.  At this size the
+    heavy-row list, the row-block table and the 32-bit adjacency offsets are in a different regime than at 2 M."""
+    import os
+    from oracle import cfast
+    n, steps = 10_000_000, 30
+    edges = synthetic.scale_free_edges(n, 5, 42)
+    assert 99_000_000 < edges.shape[0] < 101_000_000
+    f = cfast.SirFast(n, edges, beta=0.05, gamma=0.1, initial_infected=0.01, seed=42, mode=1)
+    fr = f.run(steps)
+    I = series(fr, "count_I")
+    assert I.max() > 20 * I[0]                      # the run covers the take-off, i.e. both directions in auto mode
+    for sir_mode in (None, "pull"):
+        if sir_mode:
+            os.environ["JXB_SIR_MODE"] = sir_mode
+        try:
+            m = sir.create_sir_model(n, edges, beta=0.05, gamma=0.1, initial_infected=0.01, seed=42,
+                                     config=jx.ModelConfig(seed=42, rng_mode=1))
+            r = m.run(steps=steps)
+        finally:
+            os.environ.pop("JXB_SIR_MODE", None)
+        for k in ("count_S", "count_I", "count_R"):
+            assert np.array_equal(series(r, k), series(fr, k)), (sir_mode, k)
+        assert np.array_equal(np.asarray(m.agent_collections["agents"].states["state"]), f.state), sir_mode
+        del m

@@ -299,3 +299,63 @@ def test_saltelli_sobol_through_the_ensemble_kernel(mode):
     assert sa.last_device_seconds > 0.0
     assert idx["avg_value"]["ST"]["growth_rate"] > 0.9 and idx["avg_value"]["ST"]["adjustment_rate"] < 0.02
     assert idx["price_gap"]["ST"]["adjustment_rate"] > 0.9 and idx["price_gap"]["ST"]["growth_rate"] < 0.02
+
+
+# ------------------------------------------------------------- C5: every shape of the ensemble kernel
+ENS_SHAPES = {   # env overrides -> the launch shape they force (csrc/engine.cu::jxb_ensemble_run)
+    "default": {},
+    "cluster4": {"JXB_ENS_MIN_CLUSTER": "4"},
+    "cluster8": {"JXB_ENS_MIN_CLUSTER": "8"},
+    "l2_scratch": {"JXB_ENS_MAX_CLUSTER": "1"},
+}
+
+
+@pytest.mark.parametrize("shape", list(ENS_SHAPES))
+def test_ensemble_c5_size_every_launch_shape(mode, shape, monkeypatch):
+    """C5 at its own replica size (100 000 agents = 400 KB of state per replica): the default launch is a 2-CTA
+    cluster whose CTAs exchange their partial rows through distributed shared memory; 4- and 8-CTA clusters and the
+    per-CTA L2-scratch fallback are forced through the environment.  Every shape against the oracle's serial runs
+    (analysis.py:113-157: seed i + 1000, last value per metric) over the configured 200 steps."""
+    from jaxabm_b200 import ensemble
+    for k, v in ENS_SHAPES[shape].items():
+        monkeypatch.setenv(k, v)
+    n, steps, R = 100_000, 200, 5
+    rng = np.random.RandomState(3)
+    g, a = rng.uniform(0.05, 0.2, R), rng.uniform(0.05, 0.3, R)
+    models = [growth.create_test_model(params={"growth_rate": float(g[i]), "adjustment_rate": float(a[i])},
+                                       config=jx.ModelConfig(seed=i + 1000, steps=steps, rng_mode=mode), num_agents=n)
+              for i in range(R)]
+    last, secs = ensemble.run_last_metrics(models, steps=steps)
+    assert secs > 0
+    for i in range(R):
+        om = orules.create_test_model(params={"growth_rate": float(g[i]), "adjustment_rate": float(a[i])},
+                                      config=ort.ModelConfig(seed=i + 1000, steps=steps, rng_mode=mode), num_agents=n)
+        orr = om.run()
+        np.testing.assert_allclose(float(last["avg_value"][i]), float(orr["avg_value"][-1]), rtol=2e-6)
+        assert np.float32(last["price_level"][i]) == np.float32(orr["price_level"][-1])
+        assert last["price_gap"][i] == orr["price_gap"][-1]
+
+
+@pytest.mark.parametrize("shape", ["default", "cluster2", "cluster8", "l2_scratch", "smem_forced_scratch"])
+def test_ensemble_market_every_launch_shape(mode, shape, monkeypatch):
+    """Two collections with per-agent keyed init (global indices across the cluster's slices) and four reduction
+    slots: 30 000 consumers + 8 000 producers = 576 KB per replica (default: a 4-CTA cluster).  Every launch shape
+    against single Model.run()s of the same replicas on the device, and those against the oracle."""
+    from jaxabm_b200 import ensemble
+    env = {"default": {}, "cluster2": {"JXB_ENS_MIN_CLUSTER": "2", "JXB_ENS_MAX_CLUSTER": "2"},
+           "cluster8": {"JXB_ENS_MIN_CLUSTER": "8"}, "l2_scratch": {"JXB_ENS_MAX_CLUSTER": "1"},
+           "smem_forced_scratch": {"JXB_ENS_FORCE_SCRATCH": "1"}}[shape]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    # cluster2 is forced on a state that would fit ONE CTA, smem_forced_scratch on one that would fit shared memory
+    nc, npr = {"cluster2": (9_000, 2_000), "smem_forced_scratch": (3_000, 801)}.get(shape, (30_000, 8_000))
+    kws = [dict(num_consumers=nc, num_producers=npr, params={"propensity_to_consume": ptc, "productivity": 1.0 + 0.1 * i})
+           for i, ptc in enumerate([0.6, 0.75, 0.9])]
+    models = [market.create_economy_model(config=jx.ModelConfig(seed=70 + i, rng_mode=mode), **kw) for i, kw in enumerate(kws)]
+    last, _ = ensemble.run_last_metrics(models, steps=25)
+    for i, kw in enumerate(kws):
+        r = market.create_economy_model(config=jx.ModelConfig(seed=70 + i, rng_mode=mode), **kw).run(steps=25)
+        orr = orules.create_economy_model(config=ort.ModelConfig(seed=70 + i, rng_mode=mode), **kw).run(steps=25)
+        for k in ("gdp", "price_level", "avg_utility", "avg_profit"):
+            np.testing.assert_allclose(float(last[k][i]), float(r[k][-1]), rtol=2e-6, err_msg=k)
+            np.testing.assert_allclose(float(last[k][i]), float(orr[k][-1]), rtol=1e-5, err_msg=k)

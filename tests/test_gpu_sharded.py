@@ -21,9 +21,16 @@ sys.path.insert(0, ROOT)
 def worker():
     import torch
     import torch.distributed as td
-    local = int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    one_gpu = os.environ.get("JXB_SHARD_TEST_ONE_GPU") == "1"
+    if one_gpu:
+        # all ranks time-share GPU 0: CUDA IPC peer mappings and the in-kernel spin waits work across processes on
+        # one device, so the whole exchange path is covered wherever a single GPU is visible
+        os.environ["JXB_DEVICE"] = "0"
+        td.init_process_group("gloo")
+    else:
+        local = int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local)
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = td.get_rank(), td.get_world_size()
     import jaxabm_b200 as jx
     from jaxabm_b200 import sharding, dist
@@ -41,7 +48,8 @@ def worker():
             assert np.allclose(a, b, rtol=2e-6, atol=1e-9), (mode, k, a[-1], b[-1])
         # all ranks hold identical env trajectories (folded in rank order from identical rows)
         mine = np.array([float(v) for v in r1["price_level"]])
-        t = torch.from_numpy(mine).cuda()
+        t = torch.from_numpy(mine)
+        t = t if one_gpu else t.cuda()
         parts = [torch.zeros_like(t) for _ in range(world)]
         td.all_gather(parts, t)
         for p in parts:
@@ -77,7 +85,8 @@ def worker():
                                sh.agent_collections["households"].states["cash"], rtol=1e-4)
     td.barrier()
     if rank == 0:
-        print(f"sharded market OK on {world} GPUs (exchange={os.environ.get('JXB_EXCHANGE', 'p2p')})")
+        print(f"sharded market OK on {world} {'ranks sharing one GPU' if one_gpu else 'GPUs'} "
+              f"(exchange={os.environ.get('JXB_EXCHANGE', 'p2p')})")
     td.destroy_process_group()
 
 
@@ -100,6 +109,23 @@ def test_sharded_market_two_gpus(exchange):
                           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)],
                          env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "sharded market OK" in out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_market_and_economy_ranks_share_one_gpu(world):
+    """The product exchange path (in-kernel partial-sum exchange of the market and the economy, peer-memory
+    all-reduce of the Gini histogram) with every rank on GPU 0 -- runs wherever one GPU is visible."""
+    env = dict(os.environ, JXB_SHARD_TEST_ONE_GPU="1")
+    env.pop("JXB_EXCHANGE", None)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", str(29535 + world), os.path.abspath(__file__)],
+                         env=env, capture_output=True, text=True, timeout=900)
+    if out.returncode != 0:
+        err = out.stderr
+        cut = err.find("Traceback")
+        raise AssertionError(out.stdout[-1500:] + (err[cut:cut + 4000] if cut >= 0 else err[-4000:]))
     assert "sharded market OK" in out.stdout
 
 
