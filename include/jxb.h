@@ -216,6 +216,27 @@ int jxb_model_profile(jxb_model*, double* dominant_kernel_seconds, int64_t* laun
 int jxb_host_alloc(size_t bytes, void** out);
 int jxb_host_free(void* p);
 
+/* ---- record / select ------------------------------------------------ */
+/* Per-agent time series: the facade's Results is meant to carry 'agents.<name>.<var>' entries
+ * (jaxabm/agentpy.py:1103-1106; the reference never fills them).  Opt-in: name up to 8 (collection, field)
+ * columns; every later jxb_model_run snapshots them on the device whenever it records a history row
+ * (t % collect_interval == 0) and keeps the snapshots in HBM until the next run.  n = 0 switches it off.   */
+int jxb_model_record_fields(jxb_model*, int n, const int32_t* types, const int32_t* fields);
+/* series k of the last run: n_records snapshots of bytes_per_record bytes each (the column, in agent order) */
+int jxb_model_series_info(jxb_model*, int k, int* n_records, size_t* bytes_per_record);
+int jxb_model_series_download(jxb_model*, int k, void* host, size_t bytes);
+
+/* AgentCollection.filter(condition) (jaxabm/agent.py:213-243) as a device stream compaction.
+ * select: flag every agent of collection `type` either by a postfix predicate program over its own state
+ * columns (the host shim traces `condition` into it; opcodes JP_* in csrc/record.cuh) or, when `prog` is NULL,
+ * by a host-evaluated mask of n_agents bytes; returns the number of selected agents.
+ * gather: scatter the selected agents' rows of every state column, in agent order, into collection
+ * `dst_type` of `dst` -- a model whose collection has the same rule and exactly `count` agents.          */
+typedef struct { int32_t op; int32_t a; int32_t b; float f; } jxb_pred_ins;
+int jxb_collection_filter_select(jxb_model*, int type, const jxb_pred_ins* prog, int n_ins,
+                                 const uint8_t* host_mask, size_t mask_bytes, int64_t* count_out);
+int jxb_collection_filter_gather(jxb_model* src, int type, jxb_model* dst, int dst_type);
+
 /* ---- ensembles (jaxabm/analysis.py:113-157 and :434-476) --------------------------- */
 /* R independent replicas of `desc`; replica r overrides params by
  * param_slots/params[r][n_swept] (slot < 100: model param index; slot >= 100:

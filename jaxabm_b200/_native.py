@@ -46,6 +46,11 @@ class ModelDesc(C.Structure):
                 ("grid_periodic", C.c_int32), ("world_size", C.c_int32), ("rank", C.c_int32)]
 
 
+class PredIns(C.Structure):
+    """One instruction of a filter predicate program (``jxb_pred_ins``)."""
+    _fields_ = [("op", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("f", C.c_float)]
+
+
 _lib: Optional[C.CDLL] = None
 
 # name -> (restype, argtypes); every symbol declared in include/jxb.h
@@ -95,6 +100,11 @@ SIGNATURES = {
     "jxb_model_net_shard_export": (C.c_int, [_P, _P, C.c_size_t]),
     "jxb_model_net_shard_attach": (C.c_int, [_P, _P, C.c_size_t, C.c_int]),
     "jxb_model_net_shard_sync": (C.c_int, [_P]),
+    "jxb_model_record_fields": (C.c_int, [_P, C.c_int, _P, _P]),
+    "jxb_model_series_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "jxb_model_series_download": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    "jxb_collection_filter_select": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_size_t, C.POINTER(C.c_int64)]),
+    "jxb_collection_filter_gather": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "jxb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "jxb_host_free": (C.c_int, [_P]),
     "jxb_prng_split": (C.c_int, [C.c_int, _P, C.c_int, _P]),

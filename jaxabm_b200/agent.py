@@ -186,17 +186,39 @@ class AgentCollection:
         return fn(st[variable])
 
     def filter(self, condition: Callable[[Dict[str, Any]], Any]) -> "AgentCollection":   # agent.py:213-243
-        st = self.states
-        cols = {k: st[k] for k in st}
-        mask = np.asarray(condition(cols))
-        count = int(np.sum(mask))
+        """New collection holding the agents for which ``condition(states)`` is true, in their order
+        (``{k: v[mask]}`` of the reference) -- a stream compaction on the device: flags from the traced
+        condition (``jaxabm_b200/select.py``), exclusive scan, one ordered scatter per column into the new
+        collection's HBM columns.  A condition the tracer cannot follow is evaluated on the host over the
+        columns it reads (downloaded lazily) and only the mask travels back."""
+        from . import select
+        from .trace import TraceError
+        if not self._initialized or self._dev is None:
+            raise ValueError("Agent collection not initialized. Call init() first.")
+        dev, t = self._dev, self._tidx
+        try:
+            count = dev.filter_select(t, program=select.compile_predicate(condition, dev.fields[t]))
+        except TraceError:
+            st = self.states
+
+            class _Lazy(dict):
+                def __missing__(self, k):
+                    self[k] = st[k]
+                    return self[k]
+
+                def __iter__(self):
+                    return iter(st)
+            mask = np.asarray(condition(_Lazy()))
+            if mask.dtype != np.bool_ or mask.shape != (self.num_agents,):
+                raise ValueError("filter condition must return one boolean per agent")
+            count = dev.filter_select(t, mask=mask)
         out = AgentCollection(self.agent_type, count)   # ValueError when nothing matches, as in the reference
         out.model_config = self.model_config
         out._key = self._key
-        desc = make_desc("none", [out.type_spec()],
-                         rng_mode=self.model_config.rng_mode if self.model_config else None)
+        spec = out.type_spec() if getattr(self.agent_type, "jxb_rule", None) else None
+        if spec is None:
+            raise UnregisteredRuleError("filter on a traced collection is not supported yet")
+        desc = make_desc("none", [spec], rng_mode=self.model_config.rng_mode if self.model_config else None)
         out._dev, out._tidx, out._initialized = DeviceModel(desc), 0, True
-        out._dev.collection_init(0, np.zeros(2, dtype=np.uint32))
-        for k, v in cols.items():
-            out.states[k] = v[mask]
+        dev.filter_gather(t, out._dev, 0)
         return out

@@ -341,6 +341,7 @@ class Model:
         self._current_agent_states: Dict[str, Any] = {}
         self._running = False
         self.last_device_seconds = 0.0
+        self._record_agents: Dict[str, List[str]] = {}
 
     # ---- user hooks ------------------------------------------------------------------------
     def setup(self) -> None:
@@ -380,6 +381,14 @@ class Model:
 
     def _update_agent_state(self, agent: Agent, new_state: Dict[str, Any]) -> None:
         agent._state.update(new_state)
+
+    def record_agents(self, collection_name: str, variables) -> None:
+        """Extension: fill the ``agents.<collection>.<variable>`` entries of ``Results`` that
+        ``agentpy.py:1103-1106`` intends -- one device-side snapshot of the column per recorded step."""
+        if isinstance(variables, str):
+            variables = [variables]
+        have = self._record_agents.setdefault(collection_name, [])
+        have.extend(v for v in variables if v not in have)
 
     def record(self, name: str, value: Any) -> None:                      # agentpy.py:1031-1038
         self._recorded_data.setdefault(name, []).append(value)
@@ -423,6 +432,8 @@ class Model:
             self._jax_model.add_agent_collection(name, agent_list.collection)
         for name, value in self.env.state.items():
             self._jax_model.add_env_state(name, value)
+        for cname, variables in self._record_agents.items():
+            self._jax_model.record_agent_series(cname, variables)
         start = time.time()
         self._jax_model.initialize()
         self.after_initialize()
@@ -432,7 +443,9 @@ class Model:
         self.end()
         self._running = False
         results_dict.update(self._recorded_data)
-        # agentpy.py:1103-1106: JaxModel.state never holds 'agents' -> no 'agents.*' keys (F11)
+        # agentpy.py:1103-1106: JaxModel.state never holds 'agents' -> no 'agents.*' keys (F11) unless the model
+        # opted in with record_agents(): then they are the per-step snapshots of those columns [T, N, ...]
+        results_dict.update(self._jax_model.agent_series)
         results = Results(results_dict)
         print(f"Simulation executed in {format_time(elapsed)}")
         return results

@@ -26,6 +26,7 @@
 #include "grid_shard.cuh"
 #include "sir.cuh"
 #include "ensemble.cuh"
+#include "record.cuh"
 
 using namespace jxb;
 
@@ -245,6 +246,12 @@ struct jxb_model {
   // graphs: cached executable graphs of `chunk` consecutive steps
   cudaGraphExec_t graph1 = nullptr, graphK = nullptr; int chunkK = 0;
   const void* sig_keys = nullptr; const void* sig_metrics = nullptr; const void* sig_rec = nullptr; int sig_ci = 0;
+  // per-agent series (csrc/record.cuh): recorded columns, their device ring and its layout
+  struct RecField { int type, field; size_t bytes, stride; size_t off; };
+  std::vector<RecField> rec_fields; unsigned char* d_series = nullptr; size_t series_bytes = 0, series_slots = 0;
+  int series_nrec = 0; const void* sig_series = nullptr; size_t sig_series_slots = 0;
+  // filter scratch (jxb_collection_filter_select -> _gather): exclusive scan of the selection flags
+  unsigned int* filter_pos = nullptr; size_t filter_pos_bytes = 0; int filter_type = -1; long long filter_count = -1;
   // profiling of the dominant kernel
   bool profile = false; double prof_seconds = 0; int64_t prof_launches = 0;
   std::vector<cudaEvent_t> prof_events;
@@ -434,8 +441,8 @@ extern "C" int jxb_engine_p2p_attach(jxb_engine* eng, const void* handles, size_
 // ---------------------------------------------------------------------------------------
 static bool program_accepts(int program, int rule) {
   switch (program) {
-    case JXB_PROGRAM_NONE: return rule != JXB_RULE_SCHELLING && rule != JXB_RULE_SIR && rule != JXB_RULE_HOUSEHOLD &&
-                                  rule != JXB_RULE_CONSUMER_FIRM;
+    case JXB_PROGRAM_NONE: return true;    // any registered layout as a passive container (AgentCollection.filter results);
+                                           // rules that need a grid / network / economy program do nothing under it
     case JXB_PROGRAM_RANDOM_WALK: return rule == JXB_RULE_RANDOM_WALKER || rule == JXB_RULE_SCALED_WALKER;
     case JXB_PROGRAM_MARKET: return rule == JXB_RULE_CONSUMER || rule == JXB_RULE_PRODUCER;
     case JXB_PROGRAM_GROWTH: return rule == JXB_RULE_GROWTH;
@@ -772,6 +779,8 @@ extern "C" int jxb_model_destroy(jxb_model* m) {
   if (m->ns_area) m->eng->retired_areas.emplace_back(m->ns_area, m->ns_area_bytes);
   for (auto& a : m->net_allocs) pool_free(m->eng, a.first, a.second);
   if (m->eng->hist_owner == m) m->eng->hist_owner = nullptr;
+  pool_free(m->eng, m->d_series, m->series_bytes);
+  pool_free(m->eng, m->filter_pos, m->filter_pos_bytes);
   pool_free(m->eng, m->d_keys, m->keys_cap * 4);
   pool_free(m->eng, m->d_metrics, m->rec_cap * kMaxMetrics * sizeof(double));
   pool_free(m->eng, m->d_rec, m->rec_cap * sizeof(int));
@@ -827,7 +836,7 @@ static size_t field_bytes(jxb_model* m, int type, int field) {
 
 static int sir_sync_from_api(jxb_model* m);
 static int sir_sync_to_api(jxb_model* m);
-static int schelling_export_satisfied(jxb_model* m);
+static int schelling_export_satisfied(jxb_model* m, cudaStream_t s, bool clear_dirty);
 
 static int check_field(jxb_model* m, int type, int field, size_t bytes) {
   NEED(m); NEED_TYPE(m, type);
@@ -850,19 +859,37 @@ extern "C" int jxb_model_upload(jxb_model* m, int type, int field, const void* h
   return JXB_OK;
 }
 
+// Bring the API-visible column (type, field) up to date from the engine's packed layout, stream-ordered and
+// without a host sync.  in_step: called between the launches of a step (possibly under graph capture), where the
+// host-side copies of time_step / dirty flags are stale -- everything is derived on the device.
+static int materialize_field(jxb_model* m, int type, int field, cudaStream_t s, bool in_step) {
+  (void)type;
+  if (m->has_net && m->net_built) {
+    if (in_step) {
+      sir_unpack_cur_kernel<<<m->eng->sms * 8, 256, 0, s>>>(m->sv, m->dev.ctrl, (int*)m->dev.t[0].f[0], m->desc.types[0].n_agents);
+      m->eng->launches++;
+    } else {
+      int rc = sir_sync_to_api(m);
+      if (rc) return rc;
+    }
+  }
+  if (m->has_grid && field == 2 && (in_step || m->sat_dirty)) { int rc = schelling_export_satisfied(m, s, !in_step); if (rc) return rc; }
+  if (m->grid_sharded && field == 1 && m->grid_built) {
+    // this rank's view: the agents sitting in its band, -1 for everybody else (host: max over ranks)
+    CK(cudaMemsetAsync(m->dev.t[0].f[1], 0xFF, field_bytes(m, 0, 1), s));
+    grid_shard_export_position_kernel<<<m->eng->sms * 8, 256, 0, s>>>(m->sd, m->gs, (int2*)m->dev.t[0].f[1]);
+    m->eng->launches++;
+    CK(cudaGetLastError());
+  }
+  return JXB_OK;
+}
+
 extern "C" int jxb_model_download(jxb_model* m, int type, int field, void* host, size_t bytes) {
   int rc = check_field(m, type, field, bytes);
   if (rc) return rc;
   CK(cudaSetDevice(m->eng->device));
-  if (m->has_net) { rc = sir_sync_to_api(m); if (rc) return rc; }
-  if (m->has_grid && field == 2 && m->sat_dirty) { rc = schelling_export_satisfied(m); if (rc) return rc; }
-  if (m->grid_sharded && field == 1 && m->grid_built) {
-    // this rank's view: the agents sitting in its band, -1 for everybody else (host: max over ranks)
-    CK(cudaMemsetAsync(m->dev.t[0].f[1], 0xFF, bytes, m->eng->stream));
-    grid_shard_export_position_kernel<<<m->eng->sms * 8, 256, 0, m->eng->stream>>>(m->sd, m->gs, (int2*)m->dev.t[0].f[1]);
-    m->eng->launches++;
-    CK(cudaGetLastError());
-  }
+  rc = materialize_field(m, type, field, m->eng->stream, false);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(host, m->dev.t[type].f[field], bytes, cudaMemcpyDeviceToHost, m->eng->stream));
   CK(cudaStreamSynchronize(m->eng->stream));
   // 'moves' of a sharded Grid is a sum over ranks; until the first rebuild splits the uploaded values by
@@ -1082,15 +1109,14 @@ extern "C" int jxb_model_grid_shard_attach(jxb_model* m, const void* handles, si
   return JXB_OK;
 }
 
-static int schelling_export_satisfied(jxb_model* m) {
-  cudaStream_t s = m->eng->stream;
+static int schelling_export_satisfied(jxb_model* m, cudaStream_t s, bool clear_dirty) {
   unsigned char* sat = (unsigned char*)m->dev.t[0].f[2];
   CK(cudaMemsetAsync(sat, 1, (size_t)m->desc.types[0].n_agents, s));
   if (m->grid_sharded) grid_shard_export_satisfied_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->gs, sat);   // host: min over ranks
   else satisfied_export_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->sd, m->dev.ctrl, sat);
   m->eng->launches++;
   CK(cudaGetLastError());
-  m->sat_dirty = false;
+  if (clear_dirty) m->sat_dirty = false;
   return JXB_OK;
 }
 
@@ -1114,7 +1140,6 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     if (m->graph1) { cudaGraphExecDestroy(m->graph1); m->graph1 = nullptr; }
     if (m->graphK) { cudaGraphExecDestroy(m->graphK); m->graphK = nullptr; }
     for (auto& a : m->net_allocs) pool_free(m->eng, a.first, a.second);
-  if (m->eng->hist_owner == m) m->eng->hist_owner = nullptr;
     m->net_allocs.clear();
     m->net_built = false;
   }
@@ -1420,6 +1445,21 @@ static int plan_step_blocks(jxb_model* m) {
   return JXB_OK;
 }
 
+// per-agent series (csrc/record.cuh): after the step's tail advanced the device-side counters, copy every
+// recorded column into its ring slot if this step recorded a history row.  Capture-safe.
+static int enqueue_snapshots(jxb_model* m, cudaStream_t s) {
+  for (const auto& rf : m->rec_fields) {
+    int rc = materialize_field(m, rf.type, rf.field, s, true);
+    if (rc) return rc;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>((rf.bytes / 16 + kThreads - 1) / kThreads, (size_t)m->eng->sms * 8));
+    series_snapshot_kernel<<<blocks, kThreads, 0, s>>>(m->dev.ctrl, m->dev.collect_interval, (const uint4*)m->dev.t[rf.type].f[rf.field],
+                                                       m->d_series + rf.off, (unsigned long long)rf.bytes, (unsigned long long)rf.stride);
+    m->eng->launches++;
+  }
+  CK(cudaGetLastError());
+  return JXB_OK;
+}
+
 // enqueue one Model.step (model.py:146-216) on the stream; capture-safe (no host-varying args)
 static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
   jxb_engine* eng = m->eng;
@@ -1548,7 +1588,7 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
     }
   }
   CK(cudaGetLastError());
-  return JXB_OK;
+  return enqueue_snapshots(m, s);
 }
 
 static int build_graph(jxb_model* m, int chunk, cudaGraphExec_t* out) {
@@ -1587,6 +1627,17 @@ static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
   return JXB_OK;
 }
 
+static int launches_per_step(jxb_model* m);
+static int launches_per_step_all(jxb_model* m) {
+  int extra = 0;
+  for (const auto& rf : m->rec_fields) {
+    extra += 1;
+    if (m->has_net) extra += 1;
+    if (m->has_grid && rf.field == 2) extra += 1;
+    if (m->grid_sharded && rf.field == 1) extra += 1;
+  }
+  return launches_per_step(m) + extra;
+}
 static int launches_per_step(jxb_model* m) {
   if (m->grid_sharded) return 4;
   if (m->net_sharded) return 2;
@@ -1677,6 +1728,26 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   m->dev.metrics = m->d_metrics;
   m->dev.record_steps = m->d_rec;
   m->dev.collect_interval = collect_interval;
+  m->series_nrec = 0;
+  if (!m->rec_fields.empty()) {
+    // ring of the recorded columns: field k owns rec_cap slots of stride_k bytes behind off_k
+    const size_t slots = std::max<size_t>(std::max<size_t>((size_t)n_rec, 1), m->series_slots);
+    size_t total = 0;
+    for (auto& rf : m->rec_fields) { rf.off = total; total += rf.stride * slots; }
+    static const size_t cap_bytes = (size_t)(getenv("JXB_SERIES_MAX_MB") ? atoll(getenv("JXB_SERIES_MAX_MB")) : 32768) << 20;
+    if (total > cap_bytes)
+      return fail(JXB_ERR_INVALID, "recording %d snapshots of the selected agent columns needs %.1f GB of HBM (limit JXB_SERIES_MAX_MB = %zu MB): "
+                  "raise collect_interval or record fewer columns", n_rec, (double)total / 1e9, cap_bytes >> 20);
+    if (total > m->series_bytes || m->series_slots != slots) {
+      CK(cudaStreamSynchronize(s));
+      pool_free(eng, m->d_series, m->series_bytes);
+      m->d_series = nullptr; m->series_bytes = 0;
+      CK(pool_alloc(eng, (void**)&m->d_series, total));
+      m->series_bytes = total;
+      m->series_slots = slots;
+    }
+    m->series_nrec = n_rec;
+  }
   {
     // reset the per-run counters, keep the persistent ones
     int zeros[2] = {0, 0};
@@ -1690,7 +1761,8 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
     // kernel arguments (the ModelDev snapshot) are baked into a captured graph: rebuild the
     // two cached graphs (1 step, 32 steps) whenever a pointer or the interval changed
     const bool changed = !m->graph1 || m->sig_keys != m->d_keys || m->sig_metrics != m->d_metrics ||
-                         m->sig_rec != m->d_rec || m->sig_ci != collect_interval;
+                         m->sig_rec != m->d_rec || m->sig_ci != collect_interval || m->sig_series != m->d_series ||
+                         m->sig_series_slots != m->series_slots;
     if (changed) {
       if (m->graph1) { cudaGraphExecDestroy(m->graph1); m->graph1 = nullptr; }
       if (m->graphK) { cudaGraphExecDestroy(m->graphK); m->graphK = nullptr; }
@@ -1700,19 +1772,31 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
       rc = build_graph(m, m->chunkK, &m->graphK);
       if (rc) return rc;
       m->sig_keys = m->d_keys; m->sig_metrics = m->d_metrics; m->sig_rec = m->d_rec; m->sig_ci = collect_interval;
+      m->sig_series = m->d_series; m->sig_series_slots = m->series_slots;
     }
   }
   for (auto e : m->prof_events) cudaEventDestroy(e);
   m->prof_events.clear();
 
   CK(cudaEventRecord(eng->ev0, s));
-  if (persistent) {
+  if (persistent && m->rec_fields.empty()) {
     if (steps > 0) { int rc = launch_schelling(m, steps, s); if (rc) return rc; }
+  } else if (persistent) {
+    // per-agent series: the persistent kernel runs up to the next recording step, then the snapshots are taken
+    long long t = t0;
+    int left = steps;
+    while (left > 0) {
+      const int c = (int)std::min<long long>(left, collect_interval - (t % collect_interval));
+      int rc = launch_schelling(m, c, s);
+      if (!rc) rc = enqueue_snapshots(m, s);
+      if (rc) return rc;
+      t += c; left -= c;
+    }
   } else if (graphs) {
     int left = steps;
     while (left >= m->chunkK) { CK(cudaGraphLaunch(m->graphK, s)); left -= m->chunkK; }
     while (left > 0) { CK(cudaGraphLaunch(m->graph1, s)); --left; }
-    eng->launches += (int64_t)steps * launches_per_step(m);
+    eng->launches += (int64_t)steps * launches_per_step_all(m);
   } else {
     for (int t = 0; t < steps; ++t) {
       int rc = enqueue_step(m, s, m->profile);
@@ -1785,6 +1869,177 @@ extern "C" int jxb_collection_update(jxb_model* m, int type, uint32_t k0, uint32
   m->eng->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(m->eng->stream));
+  return JXB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// record / select (csrc/record.cuh)
+// ---------------------------------------------------------------------------------------
+extern "C" int jxb_model_record_fields(jxb_model* m, int n, const int32_t* types, const int32_t* fields) {
+  NEED(m);
+  if (n < 0 || n > 8 || (n && (!types || !fields))) return fail(JXB_ERR_INVALID, "record up to 8 (collection, field) columns");
+  std::vector<jxb_model::RecField> rf;
+  for (int k = 0; k < n; ++k) {
+    NEED_TYPE(m, types[k]);
+    if (fields[k] < 0 || fields[k] >= m->rules[types[k]]->nf) return fail(JXB_ERR_INVALID, "field %d out of range", fields[k]);
+    if (m->grid_sharded && m->dev.world_size > 1)
+      return fail(JXB_ERR_UNSUPPORTED, "per-agent series of a Grid sharded over ranks: record on the single-GPU model");
+    const size_t bytes = field_bytes(m, types[k], fields[k]);
+    rf.push_back({types[k], fields[k], bytes, (bytes + 15) / 16 * 16, 0});
+  }
+  CK(cudaSetDevice(m->eng->device));
+  CK(cudaStreamSynchronize(m->eng->stream));
+  m->rec_fields = rf;
+  m->series_nrec = 0;
+  m->series_slots = 0;
+  if (m->graph1) { cudaGraphExecDestroy(m->graph1); m->graph1 = nullptr; }     // the snapshot launches are part of the step graph
+  if (m->graphK) { cudaGraphExecDestroy(m->graphK); m->graphK = nullptr; }
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_series_info(jxb_model* m, int k, int* n_records, size_t* bytes_per_record) {
+  NEED(m);
+  if (k < 0 || k >= (int)m->rec_fields.size()) return fail(JXB_ERR_INVALID, "series %d out of range", k);
+  if (n_records) *n_records = m->series_nrec;
+  if (bytes_per_record) *bytes_per_record = m->rec_fields[k].bytes;
+  return JXB_OK;
+}
+
+extern "C" int jxb_model_series_download(jxb_model* m, int k, void* host, size_t bytes) {
+  NEED(m);
+  if (k < 0 || k >= (int)m->rec_fields.size()) return fail(JXB_ERR_INVALID, "series %d out of range", k);
+  const auto& rf = m->rec_fields[k];
+  if (bytes != rf.bytes * (size_t)m->series_nrec)
+    return fail(JXB_ERR_INVALID, "series %d holds %d records of %zu bytes", k, m->series_nrec, rf.bytes);
+  if (!bytes) return JXB_OK;
+  CK(cudaSetDevice(m->eng->device));
+  CK(cudaMemcpy2DAsync(host, rf.bytes, m->d_series + rf.off, rf.stride, rf.bytes, (size_t)m->series_nrec,
+                       cudaMemcpyDeviceToHost, m->eng->stream));
+  CK(cudaStreamSynchronize(m->eng->stream));
+  return JXB_OK;
+}
+
+static int pred_check(jxb_model* m, int type, const jxb_pred_ins* prog, int n_ins) {
+  if (n_ins < 1 || n_ins > kPredMaxIns) return fail(JXB_ERR_INVALID, "predicate programs hold 1..%d instructions", kPredMaxIns);
+  int sp = 0;
+  for (int k = 0; k < n_ins; ++k) {
+    const jxb_pred_ins& in = prog[k];
+    int pop = 0, push = 1;
+    if (in.op == JP_LOAD_F32 || in.op == JP_LOAD_I32 || in.op == JP_LOAD_U8) {
+      if (in.a < 0 || in.a >= m->rules[type]->nf) return fail(JXB_ERR_INVALID, "predicate: field %d out of range", in.a);
+      const FieldSpec& f = m->rules[type]->f[in.a];
+      const int want = in.op == JP_LOAD_F32 ? 0 : (in.op == JP_LOAD_I32 ? 1 : 2);
+      if (f.dtype != want || in.b < 0 || in.b >= f.width)
+        return fail(JXB_ERR_INVALID, "predicate: load of '%s' does not match its dtype / width", f.name);
+    } else if (in.op == JP_CONST_F32 || in.op == JP_CONST_I32) {
+    } else if ((in.op >= JP_ADD_F && in.op <= JP_MAX_I) || (in.op >= JP_LT_F && in.op <= JP_XOR)) {
+      pop = 2;
+    } else if ((in.op >= JP_NEG_F && in.op <= JP_F2B) || in.op == JP_NOT || (in.op >= JP_SQRT_F && in.op <= JP_LOG_F)) {
+      pop = 1;
+    } else if (in.op == JP_SELECT) {
+      pop = 3;
+    } else {
+      return fail(JXB_ERR_INVALID, "predicate: unknown opcode %d", in.op);
+    }
+    if (sp < pop) return fail(JXB_ERR_INVALID, "predicate: stack underflow at instruction %d", k);
+    sp += push - pop;
+    if (sp > kPredStack) return fail(JXB_ERR_INVALID, "predicate: expression deeper than %d", kPredStack);
+  }
+  if (sp != 1) return fail(JXB_ERR_INVALID, "predicate: program leaves %d values", sp);
+  return JXB_OK;
+}
+
+extern "C" int jxb_collection_filter_select(jxb_model* m, int type, const jxb_pred_ins* prog, int n_ins,
+                                            const uint8_t* host_mask, size_t mask_bytes, int64_t* count_out) {
+  NEED(m); NEED_TYPE(m, type);
+  if (!count_out) return fail(JXB_ERR_INVALID, "count_out is NULL");
+  if (!m->collections_ready[type] && !m->initialized) return fail(JXB_ERR_STATE, "Agent collection not initialized. Call init() first.");
+  const long long n = m->desc.types[type].n_agents;
+  if ((prog != nullptr) == (host_mask != nullptr)) return fail(JXB_ERR_INVALID, "give either a predicate program or a host mask");
+  if (host_mask && mask_bytes != (size_t)n) return fail(JXB_ERR_INVALID, "the mask holds one byte per agent (%lld)", n);
+  if (prog) { int rc = pred_check(m, type, prog, n_ins); if (rc) return rc; }
+  if (m->grid_sharded && m->dev.world_size > 1) return fail(JXB_ERR_UNSUPPORTED, "filter on a Grid sharded over ranks");
+  jxb_engine* eng = m->eng;
+  CK(cudaSetDevice(eng->device));
+  cudaStream_t s = eng->stream;
+  PredProgram pg;
+  memset(&pg, 0, sizeof(pg));
+  FilterCols fc;
+  memset(&fc, 0, sizeof(fc));
+  const RuleSpec* rs = m->rules[type];
+  for (int f = 0; f < rs->nf; ++f) { fc.f[f] = m->dev.t[type].f[f]; fc.width[f] = rs->f[f].width; }
+  if (prog) {
+    pg.n = n_ins;
+    memcpy(pg.ins, prog, (size_t)n_ins * sizeof(jxb_pred_ins));
+    for (int k = 0; k < n_ins; ++k)
+      if (prog[k].op == JP_LOAD_F32 || prog[k].op == JP_LOAD_I32 || prog[k].op == JP_LOAD_U8) {
+        int rc = materialize_field(m, type, prog[k].a, s, false);
+        if (rc) return rc;
+      }
+  }
+  pool_free(eng, m->filter_pos, m->filter_pos_bytes);
+  m->filter_pos = nullptr; m->filter_pos_bytes = 0; m->filter_type = -1; m->filter_count = -1;
+  const int ntiles = (int)((n + kScanTile - 1) / kScanTile);
+  const size_t pos_bytes = ((size_t)n + 2) * 4, sums_bytes = ((size_t)ntiles + 2) * 4;
+  unsigned int* d_flags = nullptr; unsigned int* d_sums = nullptr; unsigned char* d_mask = nullptr;
+  CK(pool_alloc(eng, (void**)&m->filter_pos, pos_bytes));
+  m->filter_pos_bytes = pos_bytes;
+  CK(pool_alloc(eng, (void**)&d_flags, pos_bytes));
+  CK(pool_alloc(eng, (void**)&d_sums, sums_bytes));
+  if (host_mask) {
+    CK(pool_alloc(eng, (void**)&d_mask, (size_t)n));
+    CK(cudaMemcpyAsync(d_mask, host_mask, (size_t)n, cudaMemcpyHostToDevice, s));
+  }
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((n + kThreads - 1) / kThreads, (long long)eng->sms * 8));
+  filter_flags_kernel<<<blocks, kThreads, 0, s>>>(pg, fc, d_mask, n, d_flags);
+  scan_tile_sums_kernel<<<ntiles, kThreads, 0, s>>>(d_flags, n, d_sums);
+  scan_sums_kernel<<<1, 1024, 0, s>>>(d_sums, ntiles);
+  scan_apply_kernel<<<ntiles, kThreads, 0, s>>>(d_flags, n, d_sums, m->filter_pos, nullptr);
+  eng->launches += 4;
+  unsigned int count = 0;
+  cudaError_t e = cudaMemcpyAsync(&count, m->filter_pos + n, sizeof(count), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  pool_free(eng, d_flags, pos_bytes); pool_free(eng, d_sums, sums_bytes);
+  if (d_mask) pool_free(eng, d_mask, (size_t)n);
+  if (e != cudaSuccess) return fail(JXB_ERR_CUDA, "filter select failed: %s", cudaGetErrorString(e));
+  m->filter_type = type;
+  m->filter_count = count;
+  *count_out = count;
+  return JXB_OK;
+}
+
+extern "C" int jxb_collection_filter_gather(jxb_model* src, int type, jxb_model* dst, int dst_type) {
+  NEED(src); NEED(dst); NEED_TYPE(src, type); NEED_TYPE(dst, dst_type);
+  if (src->filter_type != type || src->filter_count < 0 || !src->filter_pos)
+    return fail(JXB_ERR_STATE, "call jxb_collection_filter_select on this collection first");
+  if (src->eng != dst->eng) return fail(JXB_ERR_INVALID, "source and destination live on different engines");
+  const RuleSpec* a = src->rules[type]; const RuleSpec* b = dst->rules[dst_type];
+  bool same = a->nf == b->nf;
+  for (int f = 0; same && f < a->nf; ++f) same = a->f[f].dtype == b->f[f].dtype && a->f[f].width == b->f[f].width;
+  if (!same) return fail(JXB_ERR_INVALID, "the destination collection has a different state layout");
+  if (dst->desc.types[dst_type].n_agents != src->filter_count)
+    return fail(JXB_ERR_INVALID, "the destination collection must hold exactly the %lld selected agents", src->filter_count);
+  jxb_engine* eng = src->eng;
+  CK(cudaSetDevice(eng->device));
+  cudaStream_t s = eng->stream;
+  const long long n = src->desc.types[type].n_agents;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((n + kThreads - 1) / kThreads, (long long)eng->sms * 8));
+  for (int f = 0; f < a->nf; ++f) {
+    int rc = materialize_field(src, type, f, s, false);
+    if (rc) return rc;
+    const int elem = a->f[f].width * (int)dtype_size(a->f[f].dtype);
+    filter_scatter_kernel<<<blocks, kThreads, 0, s>>>(src->filter_pos, n, (const unsigned char*)src->dev.t[type].f[f],
+                                                      (unsigned char*)dst->dev.t[dst_type].f[f], elem);
+    eng->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  pool_free(eng, src->filter_pos, src->filter_pos_bytes);
+  src->filter_pos = nullptr; src->filter_pos_bytes = 0; src->filter_type = -1; src->filter_count = -1;
+  dst->collections_ready[dst_type] = true;
+  if (dst->has_net) return sir_sync_from_api(dst);
+  if (dst->has_grid) dst->grid_built = false;
   return JXB_OK;
 }
 

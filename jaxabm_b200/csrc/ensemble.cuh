@@ -65,6 +65,9 @@ __global__ void __launch_bounds__(kEnsThreads) ensemble_kernel(const EnsDev ed) 
   unsigned char* base = ed.use_smem ? dsm : ed.scratch + (size_t)blockIdx.x * ed.state_bytes;
   unsigned int parity = 0;
   const unsigned int amask = program_acc_mask(ed.program);
+  // no store into a peer's shared memory before every CTA of the cluster has started executing (compute-sanitizer
+  // racecheck: "block that might not have entered yet")
+  if (cs > 1) cluster_barrier();
 
   for (int r = cid; r < ed.R; r += nclusters) {
     if (tid == 0) {

@@ -744,4 +744,13 @@ __global__ void sir_unpack_kernel(const signed char* s8, int* state, long long n
     state[i] = (int)s8[i];
 }
 
+// the same, for a snapshot taken between the launches of a step (possibly replayed from a graph): the current
+// buffer is chosen by the DEVICE-side step counter
+__global__ void sir_unpack_cur_kernel(const SirDev sv, const Ctrl* ctrl, int* state, long long n) {
+  const signed char* s8 = sv.state8[(int)(ctrl->time_step & 1)];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    state[i] = (int)s8[i];
+}
+
 }  // namespace jxb

@@ -250,6 +250,39 @@ class DeviceModel:
                                           C.byref(n), C.byref(secs)))
         return st[:n.value], m[:n.value, :len(self.metric_slots)], secs.value
 
+    # ---- record / select (include/jxb.h "record / select") -----------------------------
+    def record_fields(self, pairs: Sequence[Tuple[int, int]]) -> None:
+        """Snapshot the (collection, field) columns whenever a later run() records a history row."""
+        types = np.ascontiguousarray([p[0] for p in pairs], dtype=np.int32)
+        flds = np.ascontiguousarray([p[1] for p in pairs], dtype=np.int32)
+        nat.check(self._lib.jxb_model_record_fields(self.handle, len(pairs), nat.ptr(types) if len(pairs) else None,
+                                                    nat.ptr(flds) if len(pairs) else None))
+        self._recorded = list(pairs)
+
+    def series(self, k: int) -> np.ndarray:
+        """Snapshots of recorded column k taken by the last run(): ``[n_records, N(, w)]``."""
+        n, b = C.c_int(), C.c_size_t()
+        nat.check(self._lib.jxb_model_series_info(self.handle, k, C.byref(n), C.byref(b)))
+        t, f = self._recorded[k]
+        shape, dt = self._shape(t, f)
+        out = nat.result_empty((n.value,) + tuple(shape), dt)
+        nat.check(self._lib.jxb_model_series_download(self.handle, k, nat.ptr(out), out.nbytes))
+        return out
+
+    def filter_select(self, t: int, program=None, mask: Optional[np.ndarray] = None) -> int:
+        """Flag the agents of collection t (predicate program or host mask) -> number selected."""
+        count = C.c_int64()
+        if program is not None:
+            arr = (nat.PredIns * len(program))(*[nat.PredIns(*ins) for ins in program])
+            nat.check(self._lib.jxb_collection_filter_select(self.handle, t, arr, len(program), None, 0, C.byref(count)))
+        else:
+            m8 = np.ascontiguousarray(np.asarray(mask).astype(np.bool_).reshape(-1)).view(np.uint8)
+            nat.check(self._lib.jxb_collection_filter_select(self.handle, t, None, 0, nat.ptr(m8), m8.nbytes, C.byref(count)))
+        return int(count.value)
+
+    def filter_gather(self, t: int, dst: "DeviceModel", dst_t: int = 0) -> None:
+        nat.check(self._lib.jxb_collection_filter_gather(self.handle, t, dst.handle, dst_t))
+
     def set_profile(self, on: bool) -> None:
         nat.check(self._lib.jxb_model_set_profile(self.handle, int(on)))
 

@@ -88,6 +88,8 @@ class Model:
         self._shard_group = None      # how the ranks talk on the host (sharding.DistGroup)
         self._node_range = None       # (lo, hi) agents of this rank when a Network is split by node ranges
         self._pending_network = None  # env['network_edges'] set after initialize(), not yet binned into CSR
+        self._record_series: List[tuple] = []        # (collection, variable) columns snapshotted with the history rows
+        self.agent_series: Dict[str, Any] = {}       # 'agents.<name>.<var>' -> [n_records, N(, w)] of the last run()
         self.last_device_seconds = 0.0
 
     # ---- construction ---------------------------------------------------------------------
@@ -135,6 +137,30 @@ class Model:
         if pending is not None:
             self._set_network(pending)
 
+    def record_agent_series(self, collection: str, variables) -> None:
+        """Opt in to per-agent time series: every ``run()`` snapshots the named state columns on
+        the device whenever it records a history row (``t % collect_interval == 0``) and ``agent_series`` /
+        the facade's ``Results`` then hold ``'agents.<collection>.<variable>'`` arrays of shape
+        ``[n_records, N, ...]`` -- the keys ``jaxabm/agentpy.py:1103-1106`` means to fill.  Off by default, so the
+        reference's observable behaviour (no ``agents.*`` keys) is unchanged."""
+        if isinstance(variables, str):
+            variables = [variables]
+        for v in variables:
+            if (collection, v) not in self._record_series:
+                self._record_series.append((collection, v))
+        if self._dev is not None:
+            self._apply_record_series()
+
+    def _apply_record_series(self) -> None:
+        names = list(self._agent_collections)
+        pairs = []
+        for cname, var in self._record_series:
+            if cname not in names:
+                raise KeyError(f"record_agent_series: no agent collection {cname!r}")
+            t = names.index(cname)
+            pairs.append((t, self._dev.field_index(t, var)))
+        self._dev.record_fields(pairs)
+
     def model_state(self) -> Dict[str, Any]:                                # model.py:101-116
         state = {"time_step": self._time_step, "env": self._env_state}
         for name, c in self._agent_collections.items():
@@ -173,6 +199,8 @@ class Model:
         self._rng = keys[0]
         for i, c in enumerate(self._agent_collections.values()):
             c._attach(self._dev, i, self.config, keys[i + 1])
+        if self._record_series:
+            self._apply_record_series()
         self._is_initialized = True
         self._state = {"env": self._env_state.copy()}
 
@@ -263,6 +291,8 @@ class Model:
             if callable(host_init):
                 for fname, value in host_init(self.config).items():
                     self._dev.fill(i, self._dev.field_index(i, fname), value)
+        if self._record_series:
+            self._apply_record_series()
         self._is_initialized = True
         self._state = {"env": self._env_state.copy()}                       # model.py:142-144
 
@@ -346,6 +376,7 @@ class Model:
         rows = self._advance(int(steps_to_run), ci)
         if self.config.track_history:
             self._history.extend(rows)
+        self.agent_series = {f"agents.{c}.{v}": self._dev.series(k) for k, (c, v) in enumerate(self._record_series)}
         elapsed = max(time.time() - start, 1e-12)
         print(f"Ran {steps_to_run} steps in {elapsed:.2f}s ({steps_to_run / elapsed:.1f} steps/sec)")
         if self.config.track_history and self._history:

@@ -322,15 +322,16 @@ def test_ensemble_c5_size_every_launch_shape(mode, shape, monkeypatch):
     n, steps, R = 100_000, 200, 5
     rng = np.random.RandomState(3)
     g, a = rng.uniform(0.05, 0.2, R), rng.uniform(0.05, 0.3, R)
-    models = [growth.create_test_model(params={"growth_rate": float(g[i]), "adjustment_rate": float(a[i])},
+    models = [growth.create_test_model(params={"growth_rate": float(g[i]), "adjustment_rate": float(a[i])}, initial_value=1.0,
                                        config=jx.ModelConfig(seed=i + 1000, steps=steps, rng_mode=mode), num_agents=n)
               for i in range(R)]
     last, secs = ensemble.run_last_metrics(models, steps=steps)
     assert secs > 0
     for i in range(R):
-        om = orules.create_test_model(params={"growth_rate": float(g[i]), "adjustment_rate": float(a[i])},
+        om = orules.create_test_model(params={"growth_rate": float(g[i]), "adjustment_rate": float(a[i])}, initial_value=1.0,
                                       config=ort.ModelConfig(seed=i + 1000, steps=steps, rng_mode=mode), num_agents=n)
         orr = om.run()
+        assert float(orr["avg_value"][-1]) > 1000.0                     # (1 + g)^200: the values did evolve
         np.testing.assert_allclose(float(last["avg_value"][i]), float(orr["avg_value"][-1]), rtol=2e-6)
         assert np.float32(last["price_level"][i]) == np.float32(orr["price_level"][-1])
         assert last["price_gap"][i] == orr["price_gap"][-1]

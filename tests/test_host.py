@@ -331,3 +331,69 @@ def test_c_program_links_against_the_library(tmp_path):
     assert build.returncode == 0, build.stderr
     run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0 and "abi ok" in run.stdout, (run.returncode, run.stdout, run.stderr)
+
+
+def test_filter_condition_compiles_to_a_postfix_program():
+    """jaxabm_b200/select.py (AgentCollection.filter, jaxabm/agent.py:213-243): the traced condition as a postfix
+    program, checked by interpreting it here agent by agent against the NumPy mask of the same condition."""
+    from jaxabm_b200 import select
+    from jaxabm_b200.trace import TraceError
+    rng = np.random.RandomState(0)
+    n = 500
+    cols = {"wealth": rng.uniform(0, 20, n).astype(np.float32), "kind": rng.randint(0, 3, n).astype(np.int32),
+            "pos": rng.randint(0, 50, (n, 2)).astype(np.int32), "ok": rng.rand(n) < 0.5}
+    fields = [("wealth", np.float32, 1), ("kind", np.int32, 1), ("pos", np.int32, 2), ("ok", np.bool_, 1)]
+    names = {v: k for k, v in select.OP.items()}
+
+    def run(prog, i):
+        st = []
+        f32, i32 = np.float32, np.int32
+        for op, a, b, f in prog:
+            o = names[op]
+            if o.startswith("LOAD"):
+                col = cols[fields[a][0]]
+                st.append(col[i] if col.ndim == 1 else col[i, b])
+            elif o == "CONST_F32":
+                st.append(f32(f))
+            elif o == "CONST_I32":
+                st.append(i32(a))
+            elif o in ("NOT",):
+                st.append(not st.pop())
+            elif o in ("I2F", "B2F"):
+                st.append(f32(st.pop()))
+            elif o in ("F2I", "B2I"):
+                st.append(i32(st.pop()))
+            elif o in ("I2B", "F2B"):
+                st.append(bool(st.pop()))
+            elif o[:3] in ("NEG", "ABS"):
+                v = st.pop()
+                st.append(-v if o[:3] == "NEG" else abs(v))
+            elif o == "SELECT":
+                y, x, c = st.pop(), st.pop(), st.pop()
+                st.append(x if c else y)
+            else:
+                y, x = st.pop(), st.pop()
+                k = o.split("_")[0]
+                st.append({"ADD": lambda: x + y, "SUB": lambda: x - y, "MUL": lambda: x * y, "DIV": lambda: x / y,
+                           "MIN": lambda: min(x, y), "MAX": lambda: max(x, y), "LT": lambda: x < y, "LE": lambda: x <= y,
+                           "GT": lambda: x > y, "GE": lambda: x >= y, "EQ": lambda: x == y, "NE": lambda: x != y,
+                           "AND": lambda: bool(x) and bool(y), "OR": lambda: bool(x) or bool(y),
+                           "XOR": lambda: bool(x) != bool(y)}[k]())
+        assert len(st) == 1
+        return bool(st[0])
+
+    conds = [lambda s: s["wealth"] > 10,
+             lambda s: (s["wealth"] * 0.5 + 1 >= 4.25) & (s["kind"] == 1),
+             lambda s: (s["pos"][:, 0] + s["pos"][:, 1] < 40) | ~s["ok"],
+             lambda s: jx.numpy.where(s["ok"], s["wealth"], -s["wealth"]) > 3,
+             lambda s: (s["kind"] * 2 - 1 > 0) ^ (abs(s["wealth"] - 10) <= 2.5)]
+    for c in conds:
+        prog = select.compile_predicate(c, fields)
+        want = np.asarray(c({k: (v if k != "ok" else v) for k, v in cols.items()})) if c is not conds[3] else \
+            np.where(cols["ok"], cols["wealth"], -cols["wealth"]) > 3
+        got = np.array([run(prog, i) for i in range(n)])
+        assert np.array_equal(got, want)
+    with pytest.raises(TraceError):
+        select.compile_predicate(lambda s: np.logical_and(s["wealth"] > 1, s["ok"]), fields)     # a NumPy ufunc on symbols
+    with pytest.raises(TraceError):
+        select.compile_predicate(lambda s: s["wealth"] + 1, fields)                               # not boolean
