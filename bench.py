@@ -63,6 +63,10 @@ class SchellingWorkload:
     default_steps = 1000
     stationary = False
     kernel = "schelling_bits_kernel"
+    bound = "latency"
+    bound_note = ("NOT an HBM-bound kernel: grid barriers + integer issue in the converged phase (bit planes are "
+                  "L2-resident), dependent random 4-8 B accesses in the mover phase; `frac` on SURVEY 8(d) API bytes is "
+                  "reported per the contract, `engine_layout.frac` is the bandwidth the packed layout really needs")
     l2_note = ("no flush (one persistent launch runs all K steps); active-phase working set "
                "(agents SoA + cell_agent + U/E lists, ~350 MB) exceeds the 126 MB L2; the bit-plane "
                "grid (4 MB) is L2-resident by design")
@@ -145,6 +149,8 @@ class SchellingWorkload:
 class MarketWorkload:
     """C4-A: 45 M consumers + 5 M producers, well-mixed, env-level reductions fused in the step."""
     name = "market_45M_consumers_5M_producers"
+    bound = "hbm"
+    bound_note = "streaming SoA update"
     dtype = "f32"
     default_steps = 100
     stationary = True
@@ -208,6 +214,8 @@ class EconomyWorkload:
     """C4-B: 49 M households + 1 M consumer-goods firms (advanced_economic_model.py), per-agent threefry
     draws every step, 14 fused env reductions, Gini by histogram rank."""
     name = "economy_49M_households_1M_firms"
+    bound = "hbm"
+    bound_note = "streaming SoA update with a heavy integer side (3 threefry blocks per household)"
     dtype = "f32"
     default_steps = 50
     stationary = True
@@ -269,6 +277,8 @@ class EconomyWorkload:
 class WalkWorkload:
     """C1 scaled: 2^26 random walkers (48 B/agent-step), fused distance reductions."""
     name = "random_walk_2^26"
+    bound = "hbm"
+    bound_note = "streaming SoA update"
     dtype = "f32"
     default_steps = 50
     stationary = True
@@ -321,6 +331,8 @@ class WalkWorkload:
 class SirWorkload:
     """C3: SIR on a synthetic scale-free Network, 10 M agents / ~100 M adjacency entries."""
     name = "sir_10M_agents_100M_adjacency"
+    bound = "hbm"
+    bound_note = "CSR stream + random bitmap gathers / L2 reductions (L1tex-wavefront and L2-atomic bound around the epidemic's peak)"
     dtype = "i8/u32"
     default_steps = 100
     stationary = False
@@ -379,6 +391,8 @@ class EnsembleWorkload:
     """C5: 8,192 parameter samples x 100k agents x K steps (K = 200 in the config) of
     tests/unit/test_analysis.py's create_test_model, one ensemble launch."""
     name = "sensitivity_sweep_8192x100k"
+    bound = "smem"
+    bound_note = "replica state lives in shared memory / L2: HBM sees only the result rows; reported against the HBM figure for comparability"
     dtype = "f32"
     default_steps = 200
     stationary = True
@@ -483,16 +497,37 @@ def load_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic(workload):
-    """profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from
-    an `ncu --set full` capture, stored per step of the captured launch."""
+def load_traffic(workload, K):
+    """profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from an
+    `ncu --set full` capture, per launch.  Step-dependent workloads (one persistent launch = the whole timed
+    window) store one figure per captured window length; a window that was never captured reports null."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get(workload)
-        except Exception:
-            pass
-    return None
+    try:
+        t = json.load(open(p)).get(workload)
+    except Exception:
+        return None
+    if not t:
+        return None
+    if "by_steps" in t:
+        hit = t["by_steps"].get(str(K))
+        return None if hit is None else {"dram_bytes_per_launch": hit["dram_bytes"], "source": hit.get("source", t.get("source"))}
+    return {"dram_bytes_per_launch": t.get("dram_bytes_per_launch"), "source": t.get("source")}
+
+
+def cpu_record(wl, steps, warm=False):
+    """CPU restatement of the workload (oracle/, all host cores where the restatement is threaded) on a bounded
+    sample; None when the workload has none."""
+    from oracle import cfast
+    cfast.use_all_cores()                 # torchrun exports OMP_NUM_THREADS=1
+    try:
+        if warm:
+            wl.cpu_run(1)
+        secs, threads, what = wl.cpu_run(steps)
+    except NotImplementedError:
+        return None
+    cpu_steps = getattr(wl, "_cpu_steps", steps)
+    return {"value": wl.agents * cpu_steps / secs, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{what} ({secs:.1f} s)", "_steps": cpu_steps, "_secs": secs}
 
 
 def reference_arm(args, rank, world):
@@ -501,27 +536,169 @@ def reference_arm(args, rank, world):
     reference itself cannot run (DESIGN.md "Reference install")."""
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload](0)
+    wl = make_workload(args, 0, 1, False)
     steps = args.steps if args.steps is not None else wl.default_steps
     cpu_steps = max(1, min(steps, args.cpu_steps * 5))        # bounded sample: at most 200 full-size steps
-    try:
-        if args.warmup:
-            wl.cpu_run(1)
-        secs, threads, what = wl.cpu_run(cpu_steps)
-    except NotImplementedError:
+    cpu = cpu_record(wl, cpu_steps, warm=bool(args.warmup))
+    if cpu is None:
         print(json.dumps({"impl": "reference", "unavailable": f"no CPU restatement of the {args.workload} workload's whole-run "
                                                                "launch is wired into bench.py"}), flush=True)
         return
-    cpu_steps = getattr(wl, "_cpu_steps", cpu_steps)
-    value = wl.agents * cpu_steps / secs
+    cpu_steps, secs = cpu.pop("_steps"), cpu.pop("_secs")
+    cpu["sample"] += " (JAX is not installable here, so the reference itself cannot run)"
+    value = cpu["value"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": cpu_steps, "warmup": min(args.warmup, 1), "ms_per_step": secs / cpu_steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
-            "data": "synthetic", "config": {"workload": wl.name},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": what + " (JAX is not installable here, so the reference itself cannot run)"},
+            "data": "synthetic", "config": {"workload": wl.name}, "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def make_workload(args, rank, world, shard, name=None):
+    name = name or args.workload
+    if name == "ensemble":
+        return EnsembleWorkload(rank, world)
+    if name == "market":
+        return MarketWorkload(rank, world=world, shard=shard)
+    if name == "economy":
+        return EconomyWorkload(rank, world=world, shard=shard)
+    if name == "schelling":
+        n_ag = args.agents if args.agents is not None else (13_000_000 if args.grid == 4096 else int(args.grid * args.grid * 0.775))
+        return SchellingWorkload(rank, grid=args.grid, n=n_ag, shard=shard and world > 1)
+    if name == "sir":
+        return SirWorkload(rank, shard=shard and world > 1)
+    return WORKLOADS[name](rank)
+
+
+class Ctx:
+    """torch / torch.distributed plumbing of one bench process."""
+
+    def __init__(self, rank, world, local):
+        import torch
+        import torch.distributed as td
+        self.torch, self.td, self.rank, self.world, self.local = torch, td, rank, world, local
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.td.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure(ctx, eng, args, name, K, shard=False, want_e2e=True):
+    """One workload: W warm-up steps, exactly K device-timed steps (max over ranks), the dominant kernel's own
+    CUDA-event time, and the end-to-end figure through the public API with host buffers."""
+    rank, world = ctx.rank, ctx.world
+    wl = make_workload(args, rank, world, shard, name)
+    sharded = shard and world > 1 and name in ("market", "economy", "schelling", "sir")
+    total_agents = wl.agents * (1 if sharded else world)
+    if name == "ensemble":
+        total_agents = wl.samples_total * wl.n
+    extra = {}
+    if name == "ensemble":
+        from jaxabm_b200.device import ensemble_run
+        desc, slots, params, seeds, env0 = wl.plan(K)
+        for _ in range(args.warmup):
+            ensemble_run(desc, slots, params[:64], seeds[:64], min(K, 20), env0)
+        ctx.sync_all()
+        l0 = eng.launch_count
+        t0 = time.perf_counter()
+        vals, dev_s = ensemble_run(desc, slots, params, seeds, K, env0)     # host params in, last metrics out
+        wall = time.perf_counter() - t0
+        ctx.sync_all()
+        launches = eng.launch_count - l0
+        max_s = ctx.max_over_ranks(dev_s)
+        max_wall = ctx.max_over_ranks(wall)
+        res = None
+        ksecs, klaunches = dev_s, 1
+        extra["runs_per_sec"] = wl.samples_total / max_s
+        e2e = {"value": total_agents * K / max_wall, "unit": UNIT,
+               "h2d_bytes_per_step": (params.nbytes + seeds.nbytes) / K, "d2h_bytes_per_step": vals.nbytes / K,
+               "runs_per_sec": wl.samples_total / max_wall,
+               "what": "jxb_ensemble_run with host parameter/seed tables in, last-metric rows out (wall clock)"}
+    else:
+        # ---- warm-up (W untimed steps) then the timed region: exactly K steps, device-timed ----------
+        model = wl.fresh()
+        model.run(steps=args.warmup)
+        if not wl.stationary:
+            del model
+            model = wl.fresh()                     # the timed run starts from the seeded initial state
+        ctx.sync_all()
+        l0 = eng.launch_count
+        res = model.run(steps=K)
+        dev_s = model.last_device_seconds
+        ctx.sync_all()
+        launches = eng.launch_count - l0
+        max_s = ctx.max_over_ranks(dev_s)
+        # ---- dominant kernel: its own CUDA-event time -------------------------------------------------
+        if name == "schelling" and not sharded and model._dev.profile()[2] != "grid_shard_sweep_kernel":
+            ksecs, klaunches = dev_s, 1            # the persistent kernel IS the timed region (one launch)
+            wl.kernel = model._dev.profile()[2]
+        else:
+            if not wl.stationary:
+                del model
+                model = None
+            pm = model if wl.stationary else wl.fresh()
+            if name == "schelling":
+                wl.kernel = pm._dev.profile()[2]   # band kernels: whole-grid band on one GPU, or one band per rank
+            pm._dev.set_profile(True)              # events around every launch, no graph
+            res = pm.run(steps=K)
+            ksecs, klaunches, _ = pm._dev.profile()
+            pm._dev.set_profile(False)
+            model = pm
+        del model
+        # ---- end to end through the public API with host buffers ------------------------------------------
+        e2e = None
+        if want_e2e and not args.no_e2e and not sharded:
+            wl.e2e(min(K, 3))                      # warm-up of the same call
+            ctx.sync_all()
+            wall, h2d, d2h, what = wl.e2e(K)
+            ctx.torch.cuda.synchronize()
+            e2e = {"value": total_agents * K / ctx.max_over_ranks(wall), "unit": UNIT, "h2d_bytes_per_step": h2d / K,
+                   "d2h_bytes_per_step": d2h / K, "what": what}
+
+    peak, peak_kind = load_peak()
+    band = world if (sharded and name in ("schelling", "sir")) else 1     # a rank's launch covers its band / node range only
+    api_b = wl.api_bytes(res, K) / max(klaunches, 1) / band
+    eng_b = wl.engine_bytes(res, K) / max(klaunches, 1) / band
+    per_launch = ksecs / max(klaunches, 1)
+    traffic = load_traffic(name, K) if not sharded else None
+    roofline = {"bound": wl.bound, "bound_note": wl.bound_note, "kernel": wl.kernel,
+                "achieved": api_b / per_launch / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": api_b / per_launch / 1e9 / peak, "peak_kind": peak_kind,
+                "traffic": traffic and traffic["dram_bytes_per_launch"], "traffic_source": traffic and traffic["source"],
+                "bytes_per_launch": api_b, "us_per_launch": per_launch * 1e6, "launches_timed": int(klaunches),
+                "kernel_share_of_step": min(1.0, ksecs / dev_s) if dev_s > 0 else None,
+                "engine_layout": {"bytes_per_launch": eng_b, "achieved": eng_b / per_launch / 1e9,
+                                  "frac": eng_b / per_launch / 1e9 / peak},
+                "note": "achieved/frac use SURVEY.md 8(d) algorithmic bytes in the reference's API dtypes; "
+                        "engine_layout uses the bytes the packed HBM layout actually has to move "
+                        "(frac > 1 on the API figure means the engine moves fewer bytes than the reference layout implies)"}
+    par = "single-gpu"
+    if world > 1:
+        par = (f"one grid in {world} row bands, one per gpu (per-step records of the unsatisfied agents over NVLink peer memory)"
+               if (sharded and name == "schelling") else
+               f"one network in {world} node ranges, one per gpu (new infected-bitmap words stored into every rank's copy over NVLink peer memory)"
+               if (sharded and name == "sir") else
+               f"one population sharded over {world} gpus (per-step env partial-sum exchange over NVLink peer memory)" if sharded else
+               (f"replica blocks over {world} gpus (no data-path collective, final gather)" if name == "ensemble" else f"replica-per-gpu x{world}"))
+    rec = {"metric": METRIC, "value": total_agents * K / max_s, "unit": UNIT, "n_gpus": world, "steps": K,
+           "warmup": args.warmup, "ms_per_step": max_s / K * 1e3, "higher_is_better": True,
+           "scaling": "strong" if (name == "ensemble" or sharded) else "weak",
+           "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+           "config": {"workload": wl.name, "agents_per_gpu": wl.agents, "parallelism": par, "l2": wl.l2_note,
+                      "timed_region": ("K steps from the seeded initial state (fresh model after the warm-up model)"
+                                       if not wl.stationary else "K steps after W warm-up steps on the same model")},
+           "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches)}
+    rec.update(extra)
+    return rec, wl
 
 
 def main():
@@ -538,6 +715,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true",
+                    help="default run only: skip the other BASELINE configs (`also`, and `sharded` at N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -547,8 +726,8 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, rank, world)
 
-    import torch
-    import torch.distributed as td
+    ctx = Ctx(rank, world, local)
+    torch, td = ctx.torch, ctx.td
     torch.cuda.set_device(local)
     if world > 1:
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -560,156 +739,57 @@ def main():
     import jaxabm_b200 as jx  # noqa: F401
     from jaxabm_b200 import _native as nat
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            td.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        if world > 1:
-            td.all_reduce(t, op=td.ReduceOp.MAX)
-        return float(t.item())
-
     eng = nat.engine()
-    if args.workload == "ensemble":
-        wl = EnsembleWorkload(rank, world)
-    elif args.workload == "market":
-        wl = MarketWorkload(rank, world=world, shard=args.shard)
-    elif args.workload == "economy":
-        wl = EconomyWorkload(rank, world=world, shard=args.shard)
-    elif args.workload == "schelling":
-        n_ag = args.agents if args.agents is not None else (13_000_000 if args.grid == 4096 else int(args.grid * args.grid * 0.775))
-        wl = SchellingWorkload(rank, grid=args.grid, n=n_ag, shard=args.shard and world > 1)
-    elif args.workload == "sir":
-        wl = SirWorkload(rank, shard=args.shard and world > 1)
-    else:
-        wl = WORKLOADS[args.workload](rank)
-    sharded = args.shard and world > 1 and args.workload in ("market", "economy", "schelling", "sir")
-    K = args.steps if args.steps is not None else wl.default_steps
+    default_run = (args.workload == "schelling" and not args.shard and args.grid == 4096 and args.agents is None
+                   and not args.no_also)
+    # the clocks line covers the whole measurement (warm-ups, every timed region, the profiling passes and the
+    # end-to-end calls): a single timed region of a few milliseconds is shorter than one nvidia-smi sample
     sampler = ClockSampler(local)
-    total_agents = wl.agents * (1 if sharded else world)
-    if args.workload == "ensemble":
-        total_agents = wl.samples_total * wl.n
-    extra = {}
-
-    if args.workload == "ensemble":
-        from jaxabm_b200.device import ensemble_run
-        desc, slots, params, seeds, env0 = wl.plan(K)
-        for _ in range(args.warmup):
-            ensemble_run(desc, slots, params[:64], seeds[:64], min(K, 20), env0)
-        if rank == 0:
-            sampler.start()
-        sync_all()
-        l0 = eng.launch_count
-        t0 = time.perf_counter()
-        vals, dev_s = ensemble_run(desc, slots, params, seeds, K, env0)     # host params in, last metrics out
-        wall = time.perf_counter() - t0
-        sync_all()
-        launches = eng.launch_count - l0
-        clocks = sampler.stop() if rank == 0 else None
-        max_s = max_over_ranks(dev_s)
-        max_wall = max_over_ranks(wall)
-        res = None
-        ksecs, klaunches = dev_s, 1
-        extra["runs_per_sec"] = wl.samples_total / max_s
-        e2e = {"value": total_agents * K / max_wall, "unit": UNIT,
-               "h2d_bytes_per_step": (params.nbytes + seeds.nbytes) / K, "d2h_bytes_per_step": vals.nbytes / K,
-               "runs_per_sec": wl.samples_total / max_wall,
-               "what": "jxb_ensemble_run with host parameter/seed tables in, last-metric rows out (wall clock)"}
-    else:
-        # ---- warm-up (W untimed steps) then the timed region: exactly K steps, device-timed ----------
-        model = wl.fresh()
-        model.run(steps=args.warmup)
-        if not wl.stationary:
-            del model
-            model = wl.fresh()                     # the timed run starts from the seeded initial state
-        if rank == 0:
-            sampler.start()
-        sync_all()
-        l0 = eng.launch_count
-        res = model.run(steps=K)
-        dev_s = model.last_device_seconds
-        sync_all()
-        launches = eng.launch_count - l0
-        clocks = sampler.stop() if rank == 0 else None
-        max_s = max_over_ranks(dev_s)
-        # ---- dominant kernel: its own CUDA-event time -------------------------------------------------
-        if args.workload == "schelling" and not sharded and model._dev.profile()[2] != "grid_shard_sweep_kernel":
-            ksecs, klaunches = dev_s, 1            # the persistent kernel IS the timed region (one launch)
-            wl.kernel = model._dev.profile()[2]
-        else:
-            pm = model if wl.stationary else wl.fresh()
-            if args.workload == "schelling":
-                wl.kernel = pm._dev.profile()[2]   # band kernels: whole-grid band on one GPU, or one band per rank
-            pm._dev.set_profile(True)              # events around every launch, no graph
-            res = pm.run(steps=K)
-            ksecs, klaunches, _ = pm._dev.profile()
-            pm._dev.set_profile(False)
-            if pm is not model:
-                del pm
-        # ---- end to end through the public API with host buffers ------------------------------------------
-        e2e = None
-        if not args.no_e2e and not sharded:
-            del model
-            wl.e2e(min(K, 3))                      # warm-up of the same call
-            sync_all()
-            wall, h2d, d2h, what = wl.e2e(K)
-            torch.cuda.synchronize()
-            e2e = {"value": total_agents * K / max_over_ranks(wall), "unit": UNIT, "h2d_bytes_per_step": h2d / K,
-                   "d2h_bytes_per_step": d2h / K, "what": what}
-
-    value = total_agents * K / max_s
-    peak, peak_kind = load_peak()
-    band = world if (sharded and args.workload in ("schelling", "sir")) else 1     # a rank's launch covers its band / node range only
-    api_b = wl.api_bytes(res, K) / max(klaunches, 1) / band
-    eng_b = wl.engine_bytes(res, K) / max(klaunches, 1) / band
-    per_launch = ksecs / max(klaunches, 1)
-    traffic = load_traffic(args.workload)
-    roofline = {"bound": "hbm", "kernel": wl.kernel, "achieved": api_b / per_launch / 1e9, "peak": peak,
-                "unit": "GB/s", "frac": api_b / per_launch / 1e9 / peak, "peak_kind": peak_kind,
-                "traffic": (traffic or {}).get("dram_bytes_per_step", None) and traffic["dram_bytes_per_step"] *
-                           (K if klaunches == 1 else 1),
-                "traffic_source": (traffic or {}).get("source"),
-                "bytes_per_launch": api_b, "us_per_launch": per_launch * 1e6, "launches_timed": int(klaunches),
-                "kernel_share_of_step": min(1.0, ksecs / dev_s) if dev_s > 0 else None,
-                "engine_layout": {"bytes_per_launch": eng_b, "achieved": eng_b / per_launch / 1e9,
-                                  "frac": eng_b / per_launch / 1e9 / peak},
-                "note": "achieved/frac use SURVEY.md 8(d) algorithmic bytes in the reference's API dtypes; "
-                        "engine_layout uses the bytes the packed HBM layout actually has to move "
-                        "(frac > 1 on the API figure means the engine moves fewer bytes than the reference layout implies)"}
+    if rank == 0:
+        sampler.start()
+    K = args.steps if args.steps is not None else WORKLOADS[args.workload].default_steps
+    line, wl = measure(ctx, eng, args, args.workload, K, shard=args.shard)
+    if world == 1 and not args.no_cpu and rank == 0:
+        cpu = cpu_record(wl, args.cpu_steps)
+        if cpu:
+            cpu.pop("_steps"), cpu.pop("_secs")
+        line["cpu_baseline"] = cpu
+    del wl
+    if default_run and world == 1:
+        # every other BASELINE.json config in the same run, same K / W (the driver runs the defaults only)
+        also = []
+        for name in ("walk", "sir", "market", "economy", "ensemble"):
+            Kn = args.steps if args.steps is not None else WORKLOADS[name].default_steps
+            rec, w2 = measure(ctx, eng, args, name, Kn)
+            if not args.no_cpu:
+                cpu = cpu_record(w2, min(args.cpu_steps, 20))
+                if cpu:
+                    cpu.pop("_steps"), cpu.pop("_secs")
+                rec["cpu_baseline"] = cpu
+            del w2
+            for k in ("n_gpus", "warmup", "higher_is_better", "vs_baseline", "data"):
+                rec.pop(k, None)
+            also.append(rec)
+        line["also"] = also
+    if default_run and world > 1:
+        # the two partitionings north_star names, over the same N GPUs: ONE C2 grid in row bands (strong scaling,
+        # per-step exchange over NVLink peer memory) and the C5 sweep in replica blocks (no data-path collective)
+        shd = []
+        for name, sh in (("schelling", True), ("ensemble", False)):
+            Kn = args.steps if args.steps is not None else WORKLOADS[name].default_steps
+            rec, w2 = measure(ctx, eng, args, name, Kn, shard=sh, want_e2e=False)
+            del w2
+            for k in ("warmup", "higher_is_better", "vs_baseline", "data", "cpu_baseline", "e2e"):
+                rec.pop(k, None)
+            shd.append(rec)
+        line["sharded"] = shd
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         td.barrier()
         td.destroy_process_group()
     if rank != 0:
         return
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        try:
-            secs, threads, what = wl.cpu_run(args.cpu_steps)
-            cpu_steps = getattr(wl, "_cpu_steps", args.cpu_steps)
-            cpu = {"value": wl.agents * cpu_steps / secs, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{what} ({secs:.1f} s)"}
-        except NotImplementedError:
-            cpu = None
-    par = "single-gpu"
-    if world > 1:
-        par = (f"one grid in {world} row bands, one per gpu (per-step records of the unsatisfied agents over NVLink peer memory)"
-               if (sharded and args.workload == "schelling") else
-               f"one network in {world} node ranges, one per gpu (new infected-bitmap words stored into every rank's copy over NVLink peer memory)"
-               if (sharded and args.workload == "sir") else
-               f"one population sharded over {world} gpus (per-step env partial-sum exchange)" if sharded else
-               (f"replica blocks over {world} gpus" if args.workload == "ensemble" else f"replica-per-gpu x{world}"))
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": args.warmup, "ms_per_step": max_s / K * 1e3, "higher_is_better": True,
-            "scaling": "strong" if (args.workload in ("ensemble",) or sharded) else "weak",
-            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-            "config": {"workload": wl.name, "agents_per_gpu": wl.agents, "parallelism": par, "l2": wl.l2_note,
-                       "timed_region": ("K steps from the seeded initial state (fresh model after the warm-up model)"
-                                        if not wl.stationary else "K steps after W warm-up steps on the same model")},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    line.update(extra)
+    line["clocks"] = clocks
     print(json.dumps(line), flush=True)
 
 

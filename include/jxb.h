@@ -306,6 +306,11 @@ int jxb_prng_uniform(int rng_mode, const uint32_t key[2], int64_t n, float lo, f
 /* jax.random.randint(key, (n,), lo, hi) int32 (agentpy.py:510-512; analysis.py:441). */
 int jxb_prng_randint(int rng_mode, const uint32_t key[2], int64_t n, int32_t lo,
                      int32_t hi, int32_t* out);
+/* the keyed bijection of [0, n) that matches Schelling movers to empty-cell slots (DESIGN.md "Schelling
+ * rule": 4-round balanced Feistel with cycle walking, round keys = random_bits(coll_key, (8,))[0:4] / [4:8]);
+ * inverse != 0 evaluates the inverse permutation (the kernels walk the unsatisfied agents in cell order and
+ * ask which mover index each one is).                                                  */
+int jxb_prng_feistel(uint32_t n, const uint32_t round_keys[4], uint32_t idx, int inverse, uint32_t* out);
 /* raw block function, for known-answer tests.                                         */
 int jxb_prng_threefry2x32(const uint32_t key[2], const uint32_t ctr[2], uint32_t out[2]);
 

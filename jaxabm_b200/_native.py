@@ -111,6 +111,7 @@ SIGNATURES = {
     "jxb_prng_bits": (C.c_int, [C.c_int, _P, C.c_int64, _P]),
     "jxb_prng_uniform": (C.c_int, [C.c_int, _P, C.c_int64, C.c_float, C.c_float, _P]),
     "jxb_prng_randint": (C.c_int, [C.c_int, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "jxb_prng_feistel": (C.c_int, [C.c_uint32, _P, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]),
     "jxb_prng_threefry2x32": (C.c_int, [_P, _P, _P]),
 }
 

@@ -186,6 +186,18 @@ __device__ __forceinline__ void household_one(HouseholdIO& h, float rv, const Ec
 
 __device__ __forceinline__ unsigned int gini_bin(float x);
 
+// One agent's draw: u = uniform(split(split(coll_key, N)[i], 4)[0]) -- three dependent threefry blocks
+// (agent.py:156 then advanced_economic_model.py:159,174).
+template <int MODE>
+__device__ __forceinline__ float household_draw(Key ck, unsigned long long gi, unsigned long long gn) {
+  const Key ak = split_child<MODE>(ck, gi, gn);
+  return bits_to_uniform(bits_scalar<MODE>(split_child<MODE>(ak, 0, 4)), 0.f, 1.f);
+}
+
+// Four agents per thread per iteration: one 16-byte load / store per float column (4-byte for the bool column),
+// and four independent threefry / update chains in flight per thread -- the kernel is bound by instruction issue
+// with long dependent chains (3 x 20 threefry rounds per agent), so instruction-level parallelism is what fills
+// the issue slots that one chain per thread leaves empty.
 template <int MODE>
 __device__ __forceinline__ void rule_household(const TypeDev& t, const double* env, Key ck, int lb, float* fs,
                                                int& employed_count, unsigned int* bin_count, unsigned int& bin_lo,
@@ -200,23 +212,66 @@ __device__ __forceinline__ void rule_household(const TypeDev& t, const double* e
   float* consumption = (float*)t.f[11]; float* utility = (float*)t.f[12]; float* taxes = (float*)t.f[13];
   float* transfers = (float*)t.f[14];
   const long long stride = (long long)t.block_count * blockDim.x;
-  for (long long i = (long long)lb * blockDim.x + threadIdx.x; i < t.n; i += stride) {
+  const long long ngroups = t.n / 4;
+  const unsigned long long gn = (unsigned long long)t.gn;
+  for (long long g = (long long)lb * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const float4 f_inc = ld_stream((const float4*)income + g), f_dep = ld_stream((const float4*)deposits + g);
+    const float4 f_cash = ld_stream((const float4*)cash + g), f_ptc = ld_stream((const float4*)ptc + g);
+    const float4 f_pts = ld_stream((const float4*)pts + g), f_risk = ld_stream((const float4*)risk + g);
+    const float4 f_prod = ld_stream((const float4*)productivity + g);
+    const uchar4 f_emp = __ldcs((const uchar4*)employed + g);
+    HouseholdIO h[4];
+    h[0].income = f_inc.x; h[1].income = f_inc.y; h[2].income = f_inc.z; h[3].income = f_inc.w;
+    h[0].deposits = f_dep.x; h[1].deposits = f_dep.y; h[2].deposits = f_dep.z; h[3].deposits = f_dep.w;
+    h[0].cash = f_cash.x; h[1].cash = f_cash.y; h[2].cash = f_cash.z; h[3].cash = f_cash.w;
+    h[0].ptc = f_ptc.x; h[1].ptc = f_ptc.y; h[2].ptc = f_ptc.z; h[3].ptc = f_ptc.w;
+    h[0].pts = f_pts.x; h[1].pts = f_pts.y; h[2].pts = f_pts.z; h[3].pts = f_pts.w;
+    h[0].risk = f_risk.x; h[1].risk = f_risk.y; h[2].risk = f_risk.z; h[3].risk = f_risk.w;
+    h[0].productivity = f_prod.x; h[1].productivity = f_prod.y; h[2].productivity = f_prod.z; h[3].productivity = f_prod.w;
+    h[0].employed = f_emp.x != 0; h[1].employed = f_emp.y != 0; h[2].employed = f_emp.z != 0; h[3].employed = f_emp.w != 0;
+    float rv[4];
+    const unsigned long long gi0 = (unsigned long long)(t.goff + 4 * g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rv[j] = household_draw<MODE>(ck, gi0 + j, gn);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) household_one(h[j], rv[j], v, init_inc, two_init_inc);
+    st_stream((float4*)savings + g, make_float4(h[0].savings, h[1].savings, h[2].savings, h[3].savings));
+    st_stream((float4*)income + g, make_float4(h[0].income, h[1].income, h[2].income, h[3].income));
+    st_stream((float4*)deposits + g, make_float4(h[0].deposits, h[1].deposits, h[2].deposits, h[3].deposits));
+    st_stream((float4*)cash + g, make_float4(h[0].cash, h[1].cash, h[2].cash, h[3].cash));
+    __stcs((uchar4*)employed + g, make_uchar4(h[0].employed ? 1 : 0, h[1].employed ? 1 : 0, h[2].employed ? 1 : 0, h[3].employed ? 1 : 0));
+    st_stream((float4*)labor_supply + g, make_float4(h[0].labor_supply, h[1].labor_supply, h[2].labor_supply, h[3].labor_supply));
+    st_stream((float4*)consumption + g, make_float4(h[0].consumption, h[1].consumption, h[2].consumption, h[3].consumption));
+    st_stream((float4*)utility + g, make_float4(h[0].utility, h[1].utility, h[2].utility, h[3].utility));
+    st_stream((float4*)taxes + g, make_float4(h[0].taxes, h[1].taxes, h[2].taxes, h[3].taxes));
+    st_stream((float4*)transfers + g, make_float4(h[0].transfers, h[1].transfers, h[2].transfers, h[3].transfers));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      fs[0] += h[j].labor_supply; fs[1] += h[j].consumption; fs[2] += h[j].savings; fs[3] += h[j].deposits;
+      fs[4] += h[j].income; fs[5] += h[j].utility;
+      employed_count += h[j].employed ? 1 : 0;
+      // Gini histogram of the NEW incomes (metrics are computed on the post-update state): fire-and-forget L2
+      // reductions whose latency hides behind the streaming loads
+      const unsigned int bin = gini_bin(h[j].income);
+      bin_lo = min(bin_lo, bin); bin_hi = max(bin_hi, bin);
+      atomicAdd(bin_count + bin, 1u);
+    }
+  }
+  // the last t.n % 4 agents
+  for (long long i = ngroups * 4 + threadIdx.x; lb == 0 && i < t.n; i += blockDim.x) {
     HouseholdIO h;
-    h.income = __ldcs(income + i); h.deposits = __ldcs(deposits + i); h.cash = __ldcs(cash + i);
-    h.ptc = __ldcs(ptc + i); h.pts = __ldcs(pts + i); h.risk = __ldcs(risk + i);
-    h.productivity = __ldcs(productivity + i); h.employed = __ldcs(employed + i) != 0;
-    const Key ak = split_child<MODE>(ck, (unsigned long long)(t.goff + i), (unsigned long long)t.gn);
-    const float rv = bits_to_uniform(bits_scalar<MODE>(split_child<MODE>(ak, 0, 4)), 0.f, 1.f);
+    h.income = income[i]; h.deposits = deposits[i]; h.cash = cash[i];
+    h.ptc = ptc[i]; h.pts = pts[i]; h.risk = risk[i];
+    h.productivity = productivity[i]; h.employed = employed[i] != 0;
+    const float rv = household_draw<MODE>(ck, (unsigned long long)(t.goff + i), gn);
     household_one(h, rv, v, init_inc, two_init_inc);
-    __stcs(savings + i, h.savings); __stcs(income + i, h.income); __stcs(deposits + i, h.deposits);
-    __stcs(cash + i, h.cash); __stcs(employed + i, (unsigned char)(h.employed ? 1 : 0));
-    __stcs(labor_supply + i, h.labor_supply); __stcs(consumption + i, h.consumption);
-    __stcs(utility + i, h.utility); __stcs(taxes + i, h.taxes); __stcs(transfers + i, h.transfers);
+    savings[i] = h.savings; income[i] = h.income; deposits[i] = h.deposits;
+    cash[i] = h.cash; employed[i] = (unsigned char)(h.employed ? 1 : 0);
+    labor_supply[i] = h.labor_supply; consumption[i] = h.consumption;
+    utility[i] = h.utility; taxes[i] = h.taxes; transfers[i] = h.transfers;
     fs[0] += h.labor_supply; fs[1] += h.consumption; fs[2] += h.savings; fs[3] += h.deposits;
     fs[4] += h.income; fs[5] += h.utility;
     employed_count += h.employed ? 1 : 0;
-    // Gini histogram of the NEW incomes (metrics are computed on the post-update state): a
-    // fire-and-forget L2 reduction whose latency hides behind the streaming loads
     const unsigned int bin = gini_bin(h.income);
     bin_lo = min(bin_lo, bin); bin_hi = max(bin_hi, bin);
     atomicAdd(bin_count + bin, 1u);

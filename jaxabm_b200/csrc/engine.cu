@@ -223,6 +223,9 @@ struct jxb_model {
   bool grid_built = false; bool sat_dirty = false; long long n_empty_cells = 0; int sch_blocks = 0;
   // bit-sliced variant (row length a multiple of 1024): the planes are the live grid during a run
   bool sch_bits = false; SchellingBitsDev sb{}; bool ct_stale = false;
+  // persistent bit-sliced kernel: the agent id and its move count travel with the cell (sb.cell_am); the
+  // 'position' / 'moves' columns are derived from it when they are read (pos_stale = they are behind)
+  bool sch_packed = false; bool pos_stale = false;
   // row-band decomposition over the GPUs of a box (csrc/grid_shard.cuh): receive area + peers' areas
   bool grid_sharded = false; bool gs_attached = false; GridShardDev gs{}; unsigned char* gs_area = nullptr;
   size_t gs_area_bytes = 0; void* gs_opened[kMaxPeers] = {}; int gs_move_blocks = 0;
@@ -694,6 +697,10 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
       sb.occ = p0 + sb.wpr;
       sb.t1 = p1 + sb.wpr;
       TRY(dev_alloc(m, &sb.umask, (size_t)(sd.cells >> 5) + 32));
+      if (!m->grid_sharded) {
+        TRY(dev_alloc(m, &sb.cell_am, (size_t)sd.cells));
+        m->sch_packed = true;
+      }
     }
     {
       BlkPart* bp = nullptr;
@@ -836,6 +843,7 @@ static size_t field_bytes(jxb_model* m, int type, int field) {
 
 static int sir_sync_from_api(jxb_model* m);
 static int sir_sync_to_api(jxb_model* m);
+static int materialize_field(jxb_model* m, int type, int field, cudaStream_t s, bool in_step);
 static int schelling_export_satisfied(jxb_model* m, cudaStream_t s, bool clear_dirty);
 
 static int check_field(jxb_model* m, int type, int field, size_t bytes) {
@@ -851,10 +859,16 @@ extern "C" int jxb_model_upload(jxb_model* m, int type, int field, const void* h
   int rc = check_field(m, type, field, bytes);
   if (rc) return rc;
   CK(cudaSetDevice(m->eng->device));
+  if (m->sch_packed && m->pos_stale && m->grid_built) {
+    // the next rebuild packs 'position' AND 'moves' from the API columns: both must be current before one of them
+    // (or 'type') is overwritten
+    rc = materialize_field(m, 0, 1, m->eng->stream, false);
+    if (rc) return rc;
+  }
   CK(cudaMemcpyAsync(m->dev.t[type].f[field], host, bytes, cudaMemcpyHostToDevice, m->eng->stream));
   CK(cudaStreamSynchronize(m->eng->stream));
   if (m->has_net) return sir_sync_from_api(m);
-  if (m->has_grid && (field == 0 || field == 1 || (field == 3 && m->grid_sharded))) m->grid_built = false;
+  if (m->has_grid && (field == 0 || field == 1 || (field == 3 && (m->grid_sharded || m->sch_packed)))) m->grid_built = false;
   if (m->has_grid && field == 2) m->sat_dirty = false;
   return JXB_OK;
 }
@@ -872,6 +886,12 @@ static int materialize_field(jxb_model* m, int type, int field, cudaStream_t s, 
       int rc = sir_sync_to_api(m);
       if (rc) return rc;
     }
+  }
+  if (m->sch_packed && (field == 1 || field == 3) && m->grid_built && (in_step || m->pos_stale)) {
+    cell_am_unpack_kernel<<<m->eng->sms * 8, 256, 0, s>>>(m->sd, m->sb, (int2*)m->dev.t[0].f[1], (int*)m->dev.t[0].f[3]);
+    m->eng->launches++;
+    CK(cudaGetLastError());
+    if (!in_step) m->pos_stale = false;
   }
   if (m->has_grid && field == 2 && (in_step || m->sat_dirty)) { int rc = schelling_export_satisfied(m, s, !in_step); if (rc) return rc; }
   if (m->grid_sharded && field == 1 && m->grid_built) {
@@ -907,6 +927,10 @@ extern "C" int jxb_model_fill(jxb_model* m, int type, int field, const void* val
   CK(cudaSetDevice(m->eng->device));
   uint4 v = {0, 0, 0, 0};
   memcpy(&v, value, bytes);
+  if (m->sch_packed && m->pos_stale && m->grid_built) {
+    int rc = materialize_field(m, 0, 1, m->eng->stream, false);
+    if (rc) return rc;
+  }
   const long long n = m->desc.types[type].n_agents;
   int blocks = (int)std::min<long long>((n * (long long)bytes + 255) / 256, m->eng->sms * 8);
   fill_kernel<<<blocks, 256, 0, m->eng->stream>>>((unsigned char*)m->dev.t[type].f[field], n, (int)bytes, v);
@@ -914,7 +938,7 @@ extern "C" int jxb_model_fill(jxb_model* m, int type, int field, const void* val
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(m->eng->stream));
   if (m->has_net) return sir_sync_from_api(m);
-  if (m->has_grid && (field == 0 || field == 1)) m->grid_built = false;
+  if (m->has_grid && (field == 0 || field == 1 || (field == 3 && (m->grid_sharded || m->sch_packed)))) m->grid_built = false;
   return JXB_OK;
 }
 
@@ -989,6 +1013,12 @@ extern "C" int jxb_model_grid_rebuild(jxb_model* m) {
     m->eng->launches++;
     CK(cudaGetLastError());
     m->ct_stale = false;
+  }
+  if (m->sch_packed) {
+    cell_am_pack_kernel<<<blocks, 256, 0, s>>>(m->sd, m->sb, (const int*)m->dev.t[0].f[3]);
+    m->eng->launches++;
+    CK(cudaGetLastError());
+    m->pos_stale = false;
   }
   if (m->grid_sharded) {
     grid_shard_own_moves_kernel<<<blocks, 256, 0, s>>>(m->gs, (const int2*)m->dev.t[0].f[1], (int*)m->dev.t[0].f[3],
@@ -1113,6 +1143,7 @@ static int schelling_export_satisfied(jxb_model* m, cudaStream_t s, bool clear_d
   unsigned char* sat = (unsigned char*)m->dev.t[0].f[2];
   CK(cudaMemsetAsync(sat, 1, (size_t)m->desc.types[0].n_agents, s));
   if (m->grid_sharded) grid_shard_export_satisfied_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->gs, sat);   // host: min over ranks
+  else if (m->sch_packed) satisfied_export_packed_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->sd, m->sb, m->dev.ctrl, sat);
   else satisfied_export_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->sd, m->dev.ctrl, sat);
   m->eng->launches++;
   CK(cudaGetLastError());
@@ -1331,6 +1362,9 @@ static int sir_sync_from_api(jxb_model* m) {
   const long long n = m->desc.types[0].n_agents;
   const int cur = (int)(m->time_step & 1);
   const int blocks = (int)((n + 255) / 256);
+  // the push counters of rows that are not susceptible are never read or re-zeroed (sir_transition_kernel); a
+  // state upload may make such a row susceptible again
+  CK(cudaMemsetAsync(m->sv.k32, 0, ((size_t)n + 32) * 4, m->eng->stream));
   sir_pack_kernel<<<blocks, 256, 0, m->eng->stream>>>((const int*)m->dev.t[0].f[0], m->sv.state8[cur],
                                                       m->sv.infbits[cur] + (m->net_sharded ? m->sv.gw0 : 0u), n);
   m->eng->launches++;
@@ -1415,7 +1449,9 @@ static int plan_step_blocks(jxb_model* m) {
       else
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, economy_step_kernel<1, JXB_RULE_CONSUMER_FIRM>, kThreads, 0));
       if (occ < 1) occ = 1;
-      const long long need = std::max<long long>(1, (md.t[i].n + kThreads - 1) / kThreads);
+      // households: four agents per thread per iteration
+      const long long per_thread = md.t[i].rule == JXB_RULE_HOUSEHOLD ? 4 : 1;
+      const long long need = std::max<long long>(1, (md.t[i].n / per_thread + kThreads - 1) / kThreads);
       const int nb = (int)std::min<long long>(need, (long long)m->eng->sms * occ);
       md.t[i].block_begin = begin;
       md.t[i].block_count = nb;
@@ -1476,6 +1512,10 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
         if (!m->ns_attached) return fail(JXB_ERR_STATE, "sharded Network step without attached peers");
         const int pgrid = m->eng->sms * 8;
         if (timed) cudaEventRecord(e0, s);
+        if (m->sv.n_heavy > 0) {
+          sir_pull_heavy_kernel<true><<<std::min(m->sv.n_heavy, pgrid), kThreads, 0, s>>>(m->sv, m->dev);
+          eng->launches += 1;
+        }
         if (part) sir_pull_s_kernel<1, true><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
         else sir_pull_s_kernel<0, true><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
         if (timed) cudaEventRecord(e1, s);
@@ -1500,6 +1540,10 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
           eng->launches += 1;
         }
         if (m->sir_mode != 1) {          // pull direction
+          if (m->sv.n_heavy > 0) {
+            sir_pull_heavy_kernel<false><<<std::min(m->sv.n_heavy, pgrid), kThreads, 0, s>>>(m->sv, m->dev);
+            eng->launches += 1;
+          }
           if (part) sir_pull_s_kernel<1><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
           else sir_pull_s_kernel<0><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
           if (m->sir_mode == 3) eng->launches += 1;
@@ -1616,6 +1660,7 @@ static int launch_schelling(jxb_model* m, int steps, cudaStream_t s) {
     const void* fn = part ? (const void*)schelling_bits_kernel<1> : (const void*)schelling_bits_kernel<0>;
     CK(cudaLaunchCooperativeKernel(fn, dim3(m->sch_blocks), dim3(kThreads), args, 0, s));
     m->ct_stale = true;
+    m->pos_stale = true;
     m->eng->launches += 1;
     return JXB_OK;
   }
@@ -1640,8 +1685,9 @@ static int launches_per_step_all(jxb_model* m) {
 }
 static int launches_per_step(jxb_model* m) {
   if (m->grid_sharded) return 4;
-  if (m->net_sharded) return 2;
-  if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 : (m->sir_mode == 1 ? 2 : 1);
+  const int hv = (m->has_net && m->sv.n_heavy > 0) ? 1 : 0;       // sir_pull_heavy_kernel
+  if (m->net_sharded) return 2 + hv;
+  if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 + hv : (m->sir_mode == 1 ? 2 : (m->sir_mode == 2 ? 1 + hv : 1));
   if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? (m->dev.world_size > 1 ? 6 : 5) : 1);
   return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
 }
@@ -2256,6 +2302,13 @@ extern "C" int jxb_prng_uniform(int mode, const uint32_t key[2], int64_t n, floa
   if (!mode_ok(mode) || n < 0 || !out) return fail(JXB_ERR_INVALID, "bad uniform arguments");
   for (int64_t j = 0; j < n; ++j)
     out[j] = bits_to_uniform(host_bits(mode, Key{key[0], key[1]}, (uint64_t)j, (uint64_t)n), lo, hi);
+  return JXB_OK;
+}
+
+extern "C" int jxb_prng_feistel(uint32_t n, const uint32_t rk[4], uint32_t idx, int inverse, uint32_t* out) {
+  if (!rk || !out || (n > 1 && idx >= n)) return fail(JXB_ERR_INVALID, "bad feistel arguments");
+  const Feistel f = make_feistel(n, rk);
+  *out = inverse ? feistel_inverse(f, idx) : feistel_permute(f, idx);
   return JXB_OK;
 }
 

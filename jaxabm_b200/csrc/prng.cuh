@@ -166,6 +166,23 @@ JXB_HD Feistel make_feistel(uint32_t n, const uint32_t* rk) {
   return f;
 }
 
+// the inverse bijection: rounds undone in reverse order, cycle-walking through the same out-of-range values
+JXB_HD uint32_t feistel_inverse(const Feistel& f, uint32_t idx) {
+  if (f.n <= 1) return idx;
+  uint32_t v = idx;
+  do {
+    uint32_t l = v >> f.half, r = v & f.mask;
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+      uint32_t t = r ^ (mix32(l ^ f.rk[i]) & f.mask);
+      r = l;
+      l = t;
+    }
+    v = (l << f.half) | r;
+  } while (v >= f.n);
+  return v;
+}
+
 JXB_HD uint32_t feistel_permute(const Feistel& f, uint32_t idx) {
   if (f.n <= 1) return idx;
   uint32_t v = idx;

@@ -32,6 +32,8 @@ struct SchellingBitsDev {
   unsigned int* occ;           // word 0 of row 0 (a halo row of wpr words before and after)
   unsigned int* t1;
   unsigned int* umask;         // [cells / 32] unsatisfied agents of the step
+  int2* cell_am;               // persistent kernel only: per cell (agent id or -1, that agent's moves) -- the payload that
+                               // travels with a mover; 'position' / 'moves' columns are derived from it on demand
   int wpr;                     // words per row (H / 32)
   int spr;                     // 1024-cell strips per row (wpr / 32): 1, 2, 4 or 8
   unsigned int need_sel[9][4]; // need_sel[o][b] = all-ones iff bit b of need[o] is set (o = 1..8)
@@ -178,6 +180,8 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
   __shared__ unsigned int s_all[kThreads / 32];
   __shared__ unsigned int s_rk[8];
   __shared__ unsigned int s_prefix, s_total;
+  __shared__ unsigned int s_list[kThreads * 32];     // unsatisfied cells of one chunk of kThreads mask words, compacted
+  __shared__ unsigned int s_pre[8][kThreads];        // prefetched mask words of the next chunks
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -322,19 +326,48 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
     }
     const unsigned int u = s_total;
     const unsigned int m = u < e ? u : e;
+    // ---------------------------------------------------------- phase 3: moves, in cell order, CTA-local
+    // The unsatisfied agents of THIS CTA's rows are U[s_prefix .. s_prefix + my count) in ascending cell order.
+    // Every CTA walks its own segment: index j is mover k = piU^-1(j) (if k < m) and goes to slot piE(k) -- the
+    // same matching as "mover k is U[piU(k)]", evaluated from the source side, so that the source-side accesses
+    // (mask words, the cell payload, the plane words) stream through the CTA's own rows and only the target side
+    // (slot, target cell payload, target plane bits) is random.  Targets are cells that were empty when the step
+    // began, sources are occupied ones, and every slot belongs to exactly one mover: CTAs need no barrier between
+    // the compaction and the moves.  U[j] receives (agent | 1<<31) for a mover and the cell id for an agent that
+    // stays -- what the lazy 'satisfied' column needs.
     if (u > 0) {                   // uniform across the grid
+      const Feistel fu = make_feistel(u, s_rk), fe = make_feistel(e, s_rk + 4);
       unsigned int base = s_prefix;
-      for (long long w0 = wbeg; w0 < wend; w0 += kThreads) {
+      // the mask words of up to kPre chunks are fetched together (one L2 round trip instead of one per chunk), and a
+      // chunk without an unsatisfied agent costs a single barrier: once the grid has converged almost every chunk
+      // of almost every CTA is empty
+      constexpr int kPre = 8;
+      for (long long W0 = wbeg; W0 < wend; W0 += (long long)kPre * kThreads) {
+      {
+        unsigned int pre[kPre];
+#pragma unroll
+        for (int c = 0; c < kPre; ++c) {
+          const long long w = W0 + (long long)c * kThreads + tid;
+          pre[c] = w < wend ? __ldcg(sb.umask + w) : 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < kPre; ++c) s_pre[c][tid] = pre[c];      // read back by the same thread only
+      }
+#pragma unroll 1
+      for (int c = 0; c < kPre; ++c) {
+        const long long w0 = W0 + (long long)c * kThreads;
+        if (w0 >= wend) break;
         const long long w = w0 + tid;
-        unsigned int unsat = w < wend ? __ldcg(sb.umask + w) : 0u;
+        unsigned int unsat = s_pre[c][tid];
         const unsigned int cnt = __popc(unsat);
+        // also the barrier after which s_list / s_u32 of the previous chunk are no longer read
+        if (__syncthreads_count(cnt != 0u) == 0) continue;
         unsigned int inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
           if (lane >= o) inc += v;
         }
-        __syncthreads();
         if (lane == 31) s_u32[warp] = inc;
         __syncthreads();
         unsigned int woff = 0, ttot = 0;
@@ -343,77 +376,106 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
           if (ww < warp) woff += s_u32[ww];
           ttot += s_u32[ww];
         }
-        unsigned int pu = base + woff + inc - cnt;
-        const unsigned int c0 = (unsigned int)(w << 5);
-        while (unsat) {
-          const int q = __ffs(unsat) - 1;
-          unsat &= unsat - 1;
-          sd.U[pu++] = c0 + q;
+        {
+          unsigned int pu = woff + inc - cnt;
+          const unsigned int c0 = (unsigned int)(w << 5);
+          while (unsat) {
+            const int q = __ffs(unsat) - 1;
+            unsat &= unsat - 1;
+            s_list[pu++] = c0 + q;
+          }
+        }
+        __syncthreads();
+        // four list entries per thread per iteration: the chain payload / slot -> writes is latency-bound
+        constexpr int kMv = 4;
+        for (unsigned int i0 = tid; i0 < ttot; i0 += kThreads * kMv) {
+          unsigned int src[kMv], jj[kMv], dst[kMv], tw[kMv];
+          int2 am[kMv];
+          bool ok[kMv], mv[kMv];
+#pragma unroll
+          for (int i = 0; i < kMv; ++i) {
+            const unsigned int idx = i0 + i * kThreads;
+            ok[i] = idx < ttot;
+            mv[i] = false; src[i] = 0; jj[i] = 0;
+            if (ok[i]) {
+              src[i] = s_list[idx];
+              const unsigned int k = feistel_inverse(fu, base + idx);
+              mv[i] = k < m;
+              if (mv[i]) jj[i] = feistel_permute(fe, k);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kMv; ++i) {
+            dst[i] = 0; tw[i] = 0; am[i] = make_int2(-1, 0);
+            if (mv[i]) {
+              dst[i] = __ldcg(sd.E + jj[i]);
+              am[i] = __ldcg(sb.cell_am + src[i]);
+              tw[i] = __ldcg(sb.t1 + (src[i] >> 5));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kMv; ++i) {
+            if (!ok[i]) continue;
+            const unsigned int j = base + i0 + i * kThreads;
+            if (!mv[i]) { sd.U[j] = src[i]; continue; }
+            const unsigned int s_ = src[i], d_ = dst[i];
+            const unsigned int sbit = 1u << (s_ & 31), dbit = 1u << (d_ & 31);
+            const bool ty = (tw[i] & sbit) != 0;
+            sd.E[jj[i]] = s_;
+            sd.U[j] = (unsigned int)am[i].x | 0x80000000u;
+            atomicAnd(sb.occ + (s_ >> 5), ~sbit);
+            atomicOr(sb.occ + (d_ >> 5), dbit);
+            if (ty) {
+              atomicAnd(sb.t1 + (s_ >> 5), ~sbit);
+              atomicOr(sb.t1 + (d_ >> 5), dbit);
+            }
+            sb.cell_am[d_] = make_int2(am[i].x, am[i].y + 1);
+            sb.cell_am[s_] = make_int2(-1, 0);
+            if (sd.periodic) {         // keep the wrapped halo rows in step
+              if (d_ < (unsigned)H) { atomicOr(sb.occ + (d_ >> 5) + words, dbit); if (ty) atomicOr(sb.t1 + (d_ >> 5) + words, dbit); }
+              if (d_ >= sd.cells - H) { atomicOr(sb.occ + (long long)(d_ >> 5) - words, dbit); if (ty) atomicOr(sb.t1 + (long long)(d_ >> 5) - words, dbit); }
+              if (s_ < (unsigned)H) { atomicAnd(sb.occ + (s_ >> 5) + words, ~sbit); if (ty) atomicAnd(sb.t1 + (s_ >> 5) + words, ~sbit); }
+              if (s_ >= sd.cells - H) { atomicAnd(sb.occ + (long long)(s_ >> 5) - words, ~sbit); if (ty) atomicAnd(sb.t1 + (long long)(s_ >> 5) - words, ~sbit); }
+            }
+          }
         }
         base += ttot;
       }
-    }
-    if (m == 0) continue;          // uniform: nobody moves, the grid is unchanged
-    grid.sync();
-
-    // ------------------------------------------------------------------ phase 3: moves
-    {
-      const Feistel fu = make_feistel(u, s_rk), fe = make_feistel(e, s_rk + 4);
-      // four movers per thread per iteration: the dependent chain U -> cell_agent / t1 -> writes is
-      // latency-bound random access, so independent chains are issued together
-      constexpr int kMv = 4;
-      const unsigned int stride = (unsigned int)B * kThreads;
-      for (unsigned int k0 = (unsigned int)b * kThreads + tid; k0 < m; k0 += stride * kMv) {
-        unsigned int src[kMv], jj[kMv], dst[kMv];
-        int ag[kMv];
-        unsigned int tw[kMv];
-        bool ok[kMv];
-#pragma unroll
-        for (int i = 0; i < kMv; ++i) {
-          const unsigned int k = k0 + i * stride;
-          ok[i] = k < m;
-          src[i] = 0; jj[i] = 0;
-          if (ok[i]) { src[i] = __ldcg(sd.U + feistel_permute(fu, k)); jj[i] = feistel_permute(fe, k); }
-        }
-#pragma unroll
-        for (int i = 0; i < kMv; ++i) {
-          dst[i] = 0; ag[i] = 0; tw[i] = 0;
-          if (ok[i]) {
-            dst[i] = __ldcg(sd.E + jj[i]);
-            ag[i] = __ldcg(sd.cell_agent + src[i]);
-            tw[i] = __ldcg(sb.t1 + (src[i] >> 5));
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < kMv; ++i) {
-          if (!ok[i]) continue;
-          const unsigned int k = k0 + i * stride;
-          const unsigned int s_ = src[i], d_ = dst[i];
-          const int a = ag[i];
-          const unsigned int sbit = 1u << (s_ & 31), dbit = 1u << (d_ & 31);
-          const bool ty = (tw[i] & sbit) != 0;
-          sd.E[jj[i]] = s_;
-          sd.MA[k] = a;
-          atomicAnd(sb.occ + (s_ >> 5), ~sbit);
-          atomicOr(sb.occ + (d_ >> 5), dbit);
-          if (ty) {
-            atomicAnd(sb.t1 + (s_ >> 5), ~sbit);
-            atomicOr(sb.t1 + (d_ >> 5), dbit);
-          }
-          sd.cell_agent[d_] = a;
-          sd.cell_agent[s_] = -1;
-          if (sd.periodic) {         // keep the wrapped halo rows in step
-            if (d_ < (unsigned)H) { atomicOr(sb.occ + (d_ >> 5) + words, dbit); if (ty) atomicOr(sb.t1 + (d_ >> 5) + words, dbit); }
-            if (d_ >= sd.cells - H) { atomicOr(sb.occ + (long long)(d_ >> 5) - words, dbit); if (ty) atomicOr(sb.t1 + (long long)(d_ >> 5) - words, dbit); }
-            if (s_ < (unsigned)H) { atomicAnd(sb.occ + (s_ >> 5) + words, ~sbit); if (ty) atomicAnd(sb.t1 + (s_ >> 5) + words, ~sbit); }
-            if (s_ >= sd.cells - H) { atomicAnd(sb.occ + (long long)(s_ >> 5) - words, ~sbit); if (ty) atomicAnd(sb.t1 + (long long)(s_ >> 5) - words, ~sbit); }
-          }
-          ((int2*)t.f[1])[a] = make_int2((int)(d_ / sd.H), (int)(d_ % sd.H));
-          atomicAdd((int*)t.f[3] + a, 1);   // fire-and-forget L2 reduction: no load to wait for (ncu: 37 % of the mover stalls)
-        }
       }
     }
+    if (m == 0) continue;          // uniform: nobody moved, the planes are unchanged -- no barrier needed
     grid.sync();
+  }
+}
+
+// cell payload <-> the per-agent API columns (persistent kernel): pack after the grid was (re)built from the
+// uploaded positions, unpack when 'position' / 'moves' are read
+__global__ void cell_am_pack_kernel(const SchellingDev sd, const SchellingBitsDev sb, const int* moves) {
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < sd.cells; c += (long long)gridDim.x * blockDim.x) {
+    const int a = sd.cell_agent[c];
+    sb.cell_am[c] = make_int2(a, a >= 0 ? moves[a] : 0);
+  }
+}
+
+__global__ void cell_am_unpack_kernel(const SchellingDev sd, const SchellingBitsDev sb, int2* position, int* moves) {
+  const int H = sd.H;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < sd.cells; c += (long long)gridDim.x * blockDim.x) {
+    const int2 am = __ldcs(sb.cell_am + c);
+    if (am.x >= 0) {
+      position[am.x] = make_int2((int)(c / H), (int)(c % H));
+      moves[am.x] = am.y;
+    }
+  }
+}
+
+// 'satisfied' of the last step from the per-step list the persistent kernel leaves in U: (agent | 1<<31) for an
+// agent that moved, the cell of an unsatisfied agent that stayed
+__global__ void satisfied_export_packed_kernel(const SchellingDev sd, const SchellingBitsDev sb, const Ctrl* ctrl, unsigned char* sat) {
+  const unsigned int u = ctrl->n_unsat;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < u; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned int v = sd.U[i];
+    const int a = (v >> 31) ? (int)(v & 0x7FFFFFFFu) : sb.cell_am[v].x;
+    if (a >= 0) sat[a] = 0;
   }
 }
 

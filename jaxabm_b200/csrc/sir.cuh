@@ -336,21 +336,29 @@ __global__ void __launch_bounds__(kThreads) sir_push_kernel(const SirDev sv, con
   // all other rows: one warp per 32-row group, lanes striding each infected row.  (Laying the
   // infected rows' ranges end to end with a warp scan + per-entry owner search measured ~15 %
   // slower: the kernel is bound by L2 reduction throughput, not by per-row latency.)
+  // A warp scans 32 bitmap words (1024 rows) per iteration -- every lane its own word, one coalesced 128 B load --
+  // and then visits the groups that hold an infected row.  (One word per warp-iteration made the scan a chain of
+  // ~33 dependent L2 round trips per warp: 23 us per step even when almost nobody is infected.)
   const long long ngroups = (n + 31) >> 5;
-  const long long wstride = (long long)gridDim.x * (kThreads / 32);
-  for (long long g = (long long)blockIdx.x * (kThreads / 32) + (tid >> 5); g < ngroups; g += wstride) {
-    unsigned int word = __ldg(inf + g);
-    if (!word) continue;
-    const long long rbase = g << 5;
-    const unsigned int my_lo = (rbase + lane <= n) ? sv.row_ptr[rbase + lane] : 0u;
-    const unsigned int last = (rbase + 32 <= n) ? sv.row_ptr[rbase + 32] : sv.row_ptr[n];
-    while (word) {
-      const int b = __ffs(word) - 1;
-      word &= word - 1;
-      const unsigned int lo = __shfl_sync(0xffffffffu, my_lo, b);
-      const unsigned int hi = b == 31 ? last : __shfl_sync(0xffffffffu, my_lo, (b + 1) & 31);
-      if (hi - lo > (unsigned)kSirHeavy) continue;             // done by the heavy-row pass
-      for (unsigned int e = lo + lane; e < hi; e += 32) red_add_u32(sv.k32 + __ldcs(sv.col + e), 1u);
+  const long long wstride = (long long)gridDim.x * (kThreads / 32) * 32;
+  for (long long g0 = ((long long)blockIdx.x * (kThreads / 32) + (tid >> 5)) * 32; g0 < ngroups; g0 += wstride) {
+    const unsigned int my_word = g0 + lane < ngroups ? __ldg(inf + g0 + lane) : 0u;
+    unsigned int live = __ballot_sync(0xffffffffu, my_word != 0u);
+    while (live) {
+      const int gl = __ffs(live) - 1;
+      live &= live - 1;
+      unsigned int word = __shfl_sync(0xffffffffu, my_word, gl);
+      const long long rbase = (g0 + gl) << 5;
+      const unsigned int my_lo = (rbase + lane <= n) ? sv.row_ptr[rbase + lane] : 0u;
+      const unsigned int last = (rbase + 32 <= n) ? sv.row_ptr[rbase + 32] : sv.row_ptr[n];
+      while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        const unsigned int lo = __shfl_sync(0xffffffffu, my_lo, b);
+        const unsigned int hi = b == 31 ? last : __shfl_sync(0xffffffffu, my_lo, (b + 1) & 31);
+        if (hi - lo > (unsigned)kSirHeavy) continue;             // done by the heavy-row pass
+        for (unsigned int e = lo + lane; e < hi; e += 32) red_add_u32(sv.k32 + __ldcs(sv.col + e), 1u);
+      }
     }
   }
 }
@@ -381,14 +389,24 @@ __global__ void __launch_bounds__(kThreads) sir_transition_kernel(const SirDev s
 #pragma unroll
     for (int i = 0; i < kSirRowsPerThread; ++i) {       // all loads of the tile in flight first
       const long long r = base + i * kThreads + tid;
-      s[i] = 0; k[i] = 0; deg[i] = 0;
-      if (r < t.n) { s[i] = st_cur[r]; k[i] = __ldcg(k32 + r); deg[i] = sv.row_ptr[r + 1] - sv.row_ptr[r]; }
+      s[i] = 2;
+      if (r < t.n) s[i] = st_cur[r];
+    }
+    // the counter only matters for a susceptible row (a recovered / infected row is never susceptible again, so
+    // whatever the pushes leave in ITS counter is never read), the degree only for rows that stay S or I: once
+    // most agents have recovered, the pass reads one byte per agent instead of 13
+#pragma unroll
+    for (int i = 0; i < kSirRowsPerThread; ++i) {
+      const long long r = base + i * kThreads + tid;
+      k[i] = 0; deg[i] = 0;
+      if (s[i] == 0) k[i] = __ldcg(k32 + r);
+      if (s[i] != 2) deg[i] = sv.row_ptr[r + 1] - sv.row_ptr[r];
     }
 #pragma unroll
     for (int i = 0; i < kSirRowsPerThread; ++i) {
       const long long r = base + i * kThreads + tid;
       const bool active = r < t.n;
-      int sn = s[i];
+      int sn = active ? s[i] : 0;
       if (active) {
         if (k[i]) k32[r] = 0u;
         const bool need = (sn == 0 && k[i] > 0) || sn == 1;
@@ -430,6 +448,38 @@ __global__ void __launch_bounds__(kThreads) sir_transition_kernel(const SirDev s
 // the same warp.  Cost is proportional to the susceptible rows' adjacency -- the complement of the
 // push kernel's; the step's tail picks whichever is cheaper for the next step.
 // ---------------------------------------------------------------------------------------
+// Heavy rows (> kSirHeavy adjacency entries, the static list built with the CSR) that are still susceptible: one
+// CTA per row counts its infected neighbours into k32[row]; sir_pull_s_kernel picks the count up.  A hub walked by
+// a single warp held the whole step back while it was still susceptible (the first pull steps of an epidemic).
+template <bool SHARD = false>
+__global__ void __launch_bounds__(kThreads) sir_pull_heavy_kernel(const SirDev sv, const ModelDev md) {
+  __shared__ unsigned int s_cnt[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const Ctrl* ctrl = md.ctrl;
+  if (!SHARD && ctrl->sir_mode != 0) return;
+  const int cur = (int)(ctrl->time_step & 1);
+  const unsigned int* __restrict__ inf = sv.infbits[cur];
+  for (int h = blockIdx.x; h < sv.n_heavy; h += gridDim.x) {
+    const int r = sv.heavy[h];
+    if (sv.state8[cur][r] != 0) continue;
+    const unsigned int lo = sv.row_ptr[r], hi = sv.row_ptr[r + 1];
+    unsigned int cnt = 0;
+    for (unsigned int e = lo + tid; e < hi; e += kThreads) {
+      const int c = __ldcs(sv.col + e);
+      cnt += (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;
+    }
+    cnt = (unsigned int)warp_sum((int)cnt);
+    __syncthreads();
+    if (lane == 0) s_cnt[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int tot = 0;
+      for (int w = 0; w < kThreads / 32; ++w) tot += s_cnt[w];
+      sv.k32[r] = tot;
+    }
+  }
+}
+
 template <int MODE, bool SHARD = false>
 __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, const ModelDev md) {
   __shared__ int s_red[3][kThreads / 32];
@@ -457,12 +507,17 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
     unsigned int lo = 0, len = 0;
     if (active) {
       s = st_cur[r];
-      lo = sv.row_ptr[r];
-      len = sv.row_ptr[r + 1] - lo;
+      if (s != 2) {                 // a recovered row needs neither its adjacency nor its degree
+        lo = sv.row_ptr[r];
+        len = sv.row_ptr[r + 1] - lo;
+      }
     }
     unsigned int k = 0;
-    // long susceptible rows (hubs before they are infected): all 32 lanes stride the row
-    unsigned int big = __ballot_sync(0xffffffffu, active && s == 0 && len > sv.big_len);
+    // heavy susceptible rows (hubs before they are infected) were counted by sir_pull_heavy_kernel, one CTA per row
+    const bool heavy = active && s == 0 && len > (unsigned)kSirHeavy;
+    if (heavy) { k = __ldcg(sv.k32 + r); sv.k32[r] = 0u; }
+    // long susceptible rows: all 32 lanes stride the row
+    unsigned int big = __ballot_sync(0xffffffffu, active && s == 0 && len > sv.big_len && !heavy);
     while (big) {
       const int b = __ffs(big) - 1;
       big &= big - 1;
@@ -489,12 +544,13 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
     if (active && s == 0 && len > 0 && len <= sv.big_len) {
       const int* cp = sv.col + lo;
       unsigned int e = 0;
-      for (; e + 2 <= len; e += 2) {
-        const int c0 = __ldg(cp + e), c1 = __ldg(cp + e + 1);
+      for (; e + 4 <= len; e += 4) {          // four adjacency loads, then four gathers, in flight together
+        const int c0 = __ldg(cp + e), c1 = __ldg(cp + e + 1), c2 = __ldg(cp + e + 2), c3 = __ldg(cp + e + 3);
         const unsigned int w0 = __ldg(inf + (c0 >> 5)), w1 = __ldg(inf + (c1 >> 5));
-        k += ((w0 >> (c0 & 31)) & 1u) + ((w1 >> (c1 & 31)) & 1u);
+        const unsigned int w2 = __ldg(inf + (c2 >> 5)), w3 = __ldg(inf + (c3 >> 5));
+        k += ((w0 >> (c0 & 31)) & 1u) + ((w1 >> (c1 & 31)) & 1u) + ((w2 >> (c2 & 31)) & 1u) + ((w3 >> (c3 & 31)) & 1u);
       }
-      if (e < len) {
+      for (; e < len; ++e) {
         const int c0 = __ldg(cp + e);
         k += (__ldg(inf + (c0 >> 5)) >> (c0 & 31)) & 1u;
       }

@@ -111,6 +111,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline asks for the host's cores explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 void orc_threefry2x32(const uint32_t key[2], const uint32_t ctr[2], uint32_t out[2]) {
   threefry2x32(key[0], key[1], ctr[0], ctr[1], &out[0], &out[1]);
 }

@@ -45,6 +45,17 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def use_all_cores() -> int:
+    """OpenMP threads = the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would make the CPU baseline a single-thread number)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

@@ -37,3 +37,14 @@ def test_product_line_carries_every_contract_key():
                 '"gpu_launches"', '"clocks"', '"bound"', '"achieved"', '"peak"', '"frac"', '"traffic"',
                 '"h2d_bytes_per_step"', '"d2h_bytes_per_step"', '"sm_mhz"', '"sm_max_mhz"', '"reasons"'):
         assert key in src, key
+
+
+def test_reference_arm_uses_the_host_cores_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm must still time the C/OpenMP restatement
+    on all the cores the process may use, and say how many."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0", "--cpu-steps", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))

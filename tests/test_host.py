@@ -397,3 +397,27 @@ def test_filter_condition_compiles_to_a_postfix_program():
         select.compile_predicate(lambda s: np.logical_and(s["wealth"] > 1, s["ok"]), fields)     # a NumPy ufunc on symbols
     with pytest.raises(TraceError):
         select.compile_predicate(lambda s: s["wealth"] + 1, fields)                               # not boolean
+
+
+def test_feistel_inverse_is_the_inverse_permutation():
+    """The Schelling kernels walk the unsatisfied agents in cell order and ask which mover index each one is:
+    jxb_prng_feistel(..., inverse=1) must undo the forward matching permutation (cycle walking included), and the
+    forward direction must agree with the oracle's restatement."""
+    import ctypes as C
+    from jaxabm_b200 import _native as nat
+    from oracle import jaxlike as jl
+    lib = nat.lib()
+    rng = np.random.RandomState(1)
+    for n in (1, 2, 3, 5, 64, 1000, 4097, 65536, 3_777_216):
+        rk = np.ascontiguousarray(rng.randint(0, 2**32, 4, dtype=np.uint64).astype(np.uint32))
+        idx = np.arange(n) if n <= 5000 else rng.randint(0, n, 3000)
+        fwd = np.empty(len(idx), dtype=np.uint32)
+        out = C.c_uint32()
+        for i, k in enumerate(idx):
+            nat.check(lib.jxb_prng_feistel(n, nat.ptr(rk), int(k), 0, C.byref(out)))
+            fwd[i] = out.value
+            nat.check(lib.jxb_prng_feistel(n, nat.ptr(rk), int(fwd[i]), 1, C.byref(out)))
+            assert out.value == k
+        assert np.array_equal(fwd, jl.feistel_permute(np.asarray(idx, dtype=np.uint32), n, rk))
+        if n <= 5000:
+            assert np.array_equal(np.sort(fwd), np.arange(n))
