@@ -160,6 +160,7 @@ typedef struct {
   void* launch_step;
   int32_t n_consts;                                        /* float constants of the traced code ...      */
   const double* consts;                                    /* ... uploaded once; the kernels read them     */
+  int32_t field_widths[JXB_MAX_TYPES][JXB_MAX_FIELDS];     /* components per agent (1; 2 for an f32[N,2] position ...) */
 } jxb_traced_spec;
 int jxb_model_create_traced(jxb_engine*, const jxb_model_desc*, const jxb_traced_spec*, jxb_model** out);
 

@@ -95,6 +95,42 @@ class AgentWrapper(AgentType):
             raise ValueError(f"Agent.setup() must return a dictionary, got {type(state)}")
         return state
 
+    # Plain-Python agent classes (no registered kernel): the reference's adapter verbatim (agentpy.py:183-227).
+    # The rule tracer calls these ONCE on symbolic values and turns the recorded expressions into the fused
+    # update kernel (jaxabm_b200/trace.py).
+    def init_state(self, model_config, key):
+        if self.jxb_rule is not None:
+            return super().init_state(model_config, key)
+        return self.jxb_host_init(model_config)
+
+    def update(self, state, model_state, model_config, key):
+        if self.jxb_rule is not None:
+            return super().update(state, model_state, model_config, key)
+        self.agent_instance._state = state
+        new_state = self.agent_instance.step(model_state)
+        if not isinstance(new_state, dict):
+            if new_state is None:
+                return state
+            raise ValueError(f"Agent.step() must return a dictionary, got {type(new_state)}")
+        return new_state
+
+
+class _StepProbe:
+    """Stands in for ``Model._jax_model`` while the user's ``step()`` is traced: reads see the host-side state,
+    ``add_env_state`` calls are recorded instead of acting on the model under construction."""
+
+    def __init__(self, real):
+        self._real = real
+        self.state = {"env": dict((real.state or {}).get("env", {}))}
+        self.calls: List[Tuple[str, Any]] = []
+
+    def add_env_state(self, name: str, value: Any) -> None:
+        self.calls.append((name, value))
+        self.state["env"][name] = value
+
+    def __getattr__(self, name):
+        return getattr(object.__getattribute__(self, "_real"), name)
+
 
 class AgentList:
     """Container for one agent collection (``agentpy.py:230-378``)."""
@@ -358,7 +394,31 @@ class Model:
         the first step -- where a model uploads hand-built initial columns."""
 
     def update_state(self, env_state, agent_states, model_params, key):   # agentpy.py:895-924
-        raise RuntimeError("device-resident model function; it is not called on the host")
+        """The reference's bridge: run the user's ``step()``, then overlay ``Environment.state`` onto the env
+        (which resets every facade-level env entry each step -- Appendix B).  Registered device programs never
+        call it; for a plain-Python model the rule tracer runs it on symbolic values.  While it is traced,
+        ``self._jax_model`` is a probe, so that host-side calls made by ``step()`` (``add_env_state`` on the core
+        model, ``record``) do not act at trace time; ``run()`` replays them once per simulated step afterwards."""
+        from .trace import TrKey
+        self._current_env_state = env_state.copy()
+        self._current_agent_states = agent_states
+        if isinstance(key, TrKey):
+            real, probe = self._jax_model, _StepProbe(self._jax_model)
+            recorded = {k: list(v) for k, v in self._recorded_data.items()}
+            self._jax_model = probe
+            try:
+                self.step()
+            finally:
+                self._jax_model = real
+                if probe.calls or {k: len(v) for k, v in self._recorded_data.items()} != {k: len(v) for k, v in recorded.items()}:
+                    self._step_has_host_effects = True
+                self._recorded_data = recorded
+        else:
+            self.step()
+        new_env_state = {**env_state}
+        for name, value in self.env.state.items():
+            new_env_state[name] = value
+        return new_env_state
 
     def compute_metrics(self, env_state, agent_states, model_params):
         return {}
@@ -394,18 +454,24 @@ class Model:
         self._recorded_data.setdefault(name, []).append(value)
 
     # ---- run -------------------------------------------------------------------------------
-    def _program(self) -> str:
+    def _program(self) -> Optional[str]:
+        """Registered device program of this model class; None = plain Python, to be traced."""
         prog = type(self).jxb_program
         if prog is not None:
             return prog
+        registered = [al.agent_type.jxb_rule is not None for al in self._agent_lists.values()]
         overridden = [n for n in ("step", "compute_metrics", "update_state")
                       if getattr(type(self), n) is not getattr(Model, n)]
-        if overridden:
-            raise UnregisteredRuleError(
-                f"{type(self).__name__} overrides {overridden} in Python but names no registered device "
-                "program (class attribute jxb_program); the engine cannot trace Python model logic and has "
-                "no CPU fallback. See jaxabm_b200.rules for the registered models.")
-        return "none"
+        if registered and all(registered):
+            if overridden:
+                raise UnregisteredRuleError(
+                    f"{type(self).__name__} overrides {overridden} in Python but its agents are registered device "
+                    "rules: registered kernels and traced Python cannot be mixed in one model. Name the registered "
+                    "program (class attribute jxb_program), or write the agents as plain jx.Agent classes too.")
+            return "none"
+        if any(registered):
+            raise UnregisteredRuleError("registered agent rules and plain-Python agent classes cannot be mixed in one model")
+        return None
 
     def run(self, steps: Optional[int] = None) -> Results:                # agentpy.py:1040-1114
         if steps is not None:
@@ -415,18 +481,24 @@ class Model:
                              rng_mode=self.p.get("rng_mode"))
         self.setup()
         program = self._program()
+        self._step_has_host_effects = False
+        if program is None:
+            # plain-Python model: exactly what agentpy.py:1071-1076 builds -- the bound update_state bridge and
+            # compute_metrics; Model.initialize() traces them (and the agents' setup / step) into one kernel
+            self._jax_model = JaxModel(params=self.p, config=config, update_state_fn=self.update_state,
+                                       metrics_fn=self.compute_metrics)
+        else:
+            def _update(env_state, agent_states, params, key):  # pragma: no cover - device resident
+                raise RuntimeError("device-resident model function")
 
-        def _update(env_state, agent_states, params, key):  # pragma: no cover - device resident
-            raise RuntimeError("device-resident model function")
+            def _metrics(env_state, agent_states, params):  # pragma: no cover - device resident
+                raise RuntimeError("device-resident model function")
 
-        def _metrics(env_state, agent_states, params):  # pragma: no cover - device resident
-            raise RuntimeError("device-resident model function")
-
-        _update.jxb_program = program
-        _metrics.jxb_program = program
-        _metrics.__dict__["jxb_owner"] = self
-        self._jax_model = JaxModel(params=self.p, config=config, update_state_fn=_update,
-                                   metrics_fn=None if program == "none" else _metrics)
+            _update.jxb_program = program
+            _metrics.jxb_program = program
+            _metrics.__dict__["jxb_owner"] = self
+            self._jax_model = JaxModel(params=self.p, config=config, update_state_fn=_update,
+                                       metrics_fn=None if program == "none" else _metrics)
         self._jax_model._facade = self
         for name, agent_list in self._agent_lists.items():
             self._jax_model.add_agent_collection(name, agent_list.collection)
@@ -439,6 +511,17 @@ class Model:
         self.after_initialize()
         results_dict = self._jax_model.run()
         self.last_device_seconds = self._jax_model.last_device_seconds
+        if program is None and self._step_has_host_effects:
+            # the host-side part of the user's step() (core-model add_env_state bookkeeping, record()) once per
+            # simulated step, as the un-jitted reference loop would have run it
+            self._current_env_state = dict(self._jax_model._env_state)
+            self._current_agent_states = {n: c.states for n, c in self._jax_model.agent_collections.items()}
+            self._jax_model._host_replay = True
+            try:
+                for _ in range(int(self.steps)):
+                    self.step()
+            finally:
+                self._jax_model._host_replay = False
         elapsed = time.time() - start
         self.end()
         self._running = False

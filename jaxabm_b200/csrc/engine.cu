@@ -532,7 +532,11 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
       r.rule = JXB_RULE_TRACED;
       r.nf = ts->n_fields[i];
       if (r.nf < 1 || r.nf > kMaxFields) { delete m; return fail(JXB_ERR_INVALID, "collection %d: 1..%d fields", i, kMaxFields); }
-      for (int f = 0; f < r.nf; ++f) r.f[f] = FieldSpec{keep(ts->field_names[i][f]), ts->field_dtypes[i][f], 1};
+      for (int f = 0; f < r.nf; ++f) {
+        const int width = ts->field_widths[i][f];
+        if (width < 1 || width > 4) { delete m; return fail(JXB_ERR_INVALID, "collection %d field %d: width 1..4", i, f); }
+        r.f[f] = FieldSpec{keep(ts->field_names[i][f]), ts->field_dtypes[i][f], width};
+      }
     }
     ProgramSpec& p = m->traced_prog;
     p.program = JXB_PROGRAM_TRACED; p.has_env_fn = ts->has_env_fn; p.n_env = ts->n_env; p.n_metrics = ts->n_metrics;

@@ -117,7 +117,8 @@ class TracedSpec(C.Structure):
                 ("metric_dtypes", C.c_int32 * nat.MAX_METRICS),
                 ("has_env_fn", C.c_int32), ("n_acc", C.c_int32), ("n_variants", C.c_int32),
                 ("launch_init", C.c_void_p), ("launch_step", C.c_void_p),
-                ("n_consts", C.c_int32), ("consts", C.POINTER(C.c_double))]
+                ("n_consts", C.c_int32), ("consts", C.POINTER(C.c_double)),
+                ("field_widths", (C.c_int32 * 20) * nat.MAX_TYPES)]
 
 
 def build(model) -> Tuple[TracedSpec, C.CDLL, List[T.TracedModel], str]:
@@ -132,9 +133,10 @@ def build(model) -> Tuple[TracedSpec, C.CDLL, List[T.TracedModel], str]:
         if len(t["fields"]) > 20:
             raise T.TraceError("at most 20 state fields per collection")
         spec.n_fields[i] = len(t["fields"])
-        for f, (name, dt) in enumerate(t["fields"]):
+        for f, (name, dt, width) in enumerate(t["fields"]):
             spec.field_names[i][f] = name.encode()
             spec.field_dtypes[i][f] = T._DT_CODE[dt]
+            spec.field_widths[i][f] = width
     if len(tm.env_names) > 32 or len(tm.metrics) > nat.MAX_METRICS:
         raise T.TraceError("at most 32 scalar env entries and 32 metrics")
     spec.n_env = len(tm.env_names)

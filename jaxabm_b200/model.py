@@ -99,6 +99,12 @@ class Model:
         self._agent_collections[name] = agent_collection
 
     def add_env_state(self, name: str, value: Any) -> None:                 # model.py:76-99
+        if getattr(self, "_host_replay", False):
+            # the facade replays the host-side part of a traced Model.step() after the device run: only the
+            # host copy of the env (model.py:142-144) moves, the device env is what the traced kernel left
+            if self._state is not None:
+                self._state.setdefault("env", {})[name] = value
+            return
         if self._is_initialized and self._state is not None:
             self._state.setdefault("env", {})[name] = value
         self._env_state[name] = value

@@ -119,6 +119,130 @@ class TrKey:
         return "a" if k.kind == "agent" else "s"
 
 
+class TrVec:
+    """A small fixed-length vector of traced scalars: a vector-valued state field (``f32[N, 2]`` positions), a
+    non-scalar env entry, or ``jnp.array([...])`` of traced values.  Elementwise arithmetic with JAX's promotion
+    rules per component; ``v[k]`` is component k.  ``n`` is set on the columns of a collection handed to the model
+    functions (``len(positions)``)."""
+
+    __array_priority__ = 1000
+
+    def __init__(self, comps, n: Optional[int] = None):
+        self.c = [(_const(x) if not isinstance(x, Tr) else x) for x in comps]
+        self.n = n
+
+    @property
+    def shape(self):
+        return (len(self.c),) if self.n is None else (self.n, len(self.c))
+
+    @property
+    def scope(self):
+        return _scope(*self.c)
+
+    def __len__(self):
+        return len(self.c) if self.n is None else self.n
+
+    def __iter__(self):
+        if self.n is not None:
+            raise TraceError("iterating over the agents of a traced column is not available at trace time")
+        return iter(self.c)
+
+    def __getitem__(self, k):
+        if isinstance(k, tuple) and len(k) == 2 and k[0] in (slice(None), Ellipsis):
+            k = k[1]
+        if isinstance(k, (int, np.integer)):
+            return self.c[int(k)]
+        if isinstance(k, slice):
+            return TrVec(self.c[k], self.n)
+        raise TraceError("only v[k] / v[:, k] with a Python integer is traced on a vector value")
+
+    def __array__(self, dtype=None, copy=None):
+        if any(x.op != "const" for x in self.c):
+            raise TraceError("a traced vector has no concrete value at trace time")
+        dt = np.float32 if any(x.dtype in (F32, WF) for x in self.c) else (np.bool_ if all(x.dtype == BOOL for x in self.c) else np.int32)
+        return np.array([x.attr for x in self.c], dtype=dtype or dt)
+
+    def astype(self, dt):
+        return TrVec([astype(x, dt) for x in self.c], self.n)
+
+    def _zip(self, o, fn, rev=False):
+        if isinstance(o, TrVec):
+            if len(o.c) != len(self.c):
+                raise TraceError(f"vector lengths differ: {len(self.c)} vs {len(o.c)}")
+            os = o.c
+        elif isinstance(o, (list, tuple, np.ndarray)) and np.ndim(o) == 1:
+            if len(o) != len(self.c):
+                raise TraceError(f"vector lengths differ: {len(self.c)} vs {len(o)}")
+            os = [_const(x if not isinstance(o, np.ndarray) else o[i]) for i, x in enumerate(o)]
+        else:
+            os = [o] * len(self.c)
+        n = self.n if self.n is not None else getattr(o, "n", None)
+        return TrVec([fn(b, a) if rev else fn(a, b) for a, b in zip(self.c, os)], n)
+
+    def __add__(self, o): return self._zip(o, lambda a, b: binary("add", a, b))
+    def __radd__(self, o): return self._zip(o, lambda a, b: binary("add", a, b), True)
+    def __sub__(self, o): return self._zip(o, lambda a, b: binary("sub", a, b))
+    def __rsub__(self, o): return self._zip(o, lambda a, b: binary("sub", a, b), True)
+    def __mul__(self, o): return self._zip(o, lambda a, b: binary("mul", a, b))
+    def __rmul__(self, o): return self._zip(o, lambda a, b: binary("mul", a, b), True)
+    def __truediv__(self, o): return self._zip(o, lambda a, b: binary("div", a, b))
+    def __rtruediv__(self, o): return self._zip(o, lambda a, b: binary("div", a, b), True)
+    def __pow__(self, o): return self._zip(o, lambda a, b: power(a, b))
+    def __neg__(self): return TrVec([unary("neg", x) for x in self.c], self.n)
+    def __abs__(self): return TrVec([unary("abs", x) for x in self.c], self.n)
+    def __lt__(self, o): return self._zip(o, lambda a, b: compare("lt", a, b))
+    def __le__(self, o): return self._zip(o, lambda a, b: compare("le", a, b))
+    def __gt__(self, o): return self._zip(o, lambda a, b: compare("gt", a, b))
+    def __ge__(self, o): return self._zip(o, lambda a, b: compare("ge", a, b))
+    def __eq__(self, o): return self._zip(o, lambda a, b: compare("eq", a, b))      # noqa: E711
+    def __ne__(self, o): return self._zip(o, lambda a, b: compare("ne", a, b))
+    __hash__ = object.__hash__
+    def __and__(self, o): return self._zip(o, lambda a, b: logical("and", a, b))
+    def __or__(self, o): return self._zip(o, lambda a, b: logical("or", a, b))
+    def __xor__(self, o): return self._zip(o, lambda a, b: logical("xor", a, b))
+    def __invert__(self): return TrVec([unary("not", x) for x in self.c], self.n)
+
+    def __bool__(self):
+        raise TraceError("the truth value of a traced array is not available at trace time (use jnp.where)")
+
+
+def make_vector(values) -> "TrVec":
+    """``jnp.array([...])``: Python numbers become strongly typed float32 / int32 components (an all-int list is
+    int32, any float makes it float32); traced components promote together the same way."""
+    comps = [(_const(v) if not isinstance(v, Tr) else v) for v in values]
+    kinds = [_RANK[c.dtype] for c in comps]
+    top = max(kinds)
+    target = {0: bool, 1: int, 2: float}[top]
+    out = []
+    for c in comps:
+        if c.op == "const":
+            out.append(Tr("const", (), {0: BOOL, 1: I32, 2: F32}[top], "s",
+                          bool(c.attr) if top == 0 else (int(c.attr) if top == 1 else float(np.float32(c.attr)))))
+        else:
+            out.append(astype(c, target))
+    return TrVec(out)
+
+
+def _vmap(fn, *xs):
+    """Apply a scalar tracer op elementwise when any operand is a vector."""
+    vec = next((x for x in xs if isinstance(x, TrVec)), None)
+    if vec is None:
+        return fn(*xs)
+    w = len(vec.c)
+    cols = []
+    for x in xs:
+        if isinstance(x, TrVec):
+            if len(x.c) != w:
+                raise TraceError("vector lengths differ")
+            cols.append(x.c)
+        elif isinstance(x, (list, tuple, np.ndarray)) and np.ndim(x) == 1:
+            cols.append([_const(v if not isinstance(x, np.ndarray) else x[i]) for i, v in enumerate(x)])
+        else:
+            cols.append([x] * w)
+    n = next((x.n for x in xs if isinstance(x, TrVec) and x.n is not None), None)
+    return TrVec([fn(*args) for args in zip(*cols)], n)
+
+
 # ---------------------------------------------------------------------------------------------
 # constructors
 # ---------------------------------------------------------------------------------------------
@@ -137,7 +261,7 @@ def _const(v) -> Tr:
         return Tr("const", (), WF, "s", float(v))
     if isinstance(v, np.ndarray) and v.ndim == 0:
         return _const(v[()])
-    raise TraceError(f"cannot trace a value of type {type(v).__name__} (only scalars and scalar state fields)")
+    raise TraceError(f"cannot trace a value of type {type(v).__name__} as a scalar")
 
 
 def _scope(*xs: Tr) -> str:
@@ -175,7 +299,19 @@ def _fold2(op: str, a: Tr, b: Tr):
     return None
 
 
+def _as_vec(x):
+    """NumPy vectors (a non-scalar env entry such as 'bounds') take part in traced arithmetic as constant vectors."""
+    if isinstance(x, np.ndarray) and x.ndim == 1:
+        return TrVec([_const(v) for v in x])
+    if isinstance(x, (list, tuple)) and x and all(isinstance(v, (int, float, np.number, Tr)) for v in x):
+        return make_vector(x)
+    return x
+
+
 def binary(op: str, a, b) -> Tr:
+    a, b = _as_vec(a), _as_vec(b)
+    if isinstance(a, TrVec) or isinstance(b, TrVec):
+        return _vmap(lambda x, y: binary(op, x, y), a, b)
     a, b = _const(a), _const(b)
     f = _fold2(op, a, b)
     if f is not None:
@@ -189,6 +325,8 @@ def binary(op: str, a, b) -> Tr:
 
 
 def unary(op: str, a) -> Tr:
+    if isinstance(a, TrVec):
+        return TrVec([unary(op, x) for x in a.c], a.n)
     a = _const(a)
     if op == "not":
         if a.dtype != BOOL:
@@ -200,11 +338,16 @@ def unary(op: str, a) -> Tr:
 
 
 def compare(op: str, a, b) -> Tr:
+    a, b = _as_vec(a), _as_vec(b)
+    if isinstance(a, TrVec) or isinstance(b, TrVec):
+        return _vmap(lambda x, y: compare(op, x, y), a, b)
     a, b = _const(a), _const(b)
     return Tr(op, (a, b), BOOL, _scope(a, b), _promote(a, b))
 
 
 def logical(op: str, a, b) -> Tr:
+    if isinstance(a, TrVec) or isinstance(b, TrVec):
+        return _vmap(lambda x, y: logical(op, x, y), a, b)
     a, b = _const(a), _const(b)
     if a.dtype != BOOL or b.dtype != BOOL:
         raise TraceError("& | ^ are only traced on boolean values")
@@ -212,6 +355,8 @@ def logical(op: str, a, b) -> Tr:
 
 
 def power(a, b) -> Tr:
+    if isinstance(a, TrVec) or isinstance(b, TrVec):
+        return _vmap(power, a, b)
     a, b = _const(a), _const(b)
     if b.op == "const" and b.dtype == WI and 0 <= b.attr <= 64:
         # lax.integer_pow: square-and-multiply (x**4 = (x*x)*(x*x), x**3 = (x*x)*x ... the order decides the
@@ -235,6 +380,8 @@ def power(a, b) -> Tr:
 
 
 def _math(op: str, a) -> Tr:
+    if isinstance(a, TrVec):
+        return TrVec([_math(op, x) for x in a.c], a.n)
     a = _const(a)
     return Tr(op, (a,), F32, a.scope)
 
@@ -246,6 +393,9 @@ def _array_dtype(dt: str) -> str:
 
 
 def where(c, a, b) -> Tr:
+    a, b = _as_vec(a), _as_vec(b)
+    if isinstance(c, TrVec) or isinstance(a, TrVec) or isinstance(b, TrVec):
+        return _vmap(where, c, a, b)
     c, a, b = _const(c), _const(a), _const(b)
     if c.dtype != BOOL:
         c = compare("ne", c, 0)
@@ -253,11 +403,17 @@ def where(c, a, b) -> Tr:
 
 
 def minimum(a, b) -> Tr:
+    a, b = _as_vec(a), _as_vec(b)
+    if isinstance(a, TrVec) or isinstance(b, TrVec):
+        return _vmap(minimum, a, b)
     a, b = _const(a), _const(b)
     return Tr("min", (a, b), _array_dtype(_promote(a, b)), _scope(a, b))
 
 
 def maximum(a, b) -> Tr:
+    a, b = _as_vec(a), _as_vec(b)
+    if isinstance(a, TrVec) or isinstance(b, TrVec):
+        return _vmap(maximum, a, b)
     a, b = _const(a), _const(b)
     return Tr("max", (a, b), _array_dtype(_promote(a, b)), _scope(a, b))
 
@@ -267,6 +423,8 @@ def clip(x, lo, hi) -> Tr:
 
 
 def astype(a, dt) -> Tr:
+    if isinstance(a, TrVec):
+        return a.astype(dt)
     a = _const(a)
     name = getattr(dt, "__name__", str(dt))
     if dt in (float, np.float32, np.float64) or name in ("float", "float32", "float64"):
@@ -291,9 +449,46 @@ class Column:
         self.n = n
 
 
-def _reduce(kind: str, x) -> Tr:
+class TrCol(Tr):
+    """A scalar state column of a collection as the model functions see it (``agent_states[name][field]``):
+    a per-agent value that also knows the population size (``len(column)``)."""
+    __slots__ = ("n",)
+
+    def __len__(self):
+        return self.n
+
+
+def _fold(kind: str, comps):
+    """sum / max / min / mean over the components of a vector, left to right."""
+    acc = comps[0]
+    for c in comps[1:]:
+        acc = binary("add", acc, c) if kind in ("sum", "mean") else (maximum(acc, c) if kind == "max" else minimum(acc, c))
+    if kind == "mean":
+        acc = binary("div", astype(acc, float), float(len(comps)))
+    return acc
+
+
+def _reduce(kind: str, x, axis=None):
     if isinstance(x, Column):
         x = x.tr
+    x = _as_vec(x)
+    if isinstance(x, TrVec):
+        is_matrix = x.n is not None                      # (N, w): the columns of a collection
+        if axis is not None and axis < 0:
+            axis += 2 if is_matrix else 1
+        if not is_matrix:
+            if axis not in (None, 0):
+                raise TraceError(f"axis {axis} is out of range for a vector")
+            return _fold(kind, x.c)
+        if axis == 1:
+            return _fold(kind, x.c)                       # per agent, over the components
+        if axis == 0:
+            return TrVec([_reduce(kind, c) for c in x.c])  # per component, over the agents
+        if kind == "mean":
+            return binary("div", _reduce("sum", _fold("sum", x.c)), float(x.n * len(x.c)))
+        return _reduce(kind, _fold(kind, x.c))
+    if axis not in (None, 0):
+        raise TraceError(f"axis {axis} is out of range for a column")
     x = _const(x)
     if x.scope != "a":
         return x
@@ -355,12 +550,20 @@ class _Namespace:
     def logical_and(self, a, b): return logical("and", self._col(a), self._col(b))
     def logical_or(self, a, b): return logical("or", self._col(a), self._col(b))
     def logical_not(self, a): return unary("not", self._col(a))
-    def sum(self, x): return _reduce("sum", x)
-    def mean(self, x): return _reduce("mean", x)
-    def max(self, x): return _reduce("max", x)
-    def min(self, x): return _reduce("min", x)
-    def asarray(self, x, dtype=None): return astype(_const(self._col(x)), dtype) if dtype is not None else _const(self._col(x))
+    def sum(self, x, axis=None): return _reduce("sum", x, axis)
+    def mean(self, x, axis=None): return _reduce("mean", x, axis)
+    def max(self, x, axis=None): return _reduce("max", x, axis)
+    def min(self, x, axis=None): return _reduce("min", x, axis)
+    def asarray(self, x, dtype=None):
+        x = self._col(x)
+        if isinstance(x, TrVec):
+            return x.astype(dtype) if dtype is not None else x
+        if isinstance(x, (list, tuple)) or (isinstance(x, np.ndarray) and x.ndim == 1):
+            v = make_vector(list(x))
+            return v.astype(dtype) if dtype is not None else v
+        return astype(_const(x), dtype) if dtype is not None else _const(x)
     array = asarray
+    def square(self, x): return binary("mul", self._col(x), self._col(x))
     def nan_to_num(self, x, nan=0.0):
         x = _const(self._col(x))
         return where(compare("ne", x, x), nan, x)
@@ -591,29 +794,45 @@ def trace_model(collections, env_state: dict, params: dict, update_state_fn, met
         init = at.init_state(config, TrKey("agent"))
         if not isinstance(init, dict) or not init:
             raise TraceError(f"{type(at).__name__}.init_state must return a non-empty dict")
+        # fields: (name, dtype, width); init / update hold one traced scalar per component
         fields, init_tr = [], {}
         for fname, v in init.items():
-            t = _const(v) if not isinstance(v, Tr) else v
-            fields.append((fname, _STORE[t.dtype]))
-            init_tr[fname] = t
-        state = {fname: Tr("field", (), dt, "a", (ti, fi)) for fi, (fname, dt) in enumerate(fields)}
+            v = _as_vec(v)
+            comps = list(v.c) if isinstance(v, TrVec) else [(_const(v) if not isinstance(v, Tr) else v)]
+            if not 1 <= len(comps) <= 4:
+                raise TraceError(f"state field {fname!r}: vector fields of 1..4 components are traced, got {len(comps)}")
+            dt = _STORE[max((c.dtype for c in comps), key=lambda d: _RANK[d])]
+            fields.append((fname, dt, len(comps)))
+            init_tr[fname] = [c if _STORE[c.dtype] == dt else astype(c, {F32: float, I32: int, BOOL: bool}[dt]) for c in comps]
+
+        def column(op, fi, dt, w, n=None, ti=ti):
+            if w == 1:
+                if n is None:
+                    return Tr(op, (), dt, "a", (ti, fi, 0))
+                col = TrCol(op, (), dt, "a", (ti, fi, 0))
+                col.n = n
+                return col
+            return TrVec([Tr(op, (), dt, "a", (ti, fi, c)) for c in range(w)], n)
+        state = {fname: column("field", fi, dt, w) for fi, (fname, dt, w) in enumerate(fields)}
         model_state = {"time_step": Tr("time", (), WI, "s"), "env": env_view()}
         out = at.update(dict(state), model_state, config, TrKey("agent"))
         if not isinstance(out, dict) or set(out) != set(state):
             raise TraceError(f"{type(at).__name__}.update must return the same state keys as init_state "
                              f"({sorted(state)}), got {sorted(out) if isinstance(out, dict) else type(out).__name__}")
         upd = {}
-        for fname, dt in fields:
-            v = _const(out[fname]) if not isinstance(out[fname], Tr) else out[fname]
-            if _STORE[v.dtype] != dt:
-                v = astype(v, {F32: float, I32: int, BOOL: bool}[dt])       # the column keeps its dtype
-            upd[fname] = v
+        for fname, dt, w in fields:
+            v = _as_vec(out[fname])
+            comps = list(v.c) if isinstance(v, TrVec) else [(_const(v) if not isinstance(v, Tr) else v)]
+            if len(comps) != w:
+                raise TraceError(f"update returns {len(comps)} components for state field {fname!r} of width {w}")
+            upd[fname] = [c if _STORE[c.dtype] == dt else astype(c, {F32: float, I32: int, BOOL: bool}[dt])   # the column keeps its dtype
+                          for c in comps]
         tm.types.append({"name": cname, "n": coll.num_agents, "fields": fields, "init": init_tr, "update": upd,
-                         "state": state})
+                         "state": state, "column": column})
     # agent_states[name][field]: the POST-update column of a collection (model.py:182-200 hands the new
     # states to update_state_fn / metrics_fn); usable inside jnp.sum / mean / max / min
-    agent_states = {t["name"]: {fname: Tr("field_new", (), dt, "a", (ti, fi)) for fi, (fname, dt) in enumerate(t["fields"])}
-                    for ti, t in enumerate(tm.types)}
+    agent_states = {t["name"]: {fname: t["column"]("field_new", fi, dt, w, t["n"]) for fi, (fname, dt, w) in enumerate(t["fields"])}
+                    for t in tm.types}
     env_after = env_view()
     if update_state_fn is not None:
         tm.has_env_fn = True
@@ -675,31 +894,32 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
         # one 16-byte (4-byte for bool) load / store per column, like the hand-written kernels.
         for ti, t in enumerate(tm.types):
             my_reds = [r for r in reds if r.attr[1] == ti]
-            fields = t["fields"]
+            fields = t["fields"]                      # (name, dtype, width)
 
             def leaf(x, em, ti=ti):
                 if x.op == "field":
-                    tj, fj = x.attr
+                    tj, fj, cj = x.attr
                     if tj != ti:
                         raise TraceError("reading another collection's state inside update is not traced")
-                    return f"f{fj}"
+                    return f"f{fj}_{cj}"
                 if x.op == "env":
                     return _env_load(x, "env")
                 if x.op == "time":
                     return "(int)time_step"
                 raise TraceError("reductions cannot be used inside a per-agent update")
             em = Emitter(leaf, "ak", pool)
-            upd_roots = [t["update"][fname] for fname, _ in fields]
+            upd_roots = [v for fname, _, _ in fields for v in t["update"][fname]]
             used = {x.attr[1] for x in used_leaves(upd_roots + [r.args[0] for r in my_reds], "field") if x.attr[0] == ti}
-            new_names = {}
-            for fi, (fname, dt) in enumerate(fields):
-                new_names[fi] = em.cast(t["update"][fname], dt) if t["update"][fname].op != "field" or \
-                    t["update"][fname].attr != (ti, fi) else None
+            new_names = {}                            # (field, component) -> expression of the new value, None = unchanged
+            for fi, (fname, dt, wd) in enumerate(fields):
+                for c in range(wd):
+                    v = t["update"][fname][c]
+                    new_names[(fi, c)] = em.cast(v, dt) if v.op != "field" or tuple(v.attr) != (ti, fi, c) else None
 
             def leaf_new(x, em2, ti=ti, new_names=new_names):          # reductions read the NEW columns
                 if x.op == "field_new":
-                    tj, fj = x.attr
-                    return new_names[fj] if new_names[fj] is not None else f"f{fj}"
+                    tj, fj, cj = x.attr
+                    return new_names[(fj, cj)] if new_names[(fj, cj)] is not None else f"f{fj}_{cj}"
                 if x.op == "env":
                     return _env_load(x, "env")
                 if x.op == "time":
@@ -711,13 +931,16 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
             for r in my_reds:
                 red_exprs[r.id] = em2.cast(r.args[0], {"float": F32, "int": I32}[_acc_native(r.args[0].dtype)])
                 for x in used_leaves([r.args[0]], "field_new"):
-                    if new_names[x.attr[1]] is None:
+                    if new_names[(x.attr[1], x.attr[2])] is None:
                         used.add(x.attr[1])
+            stored = [fi for fi, (_, _, wd) in enumerate(fields) if any(new_names[(fi, c)] is not None for c in range(wd))]
+            for fi in stored:                         # an unchanged component of a rewritten vector field is copied through
+                if any(new_names[(fi, c)] is None for c in range(fields[fi][2])):
+                    used.add(fi)
             loaded = [fi for fi in range(len(fields)) if fi in used]
-            stored = [fi for fi in range(len(fields)) if new_names[fi] is not None]
             needs_key = any("ak" in ln for ln in em.lines)
-            sig_in = "".join(f", const {_CT[fields[fi][1]]} f{fi}" for fi in loaded)
-            sig_out = "".join(f", {_CT[fields[fi][1]]}& n{fi}" for fi in stored)
+            sig_in = "".join(f", const {_CT[fields[fi][1]]} f{fi}_{c}" for fi in loaded for c in range(fields[fi][2]))
+            sig_out = "".join(f", {_CT[fields[fi][1]]}& n{fi}_{c}" for fi in stored for c in range(fields[fi][2]))
             sig_acc = "".join(f", {_acc_native(r.args[0].dtype)}& a{red_slot[r.id]}" for r in my_reds)
             w(f"template <int MODE> __device__ __forceinline__ void jxc_one_v{var}_t{ti}(const TypeDev& t, const double* env, "
               f"const double* __restrict__ cst, long long time_step, Key ck, long long i{sig_in}{sig_out}{sig_acc}) {{")
@@ -726,7 +949,8 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
             for ln in em.lines:
                 w("  " + ln)
             for fi in stored:
-                w(f"  n{fi} = {new_names[fi]};")
+                for c in range(fields[fi][2]):
+                    w(f"  n{fi}_{c} = {new_names[(fi, c)] if new_names[(fi, c)] is not None else f'f{fi}_{c}'};")
             for r in my_reds:
                 sl, kind, nat = red_slot[r.id], r.attr[0], _acc_native(r.args[0].dtype)
                 e = red_exprs[r.id]
@@ -738,7 +962,13 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
                     w(f"  a{sl} = {kind}(a{sl}, {e});")
             w("}\n")
             # ---- driver ------------------------------------------------------------------------
+            # four agents per thread per iteration; a column of width w is w 16-byte (4-byte for bool) vectors per
+            # group: component c of agent j of the group is flat element j*w + c
             VT = {F32: ("float4", "float"), I32: ("int4", "int"), BOOL: ("uchar4", "unsigned char")}
+
+            def elem(prefix, fi, j, c):
+                flat = j * fields[fi][2] + c
+                return f"{prefix}{fi}_{flat // 4}.{'xyzw'[flat % 4]}"
             w(f"template <int MODE> __device__ __forceinline__ void jxc_agents_v{var}_t{ti}(const TypeDev& t, const double* env, "
               f"const double* __restrict__ cst, long long time_step, Key ck, int lb, double* accd) {{")
             for r in my_reds:
@@ -752,34 +982,43 @@ def generate_source(variants: List[TracedModel]) -> Tuple[str, dict]:
             w("  for (long long g = (long long)lb * blockDim.x + threadIdx.x; g < ngroups; g += stride) {")
             for fi in loaded:
                 vt, _ = VT[fields[fi][1]]
-                w(f"    const {vt} F{fi} = *(({vt}*)t.f[{fi}] + g);")
+                for v in range(fields[fi][2]):
+                    w(f"    const {vt} F{fi}_{v} = *(({vt}*)t.f[{fi}] + g * {fields[fi][2]} + {v});")
             for fi in stored:
                 vt, _ = VT[fields[fi][1]]
-                w(f"    {vt} N{fi};")
-            for lane_i, comp in enumerate("xyzw"):
-                ins = "".join(f", F{fi}.{comp}{' != 0' if fields[fi][1] == BOOL else ''}" for fi in loaded)
+                for v in range(fields[fi][2]):
+                    w(f"    {vt} N{fi}_{v};")
+            for j in range(4):
+                ins = "".join(f", {elem('F', fi, j, c)}{' != 0' if fields[fi][1] == BOOL else ''}"
+                              for fi in loaded for c in range(fields[fi][2]))
                 for fi in stored:
-                    w(f"    {_CT[fields[fi][1]]} n{fi}_{comp};")
-                outs = "".join(f", n{fi}_{comp}" for fi in stored)
-                w(f"    jxc_one_v{var}_t{ti}<MODE>(t, env, cst, time_step, ck, 4 * g + {lane_i}{ins}{outs}{acc_args});")
+                    for c in range(fields[fi][2]):
+                        w(f"    {_CT[fields[fi][1]]} n{fi}_{c}_{j};")
+                outs = "".join(f", n{fi}_{c}_{j}" for fi in stored for c in range(fields[fi][2]))
+                w(f"    jxc_one_v{var}_t{ti}<MODE>(t, env, cst, time_step, ck, 4 * g + {j}{ins}{outs}{acc_args});")
                 for fi in stored:
-                    w(f"    N{fi}.{comp} = n{fi}_{comp}{' ? 1 : 0' if fields[fi][1] == BOOL else ''};")
+                    for c in range(fields[fi][2]):
+                        w(f"    {elem('N', fi, j, c)} = n{fi}_{c}_{j}{' ? 1 : 0' if fields[fi][1] == BOOL else ''};")
             for fi in stored:
                 vt, _ = VT[fields[fi][1]]
-                w(f"    *(({vt}*)t.f[{fi}] + g) = N{fi};")
+                for v in range(fields[fi][2]):
+                    w(f"    *(({vt}*)t.f[{fi}] + g * {fields[fi][2]} + {v}) = N{fi}_{v};")
             w("  }")
             w("  for (long long i = ngroups * 4 + threadIdx.x; lb == 0 && i < t.n; i += blockDim.x) {   // tail agents")
             for fi in loaded:
                 _, st = VT[fields[fi][1]]
-                w(f"    const {_CT[fields[fi][1]]} f{fi} = (({st}*)t.f[{fi}])[i]{' != 0' if fields[fi][1] == BOOL else ''};")
+                for c in range(fields[fi][2]):
+                    w(f"    const {_CT[fields[fi][1]]} f{fi}_{c} = (({st}*)t.f[{fi}])[i * {fields[fi][2]} + {c}]{' != 0' if fields[fi][1] == BOOL else ''};")
             for fi in stored:
-                w(f"    {_CT[fields[fi][1]]} n{fi};")
-            ins = "".join(f", f{fi}" for fi in loaded)
-            outs = "".join(f", n{fi}" for fi in stored)
+                for c in range(fields[fi][2]):
+                    w(f"    {_CT[fields[fi][1]]} n{fi}_{c};")
+            ins = "".join(f", f{fi}_{c}" for fi in loaded for c in range(fields[fi][2]))
+            outs = "".join(f", n{fi}_{c}" for fi in stored for c in range(fields[fi][2]))
             w(f"    jxc_one_v{var}_t{ti}<MODE>(t, env, cst, time_step, ck, i{ins}{outs}{acc_args});")
             for fi in stored:
                 _, st = VT[fields[fi][1]]
-                w(f"    (({st}*)t.f[{fi}])[i] = n{fi}{' ? 1 : 0' if fields[fi][1] == BOOL else ''};")
+                for c in range(fields[fi][2]):
+                    w(f"    (({st}*)t.f[{fi}])[i * {fields[fi][2]} + {c}] = n{fi}_{c}{' ? 1 : 0' if fields[fi][1] == BOOL else ''};")
             w("  }")
             for r in my_reds:
                 sl, kind, nat = red_slot[r.id], r.attr[0], _acc_native(r.args[0].dtype)
@@ -925,12 +1164,12 @@ __global__ void __launch_bounds__(kThreads) jxc_step_kernel(const ModelDev md) {
         def leaf_init(x, em):
             raise TraceError("init_state can only use its key and Python constants")
         em = Emitter(leaf_init, "ak", pool)
-        vals = [(fi, dt, em.cast(t["init"][fname], dt)) for fi, (fname, dt) in enumerate(t["fields"])]
+        vals = [(fi, dt, wd, c, em.cast(t["init"][fname][c], dt)) for fi, (fname, dt, wd) in enumerate(t["fields"]) for c in range(wd)]
         for ln in em.lines:
             w("  " + ln)
-        for fi, dt, e in vals:
+        for fi, dt, wd, c, e in vals:
             ct = {F32: "float", I32: "int", BOOL: "unsigned char"}[dt]
-            w(f"  (({ct}*)t.f[{fi}])[i] = {e}{' ? 1 : 0' if dt == BOOL else ''};")
+            w(f"  (({ct}*)t.f[{fi}])[i * {wd} + {c}] = {e}{' ? 1 : 0' if dt == BOOL else ''};")
         w("}")
         w(f"template <int MODE> __global__ void __launch_bounds__(kThreads) jxc_init_kernel_t{ti}(const TypeDev t, Key key, "
           f"const double* __restrict__ cst) {{")
@@ -956,7 +1195,7 @@ __global__ void __launch_bounds__(kThreads) jxc_step_kernel(const ModelDev md) {
                            used_leaves(list(variants[-1].env_out.values()) + [v for _, v in variants[-1].metrics], "reduce")) or "0"
     kinds_first = ", ".join({"sum": "0", "mean": "0", "max": "1", "min": "2"}[r.attr[0]] for r in
                             used_leaves(list(variants[0].env_out.values()) + [v for _, v in variants[0].metrics], "reduce")) or "0"
-    field_sizes = [[{F32: 4, I32: 4, BOOL: 1}[dt] for _, dt in t["fields"]] for t in tm0.types]
+    field_sizes = [[{F32: 4, I32: 4, BOOL: 1}[dt] * wd for _, dt, wd in t["fields"]] for t in tm0.types]      # bytes per agent
     w(f"constexpr int kEnsTypes = {n_types};")
     w("constexpr int kEnsThreads2 = 1024;")
     w("struct JxcEns { int R, steps, n_consts, has_env_fn, use_smem; const double* consts; const double* env0; const unsigned int* seeds; "

@@ -118,8 +118,18 @@ def test_api_contract_without_device():
         def step(self):
             pass
 
-    with pytest.raises(jx.UnregisteredRuleError):
+    with pytest.raises(ValueError, match="No agent collections"):           # plain Python -> traced path; model.py:125-126
         MyModel({"steps": 1}).run()
+
+    class Mixed(jx.Model):                # a registered agent rule under a plain-Python Model.step cannot be fused
+        def setup(self):
+            self.add_agents(3, random_walk.RandomWalker)
+
+        def step(self):
+            pass
+
+    with pytest.raises(jx.UnregisteredRuleError, match="cannot be mixed"):
+        Mixed({"steps": 1}).run()
     with pytest.raises(NotImplementedError):
         jx.CoreModelCalibrator(growth.create_test_model, {"growth_rate": 0.1}, {"avg_value": 1.0}, method="dqn")
     with pytest.raises(ValueError):
@@ -245,7 +255,7 @@ def test_rule_tracer_generates_and_compiles_a_kernel_without_a_gpu():
     m = build.device_noisy(1000, 1, 1)
     variants = jit.trace_variants(m)
     assert [v.env_dtypes for v in variants] == [["wf64", "wf64", "wi32"], ["f32", "f32", "wi32"]]
-    assert variants[-1].types[0]["fields"] == [("wealth", "f32"), ("active", "bool"), ("trades", "i32")]
+    assert variants[-1].types[0]["fields"] == [("wealth", "f32", 1), ("active", "bool", 1), ("trades", "i32", 1)]
     src, meta = trace.generate_source(variants)
     assert "normal_scalar<MODE>" in src and "jxc_step_kernel" in src and meta["n_variants"] == 2
     lib = jit.compile_source(src)
@@ -421,3 +431,40 @@ def test_feistel_inverse_is_the_inverse_permutation():
         assert np.array_equal(fwd, jl.feistel_permute(np.asarray(idx, dtype=np.uint32), n, rk))
         if n <= 5000:
             assert np.array_equal(np.sort(fwd), np.arange(n))
+
+
+def test_facade_example_traces_and_compiles_without_a_gpu():
+    """The reference's basic example (tests/golden/basic_example_model.py = its two classes with the framework
+    imports changed) through the facade's plain-Python path: AgentWrapper + the update_state bridge are traced,
+    vector-valued fields become width-2 columns, the kernel source compiles for sm_100a."""
+    import importlib.util
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "examples"))
+    import load_example
+    assert load_example.check_against_reference() in (True, False)
+    spec = importlib.util.spec_from_file_location("basic_example_model", load_example.LOCAL)
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    from jaxabm_b200 import jit, trace as T
+    from jaxabm_b200.model import Model as CoreModel
+    m = ex.RandomWalkModel({"n_agents": 1000, "steps": 100, "seed": 42})
+    m.setup()
+    assert m._program() is None                       # nothing registered: the traced path
+    jm = CoreModel(params=m.p, config=jx.ModelConfig(steps=100, seed=42), update_state_fn=m.update_state,
+                   metrics_fn=m.compute_metrics)
+    m._jax_model = jm
+    for name, al in m._agent_lists.items():
+        jm.add_agent_collection(name, al.collection)
+    for name, value in m.env.state.items():
+        jm.add_env_state(name, value)
+    variants = jit.trace_variants(jm)
+    tm = variants[-1]
+    assert tm.types[0]["name"] == "randomwalkers"
+    assert tm.types[0]["fields"] == [("position", "f32", 2), ("velocity", "f32", 2), ("color", "i32", 1), ("steps_taken", "i32", 1)]
+    assert [k for k, _ in tm.metrics] == ["mean_x", "mean_y", "mean_distance", "max_distance", "num_red", "num_blue", "time"]
+    assert m._step_has_host_effects and m._jax_model is jm        # step()'s add_env_state hit the probe, not the model
+    assert jm._env_state["time"] == 0
+    src, meta = T.generate_source(variants)
+    assert "float4 F0_0" in src and "float4 F0_1" in src          # f32[N,2]: two 16-byte vectors per four agents
+    lib = jit.compile_source(src)
+    assert lib.jxc_n_variants() == len(variants)
