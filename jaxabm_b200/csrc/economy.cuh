@@ -36,9 +36,16 @@ enum {
 constexpr int kEcoF = 14;             // float sums
 constexpr int kEcoAcc = kEcoF + 1;    // + employed count
 constexpr int kEcoRow = kEcoAcc + 2;  // + the populated range of the income histogram: max bin, -(min bin) (both fold with max)
-constexpr int kGiniBits = 22;
+// Gini histogram: the top kGiniBits bits of the order-preserving integer image of the float = bins of 2^-10
+// relative width.  Incomes sharing a bin get their mean rank; the rank-weighted sum then differs from the sorted
+// one by about (bin width) / (6 * populated bins) ~ 1e-7 relative, far inside the 1e-5 tolerance.
+// (Round 1 used 22 bits; the populated range then spans ~16 K bins and every household update is a global L2
+// reduction -- measured bound of the whole step.  With 19 bits the populated range fits a per-CTA shared-memory
+// window.)
+constexpr int kGiniBits = 19;
 constexpr int kGiniBins = 1 << kGiniBits;
 constexpr int kGiniScanTile = 4096;   // bins per scan CTA
+constexpr int kGiniWin = 8192;        // bins of the per-CTA shared-memory histogram window (8 octaves of income)
 
 struct EcoDev {
   double* partials;          // [grid][kEcoRow]
@@ -186,6 +193,14 @@ __device__ __forceinline__ void household_one(HouseholdIO& h, float rv, const Ec
 
 __device__ __forceinline__ unsigned int gini_bin(float x);
 
+// count one income: into the CTA's shared-memory window when the bin falls inside it (the window is placed on the
+// previous step's populated range), straight into the global histogram otherwise
+__device__ __forceinline__ void hist_count(unsigned int* bin_count, unsigned int* s_hist, unsigned int win_lo, unsigned int bin) {
+  const unsigned int off = bin - win_lo;
+  if (off < (unsigned int)kGiniWin) atomicAdd(s_hist + off, 1u);
+  else atomicAdd(bin_count + bin, 1u);
+}
+
 // One agent's draw: u = uniform(split(split(coll_key, N)[i], 4)[0]) -- three dependent threefry blocks
 // (agent.py:156 then advanced_economic_model.py:159,174).
 template <int MODE>
@@ -201,7 +216,7 @@ __device__ __forceinline__ float household_draw(Key ck, unsigned long long gi, u
 template <int MODE>
 __device__ __forceinline__ void rule_household(const TypeDev& t, const double* env, Key ck, int lb, float* fs,
                                                int& employed_count, unsigned int* bin_count, unsigned int& bin_lo,
-                                               unsigned int& bin_hi) {
+                                               unsigned int& bin_hi, unsigned int* s_hist, unsigned int win_lo) {
   const EcoEnvView v = eco_env_view(env);
   const float init_inc = t.p[1];
   const float two_init_inc = (float)(2.0 * (double)t.p[1]);
@@ -254,7 +269,7 @@ __device__ __forceinline__ void rule_household(const TypeDev& t, const double* e
       // reductions whose latency hides behind the streaming loads
       const unsigned int bin = gini_bin(h[j].income);
       bin_lo = min(bin_lo, bin); bin_hi = max(bin_hi, bin);
-      atomicAdd(bin_count + bin, 1u);
+      hist_count(bin_count, s_hist, win_lo, bin);
     }
   }
   // the last t.n % 4 agents
@@ -274,7 +289,7 @@ __device__ __forceinline__ void rule_household(const TypeDev& t, const double* e
     employed_count += h.employed ? 1 : 0;
     const unsigned int bin = gini_bin(h.income);
     bin_lo = min(bin_lo, bin); bin_hi = max(bin_hi, bin);
-    atomicAdd(bin_count + bin, 1u);
+    hist_count(bin_count, s_hist, win_lo, bin);
   }
 }
 
@@ -461,13 +476,23 @@ __device__ inline void eco_compute_metrics(const double* env, float gini, double
 // compiled with the firm path's register footprint); the launches of a step share the election
 // ticket: the last CTA of the LAST launch folds all `total_ctas` partial rows.
 template <int MODE, int RULE>
-__global__ void __launch_bounds__(kThreads) economy_step_kernel(const ModelDev md, const EcoDev ed, int ti,
+__global__ void __launch_bounds__(kThreads, 3) economy_step_kernel(const ModelDev md, const EcoDev ed, int ti,
                                                                 int row_offset, int total_ctas) {
   __shared__ double s_red[(kThreads / 32) * kEcoRow];
   __shared__ double s_tot[kEcoRow];
   __shared__ int s_last;
+  __shared__ unsigned int s_hist[RULE == JXB_RULE_HOUSEHOLD ? kGiniWin : 1];
   const TypeDev& t = md.t[ti];
   const int lb = blockIdx.x;
+  // shared-memory histogram window: starts half a scan tile below the previous step's lowest populated tile (the
+  // income distribution drifts by a few percent per step); nothing is known before the first step
+  unsigned int win_lo = 0xFFFFFFFFu - (unsigned int)kGiniWin;      // disabled: every bin is "outside"
+  if (RULE == JXB_RULE_HOUSEHOLD) {
+    const int tlo = ed.tile_range[0], thi = ed.tile_range[1];
+    if (thi >= tlo) win_lo = (unsigned int)max(0, tlo * kGiniScanTile - kGiniScanTile / 2);
+    for (int i = threadIdx.x; i < kGiniWin; i += kThreads) s_hist[i] = 0u;
+    __syncthreads();
+  }
   const uint32_t* kp = md.keys + (size_t)md.ctrl->step_in_run * (md.n_types + 1) * 2;
   const Key ck = {kp[2 * ti], kp[2 * ti + 1]};
   float fs[kEcoF];
@@ -475,8 +500,15 @@ __global__ void __launch_bounds__(kThreads) economy_step_kernel(const ModelDev m
   for (int i = 0; i < kEcoF; ++i) fs[i] = 0.f;
   int emp = 0;
   unsigned int bin_lo = kGiniBins, bin_hi = 0;        // empty range: hi < lo
-  if (RULE == JXB_RULE_HOUSEHOLD) rule_household<MODE>(t, md.env, ck, lb, fs, emp, ed.hist, bin_lo, bin_hi);
+  if (RULE == JXB_RULE_HOUSEHOLD) rule_household<MODE>(t, md.env, ck, lb, fs, emp, ed.hist, bin_lo, bin_hi, s_hist, win_lo);
   else rule_firm<MODE>(t, md.env, ck, lb, fs);
+  if (RULE == JXB_RULE_HOUSEHOLD) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kGiniWin; i += kThreads) {
+      const unsigned int c = s_hist[i];
+      if (c) atomicAdd(ed.hist + win_lo + i, c);
+    }
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < kEcoF; ++i) {

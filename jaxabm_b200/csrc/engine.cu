@@ -1281,9 +1281,21 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
   m->net_built = true;
   {
     // push formulation: counters + the static list of heavy rows
-    std::vector<int> heavy;
-    for (long long i = 0; i < n; ++i)
-      if (row_ptr[i + 1] - row_ptr[i] > (unsigned)kSirHeavy) heavy.push_back((int)i);
+    sv.big_len = 256u;
+    if (const char* ev = getenv("JXB_SIR_BIG")) sv.big_len = (unsigned int)std::max(1, std::min(atoi(ev), kSirHeavy));
+    std::vector<int> heavy, big;
+    for (long long i = 0; i < n; ++i) {
+      const unsigned int len = row_ptr[i + 1] - row_ptr[i];
+      if (len > (unsigned)kSirHeavy) heavy.push_back((int)i);
+      else if (len > sv.big_len) big.push_back((int)i);
+    }
+    {
+      int* d_big = nullptr;
+      if ((rc = dev_alloc(m, &d_big, big.size() + 1, &m->net_allocs))) return rc;
+      if (!big.empty()) CK(cudaMemcpy(d_big, big.data(), big.size() * 4, cudaMemcpyHostToDevice));
+      sv.big = d_big;
+      sv.n_big = (int)big.size();
+    }
     int* d_heavy = nullptr;
     if ((rc = dev_alloc(m, &d_heavy, heavy.size() + 1, &m->net_allocs))) return rc;
     if (!heavy.empty()) CK(cudaMemcpy(d_heavy, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice));
@@ -1299,8 +1311,6 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     else if (mode && !strcmp(mode, "pull_s")) m->sir_mode = 2;
     if (m->net_sharded) m->sir_mode = 2;     // a rank only holds its own rows: pull over them (a push would scatter remotely)
     sv.auto_mode = m->sir_mode == 3;
-    sv.big_len = 256u;
-    if (const char* ev = getenv("JXB_SIR_BIG")) sv.big_len = (unsigned int)std::max(1, atoi(ev));
     const int dev_mode = m->sir_mode == 2 ? 0 : 1;       // auto starts in the push direction
     CK(cudaMemcpy(&m->dev.ctrl->sir_mode, &dev_mode, sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(&m->dev.ctrl->sir_mode_next, &dev_mode, sizeof(int), cudaMemcpyHostToDevice));
@@ -1485,6 +1495,12 @@ static int plan_step_blocks(jxb_model* m) {
   return JXB_OK;
 }
 
+// CTAs of sir_pull_heavy_kernel: one per heavy row, one per 8 big rows (a warp each)
+static int sir_heavy_grid(jxb_model* m, int cap) {
+  const int want = std::max(m->sv.n_heavy, (m->sv.n_big + kThreads / 32 - 1) / (kThreads / 32));
+  return std::max(1, std::min(want, cap));
+}
+
 // per-agent series (csrc/record.cuh): after the step's tail advanced the device-side counters, copy every
 // recorded column into its ring slot if this step recorded a history row.  Capture-safe.
 static int enqueue_snapshots(jxb_model* m, cudaStream_t s) {
@@ -1516,8 +1532,8 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
         if (!m->ns_attached) return fail(JXB_ERR_STATE, "sharded Network step without attached peers");
         const int pgrid = m->eng->sms * 8;
         if (timed) cudaEventRecord(e0, s);
-        if (m->sv.n_heavy > 0) {
-          sir_pull_heavy_kernel<true><<<std::min(m->sv.n_heavy, pgrid), kThreads, 0, s>>>(m->sv, m->dev);
+        if (m->sv.n_heavy + m->sv.n_big > 0) {
+          sir_pull_heavy_kernel<true><<<sir_heavy_grid(m, pgrid), kThreads, 0, s>>>(m->sv, m->dev);
           eng->launches += 1;
         }
         if (part) sir_pull_s_kernel<1, true><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
@@ -1544,8 +1560,8 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
           eng->launches += 1;
         }
         if (m->sir_mode != 1) {          // pull direction
-          if (m->sv.n_heavy > 0) {
-            sir_pull_heavy_kernel<false><<<std::min(m->sv.n_heavy, pgrid), kThreads, 0, s>>>(m->sv, m->dev);
+          if (m->sv.n_heavy + m->sv.n_big > 0) {
+            sir_pull_heavy_kernel<false><<<sir_heavy_grid(m, pgrid), kThreads, 0, s>>>(m->sv, m->dev);
             eng->launches += 1;
           }
           if (part) sir_pull_s_kernel<1><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
@@ -1689,7 +1705,7 @@ static int launches_per_step_all(jxb_model* m) {
 }
 static int launches_per_step(jxb_model* m) {
   if (m->grid_sharded) return 4;
-  const int hv = (m->has_net && m->sv.n_heavy > 0) ? 1 : 0;       // sir_pull_heavy_kernel
+  const int hv = (m->has_net && m->sv.n_heavy + m->sv.n_big > 0) ? 1 : 0;       // sir_pull_heavy_kernel
   if (m->net_sharded) return 2 + hv;
   if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 + hv : (m->sir_mode == 1 ? 2 : (m->sir_mode == 2 ? 1 + hv : 1));
   if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? (m->dev.world_size > 1 ? 6 : 5) : 1);
