@@ -743,9 +743,9 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
     EcoDev& ed = m->eco;
     TRY(dev_alloc(m, &ed.partials, (size_t)std::max(m->step_blocks, 1) * kEcoRow));
     TRY(dev_alloc(m, &ed.bin_count, (size_t)kGiniBins));
-    TRY(dev_alloc(m, &ed.tile_range, 2));
+    TRY(dev_alloc(m, &ed.tile_range, 4));
     {
-      const int empty[2] = {1, 0};
+      const int empty[4] = {1, 0, -1, 0};
       cudaMemcpyAsync(ed.tile_range, empty, sizeof(empty), cudaMemcpyHostToDevice, eng->stream);
     }
     if (md.world_size > 1) {
@@ -1282,20 +1282,10 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
   {
     // push formulation: counters + the static list of heavy rows
     sv.big_len = 256u;
-    if (const char* ev = getenv("JXB_SIR_BIG")) sv.big_len = (unsigned int)std::max(1, std::min(atoi(ev), kSirHeavy));
-    std::vector<int> heavy, big;
-    for (long long i = 0; i < n; ++i) {
-      const unsigned int len = row_ptr[i + 1] - row_ptr[i];
-      if (len > (unsigned)kSirHeavy) heavy.push_back((int)i);
-      else if (len > sv.big_len) big.push_back((int)i);
-    }
-    {
-      int* d_big = nullptr;
-      if ((rc = dev_alloc(m, &d_big, big.size() + 1, &m->net_allocs))) return rc;
-      if (!big.empty()) CK(cudaMemcpy(d_big, big.data(), big.size() * 4, cudaMemcpyHostToDevice));
-      sv.big = d_big;
-      sv.n_big = (int)big.size();
-    }
+    if (const char* ev = getenv("JXB_SIR_BIG")) sv.big_len = (unsigned int)std::max(1, atoi(ev));
+    std::vector<int> heavy;
+    for (long long i = 0; i < n; ++i)
+      if (row_ptr[i + 1] - row_ptr[i] > (unsigned)kSirHeavy) heavy.push_back((int)i);
     int* d_heavy = nullptr;
     if ((rc = dev_alloc(m, &d_heavy, heavy.size() + 1, &m->net_allocs))) return rc;
     if (!heavy.empty()) CK(cudaMemcpy(d_heavy, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice));
@@ -1376,9 +1366,6 @@ static int sir_sync_from_api(jxb_model* m) {
   const long long n = m->desc.types[0].n_agents;
   const int cur = (int)(m->time_step & 1);
   const int blocks = (int)((n + 255) / 256);
-  // the push counters of rows that are not susceptible are never read or re-zeroed (sir_transition_kernel); a
-  // state upload may make such a row susceptible again
-  CK(cudaMemsetAsync(m->sv.k32, 0, ((size_t)n + 32) * 4, m->eng->stream));
   sir_pack_kernel<<<blocks, 256, 0, m->eng->stream>>>((const int*)m->dev.t[0].f[0], m->sv.state8[cur],
                                                       m->sv.infbits[cur] + (m->net_sharded ? m->sv.gw0 : 0u), n);
   m->eng->launches++;
@@ -1431,6 +1418,32 @@ extern "C" int jxb_collection_init(jxb_model* m, int type, uint32_t k0, uint32_t
   return JXB_OK;
 }
 
+// Economy: where the first step's kernels put their shared-memory histogram window (later steps take it from the
+// previous step's scan).  A strided sample of the freshly initialised incomes, binned on the host.
+static int eco_seed_window(jxb_model* m) {
+  const int hh = m->eco_hh;
+  if (hh < 0) return JXB_OK;
+  const long long n = m->desc.types[hh].n_agents;
+  const long long stride = std::max<long long>(1, n / 8192);
+  const size_t rows = (size_t)((n + stride - 1) / stride);
+  std::vector<float> sample(rows);
+  CK(cudaMemcpy2D(sample.data(), sizeof(float), m->dev.t[hh].f[1], (size_t)stride * sizeof(float), sizeof(float), rows,
+                  cudaMemcpyDeviceToHost));
+  const int tiles = kGiniBins / kGiniScanTile;
+  std::vector<unsigned int> cnt((size_t)tiles + 1, 0u);
+  for (float x : sample) {
+    unsigned int b;
+    memcpy(&b, &x, 4);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);            // gini_bin (csrc/economy.cuh)
+    cnt[(b >> (32 - kGiniBits)) / kGiniScanTile] += 1u;
+  }
+  int best = 0;
+  for (int t = 0; t + 1 < tiles; ++t)
+    if (cnt[t] + cnt[t + 1] > cnt[best] + cnt[best + 1]) best = t;
+  CK(cudaMemcpy(m->eco.tile_range + 2, &best, sizeof(int), cudaMemcpyHostToDevice));
+  return JXB_OK;
+}
+
 extern "C" int jxb_model_init(jxb_model* m, uint32_t k0, uint32_t k1) {
   NEED(m);
   CK(cudaSetDevice(m->eng->device));
@@ -1443,6 +1456,7 @@ extern "C" int jxb_model_init(jxb_model* m, uint32_t k0, uint32_t k1) {
   }
   CK(cudaStreamSynchronize(m->eng->stream));
   m->initialized = true;
+  if (m->has_eco) { int rc = eco_seed_window(m); if (rc) return rc; }
   if (m->has_net) return sir_sync_from_api(m);
   if (m->has_grid) m->grid_built = false;
   return JXB_OK;
@@ -1495,12 +1509,6 @@ static int plan_step_blocks(jxb_model* m) {
   return JXB_OK;
 }
 
-// CTAs of sir_pull_heavy_kernel: one per heavy row, one per 8 big rows (a warp each)
-static int sir_heavy_grid(jxb_model* m, int cap) {
-  const int want = std::max(m->sv.n_heavy, (m->sv.n_big + kThreads / 32 - 1) / (kThreads / 32));
-  return std::max(1, std::min(want, cap));
-}
-
 // per-agent series (csrc/record.cuh): after the step's tail advanced the device-side counters, copy every
 // recorded column into its ring slot if this step recorded a history row.  Capture-safe.
 static int enqueue_snapshots(jxb_model* m, cudaStream_t s) {
@@ -1532,10 +1540,6 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
         if (!m->ns_attached) return fail(JXB_ERR_STATE, "sharded Network step without attached peers");
         const int pgrid = m->eng->sms * 8;
         if (timed) cudaEventRecord(e0, s);
-        if (m->sv.n_heavy + m->sv.n_big > 0) {
-          sir_pull_heavy_kernel<true><<<sir_heavy_grid(m, pgrid), kThreads, 0, s>>>(m->sv, m->dev);
-          eng->launches += 1;
-        }
         if (part) sir_pull_s_kernel<1, true><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
         else sir_pull_s_kernel<0, true><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
         if (timed) cudaEventRecord(e1, s);
@@ -1560,10 +1564,6 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
           eng->launches += 1;
         }
         if (m->sir_mode != 1) {          // pull direction
-          if (m->sv.n_heavy + m->sv.n_big > 0) {
-            sir_pull_heavy_kernel<false><<<sir_heavy_grid(m, pgrid), kThreads, 0, s>>>(m->sv, m->dev);
-            eng->launches += 1;
-          }
           if (part) sir_pull_s_kernel<1><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
           else sir_pull_s_kernel<0><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
           if (m->sir_mode == 3) eng->launches += 1;
@@ -1619,7 +1619,7 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       }
       if (hh >= 0) {
         gini_scan_sums_kernel<<<tiles, kThreads, 0, s>>>(m->eco, m->eco.bin_count, m->eco.scan_sums);
-        gini_scan_top_kernel<<<1, 1024, 0, s>>>(m->eco.scan_sums, tiles);
+        gini_scan_top_kernel<<<1, 1024, 0, s>>>(m->eco.scan_sums, tiles, m->eco.tile_range + 2);
         gini_scan_apply_kernel<<<tiles, kThreads, 0, s>>>(m->eco, m->eco.bin_count, m->eco.scan_sums, m->eco.bin_base);
         eng->launches += 3;
       }
@@ -1705,9 +1705,8 @@ static int launches_per_step_all(jxb_model* m) {
 }
 static int launches_per_step(jxb_model* m) {
   if (m->grid_sharded) return 4;
-  const int hv = (m->has_net && m->sv.n_heavy + m->sv.n_big > 0) ? 1 : 0;       // sir_pull_heavy_kernel
-  if (m->net_sharded) return 2 + hv;
-  if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 + hv : (m->sir_mode == 1 ? 2 : (m->sir_mode == 2 ? 1 + hv : 1));
+  if (m->net_sharded) return 2;
+  if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 : (m->sir_mode == 1 ? 2 : 1);
   if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? (m->dev.world_size > 1 ? 6 : 5) : 1);
   return (m->dev.exchange == 2) ? 2 : 1;     // + the NCCL kernels, which are not ours
 }

@@ -37,8 +37,6 @@ struct SirDev {
   unsigned int* k32;       // push formulation: infected-neighbour counters (zero between steps)
   const int* heavy;        // rows with more than kSirHeavy adjacency entries
   int n_heavy;
-  const int* big;          // rows with big_len < entries <= kSirHeavy (static list, like heavy)
-  int n_big;
   long long* degsum;       // [CTAs][2] adjacency entries of the new susceptible / infected rows per CTA
   int auto_mode;           // 1: the step's tail picks push or pull for the next step (direction-optimising)
   unsigned int big_len;    // pull over S rows: rows longer than this are walked by the whole warp, shorter ones by their own lane
@@ -335,9 +333,6 @@ __global__ void __launch_bounds__(kThreads) sir_push_kernel(const SirDev sv, con
     const unsigned int lo = sv.row_ptr[r], hi = sv.row_ptr[r + 1];
     for (unsigned int e = lo + tid; e < hi; e += kThreads) red_add_u32(sv.k32 + __ldcs(sv.col + e), 1u);
   }
-  // all other rows: one warp per 32-row group, lanes striding each infected row.  (Laying the
-  // infected rows' ranges end to end with a warp scan + per-entry owner search measured ~15 %
-  // slower: the kernel is bound by L2 reduction throughput, not by per-row latency.)
   // Warp w owns the groups g = w (mod #warps), as before (the hubs sit at low indices: consecutive groups must go to
   // different warps), but it fetches the bitmap words of 32 of its groups with ONE load instruction (lane l reads
   // the word of its l-th next group) and then visits the groups that hold an infected row.  (One word per
@@ -395,24 +390,14 @@ __global__ void __launch_bounds__(kThreads) sir_transition_kernel(const SirDev s
 #pragma unroll
     for (int i = 0; i < kSirRowsPerThread; ++i) {       // all loads of the tile in flight first
       const long long r = base + i * kThreads + tid;
-      s[i] = 2;
-      if (r < t.n) s[i] = st_cur[r];
-    }
-    // the counter only matters for a susceptible row (a recovered / infected row is never susceptible again, so
-    // whatever the pushes leave in ITS counter is never read), the degree only for rows that stay S or I: once
-    // most agents have recovered, the pass reads one byte per agent instead of 13
-#pragma unroll
-    for (int i = 0; i < kSirRowsPerThread; ++i) {
-      const long long r = base + i * kThreads + tid;
-      k[i] = 0; deg[i] = 0;
-      if (s[i] == 0) k[i] = __ldcg(k32 + r);
-      if (s[i] != 2) deg[i] = sv.row_ptr[r + 1] - sv.row_ptr[r];
+      s[i] = 0; k[i] = 0; deg[i] = 0;
+      if (r < t.n) { s[i] = st_cur[r]; k[i] = __ldcg(k32 + r); deg[i] = sv.row_ptr[r + 1] - sv.row_ptr[r]; }
     }
 #pragma unroll
     for (int i = 0; i < kSirRowsPerThread; ++i) {
       const long long r = base + i * kThreads + tid;
       const bool active = r < t.n;
-      int sn = active ? s[i] : 0;
+      int sn = s[i];
       if (active) {
         if (k[i]) k32[r] = 0u;
         const bool need = (sn == 0 && k[i] > 0) || sn == 1;
@@ -454,59 +439,6 @@ __global__ void __launch_bounds__(kThreads) sir_transition_kernel(const SirDev s
 // the same warp.  Cost is proportional to the susceptible rows' adjacency -- the complement of the
 // push kernel's; the step's tail picks whichever is cheaper for the next step.
 // ---------------------------------------------------------------------------------------
-// Long rows that are still susceptible (hubs before they are infected -- the first pull steps of an epidemic), from
-// the static lists built with the CSR: one CTA per heavy row (> kSirHeavy entries), one warp per big row
-// (big_len < entries <= kSirHeavy), counting infected neighbours into k32[row]; sir_pull_s_kernel picks the count
-// up.  Walked by their own lane (or their own warp inside the main kernel) such rows held the whole step back.
-template <bool SHARD = false>
-__global__ void __launch_bounds__(kThreads) sir_pull_heavy_kernel(const SirDev sv, const ModelDev md) {
-  __shared__ unsigned int s_cnt[kThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const Ctrl* ctrl = md.ctrl;
-  if (!SHARD && ctrl->sir_mode != 0) return;
-  const int cur = (int)(ctrl->time_step & 1);
-  const unsigned int* __restrict__ inf = sv.infbits[cur];
-  const signed char* __restrict__ st_cur = sv.state8[cur];
-  for (int h = blockIdx.x; h < sv.n_heavy; h += gridDim.x) {
-    const int r = sv.heavy[h];
-    if (st_cur[r] != 0) continue;
-    const unsigned int lo = sv.row_ptr[r], hi = sv.row_ptr[r + 1];
-    unsigned int cnt = 0;
-    for (unsigned int e = lo + tid; e < hi; e += kThreads) {
-      const int c = __ldcs(sv.col + e);
-      cnt += (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;
-    }
-    cnt = (unsigned int)warp_sum((int)cnt);
-    __syncthreads();
-    if (lane == 0) s_cnt[tid >> 5] = cnt;
-    __syncthreads();
-    if (tid == 0) {
-      unsigned int tot = 0;
-      for (int w = 0; w < kThreads / 32; ++w) tot += s_cnt[w];
-      sv.k32[r] = tot;
-    }
-  }
-  const int nwarps = gridDim.x * (kThreads / 32);
-  for (int h = blockIdx.x * (kThreads / 32) + (tid >> 5); h < sv.n_big; h += nwarps) {
-    const int r = sv.big[h];
-    if (st_cur[r] != 0) continue;
-    const unsigned int lo = sv.row_ptr[r], hi = sv.row_ptr[r + 1];
-    unsigned int cnt = 0;
-    for (unsigned int e0 = lo; e0 < hi; e0 += 128) {            // 4 independent gathers per lane in flight
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned int e = e0 + j * 32 + lane;
-        if (e < hi) {
-          const int c = __ldcs(sv.col + e);
-          cnt += (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;
-        }
-      }
-    }
-    cnt = (unsigned int)warp_sum((int)cnt);
-    if (lane == 0) sv.k32[r] = cnt;
-  }
-}
-
 template <int MODE, bool SHARD = false>
 __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, const ModelDev md) {
   __shared__ int s_red[3][kThreads / 32];
@@ -525,87 +457,82 @@ __global__ void __launch_bounds__(kThreads) sir_pull_s_kernel(const SirDev sv, c
   signed char* __restrict__ st_nxt = sv.state8[nxt];
   int cS = 0, cI = 0, cR = 0;
   long long dS = 0, dI = 0;
-  // A CTA sweeps tiles of kThreads * kSirRowsPerThread rows, every thread four rows of a tile (rows base + i *
-  // kThreads + tid: a warp-iteration covers 32 consecutive rows = one word of the new bitmap).  The loads of the
-  // four rows are issued together -- state first, then the row extents of the rows that are not recovered, then
-  // the adjacency walks -- so that a step in which almost nobody is susceptible costs a few memory round trips
-  // per TILE instead of per 32-row group.
-  constexpr int kTile = kThreads * kSirRowsPerThread;
-  for (long long base = (long long)blockIdx.x * kTile; base < n; base += (long long)gridDim.x * kTile) {
-    int s[kSirRowsPerThread];
-    unsigned int lo[kSirRowsPerThread], len[kSirRowsPerThread], k[kSirRowsPerThread];
-#pragma unroll
-    for (int i = 0; i < kSirRowsPerThread; ++i) {
-      const long long r = base + i * kThreads + tid;
-      s[i] = r < n ? (int)st_cur[r] : 3;
+  const long long ngroups = (n + 31) >> 5;
+  const long long wstride = (long long)gridDim.x * (kThreads / 32);
+  for (long long g = (long long)blockIdx.x * (kThreads / 32) + (tid >> 5); g < ngroups; g += wstride) {
+    const long long r = (g << 5) + lane;
+    const bool active = r < n;
+    int s = 3;
+    unsigned int lo = 0, len = 0;
+    if (active) {
+      s = st_cur[r];
+      lo = sv.row_ptr[r];
+      len = sv.row_ptr[r + 1] - lo;
     }
+    unsigned int k = 0;
+    // long susceptible rows (hubs before they are infected): all 32 lanes stride the row
+    unsigned int big = __ballot_sync(0xffffffffu, active && s == 0 && len > sv.big_len);
+    while (big) {
+      const int b = __ffs(big) - 1;
+      big &= big - 1;
+      const unsigned int blo = __shfl_sync(0xffffffffu, lo, b), blen = __shfl_sync(0xffffffffu, len, b);
+      unsigned int cnt = 0;
+      for (unsigned int e0 = 0; e0 < blen; e0 += 128) {          // 4 independent gathers per lane in flight
+        unsigned int bits = 0;
 #pragma unroll
-    for (int i = 0; i < kSirRowsPerThread; ++i) {
-      const long long r = base + i * kThreads + tid;
-      lo[i] = 0; len[i] = 0; k[i] = 0;
-      if (s[i] == 0 || s[i] == 1) {           // a recovered row needs neither its adjacency nor its degree
-        lo[i] = sv.row_ptr[r];
-        len[i] = sv.row_ptr[r + 1] - lo[i];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kSirRowsPerThread; ++i) {
-      if (s[i] != 0 || len[i] == 0) continue;
-      const long long r = base + i * kThreads + tid;
-      if (len[i] > sv.big_len) {              // counted by sir_pull_heavy_kernel (one warp / one CTA per row)
-        k[i] = __ldcg(sv.k32 + r);
-        sv.k32[r] = 0u;
-        continue;
-      }
-      // the row's own lane walks it; four adjacency loads, then four bitmap gathers, in flight together
-      const int* cp = sv.col + lo[i];
-      unsigned int e = 0, kk = 0;
-      for (; e + 4 <= len[i]; e += 4) {
-        const int c0 = __ldg(cp + e), c1 = __ldg(cp + e + 1), c2 = __ldg(cp + e + 2), c3 = __ldg(cp + e + 3);
-        const unsigned int w0 = __ldg(inf + (c0 >> 5)), w1 = __ldg(inf + (c1 >> 5));
-        const unsigned int w2 = __ldg(inf + (c2 >> 5)), w3 = __ldg(inf + (c3 >> 5));
-        kk += ((w0 >> (c0 & 31)) & 1u) + ((w1 >> (c1 & 31)) & 1u) + ((w2 >> (c2 & 31)) & 1u) + ((w3 >> (c3 & 31)) & 1u);
-      }
-      for (; e < len[i]; ++e) {
-        const int c0 = __ldg(cp + e);
-        kk += (__ldg(inf + (c0 >> 5)) >> (c0 & 31)) & 1u;
-      }
-      k[i] = kk;
-    }
-#pragma unroll
-    for (int i = 0; i < kSirRowsPerThread; ++i) {
-      const long long r = base + i * kThreads + tid;
-      const bool active = r < n;
-      int sn = s[i];
-      if (active) {
-        const bool need = (sn == 0 && k[i] > 0) || sn == 1;
-        if (need) {
-          const Key ak = split_child<MODE>(ck, (unsigned long long)(t.goff + r), (unsigned long long)t.gn);
-          const float u = bits_to_uniform(bits_scalar<MODE>(ak), 0.f, 1.f);
-          if (sn == 0) {
-            const float p = 1.0f - __ldg(sv.escape + (k[i] < (unsigned)kSirKCap ? k[i] : (unsigned)kSirKCap));
-            if (u < p) sn = 1;
-          } else if (u < gamma) {
-            sn = 2;
+        for (int j = 0; j < 4; ++j) {
+          const unsigned int e = e0 + j * 32 + lane;
+          if (e < blen) {
+            const int c = __ldcs(sv.col + blo + e);
+            bits += (__ldg(inf + (c >> 5)) >> (c & 31)) & 1u;
           }
         }
-        st_nxt[r] = (signed char)sn;
-        cS += (sn == 0); cI += (sn == 1); cR += (sn == 2);
-        if (sn == 0) dS += len[i];
-        if (sn == 1) dI += len[i];
+        cnt += bits;
       }
-      const unsigned int w = __ballot_sync(0xffffffffu, active && sn == 1);
-      const long long rg = base + i * kThreads + (tid >> 5) * 32;          // first row of this warp-iteration's group
-      if (rg < n) {
-        const long long g = rg >> 5;
-        if (SHARD) {
-          // the new word of this 32-row group goes straight into EVERY rank's next bitmap (remote stores over
-          // NVLink): the aggregation kernel is also the all-gather of the state slices
-          if (lane < sv.world) sir_peer_bits(sv, sir_peer(sv, lane), nxt)[sv.gw0 + g] = w;
-        } else {
-          if (lane == 0) sv.infbits[nxt][g] = w;
+      cnt = (unsigned int)warp_sum((int)cnt);
+      if (lane == b) k = cnt;
+    }
+    // every other susceptible row: its own lane walks it (consecutive lanes own consecutive CSR
+    // segments, so a warp's loads fall into a few adjacent lines that L1 keeps across the
+    // iterations); two entries per iteration for memory-level parallelism
+    if (active && s == 0 && len > 0 && len <= sv.big_len) {
+      const int* cp = sv.col + lo;
+      unsigned int e = 0;
+      for (; e + 2 <= len; e += 2) {
+        const int c0 = __ldg(cp + e), c1 = __ldg(cp + e + 1);
+        const unsigned int w0 = __ldg(inf + (c0 >> 5)), w1 = __ldg(inf + (c1 >> 5));
+        k += ((w0 >> (c0 & 31)) & 1u) + ((w1 >> (c1 & 31)) & 1u);
+      }
+      if (e < len) {
+        const int c0 = __ldg(cp + e);
+        k += (__ldg(inf + (c0 >> 5)) >> (c0 & 31)) & 1u;
+      }
+    }
+    int sn = s;
+    if (active) {
+      const bool need = (s == 0 && k > 0) || s == 1;
+      if (need) {
+        const Key ak = split_child<MODE>(ck, (unsigned long long)(t.goff + r), (unsigned long long)t.gn);
+        const float u = bits_to_uniform(bits_scalar<MODE>(ak), 0.f, 1.f);
+        if (s == 0) {
+          const float p = 1.0f - __ldg(sv.escape + (k < (unsigned)kSirKCap ? k : (unsigned)kSirKCap));
+          if (u < p) sn = 1;
+        } else if (u < gamma) {
+          sn = 2;
         }
       }
+      st_nxt[r] = (signed char)sn;
+      cS += (sn == 0); cI += (sn == 1); cR += (sn == 2);
+      if (sn == 0) dS += len;
+      if (sn == 1) dI += len;
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, active && sn == 1);
+    if (SHARD) {
+      // the new word of this 32-row group goes straight into EVERY rank's next bitmap (remote stores over
+      // NVLink): the aggregation kernel is also the all-gather of the state slices
+      if (lane < sv.world) sir_peer_bits(sv, sir_peer(sv, lane), nxt)[sv.gw0 + g] = w;
+    } else {
+      if (lane == 0) sv.infbits[nxt][g] = w;
     }
   }
   sir_publish_partials(sv, cS, cI, cR, dS, dI, s_red);
