@@ -38,7 +38,8 @@ UNIT = "agent-steps/s"
 
 def _pin(a):
     import torch
-    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.pin_memory() if torch.cuda.is_available() else t      # the reference arm also runs on a box without a GPU
 
 
 def _pinned_like(shape, dtype):
@@ -344,7 +345,9 @@ class SirWorkload:
         self.n, self.seed, self.shard = n, 42 + (0 if shard else rank), shard
         if shard:
             self.kernel = "sir_pull_s_kernel"
-        self.edges = synthetic.scale_free_edges(n, m, self.seed)
+        # the host copy of env['network_edges'] lives in pinned memory (the e2e call uploads it from there)
+        self._edges_pin = _pin(synthetic.scale_free_edges(n, m, self.seed))
+        self.edges = self._edges_pin.numpy()
         self.nnz = int(self.edges.shape[0])
         self.agents = n
 
@@ -374,8 +377,8 @@ class SirWorkload:
         st = m.agent_collections["agents"].states["state"]
         wall = time.perf_counter() - t0
         del m
-        return wall, self.edges.nbytes, st.nbytes + K * 3 * 8, ("create model, bin network_edges into CSR and upload, "
-                                                               "initialize, Model.run(K), download 'state'")
+        return wall, self.edges.nbytes, st.nbytes + K * 3 * 8, ("create model, upload network_edges from pinned host memory and bin "
+                                                               "them into CSR on the device, initialize, Model.run(K), download 'state'")
 
     def cpu_run(self, steps):
         """The first `steps` full-size steps of the same seeded epidemic on the C/OpenMP oracle."""

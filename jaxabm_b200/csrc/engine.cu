@@ -1181,7 +1181,11 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
   unsigned int* d_rp = nullptr; int* d_col = nullptr;
   if ((rc = dev_alloc(m, &d_rp, (size_t)n + 2, &m->net_allocs))) return rc;
   if ((rc = dev_alloc(m, &d_col, (size_t)std::max<int64_t>(n_edges, 1), &m->net_allocs))) return rc;
-  std::vector<unsigned int> row_ptr((size_t)n + 1, 0);
+  // the row extents come back into a page-locked block (cached by size): 40 MB at C3, ~1 ms instead of ~4
+  void* h_rp = nullptr;
+  if ((rc = jxb_host_alloc(((size_t)n + 2) * 4, &h_rp))) return rc;
+  struct HostBlock { void* p; ~HostBlock() { jxb_host_free(p); } } h_rp_guard{h_rp};
+  unsigned int* row_ptr = (unsigned int*)h_rp;
   {
     void* d_edges = nullptr; void* d_cursor = nullptr; void* d_sums = nullptr; void* d_flag = nullptr;
     const int ntiles = (int)((n + kScanTile - 1) / kScanTile);
@@ -1209,7 +1213,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     m->eng->launches += 5;
     int bad = 0;
     NCK(cudaMemcpyAsync(&bad, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    NCK(cudaMemcpyAsync(row_ptr.data(), d_rp, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    NCK(cudaMemcpyAsync(row_ptr, d_rp, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
     NCK(cudaStreamSynchronize(st));
     NCK(cudaGetLastError());
 #undef NCK

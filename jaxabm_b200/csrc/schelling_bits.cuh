@@ -180,8 +180,7 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
   __shared__ unsigned int s_all[kThreads / 32];
   __shared__ unsigned int s_rk[8];
   __shared__ unsigned int s_prefix, s_total;
-  __shared__ unsigned int s_list[kThreads * 32];     // unsatisfied cells of one chunk of kThreads mask words, compacted
-  __shared__ unsigned int s_pre[8][kThreads];        // prefetched mask words of the next chunks
+  __shared__ unsigned int s_ws[8][kThreads / 32];    // unsatisfied counts per (chunk of a super-chunk, warp)
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -337,110 +336,109 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
     // stays -- what the lazy 'satisfied' column needs.
     if (u > 0) {                   // uniform across the grid
       const Feistel fu = make_feistel(u, s_rk), fe = make_feistel(e, s_rk + 4);
-      unsigned int base = s_prefix;
-      // the mask words of up to kPre chunks are fetched together (one L2 round trip instead of one per chunk), and a
-      // chunk without an unsatisfied agent costs a single barrier: once the grid has converged almost every chunk
-      // of almost every CTA is empty
+      // (a) ordered compaction of the CTA's rows into ITS segment of U (cells ascending), kPre chunks of kThreads
+      // mask words at a time: the words of all chunks are fetched together, every warp scans its 32 words of each
+      // chunk by shuffles, ONE block barrier publishes the per-(chunk, warp) counts, and every thread then knows
+      // where the set bits of its words go.  A super-chunk without an unsatisfied agent costs that one barrier.
       constexpr int kPre = 8;
+      unsigned int base = s_prefix;
       for (long long W0 = wbeg; W0 < wend; W0 += (long long)kPre * kThreads) {
-      {
-        unsigned int pre[kPre];
+        unsigned int pre[kPre], inc[kPre];
+        unsigned int any = 0;
 #pragma unroll
         for (int c = 0; c < kPre; ++c) {
           const long long w = W0 + (long long)c * kThreads + tid;
           pre[c] = w < wend ? __ldcg(sb.umask + w) : 0u;
         }
 #pragma unroll
-        for (int c = 0; c < kPre; ++c) s_pre[c][tid] = pre[c];      // read back by the same thread only
+        for (int c = 0; c < kPre; ++c) {
+          const unsigned int cnt = __popc(pre[c]);
+          any |= cnt;
+          unsigned int v = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t2 = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t2;
+          }
+          inc[c] = v;
+          if (lane == 31) s_ws[c][warp] = v;
+        }
+        if (__syncthreads_count(any != 0u) != 0) {       // uniform; also orders s_ws writes before the reads below
+#pragma unroll
+          for (int c = 0; c < kPre; ++c) {
+            unsigned int woff = 0, ctot = 0;
+#pragma unroll
+            for (int ww = 0; ww < kWarps; ++ww) {
+              const unsigned int v = s_ws[c][ww];
+              if (ww < warp) woff += v;
+              ctot += v;
+            }
+            unsigned int unsat = pre[c];
+            unsigned int pu = base + woff + inc[c] - __popc(unsat);
+            const unsigned int c0 = (unsigned int)((W0 + (long long)c * kThreads + tid) << 5);
+            while (unsat) {
+              const int q = __ffs(unsat) - 1;
+              unsat &= unsat - 1;
+              sd.U[pu++] = c0 + q;
+            }
+            base += ctot;
+          }
+        }
+        __syncthreads();                                  // s_ws is rewritten by the next super-chunk
       }
-#pragma unroll 1
-      for (int c = 0; c < kPre; ++c) {
-        const long long w0 = W0 + (long long)c * kThreads;
-        if (w0 >= wend) break;
-        const long long w = w0 + tid;
-        unsigned int unsat = s_pre[c][tid];
-        const unsigned int cnt = __popc(unsat);
-        // also the barrier after which s_list / s_u32 of the previous chunk are no longer read
-        if (__syncthreads_count(cnt != 0u) == 0) continue;
-        unsigned int inc = cnt;
+      // (b) the moves: the CTA's segment [s_prefix, base) of U, strided over the threads, no barrier inside.  Four
+      // entries per thread per iteration: the chain slot / payload -> writes is latency-bound.  (The segment was
+      // written by this CTA's own threads: the block barrier above made it visible.)
+      constexpr int kMv = 4;
+      const unsigned int seg_end = base;
+      for (unsigned int j0 = s_prefix + tid; j0 < seg_end; j0 += kThreads * kMv) {
+        unsigned int src[kMv], jj[kMv], dst[kMv], tw[kMv];
+        int2 am[kMv];
+        bool mv[kMv];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += v;
-        }
-        if (lane == 31) s_u32[warp] = inc;
-        __syncthreads();
-        unsigned int woff = 0, ttot = 0;
-#pragma unroll
-        for (int ww = 0; ww < kWarps; ++ww) {
-          if (ww < warp) woff += s_u32[ww];
-          ttot += s_u32[ww];
-        }
-        {
-          unsigned int pu = woff + inc - cnt;
-          const unsigned int c0 = (unsigned int)(w << 5);
-          while (unsat) {
-            const int q = __ffs(unsat) - 1;
-            unsat &= unsat - 1;
-            s_list[pu++] = c0 + q;
+        for (int i = 0; i < kMv; ++i) {
+          const unsigned int j = j0 + i * kThreads;
+          mv[i] = false; src[i] = 0; jj[i] = 0;
+          if (j < seg_end) {
+            src[i] = __ldcg(sd.U + j);
+            const unsigned int k = feistel_inverse(fu, j);
+            mv[i] = k < m;
+            if (mv[i]) jj[i] = feistel_permute(fe, k);
           }
         }
-        __syncthreads();
-        // four list entries per thread per iteration: the chain payload / slot -> writes is latency-bound
-        constexpr int kMv = 4;
-        for (unsigned int i0 = tid; i0 < ttot; i0 += kThreads * kMv) {
-          unsigned int src[kMv], jj[kMv], dst[kMv], tw[kMv];
-          int2 am[kMv];
-          bool ok[kMv], mv[kMv];
 #pragma unroll
-          for (int i = 0; i < kMv; ++i) {
-            const unsigned int idx = i0 + i * kThreads;
-            ok[i] = idx < ttot;
-            mv[i] = false; src[i] = 0; jj[i] = 0;
-            if (ok[i]) {
-              src[i] = s_list[idx];
-              const unsigned int k = feistel_inverse(fu, base + idx);
-              mv[i] = k < m;
-              if (mv[i]) jj[i] = feistel_permute(fe, k);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < kMv; ++i) {
-            dst[i] = 0; tw[i] = 0; am[i] = make_int2(-1, 0);
-            if (mv[i]) {
-              dst[i] = __ldcg(sd.E + jj[i]);
-              am[i] = __ldcg(sb.cell_am + src[i]);
-              tw[i] = __ldcg(sb.t1 + (src[i] >> 5));
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < kMv; ++i) {
-            if (!ok[i]) continue;
-            const unsigned int j = base + i0 + i * kThreads;
-            if (!mv[i]) { sd.U[j] = src[i]; continue; }
-            const unsigned int s_ = src[i], d_ = dst[i];
-            const unsigned int sbit = 1u << (s_ & 31), dbit = 1u << (d_ & 31);
-            const bool ty = (tw[i] & sbit) != 0;
-            sd.E[jj[i]] = s_;
-            sd.U[j] = (unsigned int)am[i].x | 0x80000000u;
-            atomicAnd(sb.occ + (s_ >> 5), ~sbit);
-            atomicOr(sb.occ + (d_ >> 5), dbit);
-            if (ty) {
-              atomicAnd(sb.t1 + (s_ >> 5), ~sbit);
-              atomicOr(sb.t1 + (d_ >> 5), dbit);
-            }
-            sb.cell_am[d_] = make_int2(am[i].x, am[i].y + 1);
-            sb.cell_am[s_] = make_int2(-1, 0);
-            if (sd.periodic) {         // keep the wrapped halo rows in step
-              if (d_ < (unsigned)H) { atomicOr(sb.occ + (d_ >> 5) + words, dbit); if (ty) atomicOr(sb.t1 + (d_ >> 5) + words, dbit); }
-              if (d_ >= sd.cells - H) { atomicOr(sb.occ + (long long)(d_ >> 5) - words, dbit); if (ty) atomicOr(sb.t1 + (long long)(d_ >> 5) - words, dbit); }
-              if (s_ < (unsigned)H) { atomicAnd(sb.occ + (s_ >> 5) + words, ~sbit); if (ty) atomicAnd(sb.t1 + (s_ >> 5) + words, ~sbit); }
-              if (s_ >= sd.cells - H) { atomicAnd(sb.occ + (long long)(s_ >> 5) - words, ~sbit); if (ty) atomicAnd(sb.t1 + (long long)(s_ >> 5) - words, ~sbit); }
-            }
+        for (int i = 0; i < kMv; ++i) {
+          dst[i] = 0; tw[i] = 0; am[i] = make_int2(-1, 0);
+          if (mv[i]) {
+            dst[i] = __ldcg(sd.E + jj[i]);
+            am[i] = __ldcg(sb.cell_am + src[i]);
+            tw[i] = __ldcg(sb.t1 + (src[i] >> 5));
           }
         }
-        base += ttot;
-      }
+#pragma unroll
+        for (int i = 0; i < kMv; ++i) {
+          if (!mv[i]) continue;                           // an agent that stays keeps its cell id in U[j]
+          const unsigned int j = j0 + i * kThreads;
+          const unsigned int s_ = src[i], d_ = dst[i];
+          const unsigned int sbit = 1u << (s_ & 31), dbit = 1u << (d_ & 31);
+          const bool ty = (tw[i] & sbit) != 0;
+          sd.E[jj[i]] = s_;
+          sd.U[j] = (unsigned int)am[i].x | 0x80000000u;
+          atomicAnd(sb.occ + (s_ >> 5), ~sbit);
+          atomicOr(sb.occ + (d_ >> 5), dbit);
+          if (ty) {
+            atomicAnd(sb.t1 + (s_ >> 5), ~sbit);
+            atomicOr(sb.t1 + (d_ >> 5), dbit);
+          }
+          sb.cell_am[d_] = make_int2(am[i].x, am[i].y + 1);
+          sb.cell_am[s_] = make_int2(-1, 0);
+          if (sd.periodic) {         // keep the wrapped halo rows in step
+            if (d_ < (unsigned)H) { atomicOr(sb.occ + (d_ >> 5) + words, dbit); if (ty) atomicOr(sb.t1 + (d_ >> 5) + words, dbit); }
+            if (d_ >= sd.cells - H) { atomicOr(sb.occ + (long long)(d_ >> 5) - words, dbit); if (ty) atomicOr(sb.t1 + (long long)(d_ >> 5) - words, dbit); }
+            if (s_ < (unsigned)H) { atomicAnd(sb.occ + (s_ >> 5) + words, ~sbit); if (ty) atomicAnd(sb.t1 + (s_ >> 5) + words, ~sbit); }
+            if (s_ >= sd.cells - H) { atomicAnd(sb.occ + (long long)(s_ >> 5) - words, ~sbit); if (ty) atomicAnd(sb.t1 + (long long)(s_ >> 5) - words, ~sbit); }
+          }
+        }
       }
     }
     if (m == 0) continue;          // uniform: nobody moved, the planes are unchanged -- no barrier needed
