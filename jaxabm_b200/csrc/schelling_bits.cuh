@@ -26,6 +26,13 @@
 #include "common.cuh"
 #include "schelling.cuh"
 
+#ifndef JXB_SCH_MV
+#define JXB_SCH_MV 4      // list entries per thread per iteration of the mover loop (measured: profiles/r02_schelling_mv.txt)
+#endif
+#ifndef JXB_SCH_MINB
+#define JXB_SCH_MINB 2    // resident CTAs per SM the register allocation aims at (128 registers at 2)
+#endif
+
 namespace jxb {
 
 struct SchellingBitsDev {
@@ -172,7 +179,7 @@ __device__ __forceinline__ unsigned int eval_row(const RowSums& to, const RowSum
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const SchellingDev sd, const SchellingBitsDev sb,
+__global__ void __launch_bounds__(kThreads, JXB_SCH_MINB) schelling_bits_kernel(const SchellingDev sd, const SchellingBitsDev sb,
                                                                   const ModelDev md, int steps) {
   __shared__ unsigned int s_u32[kThreads / 32];
   __shared__ unsigned long long s_u64[kThreads / 32];
@@ -389,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 2) schelling_bits_kernel(const Schel
       // (b) the moves: the CTA's segment [s_prefix, base) of U, strided over the threads, no barrier inside.  Four
       // entries per thread per iteration: the chain slot / payload -> writes is latency-bound.  (The segment was
       // written by this CTA's own threads: the block barrier above made it visible.)
-      constexpr int kMv = 4;
+      constexpr int kMv = JXB_SCH_MV;
       const unsigned int seg_end = base;
       for (unsigned int j0 = s_prefix + tid; j0 < seg_end; j0 += kThreads * kMv) {
         unsigned int src[kMv], jj[kMv], dst[kMv], tw[kMv];
