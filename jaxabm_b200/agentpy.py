@@ -115,6 +115,18 @@ class AgentWrapper(AgentType):
         return new_state
 
 
+_MISSING = object()
+
+
+def _scalar(v):
+    """float value of a Python / NumPy scalar env entry, None for anything else."""
+    if isinstance(v, (bool, int, float, np.integer, np.floating, np.bool_)):
+        return float(v)
+    if isinstance(v, np.ndarray) and v.ndim == 0:
+        return float(v)
+    return None
+
+
 class _StepProbe:
     """Stands in for ``Model._jax_model`` while the user's ``step()`` is traced: reads see the host-side state,
     ``add_env_state`` calls are recorded instead of acting on the model under construction."""
@@ -378,6 +390,8 @@ class Model:
         self._running = False
         self.last_device_seconds = 0.0
         self._record_agents: Dict[str, List[str]] = {}
+        self._step_has_host_effects = False       # plain-Python models: what the trace of step() found (update_state)
+        self._host_env_keys: set = set()
 
     # ---- user hooks ------------------------------------------------------------------------
     def setup(self) -> None:
@@ -403,8 +417,10 @@ class Model:
         self._current_env_state = env_state.copy()
         self._current_agent_states = agent_states
         if isinstance(key, TrKey):
+            from .trace import Tr, TrVec
             real, probe = self._jax_model, _StepProbe(self._jax_model)
             recorded = {k: list(v) for k, v in self._recorded_data.items()}
+            env_before = dict(self.env.state)
             self._jax_model = probe
             try:
                 self.step()
@@ -413,10 +429,32 @@ class Model:
                 if probe.calls or {k: len(v) for k, v in self._recorded_data.items()} != {k: len(v) for k, v in recorded.items()}:
                     self._step_has_host_effects = True
                 self._recorded_data = recorded
+                overlay = dict(self.env.state)
+                self.env.state.clear()
+                self.env.state.update(env_before)          # the trace must not leave symbolic values in the host dict
+            for name, value in overlay.items():
+                if isinstance(value, (Tr, TrVec)):
+                    continue                               # computed from traced values: part of the kernel's tail
+                old = env_before.get(name, _MISSING)
+                changed = old is _MISSING or (not np.array_equal(np.asarray(value), np.asarray(old)))
+                if changed:
+                    # Host-side state that step() advances every step (the examples' `self.env.add_state('time',
+                    # self.env.time + 1)`): it cannot be fused into the kernel -- the traced constant would freeze at its
+                    # first value.  Such an entry stays a plain env READ in the kernel (no overlay), and run() steps the
+                    # model one device step at a time, calling step() on the host and refreshing these env slots before
+                    # each one (the reference's un-jitted loop does the same work on the host every step).
+                    if _scalar(value) is None or _scalar(old if old is not _MISSING else value) is None:
+                        raise UnregisteredRuleError(
+                            f"{type(self).__name__}.step() changes the non-scalar Environment.state[{name!r}] on the host every "
+                            "step; only scalar host-side env entries can be refreshed per step")
+                    self._host_env_keys.add(name)
+            for name in self._host_env_keys:
+                overlay.pop(name, None)                    # the kernel reads the slot the host refreshes
         else:
             self.step()
+            overlay = self.env.state
         new_env_state = {**env_state}
-        for name, value in self.env.state.items():
+        for name, value in overlay.items():
             new_env_state[name] = value
         return new_env_state
 
@@ -482,6 +520,7 @@ class Model:
         self.setup()
         program = self._program()
         self._step_has_host_effects = False
+        self._host_env_keys = set()
         if program is None:
             # plain-Python model: exactly what agentpy.py:1071-1076 builds -- the bound update_state bridge and
             # compute_metrics; Model.initialize() traces them (and the agents' setup / step) into one kernel
@@ -509,6 +548,23 @@ class Model:
         start = time.time()
         self._jax_model.initialize()
         self.after_initialize()
+        if program is None and self._host_env_keys:
+            # step() carries per-step host-side state (see update_state): one device step at a time, step() on the host
+            # and the refreshed env slots before each
+            jm = self._jax_model
+
+            def _before_step():
+                jm._host_replay = True
+                try:
+                    self.step()
+                finally:
+                    jm._host_replay = False
+                for name in self._host_env_keys:
+                    jm._dev.set_env(jm._dev.env_index(name), _scalar(self.env.state[name]))
+            self._current_env_state = dict(jm._env_state)
+            self._current_agent_states = {n: c.states for n, c in jm.agent_collections.items()}
+            jm._before_each_step = _before_step
+            self._step_has_host_effects = False             # the per-step calls above ARE the replay
         results_dict = self._jax_model.run()
         self.last_device_seconds = self._jax_model.last_device_seconds
         if program is None and self._step_has_host_effects:

@@ -379,7 +379,18 @@ class Model:
             self._history = []
         start = time.time()
         ci = self.config.collect_interval if self.config.track_history else (1 << 30)
-        rows = self._advance(int(steps_to_run), ci)
+        hook = getattr(self, "_before_each_step", None)
+        if hook is None:
+            rows = self._advance(int(steps_to_run), ci)
+        else:
+            # a traced facade model whose Model.step() advances host-side state every step (agentpy.update_state):
+            # the host hook runs before each device step
+            rows, secs = [], 0.0
+            for _ in range(int(steps_to_run)):
+                hook()
+                rows.extend(self._advance(1, ci))
+                secs += self.last_device_seconds
+            self.last_device_seconds = secs
         if self.config.track_history:
             self._history.extend(rows)
         self.agent_series = {f"agents.{c}.{v}": self._dev.series(k) for k, (c, v) in enumerate(self._record_series)}

@@ -93,3 +93,40 @@ def test_reference_example_with_the_collection_named_walkers(mode):
     st, rst = model.walkers.collection.states, ref.walkers.collection.states
     for k in ("position", "velocity", "color", "steps_taken"):
         assert np.array_equal(st[k], rst[k]), k
+
+
+def test_reference_sensitivity_example_model_with_host_side_step_state(mode):
+    """examples/sensitivity/simple_sensitivity_example.py (tests/golden/simple_sensitivity_model.py: one import line
+    changed).  Its Model.step() advances host-side state every step (`self.env.add_state('time', self.env.time + 1)`),
+    which cannot be fused into the kernel: the traced kernel keeps 'time' as an env READ, and run() performs one device
+    step at a time with step() on the host and the refreshed slot before each -- what the reference's un-jitted loop
+    does.  Expected values are the closed forms of the example: size_t = prod fl32(1 + g), mean_size stays 1.0 (the
+    core model's state never holds 'agents'), efficiency_t = 1 / (t g + 1)."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "examples"))
+    import load_example
+    load_example.check_against_reference()
+    ex = load_example.load(load_example.LOCAL_SENS)
+    g, cap, n, T = 0.13, 80.0, 37, 25
+    model = ex.SimpleModel({"n_agents": n, "steps": T, "growth_rate": g, "carrying_capacity": cap, "rng_mode": mode})
+    res = model.run()
+    assert model._jax_model._program == "traced" and model._host_env_keys == {"time"}
+    assert [float(v) for v in res._data["final_size"]] == [1.0] * T
+    assert [float(v) for v in res._data["resource_usage"]] == [1.0 / cap] * T
+    np.testing.assert_allclose([float(v) for v in res._data["efficiency"]], [1.0 / (t * g + 1.0) for t in range(1, T + 1)], rtol=1e-15)
+    size = np.float32(1.0)
+    for _ in range(T):
+        size = np.float32(size * np.float32(1.0 + g))
+    st = model.agents.collection.states
+    assert np.array_equal(st["size"], np.full(n, size, dtype=np.float32))
+    assert np.array_equal(st["growth_rate"], np.full(n, np.float32(g), dtype=np.float32))
+    assert model.env.time == T and model._jax_model.state["env"]["time"] == T
+    # the example's driver: jx.SensitivityAnalyzer over the model class (host glue around model_class(params).run())
+    import jaxabm_b200 as jx
+    an = jx.SensitivityAnalyzer(model_class=ex.SimpleModel,
+                                parameters=[jx.Parameter("growth_rate", bounds=(0.05, 0.3)),
+                                            jx.Parameter("carrying_capacity", bounds=(50.0, 200.0))],
+                                n_samples=3, metrics=["final_size", "resource_usage", "efficiency"])
+    an.run()
+    sens = an.calculate_sensitivity()
+    assert set(sens) == {"final_size", "resource_usage", "efficiency"}

@@ -468,3 +468,27 @@ def test_facade_example_traces_and_compiles_without_a_gpu():
     assert "float4 F0_0" in src and "float4 F0_1" in src          # f32[N,2]: two 16-byte vectors per four agents
     lib = jit.compile_source(src)
     assert lib.jxc_n_variants() == len(variants)
+
+
+def test_facade_step_with_host_side_state_is_not_frozen_into_the_kernel():
+    """A Model.step() that advances Environment.state on the host every step (the reference's sensitivity example)
+    must not be traced as a constant: the entry stays an env read and the model is flagged for per-step host calls."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "examples"))
+    import load_example
+    ex = load_example.load(load_example.LOCAL_SENS)
+    from jaxabm_b200 import jit
+    from jaxabm_b200.model import Model as CoreModel
+    m = ex.SimpleModel({"n_agents": 5, "steps": 3, "growth_rate": 0.2})
+    m.setup()
+    m._host_env_keys, m._step_has_host_effects = set(), False
+    jm = CoreModel(params=m.p, config=jx.ModelConfig(steps=3), update_state_fn=m.update_state, metrics_fn=m.compute_metrics)
+    m._jax_model = jm
+    for name, al in m._agent_lists.items():
+        jm.add_agent_collection(name, al.collection)
+    for name, value in m.env.state.items():
+        jm.add_env_state(name, value)
+    variants = jit.trace_variants(jm)
+    assert m._host_env_keys == {"time"} and m.env.state["time"] == 0           # the trace left the host state alone
+    assert "time" not in variants[-1].env_out and "growth_rate" in variants[-1].env_out
+    assert dict(variants[-1].metrics)["efficiency"].op != "const"               # 1 / (time * g + 1) reads the env slot
