@@ -1171,6 +1171,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
   if (!m->net_allocs.empty()) {
     // rebuild (Model.add_env_state('network_edges') after initialize(), Network.add_edge): the previous CSR,
     // state and counter buffers go back to the pool; their pointers are baked into the cached step graphs
+    if (m->net_built) { rc = sir_sync_to_api(m); if (rc) return rc; }     // the live state lives in the packed buffers
     CK(cudaStreamSynchronize(st));
     if (m->graph1) { cudaGraphExecDestroy(m->graph1); m->graph1 = nullptr; }
     if (m->graphK) { cudaGraphExecDestroy(m->graphK); m->graphK = nullptr; }

@@ -170,3 +170,62 @@ def test_filter_matches_oracle_filter(mode):
     assert f.num_agents == int((pr > np.float32(0.35)).sum())
     assert abs(f.num_agents - of.num_agents) <= max(3, of.num_agents // 200)
     assert np.array_equal(f.states["capital"], np.array(m.agent_collections["producers"].states["capital"])[pr > np.float32(0.35)])
+
+
+# ------------------------------------------------------------------------------- state edits between runs
+def test_schelling_uploads_between_runs_with_packed_cell_payload(mode):
+    """The persistent bit-sliced kernel keeps (agent, moves) with the cell and derives 'position' / 'moves' on read.
+    Uploading one of the API columns between runs must first bring the other one up to date (the rebuild packs both):
+    re-uploading a model's own positions changes nothing; uploading zeros to 'moves' restarts the move counts only."""
+    def build():
+        return schelling.create_schelling_model(1024, 800_000, seed=5, config=jx.ModelConfig(seed=9, rng_mode=mode))
+    a, b = build(), build()
+    a.run(steps=4), b.run(steps=4)
+    sa = a.agent_collections["agents"].states
+    sa["position"] = np.array(sa["position"])                    # no-op upload: forces a rebuild from the API columns
+    ra, rb = a.run(steps=4), b.run(steps=4)
+    sb = b.agent_collections["agents"].states
+    for k in ("type", "position", "satisfied", "moves"):
+        assert np.array_equal(sa[k], sb[k]), k
+    assert [int(v) for v in ra["total_moves"]] == [int(v) for v in rb["total_moves"]]
+    moves_before = np.array(sb["moves"])
+    sa["moves"] = np.zeros(800_000, dtype=np.int32)
+    a.run(steps=3), b.run(steps=3)
+    assert np.array_equal(sa["position"], sb["position"])
+    assert np.array_equal(np.array(sa["moves"]) + moves_before, sb["moves"])
+
+
+def test_network_rebuild_after_initialize(mode):
+    """Model.add_env_state('network_edges', ...) after initialize() (what Network.add_edge does, agentpy.py:574-582):
+    edits are batched on the host, ONE CSR rebuild happens before the next step and the previous CSR goes back to the
+    pool; the run then equals the oracle's on the final edge list."""
+    n = 30_000
+    e1 = synthetic.ring_lattice_edges(n, 2)
+    e2 = synthetic.scale_free_edges(n, 3, 11)
+    kw = dict(beta=0.25, gamma=0.1, initial_infected=0.02, seed=4)
+    m = sir.create_sir_model(n, e1, config=jx.ModelConfig(seed=4, rng_mode=mode), **kw)
+    m.initialize()
+    launches0 = jx._native.engine().launch_count
+    for k in range(5):                                           # five edits, one rebuild
+        m.add_env_state("network_edges", e2[: len(e2) // 5 * (k + 1)])
+    m.add_env_state("network_edges", e2)
+    assert jx._native.engine().launch_count == launches0         # nothing was built yet
+    r = m.run(steps=12)
+    om = orules.create_sir_model(n, e2, config=ort.ModelConfig(seed=4, rng_mode=mode), **kw)
+    orr = om.run(steps=12)
+    for k in ("count_S", "count_I", "count_R"):
+        assert [int(v) for v in r[k]] == [int(v) for v in orr[k]], k
+    assert np.array_equal(m.agent_collections["agents"].states["state"], om.agent_collections["agents"].states["state"])
+    # a rebuild in the middle of a run keeps the current epidemic state (it lives in the packed buffers being replaced)
+    m.add_env_state("network_edges", np.array(e2))
+    r2, or2 = m.run(steps=5), om.run(steps=5)
+    assert [int(v) for v in r2["count_I"]] == [int(v) for v in or2["count_I"]]
+    assert np.array_equal(m.agent_collections["agents"].states["state"], om.agent_collections["agents"].states["state"])
+    # a bad edge list is rejected at the rebuild, with the model still usable afterwards
+    bad = np.array(e2)
+    bad[7, 1] = n + 5
+    m.add_env_state("network_edges", bad)
+    with pytest.raises(jx._native.JxbError, match="outside"):
+        m.run(steps=1)
+    m.add_env_state("network_edges", e2)
+    m.run(steps=1)
