@@ -859,6 +859,21 @@ static int check_field(jxb_model* m, int type, int field, size_t bytes) {
   return JXB_OK;
 }
 
+// a Schelling state column was written by the caller (upload / fill)
+static int grid_after_write(jxb_model* m, int field) {
+  if (!m->has_grid) return JXB_OK;
+  if (field == 0 || field == 1 || (field == 3 && m->grid_sharded)) m->grid_built = false;     // cell binning is rebuilt (slot order restarts)
+  if (field == 2) m->sat_dirty = false;
+  if (field == 3 && m->sch_packed && m->grid_built) {
+    // the move counts travel with the cells: refresh them from the column, keep the grid and the slot order
+    cell_am_set_moves_kernel<<<m->eng->sms * 8, 256, 0, m->eng->stream>>>(m->sd, m->sb, (const int*)m->dev.t[0].f[3]);
+    m->eng->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(m->eng->stream));
+  }
+  return JXB_OK;
+}
+
 extern "C" int jxb_model_upload(jxb_model* m, int type, int field, const void* host, size_t bytes) {
   int rc = check_field(m, type, field, bytes);
   if (rc) return rc;
@@ -872,9 +887,7 @@ extern "C" int jxb_model_upload(jxb_model* m, int type, int field, const void* h
   CK(cudaMemcpyAsync(m->dev.t[type].f[field], host, bytes, cudaMemcpyHostToDevice, m->eng->stream));
   CK(cudaStreamSynchronize(m->eng->stream));
   if (m->has_net) return sir_sync_from_api(m);
-  if (m->has_grid && (field == 0 || field == 1 || (field == 3 && (m->grid_sharded || m->sch_packed)))) m->grid_built = false;
-  if (m->has_grid && field == 2) m->sat_dirty = false;
-  return JXB_OK;
+  return grid_after_write(m, field);
 }
 
 // Bring the API-visible column (type, field) up to date from the engine's packed layout, stream-ordered and
@@ -942,8 +955,7 @@ extern "C" int jxb_model_fill(jxb_model* m, int type, int field, const void* val
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(m->eng->stream));
   if (m->has_net) return sir_sync_from_api(m);
-  if (m->has_grid && (field == 0 || field == 1 || (field == 3 && (m->grid_sharded || m->sch_packed)))) m->grid_built = false;
-  return JXB_OK;
+  return grid_after_write(m, field);
 }
 
 extern "C" int jxb_model_set_env(jxb_model* m, int slot, double value) {

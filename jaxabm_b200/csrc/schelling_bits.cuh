@@ -462,6 +462,15 @@ __global__ void cell_am_pack_kernel(const SchellingDev sd, const SchellingBitsDe
   }
 }
 
+// 'moves' was uploaded between runs: refresh the move counts that travel with the cells (no grid rebuild: the
+// empty-cell slot order must survive)
+__global__ void cell_am_set_moves_kernel(const SchellingDev sd, const SchellingBitsDev sb, const int* moves) {
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < sd.cells; c += (long long)gridDim.x * blockDim.x) {
+    const int a = sb.cell_am[c].x;
+    if (a >= 0) sb.cell_am[c].y = moves[a];
+  }
+}
+
 __global__ void cell_am_unpack_kernel(const SchellingDev sd, const SchellingBitsDev sb, int2* position, int* moves) {
   const int H = sd.H;
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < sd.cells; c += (long long)gridDim.x * blockDim.x) {

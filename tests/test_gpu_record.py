@@ -175,24 +175,31 @@ def test_filter_matches_oracle_filter(mode):
 # ------------------------------------------------------------------------------- state edits between runs
 def test_schelling_uploads_between_runs_with_packed_cell_payload(mode):
     """The persistent bit-sliced kernel keeps (agent, moves) with the cell and derives 'position' / 'moves' on read.
-    Uploading one of the API columns between runs must first bring the other one up to date (the rebuild packs both):
-    re-uploading a model's own positions changes nothing; uploading zeros to 'moves' restarts the move counts only."""
-    def build():
-        return schelling.create_schelling_model(1024, 800_000, seed=5, config=jx.ModelConfig(seed=9, rng_mode=mode))
+    Uploading 'moves' between runs refreshes the counts that travel with the cells WITHOUT rebuilding the grid (the
+    empty-cell slot order, hence the trajectory, is unchanged); uploading 'position' rebuilds the cell binning -- with the
+    other derived column brought up to date first -- exactly like a fresh model created from those columns."""
+    def build(**kw):
+        return schelling.create_schelling_model(1024, 800_000, seed=5, config=jx.ModelConfig(seed=9, rng_mode=mode), **kw)
     a, b = build(), build()
     a.run(steps=4), b.run(steps=4)
-    sa = a.agent_collections["agents"].states
-    sa["position"] = np.array(sa["position"])                    # no-op upload: forces a rebuild from the API columns
-    ra, rb = a.run(steps=4), b.run(steps=4)
-    sb = b.agent_collections["agents"].states
-    for k in ("type", "position", "satisfied", "moves"):
-        assert np.array_equal(sa[k], sb[k]), k
-    assert [int(v) for v in ra["total_moves"]] == [int(v) for v in rb["total_moves"]]
+    sa, sb = a.agent_collections["agents"].states, b.agent_collections["agents"].states
     moves_before = np.array(sb["moves"])
     sa["moves"] = np.zeros(800_000, dtype=np.int32)
-    a.run(steps=3), b.run(steps=3)
-    assert np.array_equal(sa["position"], sb["position"])
+    ra, rb = a.run(steps=3), b.run(steps=3)
+    assert np.array_equal(sa["position"], sb["position"]) and np.array_equal(sa["satisfied"], sb["satisfied"])
     assert np.array_equal(np.array(sa["moves"]) + moves_before, sb["moves"])
+    assert [float(v) for v in ra["percent_satisfied"]] == [float(v) for v in rb["percent_satisfied"]]
+    # position upload = rebuild of the cell binning from the API columns; 'moves' (derived lazily from the cell
+    # payload) must have been brought up to date before the rebuild packs it again
+    types, pos, mv = np.array(sb["type"]), np.array(sb["position"]), np.array(sb["moves"])
+    sb["position"] = pos
+    assert np.array_equal(sb["moves"], mv)
+    rb2 = b.run(steps=3)
+    assert int(np.array(sb["moves"]).sum() - mv.sum()) == int(rb2["total_moves"][-1]) - int(rb["total_moves"][-1])
+    grid = b._dev.download_grid()
+    p2 = np.array(sb["position"]).astype(np.int64)
+    cells = p2[:, 0] * 1024 + p2[:, 1]
+    assert np.unique(cells).size == 800_000 and np.array_equal(grid.reshape(-1)[cells], types)
 
 
 def test_network_rebuild_after_initialize(mode):
