@@ -18,8 +18,11 @@
 // sum(same * 840 / o) is accumulated as popcounts of (o == k) & bit_b(same).  ~6 integer
 // instructions per cell instead of ~25 for the byte/LUT sweep; results are bit-identical.
 //
-// Phases 2 (ordered compaction of the unsatisfied cells) and 3 (keyed Feistel matching of movers
-// to empty-cell slots) are those of schelling.cuh, with the plane bits flipped by atomicAnd/Or.
+// Phase 2 (ordered compaction of the unsatisfied cells) and phase 3 (keyed Feistel matching of movers to empty-cell
+// slots, the same matching as in schelling.cuh) are CTA-local here: every CTA compacts the unsatisfied cells of ITS
+// rows into its segment of U and walks that segment in cell order, asking the inverse permutation which mover index
+// each entry is.  The agent id and its move count travel with the cell (cell_am); 'position' / 'moves' are derived
+// from it when they are read.  Plane bits are flipped by atomicAnd/Or.
 #pragma once
 #include <cooperative_groups.h>
 
