@@ -238,7 +238,7 @@ struct jxb_model {
   // transitions; 1 "push" = infected rows scatter-add into k32 + transition kernel; 2 "pull_s" = pull
   // over the susceptible rows only; 3 "auto" (default) = direction-optimising, the step's tail picks
   // push or pull_s for the next step on the device
-  int sir_mode = 3; int sir_tblocks = 0;
+  int sir_mode = 3; int sir_tblocks = 0; int sir_pull_cps = 8;
   // traced model (jxb_model_create_traced): layout owned by the model, kernels in a generated library
   bool traced = false; RuleSpec traced_rules[JXB_MAX_TYPES]; ProgramSpec traced_prog;
   std::vector<std::string> traced_names; int traced_acc = 0, traced_variants = 1; bool traced_started = false;
@@ -1311,6 +1311,7 @@ extern "C" int jxb_model_set_network(jxb_model* m, const int32_t* edges, int64_t
     sv.heavy = d_heavy;
     sv.n_heavy = (int)heavy.size();
     m->sir_tblocks = (int)std::max<long long>(1, std::min<long long>((n + kThreads * kSirRowsPerThread - 1) / (kThreads * kSirRowsPerThread), (long long)m->eng->sms * 8));
+    if (const char* cps = getenv("JXB_SIR_PULL_CPS")) m->sir_pull_cps = std::max(1, std::min(8, atoi(cps)));
     const char* mode = getenv("JXB_SIR_MODE");
     m->sir_mode = 3;
     if (mode && !strcmp(mode, "pull")) m->sir_mode = 0;
@@ -1555,7 +1556,7 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       if (m->net_sharded) {
         // node-range shard: pull over my rows (new bitmap words stored into every rank's copy) + flag wait
         if (!m->ns_attached) return fail(JXB_ERR_STATE, "sharded Network step without attached peers");
-        const int pgrid = m->eng->sms * 8;
+        const int pgrid = m->eng->sms * m->sir_pull_cps;
         if (timed) cudaEventRecord(e0, s);
         if (part) sir_pull_s_kernel<1, true><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
         else sir_pull_s_kernel<0, true><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
@@ -1581,8 +1582,9 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
           eng->launches += 1;
         }
         if (m->sir_mode != 1) {          // pull direction
-          if (part) sir_pull_s_kernel<1><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
-          else sir_pull_s_kernel<0><<<pgrid, kThreads, 0, s>>>(m->sv, m->dev);
+          const int qgrid = m->eng->sms * m->sir_pull_cps;
+          if (part) sir_pull_s_kernel<1><<<qgrid, kThreads, 0, s>>>(m->sv, m->dev);
+          else sir_pull_s_kernel<0><<<qgrid, kThreads, 0, s>>>(m->sv, m->dev);
           if (m->sir_mode == 3) eng->launches += 1;
         }
       }
