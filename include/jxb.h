@@ -270,14 +270,18 @@ int jxb_engine_p2p_attach(jxb_engine*, const void* handles, size_t bytes_each, i
 
 /* ---- ONE grid split into row bands over the GPUs of a box (Grid) ------ */
 /* jaxabm/agentpy.py:480-527 keeps one env['grid'] for all agents; here rank r of desc.world_size owns
- * the rows [row_begin, row_end) (consecutive bands in rank order, at most ceil(W / world) rows each)
- * and every rank holds the whole per-agent columns.  export allocates this rank's receive area and
- * returns its CUDA IPC handle (JXB_IPC_HANDLE_BYTES); the host shim all-gathers the handles and
- * attach maps the peers' areas (one process per rank; the ranks may share a device).  After that jxb_model_run
- * steps the band with no host round trip: the unsatisfied agents' records are stored straight into
- * every peer's area over NVLink by the compaction kernel (no NCCL call on the step path).
+ * the rows [row_begin, row_end) (consecutive bands in rank order that tile the grid, at most
+ * ceil(W / world) rows each) and every rank is handed the whole per-agent columns.  export allocates
+ * this rank's receive area (its range of the empty-cell slots + the record segments) and returns
+ * JXB_GRID_HANDLE_BYTES: the area's CUDA IPC handle followed by the band as two int32; the host shim
+ * all-gathers the entries and attach maps the peers' areas (one process per rank; the ranks may share
+ * a device).  After that jxb_model_run steps the band with no host round trip: a rank walks only the
+ * movers of its own rows, rewrites their slots in the owner's area and stores their records straight
+ * into the target rows' owner over NVLink (no NCCL call on the step path).
  * Downloads of a shard return ITS view; the host combines the ranks: 'position' max (-1 = agent is
- * not in my band), 'satisfied' min, 'moves' sum, 'type' any; env grid rows [row_begin, row_end).     */
+ * not in my band), 'satisfied' min, 'moves' sum (0 = not in my band), 'type' any; env grid rows
+ * [row_begin, row_end); empty_cells is gathered from the ranks' areas (barrier first).              */
+#define JXB_GRID_HANDLE_BYTES 72
 int jxb_model_grid_shard_export(jxb_model*, int row_begin, int row_end, void* handle_out, size_t bytes);
 int jxb_model_grid_shard_attach(jxb_model*, const void* handles, size_t bytes_each, int n_ranks);
 

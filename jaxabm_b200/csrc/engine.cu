@@ -228,7 +228,7 @@ struct jxb_model {
   bool sch_packed = false; bool pos_stale = false;
   // row-band decomposition over the GPUs of a box (csrc/grid_shard.cuh): receive area + peers' areas
   bool grid_sharded = false; bool gs_attached = false; GridShardDev gs{}; unsigned char* gs_area = nullptr;
-  size_t gs_area_bytes = 0; void* gs_opened[kMaxPeers] = {}; int gs_move_blocks = 0;
+  size_t gs_area_bytes = 0; void* gs_opened[kMaxPeers] = {};
   // SIR
   bool has_net = false; SirDev sv{}; bool net_built = false; long long nnz = 0;
   // node-range sharding of the network over ranks (csrc/sir.cuh): IPC-shared area [hdr | bitmap 0 | bitmap 1]
@@ -701,10 +701,8 @@ static int model_create(jxb_engine* eng, const jxb_model_desc* d, const jxb_trac
       sb.occ = p0 + sb.wpr;
       sb.t1 = p1 + sb.wpr;
       TRY(dev_alloc(m, &sb.umask, (size_t)(sd.cells >> 5) + 32));
-      if (!m->grid_sharded) {
-        TRY(dev_alloc(m, &sb.cell_am, (size_t)sd.cells));
-        m->sch_packed = true;
-      }
+      TRY(dev_alloc(m, &sb.cell_am, (size_t)sd.cells));
+      m->sch_packed = true;
     }
     {
       BlkPart* bp = nullptr;
@@ -859,10 +857,13 @@ static int check_field(jxb_model* m, int type, int field, size_t bytes) {
   return JXB_OK;
 }
 
+// ONE grid over several ranks: the API columns of a rank only hold its band's view after a read
+static inline bool grid_multi_rank(const jxb_model* m) { return m->grid_sharded && m->dev.world_size > 1; }
+
 // a Schelling state column was written by the caller (upload / fill)
 static int grid_after_write(jxb_model* m, int field) {
   if (!m->has_grid) return JXB_OK;
-  if (field == 0 || field == 1 || (field == 3 && m->grid_sharded)) m->grid_built = false;     // cell binning is rebuilt (slot order restarts)
+  if (field == 0 || field == 1) m->grid_built = false;     // cell binning is rebuilt (slot order restarts)
   if (field == 2) m->sat_dirty = false;
   if (field == 3 && m->sch_packed && m->grid_built) {
     // the move counts travel with the cells: refresh them from the column, keep the grid and the slot order
@@ -870,6 +871,7 @@ static int grid_after_write(jxb_model* m, int field) {
     m->eng->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(m->eng->stream));
+    if (grid_multi_rank(m)) m->pos_stale = true;      // the column is whole again on every rank: reads re-derive the band view
   }
   return JXB_OK;
 }
@@ -878,7 +880,7 @@ extern "C" int jxb_model_upload(jxb_model* m, int type, int field, const void* h
   int rc = check_field(m, type, field, bytes);
   if (rc) return rc;
   CK(cudaSetDevice(m->eng->device));
-  if (m->sch_packed && m->pos_stale && m->grid_built) {
+  if (m->sch_packed && !grid_multi_rank(m) && m->pos_stale && m->grid_built) {
     // the next rebuild packs 'position' AND 'moves' from the API columns: both must be current before one of them
     // (or 'type') is overwritten
     rc = materialize_field(m, 0, 1, m->eng->stream, false);
@@ -904,19 +906,21 @@ static int materialize_field(jxb_model* m, int type, int field, cudaStream_t s, 
       if (rc) return rc;
     }
   }
-  if (m->sch_packed && (field == 1 || field == 3) && m->grid_built && (in_step || m->pos_stale)) {
+  if (m->sch_packed && !m->grid_sharded && (field == 1 || field == 3) && m->grid_built && (in_step || m->pos_stale)) {
     cell_am_unpack_kernel<<<m->eng->sms * 8, 256, 0, s>>>(m->sd, m->sb, (int2*)m->dev.t[0].f[1], (int*)m->dev.t[0].f[3]);
     m->eng->launches++;
     CK(cudaGetLastError());
     if (!in_step) m->pos_stale = false;
   }
   if (m->has_grid && field == 2 && (in_step || m->sat_dirty)) { int rc = schelling_export_satisfied(m, s, !in_step); if (rc) return rc; }
-  if (m->grid_sharded && field == 1 && m->grid_built) {
-    // this rank's view: the agents sitting in its band, -1 for everybody else (host: max over ranks)
+  if (m->grid_sharded && (field == 1 || field == 3) && m->grid_built && (in_step || m->pos_stale)) {
+    // this rank's view: the agents sitting in its band; -1 / 0 for everybody else (host: max / sum over ranks)
     CK(cudaMemsetAsync(m->dev.t[0].f[1], 0xFF, field_bytes(m, 0, 1), s));
-    grid_shard_export_position_kernel<<<m->eng->sms * 8, 256, 0, s>>>(m->sd, m->gs, (int2*)m->dev.t[0].f[1]);
+    CK(cudaMemsetAsync(m->dev.t[0].f[3], 0, field_bytes(m, 0, 3), s));
+    grid_shard_unpack_kernel<<<m->eng->sms * 8, 256, 0, s>>>(m->sd, m->sb, m->gs, (int2*)m->dev.t[0].f[1], (int*)m->dev.t[0].f[3]);
     m->eng->launches++;
     CK(cudaGetLastError());
+    if (!in_step) m->pos_stale = false;
   }
   return JXB_OK;
 }
@@ -944,7 +948,7 @@ extern "C" int jxb_model_fill(jxb_model* m, int type, int field, const void* val
   CK(cudaSetDevice(m->eng->device));
   uint4 v = {0, 0, 0, 0};
   memcpy(&v, value, bytes);
-  if (m->sch_packed && m->pos_stale && m->grid_built) {
+  if (m->sch_packed && !grid_multi_rank(m) && m->pos_stale && m->grid_built) {
     int rc = materialize_field(m, 0, 1, m->eng->stream, false);
     if (rc) return rc;
   }
@@ -1034,13 +1038,14 @@ extern "C" int jxb_model_grid_rebuild(jxb_model* m) {
     cell_am_pack_kernel<<<blocks, 256, 0, s>>>(m->sd, m->sb, (const int*)m->dev.t[0].f[3]);
     m->eng->launches++;
     CK(cudaGetLastError());
-    m->pos_stale = false;
+    m->pos_stale = grid_multi_rank(m);      // every rank holds the whole columns now: reads derive the band view
   }
   if (m->grid_sharded) {
-    grid_shard_own_moves_kernel<<<blocks, 256, 0, s>>>(m->gs, (const int2*)m->dev.t[0].f[1], (int*)m->dev.t[0].f[3],
-                                                       m->desc.types[0].n_agents);
-    m->eng->launches++;
-    CK(cudaGetLastError());
+    // my range of the empty-cell slots moves into the receive area, where the peers reach it
+    const GridShardDev& gs = m->gs;
+    const unsigned int e = m->sd.n_empty, lo = std::min(e, (unsigned int)gs.rank * gs.eper), hi = std::min(e, lo + gs.eper);
+    if (hi > lo) CK(cudaMemcpyAsync(m->gs_area + sizeof(GridXchgHdr), m->sd.E + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaStreamSynchronize(s));
   }
   m->grid_built = true;
   return JXB_OK;
@@ -1073,7 +1078,17 @@ extern "C" int jxb_model_download_empty_cells(jxb_model* m, int32_t* host, size_
   if (bytes != (size_t)m->sd.n_empty * 4) return fail(JXB_ERR_INVALID, "empty_cells holds %u int32", m->sd.n_empty);
   CK(cudaSetDevice(m->eng->device));
   if (!m->grid_built) { int rc = jxb_model_grid_rebuild(m); if (rc) return rc; }
-  if (bytes) CK(cudaMemcpyAsync(host, m->sd.E, bytes, cudaMemcpyDeviceToHost, m->eng->stream));
+  if (m->grid_sharded) {
+    // the slots live in the ranks' receive areas (call after a barrier: the peers must have finished their run)
+    const GridShardDev& gs = m->gs;
+    const unsigned int e = m->sd.n_empty;
+    for (int q = 0; q < gs.world; ++q) {
+      const unsigned int lo = std::min(e, (unsigned int)q * gs.eper), hi = std::min(e, lo + gs.eper);
+      if (hi > lo) CK(cudaMemcpyAsync(host + lo, gs.peer[q] + sizeof(GridXchgHdr), (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, m->eng->stream));
+    }
+  } else if (bytes) {
+    CK(cudaMemcpyAsync(host, m->sd.E, bytes, cudaMemcpyDeviceToHost, m->eng->stream));
+  }
   CK(cudaStreamSynchronize(m->eng->stream));
   return JXB_OK;
 }
@@ -1090,9 +1105,15 @@ static int grid_shard_prepare(jxb_model* m, int row_begin, int row_end) {
   CK(cudaSetDevice(m->eng->device));
   GridShardDev& gs = m->gs;
   gs.rank = m->dev.rank; gs.world = G; gs.X0 = row_begin; gs.X1 = row_end;
-  gs.cap = (unsigned long long)std::min<long long>(m->desc.types[0].n_agents, (long long)max_rows * H);
+  if (G == 1) { gs.xb[0] = 0; gs.xb[1] = W; }
+  // a segment takes the cell records of one sender (targets that were empty cells of my band) from the front and its
+  // halo records (sets in my two halo rows, clears from the sender's boundary rows) from the back
+  gs.halo_cap = (unsigned int)(4 * H);
+  gs.cap = (unsigned int)std::min<long long>((long long)max_rows * H, (long long)m->sd.n_empty) + gs.halo_cap;
+  gs.eper = std::max(1u, (m->sd.n_empty + (unsigned int)G - 1u) / (unsigned int)G);
+  gs.rec_off = (sizeof(GridXchgHdr) + (size_t)gs.eper * 4 + 15) / 16 * 16;
   if (!m->gs_area) {
-    m->gs_area_bytes = sizeof(GridXchgHdr) + (size_t)2 * G * gs.cap * sizeof(uint2);
+    m->gs_area_bytes = gs.rec_off + (size_t)2 * G * gs.cap * sizeof(uint4);
     m->gs_area = G > 1 ? (unsigned char*)take_retired_area(m->eng, m->gs_area_bytes) : nullptr;
     if (!m->gs_area) CK(cudaMalloc((void**)&m->gs_area, m->gs_area_bytes));      // its own allocation: IPC handles name whole allocations
     // flags / counts of a recycled area hold the step tags of its previous model: clear them before the handle
@@ -1107,11 +1128,8 @@ static int grid_shard_prepare(jxb_model* m, int row_begin, int row_end) {
     gs.blocks = (int)std::max<long long>(1, std::min<long long>(std::min<long long>((long long)m->eng->sms * 2, nrows),
                                                                 ((long long)nrows * strips + 15) / 16));
     if ((rc = dev_alloc(m, &gs.part, (size_t)gs.blocks))) return rc;
-    // the mover walk is latency-bound random access (ncu: long-scoreboard stalls, 4 % issue utilisation, 49 %
-    // occupancy at 4 CTAs per SM -- the measured configuration; JXB_GS_MOVE_BPS tries more resident CTAs)
-    int mv_bps = 4;
-    if (const char* ev = getenv("JXB_GS_MOVE_BPS")) mv_bps = std::max(1, std::min(8, atoi(ev)));
-    m->gs_move_blocks = m->eng->sms * mv_bps;
+    if ((rc = dev_alloc(m, &gs.sendcnt, (size_t)2 * kMaxPeers))) return rc;
+    CK(cudaMemset(gs.sendcnt, 0, 2 * kMaxPeers * sizeof(unsigned int)));
   }
   gs.peer[gs.rank] = m->gs_area;
   gs.self = m->gs_area;
@@ -1122,14 +1140,16 @@ extern "C" int jxb_model_grid_shard_export(jxb_model* m, int row_begin, int row_
   NEED(m);
   if (!m->grid_sharded || m->dev.world_size < 2)
     return fail(JXB_ERR_STATE, "model is not a sharded Grid (desc.world_size > 1 with a Schelling program)");
-  if (!handle_out || bytes < sizeof(cudaIpcMemHandle_t))
-    return fail(JXB_ERR_INVALID, "need %zu bytes for the IPC handle", sizeof(cudaIpcMemHandle_t));
+  if (!handle_out || bytes < JXB_GRID_HANDLE_BYTES)
+    return fail(JXB_ERR_INVALID, "need %d bytes for the IPC handle + the band", JXB_GRID_HANDLE_BYTES);
   int rc = grid_shard_prepare(m, row_begin, row_end);
   if (rc) return rc;
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, m->gs_area));
   memset(handle_out, 0, bytes);
   memcpy(handle_out, &h, sizeof(h));
+  const int32_t band[2] = {row_begin, row_end};
+  memcpy((char*)handle_out + sizeof(h), band, sizeof(band));
   return JXB_OK;
 }
 
@@ -1137,8 +1157,19 @@ extern "C" int jxb_model_grid_shard_attach(jxb_model* m, const void* handles, si
   NEED(m);
   if (!m->grid_sharded || !m->gs_area) return fail(JXB_ERR_STATE, "call jxb_model_grid_shard_export first");
   if (!handles || n_ranks != m->dev.world_size) return fail(JXB_ERR_INVALID, "need the handles of all %d ranks", m->dev.world_size);
-  if (bytes_each < sizeof(cudaIpcMemHandle_t)) return fail(JXB_ERR_INVALID, "handle entries too small");
+  if (bytes_each < JXB_GRID_HANDLE_BYTES) return fail(JXB_ERR_INVALID, "handle entries too small");
   CK(cudaSetDevice(m->eng->device));
+  // the bands must tile the rows in rank order (a mover's record goes to the owner of its target row)
+  int next = 0;
+  for (int p = 0; p < n_ranks; ++p) {
+    int32_t band[2];
+    memcpy(band, (const char*)handles + (size_t)p * bytes_each + sizeof(cudaIpcMemHandle_t), sizeof(band));
+    if (band[0] != next || band[1] <= band[0]) return fail(JXB_ERR_INVALID, "rank %d's band [%d,%d) does not continue at row %d", p, band[0], band[1], next);
+    m->gs.xb[p] = band[0];
+    next = band[1];
+  }
+  if (next != m->sd.W) return fail(JXB_ERR_INVALID, "the bands cover %d of %d rows", next, m->sd.W);
+  m->gs.xb[n_ranks] = next;
   for (int p = 0; p < n_ranks; ++p) {
     if (p == m->dev.rank) continue;
     cudaIpcMemHandle_t h;
@@ -1158,7 +1189,7 @@ extern "C" int jxb_model_grid_shard_attach(jxb_model* m, const void* handles, si
 static int schelling_export_satisfied(jxb_model* m, cudaStream_t s, bool clear_dirty) {
   unsigned char* sat = (unsigned char*)m->dev.t[0].f[2];
   CK(cudaMemsetAsync(sat, 1, (size_t)m->desc.types[0].n_agents, s));
-  if (m->grid_sharded) grid_shard_export_satisfied_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->gs, sat);   // host: min over ranks
+  if (m->grid_sharded) grid_shard_export_satisfied_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->sb, m->sd, m->gs, sat);   // host: min over ranks
   else if (m->sch_packed) satisfied_export_packed_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->sd, m->sb, m->dev.ctrl, sat);
   else satisfied_export_kernel<<<m->eng->sms * 4, 256, 0, s>>>(m->sd, m->dev.ctrl, sat);
   m->eng->launches++;
@@ -1597,11 +1628,12 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       if (timed) cudaEventRecord(e0, s);
       grid_shard_sweep_kernel<<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs);
       if (timed) cudaEventRecord(e1, s);
-      grid_shard_publish_kernel<<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
-      grid_shard_wait_kernel<<<1, 32, 0, s>>>(m->sd, m->gs, m->dev);
-      if (part) grid_shard_move_kernel<1><<<m->gs_move_blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
-      else grid_shard_move_kernel<0><<<m->gs_move_blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
-      eng->launches += 4;
+      grid_shard_counts_kernel<<<1, kThreads, 0, s>>>(m->sd, m->gs, m->dev);
+      if (part) grid_shard_moveout_kernel<1><<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
+      else grid_shard_moveout_kernel<0><<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
+      grid_shard_wait_kernel<<<1, 32, 0, s>>>(m->gs);
+      grid_shard_apply_kernel<<<eng->sms * 4, 256, 0, s>>>(m->sd, m->sb, m->gs);
+      eng->launches += 5;
       break;
     }
     case JXB_PROGRAM_TRACED: {
@@ -1718,12 +1750,12 @@ static int launches_per_step_all(jxb_model* m) {
     extra += 1;
     if (m->has_net) extra += 1;
     if (m->has_grid && rf.field == 2) extra += 1;
-    if (m->grid_sharded && rf.field == 1) extra += 1;
+    if (m->grid_sharded && (rf.field == 1 || rf.field == 3)) extra += 1;
   }
   return launches_per_step(m) + extra;
 }
 static int launches_per_step(jxb_model* m) {
-  if (m->grid_sharded) return 4;
+  if (m->grid_sharded) return 5;
   if (m->net_sharded) return 2;
   if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 : (m->sir_mode == 1 ? 2 : 1);
   if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? (m->dev.world_size > 1 ? 6 : 5) : 1);
@@ -1921,7 +1953,7 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
     if (nerr) return fail(JXB_ERR_NCCL, "sharded Network: a rank did not publish its step within the spin budget");
   }
   if (m->grid_sharded) {
-    if (steps > 0) m->ct_stale = true;
+    if (steps > 0) { m->ct_stale = true; m->pos_stale = true; }
     unsigned int gerr = 0;
     CK(cudaMemcpy(&gerr, &((GridXchgHdr*)m->gs_area)->err, sizeof(gerr), cudaMemcpyDeviceToHost));
     if (gerr) return fail(JXB_ERR_NCCL, "sharded Grid: a rank did not publish its band within the spin budget");

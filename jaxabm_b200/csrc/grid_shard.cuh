@@ -2,29 +2,36 @@
 // 8(e) "Grid: row blocks + halo"; one process per GPU, peers' receive areas mapped over NVLink by
 // CUDA IPC).  Results are bit-identical to the single-GPU kernels (schelling_bits.cuh).
 //
-// Rank r owns rows [X0, X1) of the W x H grid.  Every rank keeps the global-indexed arrays of the
-// single-GPU engine (bit planes occ / t1, cell_agent, the replicated empty-cell slots E), but only
-// rows [X0-1, X1] of the planes (the band + one halo row each side) and rows [X0, X1) of cell_agent
-// are kept coherent and touched per step.
+// Everything a step touches is PARTITIONED -- a rank only walks the movers of its own band:
+//   cells   rank r owns rows [X0, X1): the bit planes occ / t1 (plus one halo row each side, kept
+//           coherent by the movers' records) and the cell payload cell_am (agent, moves);
+//   U       the ordered list of unsatisfied cells: the bands' lists in rank order, so rank r holds
+//           U[prefix[r] .. prefix[r+1]) -- its own rows, compacted CTA-locally;
+//   E       the empty-cell slots: rank q holds slots [q * eper, (q+1) * eper) inside its receive
+//           area.  A slot is matched to exactly one mover per step, so the mover's rank reads and
+//           rewrites it in place over NVLink (peer load + store, no synchronisation needed).
 //
-// A step is four launches per rank, graph-captured, with no host round trip and no NCCL call:
+// A step is five launches per rank, graph-captured, with no host round trip and no NCCL call:
 //   1 sweep    bit-sliced neighbour counts of the band (eval_row of schelling_bits.cuh): unsatisfied
 //              mask + exact integer partials per CTA.
-//   2 publish  ordered compaction of the band's unsatisfied cells into (cell, agent | type<<31)
-//              records, stored straight into segment [parity][r] of EVERY rank's receive area
-//              (remote stores over NVLink: the compaction IS the all-gather); CTA 0 adds the band's
-//              counts; the last CTA to finish releases flag[parity][r] = step tag on every rank.
-//   3 wait     one warp spins (ld.acquire.sys) on the world's flags in its OWN area, folds the counts
-//              in rank order (exact integers -> the metrics row is identical on every rank), and
-//              leaves u, m = min(u, e) and the ranks' prefix offsets for the movers.
-//   4 move     every rank walks ALL movers k < m (keyed Feistel matching, as on one GPU): the mover's
-//              record is read from the gathered segments, its target slot from the replicated E, and
-//              E is updated identically everywhere.  Plane bits are flipped wherever the cell lies in
-//              the rank's band OR its halo rows -- so the halo rows are maintained by the movers
-//              themselves and no halo exchange exists -- and cell_agent / position / moves are
-//              written by the owner of the target cell only.
-// Segments are double-buffered by step parity: a rank can run at most one publish ahead of a peer
-// that is still reading the previous step's records.
+//   2 counts   one CTA: folds the partials, stores the band's counts + flag A into every rank's
+//              header, waits for the world's flags, folds the counts in rank order (exact integers
+//              -> the metrics row is identical everywhere) and leaves u, m = min(u, e) and the
+//              ranks' prefixes in U.
+//   3 moveout  every CTA compacts the unsatisfied cells of ITS rows into its segment of U and walks
+//              them in cell order: entry j is mover k = piU^-1(j) (if k < m) and takes slot piE(k) --
+//              the single-GPU matching, evaluated from the source side.  The source cell is cleared
+//              locally; the target cell travels as a 16-byte record (cell, agent | type<<31, moves,
+//              set) to the rank that owns its row, and as a plane-only copy to the ranks that hold
+//              that row -- or the source row -- as a halo.  Records are appended to segment
+//              [parity][me] of the target's receive area (remote stores over NVLink); the last CTA
+//              releases the per-target counts + flag C.
+//   4 wait     one warp spins on the world's C flags in its OWN area and leaves the record counts.
+//   5 apply    every received record sets / clears the plane bits wherever this rank keeps that row
+//              (band, halo, wrapped halo of a periodic grid) and, for a cell of the band, writes the
+//              payload.
+// Segments and counts are double-buffered by step parity: a rank runs at most one exchange ahead of
+// a peer that is still reading the previous one.
 #pragma once
 #include "common.cuh"
 #include "schelling.cuh"
@@ -33,29 +40,36 @@
 namespace jxb {
 
 struct GridXchgHdr {
-  unsigned int flag[2][kMaxPeers];        // step tag of rank p's last publish of this parity
-  unsigned int cnt[2][kMaxPeers][4];      // rank p's band: #unsatisfied, #with a neighbour, numerator lo / hi
-  unsigned int err;                       // a peer's flag did not arrive within the spin budget
-  unsigned int pad[128 - 2 * kMaxPeers - 8 * kMaxPeers - 1];
+  unsigned int flagA[2][kMaxPeers];       // step tag: rank p's band counts of this parity are in cntA
+  unsigned int cntA[2][kMaxPeers][4];     // rank p's band: #unsatisfied, #with a neighbour, numerator lo / hi
+  unsigned int flagC[2][kMaxPeers];       // step tag: rank p's records of this parity are complete
+  unsigned int cntC[2][kMaxPeers][2];     // how many records rank p sent here: cell records (front), halo records (back)
+  unsigned int err;                       // 1: a peer's flag did not arrive within the spin budget, 2: a segment overflowed
+  unsigned int pad[256 - 4 * kMaxPeers - 8 * kMaxPeers - 4 * kMaxPeers - 1];
 };
-static_assert(sizeof(GridXchgHdr) == 512, "receive-area header is 512 bytes");
+static_assert(sizeof(GridXchgHdr) == 1024, "receive-area header is 1 KiB");
 
 struct GridStepInfo {
   unsigned int tag, par, u, m;
   int key_row;                            // row of the run's key table that belongs to this step
-  unsigned int ticket;                    // last-CTA election of the publish kernel
-  unsigned int prefix[kMaxPeers + 1];     // rank q's records are U[prefix[q] .. prefix[q+1])
+  unsigned int ticket;                    // last-CTA election of the moveout kernel
+  unsigned int prefix[kMaxPeers + 1];     // rank q's unsatisfied cells are U[prefix[q] .. prefix[q+1])
+  unsigned int rcv[2 * kMaxPeers + 1];    // prefix of the received records: cell records of rank 0.., then halo records
 };
 
 struct GridShardDev {
   int rank, world;
   int X0, X1;                             // rows owned by this rank
-  unsigned long long cap;                 // records per (parity, rank) segment, identical on all ranks
+  int xb[kMaxPeers + 1];                  // rank q owns rows [xb[q], xb[q+1])
+  unsigned int cap, halo_cap;             // records per (parity, rank) segment; its last halo_cap entries take the halo records
+  unsigned int eper;                      // empty-cell slots per rank
+  unsigned long long rec_off;             // byte offset of the record segments in a receive area (after header + slots)
   unsigned char* peer[kMaxPeers];         // every rank's receive area as mapped here (own = local)
   unsigned char* self;                    // == peer[rank]
   GridStepInfo* info;
   BlkPart* part;                          // [blocks] per-CTA partials of the sweep
-  int blocks;                             // CTAs of the sweep AND the publish kernel (same row split)
+  unsigned int* sendcnt;                  // [2][kMaxPeers] records appended for each target this step (cell / halo)
+  int blocks;                             // CTAs of the sweep AND the moveout kernel (same row split)
 };
 
 __device__ __forceinline__ GridXchgHdr* gs_hdr(unsigned char* base) { return (GridXchgHdr*)base; }
@@ -67,8 +81,28 @@ __device__ __forceinline__ unsigned char* gs_peer(const GridShardDev& gs, int p)
     if (p == i) r = gs.peer[i];
   return r;
 }
-__device__ __forceinline__ uint2* gs_seg(unsigned char* base, const GridShardDev& gs, unsigned int par, int from) {
-  return (uint2*)(base + sizeof(GridXchgHdr)) + ((size_t)par * gs.world + from) * gs.cap;
+__device__ __forceinline__ int gs_owner(const GridShardDev& gs, int x) {
+  int q = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxPeers; ++i)
+    if (i < gs.world && x >= gs.xb[i]) q = i;
+  return q;
+}
+__device__ __forceinline__ uint4* gs_seg(unsigned char* base, const GridShardDev& gs, unsigned int par, int from) {
+  return (uint4*)(base + gs.rec_off) + ((size_t)par * gs.world + from) * gs.cap;
+}
+// slot jj of the partitioned empty-cell list, wherever it lives
+__device__ __forceinline__ unsigned int* gs_slot(const GridShardDev& gs, unsigned int jj) {
+  const unsigned int q = jj / gs.eper;
+  return (unsigned int*)(gs_peer(gs, (int)q) + sizeof(GridXchgHdr)) + (jj - q * gs.eper);
+}
+__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ------------------------------------------------------------------------------------ 1 sweep
@@ -151,127 +185,57 @@ __global__ void __launch_bounds__(kThreads, 2) grid_shard_sweep_kernel(const Sch
   }
 }
 
-// ------------------------------------------------------------------------------------ 2 publish
-__global__ void __launch_bounds__(kThreads) grid_shard_publish_kernel(const SchellingDev sd, const SchellingBitsDev sb,
-                                                                   const GridShardDev gs, const ModelDev md) {
+// ------------------------------------------------------------------------------------ 2 counts
+__global__ void __launch_bounds__(kThreads) grid_shard_counts_kernel(const SchellingDev sd, const GridShardDev gs, const ModelDev md) {
   constexpr int kWarps = kThreads / 32;
-  __shared__ unsigned int s_u32[kWarps], s_all[kWarps], s_occ[kWarps];
+  __shared__ unsigned int s_u32[kWarps], s_occ[kWarps];
   __shared__ unsigned long long s_u64[kWarps];
-  __shared__ unsigned int s_prefix, s_total, s_occ_total, s_last;
-  __shared__ unsigned long long s_num_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int B = gridDim.x, b = blockIdx.x;
-  const unsigned int tag = (unsigned int)(md.ctrl->time_step + 1);
-  const unsigned int par = tag & 1u;
-  const int wpr = sb.wpr;
-  const int nrows = gs.X1 - gs.X0;
-  const int R0 = gs.X0 + (int)((long long)nrows * b / B), R1 = gs.X0 + (int)((long long)nrows * (b + 1) / B);
-  const long long wbeg = (long long)R0 * wpr, wend = (long long)R1 * wpr;
-  {
-    unsigned int before = 0, all = 0, occ = 0;
-    unsigned long long num = 0;
-    for (int i = tid; i < B; i += kThreads) {
-      const uint4 raw = __ldcg((const uint4*)(gs.part + i));
-      all += raw.x;
-      if (i < b) before += raw.x;
-      occ += raw.y;
-      num += ((unsigned long long)raw.w << 32) | raw.z;
-    }
-    before = warp_sum((int)before);
-    all = warp_sum((int)all);
-    occ = warp_sum((int)occ);
-#pragma unroll
-    for (int dd = 16; dd > 0; dd >>= 1) num += __shfl_xor_sync(0xffffffffu, num, dd);
-    if (lane == 0) { s_u32[warp] = before; s_all[warp] = all; s_occ[warp] = occ; s_u64[warp] = num; }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned int p = 0, a = 0, oc = 0;
-      unsigned long long nm = 0;
-      for (int w = 0; w < kWarps; ++w) { p += s_u32[w]; a += s_all[w]; oc += s_occ[w]; nm += s_u64[w]; }
-      s_prefix = p; s_total = a; s_occ_total = oc; s_num_total = nm;
-    }
-    __syncthreads();
-  }
-  if (b == 0 && tid < gs.world) {            // the band's counts into every rank's header
-    unsigned int* c = gs_hdr(gs_peer(gs, tid))->cnt[par][gs.rank];
-    c[0] = s_total;
-    c[1] = s_occ_total;
-    c[2] = (unsigned int)s_num_total;
-    c[3] = (unsigned int)(s_num_total >> 32);
-  }
-  if (s_total > 0) {
-    uint2* seg[kMaxPeers];
-#pragma unroll
-    for (int p = 0; p < kMaxPeers; ++p) seg[p] = p < gs.world ? gs_seg(gs.peer[p], gs, par, gs.rank) : nullptr;
-    unsigned int base = s_prefix;
-    for (long long w0 = wbeg; w0 < wend; w0 += kThreads) {
-      const long long w = w0 + tid;
-      unsigned int unsat = 0, tw = 0;
-      if (w < wend) { unsat = __ldcg(sb.umask + w); tw = __ldcg(sb.t1 + w); }
-      const unsigned int cnt = __popc(unsat);
-      unsigned int inc = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-      }
-      __syncthreads();
-      if (lane == 31) s_u32[warp] = inc;
-      __syncthreads();
-      unsigned int woff = 0, ttot = 0;
-#pragma unroll
-      for (int ww = 0; ww < kWarps; ++ww) {
-        if (ww < warp) woff += s_u32[ww];
-        ttot += s_u32[ww];
-      }
-      unsigned int pu = base + woff + inc - cnt;
-      const unsigned int c0 = (unsigned int)(w << 5);
-      while (unsat) {
-        const int q = __ffs(unsat) - 1;
-        unsat &= unsat - 1;
-        const unsigned int cell = c0 + q;
-        const unsigned int ag = (unsigned int)__ldcg(sd.cell_agent + cell);
-        const uint2 rec = make_uint2(cell, (ag & 0x7FFFFFFFu) | (((tw >> q) & 1u) << 31));
-#pragma unroll
-        for (int p = 0; p < kMaxPeers; ++p)
-          if (p < gs.world) seg[p][pu] = rec;
-        ++pu;
-      }
-      base += ttot;
-    }
-  }
-  // last CTA to finish publishes the flag: records + counts of ALL CTAs precede it
-  __threadfence_system();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&gs.info->ticket, 1u) == (unsigned int)(B - 1)) ? 1u : 0u;
-  __syncthreads();
-  if (s_last) {
-    if (tid == 0) gs.info->ticket = 0u;
-    __threadfence_system();
-    if (tid < gs.world) st_release_sys(&gs_hdr(gs_peer(gs, tid))->flag[par][gs.rank], tag);
-  }
-}
-
-// ------------------------------------------------------------------------------------ 3 wait
-__global__ void __launch_bounds__(32) grid_shard_wait_kernel(const SchellingDev sd, const GridShardDev gs, const ModelDev md) {
-  const int lane = threadIdx.x;
   Ctrl* ctrl = md.ctrl;
   const TypeDev& t = md.t[0];
   const unsigned int tag = (unsigned int)(ctrl->time_step + 1);
   const unsigned int par = tag & 1u;
+  {
+    unsigned int all = 0, occ = 0;
+    unsigned long long num = 0;
+    for (int i = tid; i < gs.blocks; i += kThreads) {
+      const uint4 raw = __ldcg((const uint4*)(gs.part + i));
+      all += raw.x;
+      occ += raw.y;
+      num += ((unsigned long long)raw.w << 32) | raw.z;
+    }
+    all = warp_sum((int)all);
+    occ = warp_sum((int)occ);
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) num += __shfl_xor_sync(0xffffffffu, num, dd);
+    if (lane == 0) { s_u32[warp] = all; s_occ[warp] = occ; s_u64[warp] = num; }
+    __syncthreads();
+  }
+  if (warp != 0) return;
   GridXchgHdr* h = gs_hdr(gs.self);
   unsigned int c0 = 0, c1 = 0;
   unsigned long long num = 0;
   if (lane < gs.world) {
+    unsigned int a = 0, oc = 0;
+    unsigned long long nm = 0;
+    for (int w = 0; w < kWarps; ++w) { a += s_u32[w]; oc += s_occ[w]; nm += s_u64[w]; }
+    // my band's counts into rank `lane`'s header, then the flag (release: the counts precede it)
+    GridXchgHdr* ph = gs_hdr(gs_peer(gs, lane));
+    unsigned int* c = ph->cntA[par][gs.rank];
+    c[0] = a;
+    c[1] = oc;
+    c[2] = (unsigned int)nm;
+    c[3] = (unsigned int)(nm >> 32);
+    st_release_sys(&ph->flagA[par][gs.rank], tag);
     if (!*(volatile unsigned int*)&h->err) {
       const long long t0 = clock64();
-      while (ld_acquire_sys(&h->flag[par][lane]) != tag) {
+      while (ld_acquire_sys(&h->flagA[par][lane]) != tag) {
         if (clock64() - t0 > (20ll << 30)) { h->err = 1u; break; }     // ~10 s: a peer is gone
       }
     }
-    c0 = __ldcv(&h->cnt[par][lane][0]);
-    c1 = __ldcv(&h->cnt[par][lane][1]);
-    num = ((unsigned long long)__ldcv(&h->cnt[par][lane][3]) << 32) | __ldcv(&h->cnt[par][lane][2]);
+    c0 = __ldcv(&h->cntA[par][lane][0]);
+    c1 = __ldcv(&h->cntA[par][lane][1]);
+    num = ((unsigned long long)__ldcv(&h->cntA[par][lane][3]) << 32) | __ldcv(&h->cntA[par][lane][2]);
   }
   __syncwarp();
   unsigned int inc = c0;
@@ -313,7 +277,7 @@ __global__ void __launch_bounds__(32) grid_shard_wait_kernel(const SchellingDev 
   }
 }
 
-// ------------------------------------------------------------------------------------ 4 move
+// ------------------------------------------------------------------------------------ 3 moveout
 __device__ __forceinline__ void gs_plane_write(const SchellingBitsDev& sb, long long w, unsigned int bit, bool ty, bool set) {
   if (set) {
     atomicOr(sb.occ + w, bit);
@@ -337,97 +301,273 @@ __device__ __forceinline__ void gs_flip(const SchellingDev& sd, const SchellingB
   }
 }
 
+// the ranks other than `own` that keep row x as a halo row: the owners of the rows above and below it
+__device__ __forceinline__ void gs_halo_ranks(const SchellingDev& sd, const GridShardDev& gs, int x, int own, int& ha, int& hb) {
+  int xa = x - 1, xc = x + 1;
+  if (sd.periodic) { if (xa < 0) xa = sd.W - 1; if (xc >= sd.W) xc = 0; }
+  ha = xa >= 0 ? gs_owner(gs, xa) : own;
+  hb = xc < sd.W ? gs_owner(gs, xc) : own;
+  if (ha == own) ha = -1;
+  if (hb == own || hb == ha) hb = -1;
+}
+
+// a record that only concerns a halo copy: rare (boundary rows), appended from the back of the segment
+__device__ __forceinline__ void gs_send_halo(const GridShardDev& gs, unsigned int par, int p, uint4 rec) {
+  const unsigned int i = atomicAdd(gs.sendcnt + kMaxPeers + p, 1u);
+  if (i < gs.halo_cap) gs_seg(gs_peer(gs, p), gs, par, gs.rank)[gs.cap - 1u - i] = rec;
+  else gs_hdr(gs.self)->err = 2u;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) grid_shard_move_kernel(const SchellingDev sd, const SchellingBitsDev sb,
-                                                                const GridShardDev gs, const ModelDev md) {
+__global__ void __launch_bounds__(kThreads, 2) grid_shard_moveout_kernel(const SchellingDev sd, const SchellingBitsDev sb,
+                                                                      const GridShardDev gs, const ModelDev md) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ unsigned int s_u32[kWarps];
+  __shared__ unsigned int s_ws[8][kWarps];
   __shared__ unsigned int s_rk[8];
-  __shared__ unsigned int s_prefix[kMaxPeers + 1];
+  __shared__ unsigned int s_cnt[kMaxPeers], s_base[kMaxPeers];
+  __shared__ unsigned int s_prefix, s_last;
   const GridStepInfo* info = gs.info;
-  const unsigned int u = info->u, m = info->m;
-  if (m == 0) return;
-  const int tid = threadIdx.x;
+  const unsigned int u = info->u, m = info->m, par = info->par;
+  if (u == 0) return;                    // uniform over the world: nobody sends, nobody waits
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = gridDim.x, b = blockIdx.x;
+  const int wpr = sb.wpr, H = sd.H;
+  const int nrows = gs.X1 - gs.X0;
+  const int R0 = gs.X0 + (int)((long long)nrows * b / B), R1 = gs.X0 + (int)((long long)nrows * (b + 1) / B);
+  const long long wbeg = (long long)R0 * wpr, wend = (long long)R1 * wpr;
   if (tid < 8) {
     const uint32_t* kp = md.keys + (size_t)info->key_row * (md.n_types + 1) * 2;
     const Key ck = {kp[0], kp[1]};
     s_rk[tid] = bits_elem<MODE>(ck, tid, 8);
   }
-  if (tid <= gs.world) s_prefix[tid] = info->prefix[tid];
+  {
+    unsigned int before = 0;
+    for (int i = tid; i < b; i += kThreads) before += __ldcg(&gs.part[i].unsat);
+    before = warp_sum((int)before);
+    if (lane == 0) s_u32[warp] = before;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int p = info->prefix[gs.rank];
+      for (int w = 0; w < kWarps; ++w) p += s_u32[w];
+      s_prefix = p;
+    }
+    __syncthreads();
+  }
+  // (a) ordered compaction of the CTA's rows into ITS segment of U (as in schelling_bits_kernel)
+  constexpr int kPre = 8;
+  unsigned int base = s_prefix;
+  for (long long W0 = wbeg; W0 < wend; W0 += (long long)kPre * kThreads) {
+    unsigned int pre[kPre], inc[kPre];
+    unsigned int any = 0;
+#pragma unroll
+    for (int c = 0; c < kPre; ++c) {
+      const long long w = W0 + (long long)c * kThreads + tid;
+      pre[c] = w < wend ? __ldcg(sb.umask + w) : 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < kPre; ++c) {
+      const unsigned int cnt = __popc(pre[c]);
+      any |= cnt;
+      unsigned int v = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t2 = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t2;
+      }
+      inc[c] = v;
+      if (lane == 31) s_ws[c][warp] = v;
+    }
+    if (__syncthreads_count(any != 0u) != 0) {
+#pragma unroll
+      for (int c = 0; c < kPre; ++c) {
+        unsigned int woff = 0, ctot = 0;
+#pragma unroll
+        for (int ww = 0; ww < kWarps; ++ww) {
+          const unsigned int v = s_ws[c][ww];
+          if (ww < warp) woff += v;
+          ctot += v;
+        }
+        unsigned int unsat = pre[c];
+        unsigned int pu = base + woff + inc[c] - __popc(unsat);
+        const unsigned int c0 = (unsigned int)((W0 + (long long)c * kThreads + tid) << 5);
+        while (unsat) {
+          const int q = __ffs(unsat) - 1;
+          unsat &= unsat - 1;
+          sd.U[pu++] = c0 + q;
+        }
+        base += ctot;
+      }
+    }
+    __syncthreads();
+  }
+  // (b) the moves of the CTA's segment [s_prefix, base), in cell order.  U[j] receives (agent | 1<<31) for a mover
+  // and keeps the cell id of an agent that stays -- what the lazy 'satisfied' column needs.
+  if (m > 0) {
+    const Feistel fu = make_feistel(u, s_rk), fe = make_feistel(sd.n_empty, s_rk + 4);
+    constexpr int kMv = 4;
+    const unsigned int seg_end = base;
+    const int me = gs.rank;
+    for (unsigned int b0 = s_prefix; b0 < seg_end; b0 += kThreads * kMv) {     // uniform trip count: barriers inside
+      unsigned int src[kMv], dst[kMv], tw[kMv], li[kMv];
+      unsigned int* slot[kMv];
+      int2 am[kMv];
+      int tgt[kMv];                      // rank that owns the target cell, -1: not a mover
+      if (tid < kMaxPeers) s_cnt[tid] = 0u;
+#pragma unroll
+      for (int i = 0; i < kMv; ++i) {
+        const unsigned int j = b0 + i * kThreads + tid;
+        tgt[i] = -1; src[i] = 0; slot[i] = nullptr;
+        if (j < seg_end) {
+          src[i] = __ldcg(sd.U + j);
+          const unsigned int k = feistel_inverse(fu, j);
+          if (k < m) { slot[i] = gs_slot(gs, feistel_permute(fe, k)); tgt[i] = 0; }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kMv; ++i) {
+        dst[i] = 0; tw[i] = 0; am[i] = make_int2(-1, 0);
+        if (tgt[i] >= 0) {
+          dst[i] = ld_relaxed_sys(slot[i]);
+          am[i] = __ldcg(sb.cell_am + src[i]);
+          tw[i] = __ldcg(sb.t1 + (src[i] >> 5));
+        }
+      }
+      __syncthreads();                   // s_cnt is zero, and the previous iteration's s_base reads are done
+#pragma unroll
+      for (int i = 0; i < kMv; ++i) {
+        li[i] = 0;
+        if (tgt[i] < 0) continue;
+        const unsigned int j = b0 + i * kThreads + tid;
+        const unsigned int s_ = src[i], d_ = dst[i];
+        const bool ty = (tw[i] >> (s_ & 31)) & 1u;
+        const int xs = (int)(s_ / (unsigned int)H), xd = (int)(d_ / (unsigned int)H);
+        st_relaxed_sys(slot[i], s_);
+        sd.U[j] = (unsigned int)am[i].x | 0x80000000u;
+        gs_flip(sd, sb, gs, s_, xs, ty, false);
+        sb.cell_am[s_] = make_int2(-1, 0);
+        const unsigned int tybit = ty ? 0x80000000u : 0u;
+        int ha, hb;
+        gs_halo_ranks(sd, gs, xs, me, ha, hb);
+        if (ha >= 0) gs_send_halo(gs, par, ha, make_uint4(s_, tybit, 0u, 0u));
+        if (hb >= 0) gs_send_halo(gs, par, hb, make_uint4(s_, tybit, 0u, 0u));
+        const int p = gs_owner(gs, xd);
+        tgt[i] = p;
+        li[i] = atomicAdd(&s_cnt[p], 1u);
+        gs_halo_ranks(sd, gs, xd, p, ha, hb);
+        const uint4 rec = make_uint4(d_, (unsigned int)am[i].x | tybit, (unsigned int)(am[i].y + 1), 1u);
+        if (ha >= 0) gs_send_halo(gs, par, ha, rec);
+        if (hb >= 0) gs_send_halo(gs, par, hb, rec);
+      }
+      __syncthreads();
+      if (tid < gs.world) s_base[tid] = s_cnt[tid] ? atomicAdd(gs.sendcnt + tid, s_cnt[tid]) : 0u;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kMv; ++i) {
+        if (tgt[i] < 0) continue;
+        const unsigned int idx = s_base[tgt[i]] + li[i];
+        const uint4 rec = make_uint4(dst[i], (unsigned int)am[i].x | (((tw[i] >> (src[i] & 31)) & 1u) << 31),
+                                     (unsigned int)(am[i].y + 1), 1u);
+        if (idx < gs.cap - gs.halo_cap) gs_seg(gs_peer(gs, tgt[i]), gs, par, me)[idx] = rec;
+        else gs_hdr(gs.self)->err = 2u;
+      }
+    }
+    // the last CTA to finish publishes the counts + flag: the records of ALL CTAs precede it
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&gs.info->ticket, 1u) == (unsigned int)(B - 1)) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      if (tid == 0) gs.info->ticket = 0u;
+      __threadfence_system();
+      if (tid < gs.world) {
+        GridXchgHdr* ph = gs_hdr(gs_peer(gs, tid));
+        ph->cntC[par][me][0] = atomicExch(gs.sendcnt + tid, 0u);
+        ph->cntC[par][me][1] = atomicExch(gs.sendcnt + kMaxPeers + tid, 0u);
+        st_release_sys(&ph->flagC[par][me], info->tag);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ 4 wait
+__global__ void __launch_bounds__(32) grid_shard_wait_kernel(const GridShardDev gs) {
+  const int lane = threadIdx.x;
+  GridStepInfo* info = gs.info;
+  if (info->m == 0) { if (lane <= 2 * gs.world) info->rcv[lane] = 0u; return; }
+  const unsigned int tag = info->tag, par = info->par;
+  GridXchgHdr* h = gs_hdr(gs.self);
+  unsigned int c = 0;
+  if (lane < 2 * gs.world) {
+    const int from = lane < gs.world ? lane : lane - gs.world;
+    if (!*(volatile unsigned int*)&h->err) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys(&h->flagC[par][from]) != tag) {
+        if (clock64() - t0 > (20ll << 30)) { h->err = 1u; break; }
+      }
+    }
+    c = __ldcv(&h->cntC[par][from][lane < gs.world ? 0 : 1]);
+  }
+  __syncwarp();
+  unsigned int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane <= 2 * gs.world) info->rcv[lane] = inc - c;          // lane 2*world: c = 0 -> the total
+}
+
+// ------------------------------------------------------------------------------------ 5 apply
+__global__ void __launch_bounds__(256) grid_shard_apply_kernel(const SchellingDev sd, const SchellingBitsDev sb, const GridShardDev gs) {
+  __shared__ unsigned int s_rcv[2 * kMaxPeers + 1];
+  const GridStepInfo* info = gs.info;
+  if (info->m == 0) return;
+  const int nseg = 2 * gs.world;
+  if ((int)threadIdx.x <= nseg) s_rcv[threadIdx.x] = info->rcv[threadIdx.x];
   __syncthreads();
-  const TypeDev& t = md.t[0];
-  const unsigned int e = sd.n_empty;
-  const int H = sd.H, world = gs.world;
-  const uint2* segs = gs_seg(gs.self, gs, info->par, 0);
-  const Feistel fu = make_feistel(u, s_rk), fe = make_feistel(e, s_rk + 4);
-  constexpr int kMv = 4;
-  const unsigned int stride = gridDim.x * kThreads;
-  for (unsigned int k0 = blockIdx.x * kThreads + tid; k0 < m; k0 += stride * kMv) {
-    uint2 rec[kMv];
-    unsigned int jj[kMv], dst[kMv];
-    bool ok[kMv];
-#pragma unroll
-    for (int i = 0; i < kMv; ++i) {
-      const unsigned int k = k0 + i * stride;
-      ok[i] = k < m;
-      rec[i] = make_uint2(0u, 0u); jj[i] = 0; dst[i] = 0;
-      if (ok[i]) {
-        const unsigned int j = feistel_permute(fu, k);
-        int q = 0;
-        while (q + 1 < world && j >= s_prefix[q + 1]) ++q;
-        rec[i] = __ldcg(segs + (size_t)q * gs.cap + (j - s_prefix[q]));
-        jj[i] = feistel_permute(fe, k);
-        dst[i] = __ldcg(sd.E + jj[i]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kMv; ++i) {
-      if (!ok[i]) continue;
-      const unsigned int s_ = rec[i].x, d_ = dst[i];
-      const int a = (int)(rec[i].y & 0x7FFFFFFFu);
-      const bool ty = (rec[i].y >> 31) != 0;
-      const int xs = (int)(s_ / (unsigned int)H), xd = (int)(d_ / (unsigned int)H);
-      sd.E[jj[i]] = s_;                               // replicated: identical on every rank
-      gs_flip(sd, sb, gs, s_, xs, ty, false);
-      gs_flip(sd, sb, gs, d_, xd, ty, true);
-      if (xs >= gs.X0 && xs < gs.X1) sd.cell_agent[s_] = -1;
-      if (xd >= gs.X0 && xd < gs.X1) {
-        sd.cell_agent[d_] = a;
-        ((int2*)t.f[1])[a] = make_int2(xd, (int)(d_ - (unsigned int)xd * (unsigned int)H));
-        atomicAdd((int*)t.f[3] + a, 1);   // fire-and-forget L2 reduction: no load to wait for (ncu: 37 % of the mover stalls)
-      }
-    }
+  const unsigned int total = s_rcv[nseg], par = info->par;
+  const int H = sd.H;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int s = 0;
+    while (s + 1 < nseg && i >= s_rcv[s + 1]) ++s;
+    const unsigned int off = i - s_rcv[s];
+    const uint4* seg = gs_seg(gs.self, gs, par, s < gs.world ? s : s - gs.world);
+    const uint4 rec = __ldcg(seg + (s < gs.world ? off : gs.cap - 1u - off));
+    const unsigned int c = rec.x;
+    const bool ty = (rec.y >> 31) != 0, set = rec.w != 0u;
+    const int x = (int)(c / (unsigned int)H);
+    gs_flip(sd, sb, gs, c, x, ty, set);
+    if (set && x >= gs.X0 && x < gs.X1) sb.cell_am[c] = make_int2((int)(rec.y & 0x7FFFFFFFu), (int)rec.z);
   }
 }
 
 // ------------------------------------------------------------------------------------ setup / export
-// 'moves' is a per-agent sum over ranks: every rank counts the moves INTO its band, and the value
-// uploaded by the caller stays only with the rank whose band holds the agent initially
-__global__ void grid_shard_own_moves_kernel(const GridShardDev gs, const int2* pos, int* moves, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int x = pos[i].x;
-    if (x < gs.X0 || x >= gs.X1) moves[i] = 0;
-  }
-}
-
-// 'position' of the agents of the band from the cell binning (others keep the -1 fill: the host
-// combines the ranks with max)
-__global__ void grid_shard_export_position_kernel(const SchellingDev sd, const GridShardDev gs, int2* pos) {
+// 'position' / 'moves' of the agents sitting in the band from the cell payload; everybody else keeps the
+// fill (-1 / 0: the host combines the ranks with max / sum)
+__global__ void grid_shard_unpack_kernel(const SchellingDev sd, const SchellingBitsDev sb, const GridShardDev gs, int2* pos, int* moves) {
   const long long c_begin = (long long)gs.X0 * sd.H, c_end = (long long)gs.X1 * sd.H;
   for (long long c = c_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; c < c_end;
        c += (long long)gridDim.x * blockDim.x) {
-    const int a = sd.cell_agent[c];
-    if (a >= 0) pos[a] = make_int2((int)(c / sd.H), (int)(c % sd.H));
+    const int2 am = __ldcs(sb.cell_am + c);
+    if (am.x >= 0) {
+      pos[am.x] = make_int2((int)(c / sd.H), (int)(c % sd.H));
+      moves[am.x] = am.y;
+    }
   }
 }
 
-// 'satisfied' of the last step: the band's unsatisfied agents (movers and stayers alike) are the
-// records this rank published; everybody else keeps the 1 fill (the host combines with min)
-__global__ void grid_shard_export_satisfied_kernel(const GridShardDev gs, unsigned char* sat) {
+// 'satisfied' of the last step: the band's unsatisfied agents are this rank's segment of U -- (agent | 1<<31)
+// for one that moved, the cell of one that stayed; everybody else keeps the 1 fill (the host combines with min)
+__global__ void grid_shard_export_satisfied_kernel(const SchellingBitsDev sb, const SchellingDev sd, const GridShardDev gs,
+                                                   unsigned char* sat) {
   const GridStepInfo* info = gs.info;
-  const unsigned int par = info->par;
-  const unsigned int n = info->prefix[gs.rank + 1] - info->prefix[gs.rank];
-  const uint2* seg = gs_seg(gs.self, gs, par, gs.rank);
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    sat[seg[i].y & 0x7FFFFFFFu] = 0;
+  const unsigned int lo = info->prefix[gs.rank], hi = info->prefix[gs.rank + 1];
+  for (unsigned int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+    const unsigned int v = sd.U[i];
+    const int a = (v >> 31) ? (int)(v & 0x7FFFFFFFu) : sb.cell_am[v].x;
+    if (a >= 0) sat[a] = 0;
+  }
 }
 
 }  // namespace jxb

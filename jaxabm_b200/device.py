@@ -136,7 +136,7 @@ class DeviceModel:
         """Row band of this rank + receive areas of all ranks (``jxb_model_grid_shard_export/attach``)."""
         from .dist import shard_bounds
         lo, hi = shard_bounds(int(self.desc.grid_w), group.rank, group.world)
-        handle = np.zeros(64, dtype=np.uint8)
+        handle = np.zeros(72, dtype=np.uint8)          # JXB_GRID_HANDLE_BYTES: IPC handle + the band
         nat.check(self._lib.jxb_model_grid_shard_export(self.handle, lo, hi, nat.ptr(handle), handle.nbytes))
         table = np.ascontiguousarray(group.all_gather_bytes(handle))
         nat.check(self._lib.jxb_model_grid_shard_attach(self.handle, nat.ptr(table), table.shape[1], group.world))
@@ -215,6 +215,8 @@ class DeviceModel:
         """env['empty_cells'] as int32[e, 2] (x, y) pairs in slot order."""
         e = int(self.desc.grid_w) * int(self.desc.grid_h) - self.n_agents(0)
         ids = np.empty(e, dtype=np.int32)
+        if self.group is not None:         # the slots live in the ranks' receive areas: every rank must be done stepping
+            self.group.barrier()
         nat.check(self._lib.jxb_model_download_empty_cells(self.handle, nat.ptr(ids), ids.nbytes))
         h = int(self.desc.grid_h)
         return np.stack([ids // h, ids % h], axis=1).astype(np.int32)

@@ -7,11 +7,15 @@ algorithms rank by rank in NumPy -- every rank only reads what the device kernel
 ``tests/test_oracle_sharded.py`` checks that they reproduce the plain oracle (``oracle/rules.py``) exactly.
 That pins the design decisions the kernels rely on without a GPU:
 
-  * a band only needs rows [X0-1, X1] of the grid, and those stay coherent when every rank replays ALL
-    movers against its own copy (no halo exchange), including the wrapped rows of a periodic grid;
-  * the ordered per-band unsatisfied lists, concatenated in rank order, are the global list ``U``;
-  * ``empty_cells`` can be replicated because every rank derives the same (source, slot) pairs;
-  * per-agent columns combine as position = max, satisfied = min, moves = sum over the ranks' views;
+  * a band only needs rows [X0-1, X1] of the grid; they stay coherent when every mover's record goes to the
+    owner of its target row AND to the ranks that keep the target row -- or the source row -- as a halo
+    (including the wrapped rows of a periodic grid): no halo exchange besides the movers themselves;
+  * the ordered per-band unsatisfied lists, concatenated in rank order, are the global list ``U``, so a rank
+    can walk ITS movers alone: entry j of its segment is mover k = piU^-1(j);
+  * ``empty_cells`` can be partitioned by slot range: a slot is matched to exactly one mover per step, whose
+    rank reads and rewrites it in place wherever it lives;
+  * the agent id and its move count travel with the cell (the record), so no rank needs a per-agent column
+    during the run; columns combine as position = max, satisfied = min, moves = sum over the ranks' views;
   * a node range of the SIR network only needs its own rows + the global infected bitmap.
 """
 from __future__ import annotations
@@ -32,29 +36,30 @@ def _bounds(n, rank, world):
 
 
 class _BandRank:
-    """One rank's view: its own copy of the grid (only rows [X0-1, X1] are meaningful), the binning of its
-    rows, the replicated empty-cell slots and whole per-agent columns."""
+    """One rank's state: its own copy of the grid (only rows [X0-1, X1] are meaningful), the payload
+    (agent, moves) of the cells of its rows, and ITS range of the empty-cell slots."""
 
     def __init__(self, rank, world, W, H, periodic, types, positions, threshold):
         self.rank, self.world, self.W, self.H, self.periodic = rank, world, W, H, periodic
         self.X0, self.X1 = _bounds(W, rank, world)
+        self.xb = [_bounds(W, q, world)[0] for q in range(world)] + [W]
         self.thr = f32(threshold)
-        n = len(types)
+        self.n = len(types)
         grid = -np.ones((W, H), dtype=i32)
         grid[positions[:, 0], positions[:, 1]] = types
-        empty = np.flatnonzero(grid.reshape(-1) < 0)
-        self.E = empty.astype(np.int64)                            # replicated, slot order = ascending at start
+        empty = np.flatnonzero(grid.reshape(-1) < 0).astype(np.int64)      # slot order = ascending at start
+        self.e = len(empty)
+        self.eper = max(1, -(-self.e // world))
+        self.E = empty[rank * self.eper:(rank + 1) * self.eper].copy()     # my slots only
         self.grid = np.full((W, H), STALE, dtype=i32)
         for x in self._kept_rows():
             self.grid[x] = grid[x]
         self.cell_agent = -np.ones((W, H), dtype=np.int64)          # rows [X0, X1) only
+        self.cell_moves = np.zeros((W, H), dtype=np.int64)
         own = (positions[:, 0] >= self.X0) & (positions[:, 0] < self.X1)
         self.cell_agent[positions[own, 0], positions[own, 1]] = np.flatnonzero(own)
-        self.types = types
-        self.position = -np.ones((n, 2), dtype=i32)                 # my view: agents sitting in my band
-        self.position[own] = positions[own]
-        self.moves = np.zeros(n, dtype=i32)                         # moves INTO my band
-        self.satisfied = np.ones(n, dtype=bool)
+        self.inbox = []                                             # records received this step
+        self.last_unsat = np.zeros(0, dtype=np.int64)
 
     def _kept_rows(self):
         rows = set(range(max(self.X0 - 1, 0), min(self.X1 + 1, self.W)))
@@ -63,8 +68,23 @@ class _BandRank:
             rows.add(self.X1 % self.W)
         return rows
 
+    def _owner(self, x):
+        return max(q for q in range(self.world) if x >= self.xb[q])
+
+    def _halo_ranks(self, x, own):
+        """The ranks other than ``own`` that keep row x as a halo row: the owners of the rows next to it."""
+        out = []
+        for xn in (x - 1, x + 1):
+            if self.periodic:
+                xn %= self.W
+            if 0 <= xn < self.W:
+                q = self._owner(xn)
+                if q != own and q not in out:
+                    out.append(q)
+        return out
+
     def sweep(self):
-        """Unsatisfied agents of my rows from rows [X0-1, X1] of MY copy -> ordered records + integer partials."""
+        """Unsatisfied agents of my rows from rows [X0-1, X1] of MY copy -> ordered cells + integer partials."""
         X0, X1, W = self.X0, self.X1, self.W
         rows = [(x % W) if self.periodic else x for x in range(X0 - 1, X1 + 1)]
         pad = -np.ones((1, self.H), dtype=i32)
@@ -91,50 +111,64 @@ class _BandRank:
         agent = band >= 0
         unsat = agent & (o > 0) & ~(frac >= self.thr)
         xs, ys = np.nonzero(unsat)                                  # row-major = ascending cell id
-        cells = (xs + X0).astype(np.int64) * self.H + ys
-        ag = self.cell_agent[xs + X0, ys]
-        self.last_records = (cells, ag, band[xs, ys])
+        self.U = (xs + X0).astype(np.int64) * self.H + ys           # my segment of the global list
+        self.last_unsat = self.cell_agent[xs + X0, ys].copy()
         sel = agent & (o > 0)
         num = int(np.sum(same[sel].astype(np.int64) * (840 // np.maximum(o[sel], 1))))
-        return self.last_records, (len(cells), int(sel.sum()), num)
+        return len(self.U), int(sel.sum()), num
 
-    def move(self, records, rk, mode):
-        """Replay ALL movers of the step: update my E copy, my kept rows, my binning / columns."""
-        cells = np.concatenate([r[0] for r in records]); agents = np.concatenate([r[1] for r in records])
-        types = np.concatenate([r[2] for r in records])
-        u, e = len(cells), len(self.E)
-        m = min(u, e)
-        if m == 0:
-            return 0
+    def moveout(self, ranks, prefix, u, m, rk):
+        """Walk MY movers: entry j of my segment is mover k with piU(k) = j; it takes slot piE(k), wherever that
+        slot lives.  The source cell is cleared here; everything else travels as records."""
         k = np.arange(m, dtype=np.uint32)
         j = jl.feistel_permute(k, u, rk[0:4]).astype(np.int64)
-        slots = jl.feistel_permute(k, e, rk[4:8]).astype(np.int64)
-        src, a, ty = cells[j], agents[j], types[j]
-        dst = self.E[slots].copy()
-        self.E[slots] = src
-        kept = self._kept_rows()
+        mine = (j >= prefix[self.rank]) & (j < prefix[self.rank + 1])
+        slots = jl.feistel_permute(k[mine], self.e, rk[4:8]).astype(np.int64)
         H = self.H
-        for s_, d_, a_, t_ in zip(src, dst, a, ty):
-            xs, xd = int(s_ // H), int(d_ // H)
-            if xs in kept:
-                self.grid[xs, s_ % H] = -1
-            if xd in kept:
-                self.grid[xd, d_ % H] = t_
-            if self.X0 <= xs < self.X1:
-                self.cell_agent[xs, s_ % H] = -1
-            if self.X0 <= xd < self.X1:
-                self.cell_agent[xd, d_ % H] = a_
-                self.moves[a_] += 1
-        return m
+        for jj, sl in zip(j[mine] - prefix[self.rank], slots):
+            s_ = int(self.U[jj])
+            q, off = divmod(int(sl), self.eper)
+            d_ = int(ranks[q].E[off])                              # peer load + store: nobody else touches this slot
+            ranks[q].E[off] = s_
+            xs, xd = s_ // H, d_ // H
+            a, mv, ty = self.cell_agent[xs, s_ % H], self.cell_moves[xs, s_ % H], self.grid[xs, s_ % H]
+            assert a >= 0 and ty >= 0
+            self._flip(s_, -1)
+            self.cell_agent[xs, s_ % H] = -1
+            self.cell_moves[xs, s_ % H] = 0
+            for p in self._halo_ranks(xs, self.rank):
+                ranks[p].inbox.append((s_, -1, 0, -1))
+            p = self._owner(xd)
+            rec = (d_, int(a), int(mv) + 1, int(ty))
+            ranks[p].inbox.append(rec)
+            for ph in self._halo_ranks(xd, p):
+                ranks[ph].inbox.append(rec)
+
+    def _flip(self, c, value):
+        x = c // self.H
+        if x in self._kept_rows():
+            self.grid[x, c % self.H] = value
+
+    def apply(self):
+        for c, a, mv, ty in self.inbox:
+            self._flip(c, ty)
+            x = c // self.H
+            if ty >= 0 and self.X0 <= x < self.X1:
+                self.cell_agent[x, c % self.H] = a
+                self.cell_moves[x, c % self.H] = mv
+        self.inbox = []
 
     def export(self):
         """My view of the per-agent columns after the last step (what jxb_model_download returns)."""
-        pos = -np.ones_like(self.position)
+        pos = -np.ones((self.n, 2), dtype=i32)
+        moves = np.zeros(self.n, dtype=i32)
         xs, ys = np.nonzero(self.cell_agent[self.X0:self.X1] >= 0)
-        pos[self.cell_agent[xs + self.X0, ys]] = np.stack([xs + self.X0, ys], axis=1)
-        sat = np.ones(len(self.types), dtype=bool)
-        sat[self.last_records[1]] = False
-        return pos, sat, self.moves
+        ag = self.cell_agent[xs + self.X0, ys]
+        pos[ag] = np.stack([xs + self.X0, ys], axis=1)
+        moves[ag] = self.cell_moves[xs + self.X0, ys]
+        sat = np.ones(self.n, dtype=bool)
+        sat[self.last_unsat] = False
+        return pos, sat, moves
 
 
 def schelling_bands_run(grid_size, types, positions, world, steps, seed_key, mode, threshold=0.5, periodic=False):
@@ -144,26 +178,30 @@ def schelling_bands_run(grid_size, types, positions, world, steps, seed_key, mod
     W = H = grid_size
     n = len(types)
     ranks = [_BandRank(r, world, W, H, periodic, types, positions, threshold) for r in range(world)]
+    e = ranks[0].e
     rng = jl.split(seed_key, 2, mode)[0]                          # initialize(): keys = split(rng, C + 1), rng = keys[0]
     rows, total_moves = [], 0
     for _ in range(steps):
         rng, step_key = jl.split(rng, 2, mode)
         step_key, coll_key = jl.split(step_key, 2, mode)
         rk = jl.random_bits(coll_key, (8,), mode)
-        pub = [rk_.sweep() for rk_ in ranks]                      # publish: records + counts of every band
-        records = [p[0] for p in pub]
-        u = sum(p[1][0] for p in pub); occ = sum(p[1][1] for p in pub); num = sum(p[1][2] for p in pub)
-        ms = {r.move(records, rk, mode) for r in ranks}           # every rank replays all movers
-        assert len(ms) == 1
-        total_moves += ms.pop()
+        counts = [rk_.sweep() for rk_ in ranks]                   # the bands' counts, folded in rank order everywhere
+        u = sum(c[0] for c in counts); occ = sum(c[1] for c in counts); num = sum(c[2] for c in counts)
+        prefix = np.concatenate([[0], np.cumsum([c[0] for c in counts])])
+        m = min(u, e)
+        if m > 0:
+            for r in ranks:
+                r.moveout(ranks, prefix, u, m, rk)
+            for r in ranks:
+                r.apply()
+        total_moves += m
         rows.append((f32((n - u) / n), f32(num / 840.0 / max(occ, 1)), total_moves))
     views = [r.export() for r in ranks]
     pos = np.max(np.stack([v[0] for v in views]), axis=0)
     sat = np.min(np.stack([v[1] for v in views]), axis=0)
     moves = np.sum(np.stack([v[2] for v in views]), axis=0).astype(i32)
-    for r in ranks[1:]:
-        assert np.array_equal(r.E, ranks[0].E), "the replicated empty-cell slots diverged"
-    return {"type": types, "position": pos, "satisfied": sat, "moves": moves}, rows, ranks[0].E
+    E = np.concatenate([r.E for r in ranks])
+    return {"type": types, "position": pos, "satisfied": sat, "moves": moves}, rows, E
 
 
 def sir_node_ranges_run(n, edges, cuts, steps, seed_key, mode, beta=0.05, gamma=0.1, initial_infected=0.01,

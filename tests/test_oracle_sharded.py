@@ -1,6 +1,6 @@
 """The multi-GPU decompositions restated on the CPU (``oracle/sharded.py``) against the plain oracle: the band
-algorithm of ``csrc/grid_shard.cuh`` (no halo exchange: every rank replays all movers on its own band + halo
-rows; replicated empty-cell slots; max / min / sum combines of the per-agent columns) and the node-range
+algorithm of ``csrc/grid_shard.cuh`` (a rank walks only ITS movers; empty-cell slots partitioned by slot range;
+the movers' records keep the halo rows coherent; max / min / sum combines of the per-agent columns) and the node-range
 algorithm of ``csrc/sir.cuh`` (own CSR rows + global infected bitmap, draws by global agent index) must give
 exactly the single-device results.  The GPU parity tests (``test_gpu_grid_sharded.py``,
 ``test_gpu_net_sharded.py``) check the kernels; this file pins the design they implement."""
