@@ -258,6 +258,7 @@ struct jxb_model {
   // profiling of the dominant kernel
   bool profile = false; double prof_seconds = 0; int64_t prof_launches = 0;
   std::vector<cudaEvent_t> prof_events;
+  std::vector<cudaEvent_t> gs_trace;      // JXB_GS_TRACE=1 (with JXB_NO_GRAPH=1): events around each band kernel of each step
   int step_blocks = 0;
 };
 
@@ -1625,14 +1626,25 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
     }
     case JXB_PROGRAM_SCHELLING: {     // row-band shard of a grid (the single-GPU run is one persistent launch)
       if (!m->grid_sharded || !m->gs_attached) return fail(JXB_ERR_STATE, "sharded Grid step without attached peers");
+      static const bool trace = getenv("JXB_GS_TRACE") && atoi(getenv("JXB_GS_TRACE")) != 0;
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(s, &cap);
+      const bool tr = trace && cap == cudaStreamCaptureStatusNone;
+      auto mark = [&]() { if (tr) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); m->gs_trace.push_back(e); } };
+      mark();
       if (timed) cudaEventRecord(e0, s);
       grid_shard_sweep_kernel<<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs);
       if (timed) cudaEventRecord(e1, s);
+      mark();
       grid_shard_counts_kernel<<<1, kThreads, 0, s>>>(m->sd, m->gs, m->dev);
+      mark();
       if (part) grid_shard_moveout_kernel<1><<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
       else grid_shard_moveout_kernel<0><<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
+      mark();
       grid_shard_wait_kernel<<<1, 32, 0, s>>>(m->gs);
-      grid_shard_apply_kernel<<<eng->sms * 4, 256, 0, s>>>(m->sd, m->sb, m->gs);
+      mark();
+      grid_shard_apply_kernel<<<eng->sms * 8, 256, 0, s>>>(m->sd, m->sb, m->gs);
+      mark();
       eng->launches += 5;
       break;
     }
@@ -1944,6 +1956,24 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
     }
     m->prof_seconds = tot * 1e-3;
     m->prof_launches = (int64_t)m->prof_events.size() / 2;
+  }
+  if (!m->gs_trace.empty()) {
+    // per-kernel device time of the band steps, summed over the run and for the first steps
+    static const char* names[5] = {"sweep", "counts", "moveout", "wait", "apply"};
+    const size_t nst = m->gs_trace.size() / 6;
+    double sum[5] = {0, 0, 0, 0, 0};
+    std::string first;
+    for (size_t st = 0; st < nst; ++st)
+      for (int k = 0; k < 5; ++k) {
+        float us = 0;
+        cudaEventElapsedTime(&us, m->gs_trace[st * 6 + k], m->gs_trace[st * 6 + k + 1]);
+        sum[k] += us * 1e3;
+        if (st < 3) { char b[64]; snprintf(b, sizeof b, " %s[%zu]=%.1f", names[k], st, us * 1e3); first += b; }
+      }
+    fprintf(stderr, "[jxb gs_trace] rank %d, %zu steps, us: sweep %.1f counts %.1f moveout %.1f wait %.1f apply %.1f |%s\n",
+            m->dev.rank, nst, sum[0], sum[1], sum[2], sum[3], sum[4], first.c_str());
+    for (auto e : m->gs_trace) cudaEventDestroy(e);
+    m->gs_trace.clear();
   }
   m->time_step = t0 + steps;
   if (m->has_grid && steps > 0) m->sat_dirty = true;

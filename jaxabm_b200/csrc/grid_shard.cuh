@@ -301,6 +301,16 @@ __device__ __forceinline__ void gs_flip(const SchellingDev& sd, const SchellingB
   }
 }
 
+// owner of row x and its band [lo, hi)
+__device__ __forceinline__ int gs_owner3(const GridShardDev& gs, int x, int& lo, int& hi) {
+  int q = 0;
+  lo = gs.xb[0]; hi = gs.xb[1];
+#pragma unroll
+  for (int i = 1; i < kMaxPeers; ++i)
+    if (i < gs.world && x >= gs.xb[i]) { q = i; lo = gs.xb[i]; hi = gs.xb[i + 1]; }
+  return q;
+}
+
 // the ranks other than `own` that keep row x as a halo row: the owners of the rows above and below it
 __device__ __forceinline__ void gs_halo_ranks(const SchellingDev& sd, const GridShardDev& gs, int x, int own, int& ha, int& hb) {
   int xa = x - 1, xc = x + 1;
@@ -318,14 +328,20 @@ __device__ __forceinline__ void gs_send_halo(const GridShardDev& gs, unsigned in
   else gs_hdr(gs.self)->err = 2u;
 }
 
+#ifndef JXB_GS_MINB
+#define JXB_GS_MINB 2     // resident CTAs per SM the moveout kernel's register allocation aims at
+#endif
+
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2) grid_shard_moveout_kernel(const SchellingDev sd, const SchellingBitsDev sb,
+__global__ void __launch_bounds__(kThreads, JXB_GS_MINB) grid_shard_moveout_kernel(const SchellingDev sd, const SchellingBitsDev sb,
                                                                       const GridShardDev gs, const ModelDev md) {
   constexpr int kWarps = kThreads / 32;
   __shared__ unsigned int s_u32[kWarps];
   __shared__ unsigned int s_ws[8][kWarps];
   __shared__ unsigned int s_rk[8];
-  __shared__ unsigned int s_cnt[kMaxPeers], s_base[kMaxPeers];
+  __shared__ unsigned int s_cnt[2][kMaxPeers], s_base[2][kMaxPeers];
+  __shared__ unsigned int* s_slots[kMaxPeers];     // rank q's range of the empty-cell slots
+  __shared__ uint4* s_seg[kMaxPeers];              // my segment of this parity in rank q's receive area
   __shared__ unsigned int s_prefix, s_last;
   const GridStepInfo* info = gs.info;
   const unsigned int u = info->u, m = info->m, par = info->par;
@@ -340,6 +356,12 @@ __global__ void __launch_bounds__(kThreads, 2) grid_shard_moveout_kernel(const S
     const uint32_t* kp = md.keys + (size_t)info->key_row * (md.n_types + 1) * 2;
     const Key ck = {kp[0], kp[1]};
     s_rk[tid] = bits_elem<MODE>(ck, tid, 8);
+  }
+  if (tid < kMaxPeers) {
+    unsigned char* base = gs_peer(gs, tid < gs.world ? tid : 0);
+    s_slots[tid] = (unsigned int*)(base + sizeof(GridXchgHdr));
+    s_seg[tid] = gs_seg(base, gs, par, gs.rank);
+    s_cnt[0][tid] = 0u; s_cnt[1][tid] = 0u;
   }
   {
     unsigned int before = 0;
@@ -408,74 +430,96 @@ __global__ void __launch_bounds__(kThreads, 2) grid_shard_moveout_kernel(const S
     constexpr int kMv = 4;
     const unsigned int seg_end = base;
     const int me = gs.rank;
-    for (unsigned int b0 = s_prefix; b0 < seg_end; b0 += kThreads * kMv) {     // uniform trip count: barriers inside
-      unsigned int src[kMv], dst[kMv], tw[kMv], li[kMv];
-      unsigned int* slot[kMv];
+    const int hs = (H & (H - 1)) == 0 ? __ffs(H) - 1 : -1;       // rows by shift when the row length is a power of two
+    const long long words = sd.cells >> 5;
+    int it = 0;
+    for (unsigned int b0 = s_prefix; b0 < seg_end; b0 += kThreads * kMv, it ^= 1) {     // uniform trip count: barriers inside
+      unsigned int src[kMv], k[kMv], dst[kMv], tw[kMv], li[kMv];
       int2 am[kMv];
-      int tgt[kMv];                      // rank that owns the target cell, -1: not a mover
-      if (tid < kMaxPeers) s_cnt[tid] = 0u;
+      int tgt[kMv];                      // rank that owns the target cell
+      const unsigned int j0 = b0 + tid;
+      const int cnt = j0 < seg_end ? (int)min((unsigned int)kMv, (seg_end - j0 + kThreads - 1) / kThreads) : 0;
+#pragma unroll
+      for (int i = 0; i < kMv; ++i) src[i] = i < cnt ? __ldcg(sd.U + j0 + i * kThreads) : 0u;
+      feistel_inverse_strided<kMv>(fu, j0, kThreads, cnt, k);
+      unsigned int mv = 0;               // bit i: entry i moves
+#pragma unroll
+      for (int i = 0; i < kMv; ++i)
+        if (i < cnt && k[i] < m) mv |= 1u << i;
+      feistel_permute_masked<kMv>(fe, mv, k);         // k[i] is now the slot index of mover i
+      unsigned int* slot[kMv];
 #pragma unroll
       for (int i = 0; i < kMv; ++i) {
-        const unsigned int j = b0 + i * kThreads + tid;
-        tgt[i] = -1; src[i] = 0; slot[i] = nullptr;
-        if (j < seg_end) {
-          src[i] = __ldcg(sd.U + j);
-          const unsigned int k = feistel_inverse(fu, j);
-          if (k < m) { slot[i] = gs_slot(gs, feistel_permute(fe, k)); tgt[i] = 0; }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < kMv; ++i) {
-        dst[i] = 0; tw[i] = 0; am[i] = make_int2(-1, 0);
-        if (tgt[i] >= 0) {
+        dst[i] = 0; tw[i] = 0; am[i] = make_int2(-1, 0); slot[i] = nullptr;
+        if ((mv >> i) & 1u) {
+          const unsigned int q = k[i] / gs.eper;
+          slot[i] = s_slots[q] + (k[i] - q * gs.eper);
           dst[i] = ld_relaxed_sys(slot[i]);
           am[i] = __ldcg(sb.cell_am + src[i]);
           tw[i] = __ldcg(sb.t1 + (src[i] >> 5));
         }
       }
-      __syncthreads();                   // s_cnt is zero, and the previous iteration's s_base reads are done
 #pragma unroll
       for (int i = 0; i < kMv; ++i) {
-        li[i] = 0;
-        if (tgt[i] < 0) continue;
-        const unsigned int j = b0 + i * kThreads + tid;
+        li[i] = 0; tgt[i] = 0;
+        if (!((mv >> i) & 1u)) continue;
         const unsigned int s_ = src[i], d_ = dst[i];
-        const bool ty = (tw[i] >> (s_ & 31)) & 1u;
-        const int xs = (int)(s_ / (unsigned int)H), xd = (int)(d_ / (unsigned int)H);
+        const unsigned int sbit = 1u << (s_ & 31);
+        const bool ty = (tw[i] & sbit) != 0;
+        const int xs = hs >= 0 ? (int)(s_ >> hs) : (int)(s_ / (unsigned int)H);
+        const int xd = hs >= 0 ? (int)(d_ >> hs) : (int)(d_ / (unsigned int)H);
         st_relaxed_sys(slot[i], s_);
-        sd.U[j] = (unsigned int)am[i].x | 0x80000000u;
-        gs_flip(sd, sb, gs, s_, xs, ty, false);
+        sd.U[j0 + i * kThreads] = (unsigned int)am[i].x | 0x80000000u;
+        atomicAnd(sb.occ + (s_ >> 5), ~sbit);            // the source is a cell of my band
+        if (ty) atomicAnd(sb.t1 + (s_ >> 5), ~sbit);
         sb.cell_am[s_] = make_int2(-1, 0);
         const unsigned int tybit = ty ? 0x80000000u : 0u;
-        int ha, hb;
-        gs_halo_ranks(sd, gs, xs, me, ha, hb);
-        if (ha >= 0) gs_send_halo(gs, par, ha, make_uint4(s_, tybit, 0u, 0u));
-        if (hb >= 0) gs_send_halo(gs, par, hb, make_uint4(s_, tybit, 0u, 0u));
-        const int p = gs_owner(gs, xd);
+        if (xs == gs.X0 || xs == gs.X1 - 1) {            // boundary row: my wrapped halo copy, the neighbours' halo copies
+          if (sd.periodic) {
+            if (xs == 0 && gs.X1 == sd.W) gs_plane_write(sb, (long long)(s_ >> 5) + words, sbit, ty, false);
+            if (xs == sd.W - 1 && gs.X0 == 0) gs_plane_write(sb, (long long)(s_ >> 5) - words, sbit, ty, false);
+          }
+          int ha, hb;
+          gs_halo_ranks(sd, gs, xs, me, ha, hb);
+          if (ha >= 0) gs_send_halo(gs, par, ha, make_uint4(s_, tybit, 0u, 0u));
+          if (hb >= 0) gs_send_halo(gs, par, hb, make_uint4(s_, tybit, 0u, 0u));
+        }
+        int lo, hi;
+        const int p = gs_owner3(gs, xd, lo, hi);
         tgt[i] = p;
-        li[i] = atomicAdd(&s_cnt[p], 1u);
-        gs_halo_ranks(sd, gs, xd, p, ha, hb);
-        const uint4 rec = make_uint4(d_, (unsigned int)am[i].x | tybit, (unsigned int)(am[i].y + 1), 1u);
-        if (ha >= 0) gs_send_halo(gs, par, ha, rec);
-        if (hb >= 0) gs_send_halo(gs, par, hb, rec);
+        li[i] = atomicAdd(&s_cnt[it][p], 1u);
+        if (xd == lo || xd == hi - 1) {                  // the target row is somebody's halo row
+          int ha, hb;
+          gs_halo_ranks(sd, gs, xd, p, ha, hb);
+          const uint4 rec = make_uint4(d_, (unsigned int)am[i].x | tybit, (unsigned int)(am[i].y + 1), 1u);
+          if (ha >= 0) gs_send_halo(gs, par, ha, rec);
+          if (hb >= 0) gs_send_halo(gs, par, hb, rec);
+        }
       }
       __syncthreads();
-      if (tid < gs.world) s_base[tid] = s_cnt[tid] ? atomicAdd(gs.sendcnt + tid, s_cnt[tid]) : 0u;
+      if (tid < kMaxPeers) {
+        const unsigned int c = s_cnt[it][tid];
+        s_base[it][tid] = c ? atomicAdd(gs.sendcnt + tid, c) : 0u;
+        s_cnt[it ^ 1][tid] = 0u;          // the other buffer: read two barriers ago, next written after the barrier below
+      }
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < kMv; ++i) {
-        if (tgt[i] < 0) continue;
-        const unsigned int idx = s_base[tgt[i]] + li[i];
+        if (!((mv >> i) & 1u)) continue;
+        const unsigned int idx = s_base[it][tgt[i]] + li[i];
         const uint4 rec = make_uint4(dst[i], (unsigned int)am[i].x | (((tw[i] >> (src[i] & 31)) & 1u) << 31),
                                      (unsigned int)(am[i].y + 1), 1u);
-        if (idx < gs.cap - gs.halo_cap) gs_seg(gs_peer(gs, tgt[i]), gs, par, me)[idx] = rec;
+        if (idx < gs.cap - gs.halo_cap) s_seg[tgt[i]][idx] = rec;
         else gs_hdr(gs.self)->err = 2u;
       }
     }
-    // the last CTA to finish publishes the counts + flag: the records of ALL CTAs precede it
-    __threadfence_system();
+    // the last CTA to finish publishes the counts + flag: the records of ALL CTAs precede it (the block barrier
+    // orders every thread's stores before thread 0's system-scope fence, which is cumulative)
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&gs.info->ticket, 1u) == (unsigned int)(B - 1)) ? 1u : 0u;
+    if (tid == 0) {
+      __threadfence_system();
+      s_last = (atomicAdd(&gs.info->ticket, 1u) == (unsigned int)(B - 1)) ? 1u : 0u;
+    }
     __syncthreads();
     if (s_last) {
       if (tid == 0) gs.info->ticket = 0u;
@@ -528,17 +572,32 @@ __global__ void __launch_bounds__(256) grid_shard_apply_kernel(const SchellingDe
   __syncthreads();
   const unsigned int total = s_rcv[nseg], par = info->par;
   const int H = sd.H;
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int s = 0;
-    while (s + 1 < nseg && i >= s_rcv[s + 1]) ++s;
-    const unsigned int off = i - s_rcv[s];
-    const uint4* seg = gs_seg(gs.self, gs, par, s < gs.world ? s : s - gs.world);
-    const uint4 rec = __ldcg(seg + (s < gs.world ? off : gs.cap - 1u - off));
-    const unsigned int c = rec.x;
-    const bool ty = (rec.y >> 31) != 0, set = rec.w != 0u;
-    const int x = (int)(c / (unsigned int)H);
-    gs_flip(sd, sb, gs, c, x, ty, set);
-    if (set && x >= gs.X0 && x < gs.X1) sb.cell_am[c] = make_int2((int)(rec.y & 0x7FFFFFFFu), (int)rec.z);
+  const int hs = (H & (H - 1)) == 0 ? __ffs(H) - 1 : -1;
+  constexpr int kRec = 4;                // records in flight per thread: the loop is a chain of dependent random accesses
+  const unsigned int stride = gridDim.x * blockDim.x;
+  for (unsigned int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kRec) {
+    uint4 rec[kRec];
+#pragma unroll
+    for (int r = 0; r < kRec; ++r) {
+      const unsigned int i = i0 + r * stride;
+      rec[r] = make_uint4(0u, 0u, 0u, 2u);
+      if (i < total) {
+        int s = 0;
+        while (s + 1 < nseg && i >= s_rcv[s + 1]) ++s;
+        const unsigned int off = i - s_rcv[s];
+        const uint4* seg = gs_seg(gs.self, gs, par, s < gs.world ? s : s - gs.world);
+        rec[r] = __ldcg(seg + (s < gs.world ? off : gs.cap - 1u - off));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRec; ++r) {
+      if (rec[r].w > 1u) continue;
+      const unsigned int c = rec[r].x;
+      const bool ty = (rec[r].y >> 31) != 0, set = rec[r].w != 0u;
+      const int x = hs >= 0 ? (int)(c >> hs) : (int)(c / (unsigned int)H);
+      gs_flip(sd, sb, gs, c, x, ty, set);
+      if (set && x >= gs.X0 && x < gs.X1) sb.cell_am[c] = make_int2((int)(rec[r].y & 0x7FFFFFFFu), (int)rec[r].z);
+    }
   }
 }
 

@@ -199,4 +199,65 @@ JXB_HD uint32_t feistel_permute(const Feistel& f, uint32_t idx) {
   return v;
 }
 
+// Several walks per thread, advanced in ONE loop: a lane moves on to its next entry as soon as the current one lands
+// inside [0, n), so a warp runs for the slowest lane's TOTAL number of applications instead of the sum over the
+// entries of the slowest lane of each (cycle walking over a domain up to 4x the range diverges badly otherwise).
+// Entries are j0 + i * stride, i < cnt; k[i] = feistel_inverse(f, j0 + i * stride).
+template <int N>
+__device__ __forceinline__ void feistel_inverse_strided(const Feistel& f, uint32_t j0, uint32_t stride, int cnt, uint32_t (&k)[N]) {
+#pragma unroll
+  for (int q = 0; q < N; ++q) k[q] = j0 + q * stride;
+  if (f.n <= 1) return;
+  int i = 0;
+  uint32_t v = j0;
+  while (i < cnt) {
+    uint32_t l = v >> f.half, r = v & f.mask;
+#pragma unroll
+    for (int q = 3; q >= 0; --q) {
+      uint32_t t = r ^ (mix32(l ^ f.rk[q]) & f.mask);
+      r = l;
+      l = t;
+    }
+    v = (l << f.half) | r;
+    if (v < f.n) {
+#pragma unroll
+      for (int q = 0; q < N; ++q)
+        if (i == q) k[q] = v;
+      ++i;
+      v = j0 + i * stride;
+    }
+  }
+}
+
+// x[i] <- feistel_permute(f, x[i]) for the entries whose bit is set in `todo`, advanced in one flat loop as above
+template <int N>
+__device__ __forceinline__ void feistel_permute_masked(const Feistel& f, unsigned int todo, uint32_t (&x)[N]) {
+  if (f.n <= 1) return;
+  int i = __ffs(todo) - 1;
+  uint32_t v = 0;
+#pragma unroll
+  for (int q = 0; q < N; ++q)
+    if (i == q) v = x[q];
+  while (todo) {
+    uint32_t l = v >> f.half, r = v & f.mask;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t t = l ^ (mix32(r ^ f.rk[q]) & f.mask);
+      l = r;
+      r = t;
+    }
+    v = (l << f.half) | r;
+    if (v < f.n) {
+#pragma unroll
+      for (int q = 0; q < N; ++q)
+        if (i == q) x[q] = v;
+      todo &= todo - 1;
+      i = __ffs(todo) - 1;
+#pragma unroll
+      for (int q = 0; q < N; ++q)
+        if (i == q) v = x[q];
+    }
+  }
+}
+
 }  // namespace jxb
