@@ -273,15 +273,16 @@ int jxb_engine_p2p_attach(jxb_engine*, const void* handles, size_t bytes_each, i
  * the rows [row_begin, row_end) (consecutive bands in rank order that tile the grid, at most
  * ceil(W / world) rows each) and every rank is handed the whole per-agent columns.  export allocates
  * this rank's receive area (its range of the empty-cell slots + the record segments) and returns
- * JXB_GRID_HANDLE_BYTES: the area's CUDA IPC handle followed by the band as two int32; the host shim
+ * JXB_GRID_HANDLE_BYTES: the area's CUDA IPC handle followed by the band and a launch shape as int32[4]; the host shim
  * all-gathers the entries and attach maps the peers' areas (one process per rank; the ranks may share
  * a device).  After that jxb_model_run steps the band with no host round trip: a rank walks only the
- * movers of its own rows, rewrites their slots in the owner's area and stores their records straight
- * into the target rows' owner over NVLink (no NCCL call on the step path).
+ * movers of its own rows and stores each as a request into the area of the rank that holds the mover's
+ * slot; that rank rewrites the slot and forwards the mover to the owner of the target row -- posted
+ * stores over NVLink and step flags only (no NCCL call, no remote load on the step path).
  * Downloads of a shard return ITS view; the host combines the ranks: 'position' max (-1 = agent is
  * not in my band), 'satisfied' min, 'moves' sum (0 = not in my band), 'type' any; env grid rows
  * [row_begin, row_end); empty_cells is gathered from the ranks' areas (barrier first).              */
-#define JXB_GRID_HANDLE_BYTES 72
+#define JXB_GRID_HANDLE_BYTES 80
 int jxb_model_grid_shard_export(jxb_model*, int row_begin, int row_end, void* handle_out, size_t bytes);
 int jxb_model_grid_shard_attach(jxb_model*, const void* handles, size_t bytes_each, int n_ranks);
 

@@ -1045,7 +1045,7 @@ extern "C" int jxb_model_grid_rebuild(jxb_model* m) {
     // my range of the empty-cell slots moves into the receive area, where the peers reach it
     const GridShardDev& gs = m->gs;
     const unsigned int e = m->sd.n_empty, lo = std::min(e, (unsigned int)gs.rank * gs.eper), hi = std::min(e, lo + gs.eper);
-    if (hi > lo) CK(cudaMemcpyAsync(m->gs_area + sizeof(GridXchgHdr), m->sd.E + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToDevice, s));
+    if (hi > lo) CK(cudaMemcpyAsync(m->gs_area + gs.slot_off, m->sd.E + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToDevice, s));
     CK(cudaStreamSynchronize(s));
   }
   m->grid_built = true;
@@ -1085,7 +1085,7 @@ extern "C" int jxb_model_download_empty_cells(jxb_model* m, int32_t* host, size_
     const unsigned int e = m->sd.n_empty;
     for (int q = 0; q < gs.world; ++q) {
       const unsigned int lo = std::min(e, (unsigned int)q * gs.eper), hi = std::min(e, lo + gs.eper);
-      if (hi > lo) CK(cudaMemcpyAsync(host + lo, gs.peer[q] + sizeof(GridXchgHdr), (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, m->eng->stream));
+      if (hi > lo) CK(cudaMemcpyAsync(host + lo, gs.peer[q] + gs.slot_off, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, m->eng->stream));
     }
   } else if (bytes) {
     CK(cudaMemcpyAsync(host, m->sd.E, bytes, cudaMemcpyDeviceToHost, m->eng->stream));
@@ -1109,17 +1109,22 @@ static int grid_shard_prepare(jxb_model* m, int row_begin, int row_end) {
   if (G == 1) { gs.xb[0] = 0; gs.xb[1] = W; }
   // a segment takes the cell records of one sender (targets that were empty cells of my band) from the front and its
   // halo records (sets in my two halo rows, clears from the sender's boundary rows) from the back
+  // (a slot owner forwards at most one record per slot it holds)
   gs.halo_cap = (unsigned int)(4 * H);
-  gs.cap = (unsigned int)std::min<long long>((long long)max_rows * H, (long long)m->sd.n_empty) + gs.halo_cap;
   gs.eper = std::max(1u, (m->sd.n_empty + (unsigned int)G - 1u) / (unsigned int)G);
-  gs.rec_off = (sizeof(GridXchgHdr) + (size_t)gs.eper * 4 + 15) / 16 * 16;
+  gs.nfwd = (unsigned int)m->eng->sms * 2u;                       // checked to be the same on every rank at attach
+  gs.fchunk = (gs.eper + gs.nfwd - 1u) / gs.nfwd;                  // a forward CTA serves at most this many requests
+  gs.cap = gs.nfwd * gs.fchunk + gs.halo_cap;
+  gs.slot_off = (sizeof(GridXchgHdr) + (size_t)2 * G * gs.nfwd * 4 + 15) / 16 * 16;
+  gs.req_off = (gs.slot_off + (size_t)gs.eper * 4 + 15) / 16 * 16;
+  gs.rec_off = gs.req_off + (size_t)2 * G * gs.eper * sizeof(uint4);
   if (!m->gs_area) {
     m->gs_area_bytes = gs.rec_off + (size_t)2 * G * gs.cap * sizeof(uint4);
     m->gs_area = G > 1 ? (unsigned char*)take_retired_area(m->eng, m->gs_area_bytes) : nullptr;
     if (!m->gs_area) CK(cudaMalloc((void**)&m->gs_area, m->gs_area_bytes));      // its own allocation: IPC handles name whole allocations
     // flags / counts of a recycled area hold the step tags of its previous model: clear them before the handle
     // leaves this call (the peers only store into the area after the attach barrier that follows)
-    CK(cudaMemset(m->gs_area, 0, sizeof(GridXchgHdr)));
+    CK(cudaMemset(m->gs_area, 0, gs.slot_off));
     CK(cudaDeviceSynchronize());
     int rc;
     if ((rc = dev_alloc(m, &gs.info, 1))) return rc;
@@ -1129,8 +1134,8 @@ static int grid_shard_prepare(jxb_model* m, int row_begin, int row_end) {
     gs.blocks = (int)std::max<long long>(1, std::min<long long>(std::min<long long>((long long)m->eng->sms * 2, nrows),
                                                                 ((long long)nrows * strips + 15) / 16));
     if ((rc = dev_alloc(m, &gs.part, (size_t)gs.blocks))) return rc;
-    if ((rc = dev_alloc(m, &gs.sendcnt, (size_t)2 * kMaxPeers))) return rc;
-    CK(cudaMemset(gs.sendcnt, 0, 2 * kMaxPeers * sizeof(unsigned int)));
+    if ((rc = dev_alloc(m, &gs.sendcnt, (size_t)3 * kMaxPeers))) return rc;
+    CK(cudaMemset(gs.sendcnt, 0, 3 * kMaxPeers * sizeof(unsigned int)));
   }
   gs.peer[gs.rank] = m->gs_area;
   gs.self = m->gs_area;
@@ -1149,7 +1154,7 @@ extern "C" int jxb_model_grid_shard_export(jxb_model* m, int row_begin, int row_
   CK(cudaIpcGetMemHandle(&h, m->gs_area));
   memset(handle_out, 0, bytes);
   memcpy(handle_out, &h, sizeof(h));
-  const int32_t band[2] = {row_begin, row_end};
+  const int32_t band[3] = {row_begin, row_end, (int32_t)m->gs.nfwd};
   memcpy((char*)handle_out + sizeof(h), band, sizeof(band));
   return JXB_OK;
 }
@@ -1163,9 +1168,10 @@ extern "C" int jxb_model_grid_shard_attach(jxb_model* m, const void* handles, si
   // the bands must tile the rows in rank order (a mover's record goes to the owner of its target row)
   int next = 0;
   for (int p = 0; p < n_ranks; ++p) {
-    int32_t band[2];
+    int32_t band[3];
     memcpy(band, (const char*)handles + (size_t)p * bytes_each + sizeof(cudaIpcMemHandle_t), sizeof(band));
     if (band[0] != next || band[1] <= band[0]) return fail(JXB_ERR_INVALID, "rank %d's band [%d,%d) does not continue at row %d", p, band[0], band[1], next);
+    if ((unsigned int)band[2] != m->gs.nfwd) return fail(JXB_ERR_INVALID, "rank %d runs on a different GPU model (%d vs %u forward CTAs)", p, band[2], m->gs.nfwd);
     m->gs.xb[p] = band[0];
     next = band[1];
   }
@@ -1641,11 +1647,15 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       if (part) grid_shard_moveout_kernel<1><<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
       else grid_shard_moveout_kernel<0><<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
       mark();
-      grid_shard_wait_kernel<<<1, 32, 0, s>>>(m->gs);
+      grid_shard_wait_kernel<0><<<1, 32, 0, s>>>(m->gs);
+      mark();
+      grid_shard_forward_kernel<<<m->gs.nfwd, kThreads, 0, s>>>(m->sd, m->gs);
+      mark();
+      grid_shard_wait_kernel<1><<<1, 32, 0, s>>>(m->gs);
       mark();
       grid_shard_apply_kernel<<<eng->sms * 8, 256, 0, s>>>(m->sd, m->sb, m->gs);
       mark();
-      eng->launches += 5;
+      eng->launches += 7;
       break;
     }
     case JXB_PROGRAM_TRACED: {
@@ -1767,7 +1777,7 @@ static int launches_per_step_all(jxb_model* m) {
   return launches_per_step(m) + extra;
 }
 static int launches_per_step(jxb_model* m) {
-  if (m->grid_sharded) return 5;
+  if (m->grid_sharded) return 7;
   if (m->net_sharded) return 2;
   if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 : (m->sir_mode == 1 ? 2 : 1);
   if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? (m->dev.world_size > 1 ? 6 : 5) : 1);
@@ -1959,19 +1969,19 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   }
   if (!m->gs_trace.empty()) {
     // per-kernel device time of the band steps, summed over the run and for the first steps
-    static const char* names[5] = {"sweep", "counts", "moveout", "wait", "apply"};
-    const size_t nst = m->gs_trace.size() / 6;
-    double sum[5] = {0, 0, 0, 0, 0};
+    static const char* names[7] = {"sweep", "counts", "moveout", "waitB", "forward", "waitC", "apply"};
+    const size_t nst = m->gs_trace.size() / 8;
+    double sum[7] = {0, 0, 0, 0, 0, 0, 0};
     std::string first;
     for (size_t st = 0; st < nst; ++st)
-      for (int k = 0; k < 5; ++k) {
+      for (int k = 0; k < 7; ++k) {
         float us = 0;
-        cudaEventElapsedTime(&us, m->gs_trace[st * 6 + k], m->gs_trace[st * 6 + k + 1]);
+        cudaEventElapsedTime(&us, m->gs_trace[st * 8 + k], m->gs_trace[st * 8 + k + 1]);
         sum[k] += us * 1e3;
-        if (st < 3) { char b[64]; snprintf(b, sizeof b, " %s[%zu]=%.1f", names[k], st, us * 1e3); first += b; }
+        if (st < 2) { char b[64]; snprintf(b, sizeof b, " %s[%zu]=%.1f", names[k], st, us * 1e3); first += b; }
       }
-    fprintf(stderr, "[jxb gs_trace] rank %d, %zu steps, us: sweep %.1f counts %.1f moveout %.1f wait %.1f apply %.1f |%s\n",
-            m->dev.rank, nst, sum[0], sum[1], sum[2], sum[3], sum[4], first.c_str());
+    fprintf(stderr, "[jxb gs_trace] rank %d, %zu steps, us: sweep %.1f counts %.1f moveout %.1f waitB %.1f forward %.1f waitC %.1f apply %.1f |%s\n",
+            m->dev.rank, nst, sum[0], sum[1], sum[2], sum[3], sum[4], sum[5], sum[6], first.c_str());
     for (auto e : m->gs_trace) cudaEventDestroy(e);
     m->gs_trace.clear();
   }

@@ -2,16 +2,15 @@
 // 8(e) "Grid: row blocks + halo"; one process per GPU, peers' receive areas mapped over NVLink by
 // CUDA IPC).  Results are bit-identical to the single-GPU kernels (schelling_bits.cuh).
 //
-// Everything a step touches is PARTITIONED -- a rank only walks the movers of its own band:
+// Everything a step touches is PARTITIONED -- a rank only walks the movers of its own band, the slots of its own
+// range and the records addressed to its own rows; every remote access is a posted store:
 //   cells   rank r owns rows [X0, X1): the bit planes occ / t1 (plus one halo row each side, kept
 //           coherent by the movers' records) and the cell payload cell_am (agent, moves);
 //   U       the ordered list of unsatisfied cells: the bands' lists in rank order, so rank r holds
 //           U[prefix[r] .. prefix[r+1]) -- its own rows, compacted CTA-locally;
-//   E       the empty-cell slots: rank q holds slots [q * eper, (q+1) * eper) inside its receive
-//           area.  A slot is matched to exactly one mover per step, so the mover's rank reads and
-//           rewrites it in place over NVLink (peer load + store, no synchronisation needed).
+//   E       the empty-cell slots: rank q holds slots [q * eper, (q+1) * eper) inside its receive area.
 //
-// A step is five launches per rank, graph-captured, with no host round trip and no NCCL call:
+// A step is seven launches per rank, graph-captured, with no host round trip and no NCCL call:
 //   1 sweep    bit-sliced neighbour counts of the band (eval_row of schelling_bits.cuh): unsatisfied
 //              mask + exact integer partials per CTA.
 //   2 counts   one CTA: folds the partials, stores the band's counts + flag A into every rank's
@@ -21,15 +20,22 @@
 //   3 moveout  every CTA compacts the unsatisfied cells of ITS rows into its segment of U and walks
 //              them in cell order: entry j is mover k = piU^-1(j) (if k < m) and takes slot piE(k) --
 //              the single-GPU matching, evaluated from the source side.  The source cell is cleared
-//              locally; the target cell travels as a 16-byte record (cell, agent | type<<31, moves,
-//              set) to the rank that owns its row, and as a plane-only copy to the ranks that hold
-//              that row -- or the source row -- as a halo.  Records are appended to segment
-//              [parity][me] of the target's receive area (remote stores over NVLink); the last CTA
-//              releases the per-target counts + flag C.
-//   4 wait     one warp spins on the world's C flags in its OWN area and leaves the record counts.
-//   5 apply    every received record sets / clears the plane bits wherever this rank keeps that row
+//              locally (and, for a boundary row, in the neighbours' halo copies by a record); the
+//              mover leaves as a 16-byte request (slot, source cell, agent | type<<31, moves) stored
+//              into segment [parity][me] of the SLOT OWNER's receive area; the last CTA releases the
+//              per-target counts + flag B.
+//   4 wait B   one warp spins on the world's B flags in its OWN area and leaves the request counts.
+//   5 forward  the slot owner reads each request's slot (the target cell), rewrites it with the source
+//              cell, and forwards (target cell, agent | type<<31, moves + 1, set) to the rank that
+//              owns the target row -- plus a plane-only copy to the ranks that hold that row as a
+//              halo; the last CTA releases the counts + flag C.
+//   6 wait C   as 4, for the records.
+//   7 apply    every received record sets / clears the plane bits wherever this rank keeps that row
 //              (band, halo, wrapped halo of a periodic grid) and, for a cell of the band, writes the
 //              payload.
+// (A first version let the mover's rank read and rewrite the slot in place over NVLink: half of the
+// slot reads at 2 GPUs being remote loads cost more than the halved work saved -- measured,
+// profiles/r02_grid_bands_v2.txt -- so the slot owner became a party of its own.)
 // Segments and counts are double-buffered by step parity: a rank runs at most one exchange ahead of
 // a peer that is still reading the previous one.
 #pragma once
@@ -42,19 +48,22 @@ namespace jxb {
 struct GridXchgHdr {
   unsigned int flagA[2][kMaxPeers];       // step tag: rank p's band counts of this parity are in cntA
   unsigned int cntA[2][kMaxPeers][4];     // rank p's band: #unsatisfied, #with a neighbour, numerator lo / hi
+  unsigned int flagB[2][kMaxPeers];       // step tag: rank p's requests of this parity are complete
+  unsigned int cntB[2][kMaxPeers];        // how many requests rank p sent here
   unsigned int flagC[2][kMaxPeers];       // step tag: rank p's records of this parity are complete
   unsigned int cntC[2][kMaxPeers][2];     // how many records rank p sent here: cell records (front), halo records (back)
   unsigned int err;                       // 1: a peer's flag did not arrive within the spin budget, 2: a segment overflowed
-  unsigned int pad[256 - 4 * kMaxPeers - 8 * kMaxPeers - 4 * kMaxPeers - 1];
+  unsigned int pad[256 - 20 * kMaxPeers - 1];
 };
 static_assert(sizeof(GridXchgHdr) == 1024, "receive-area header is 1 KiB");
 
 struct GridStepInfo {
   unsigned int tag, par, u, m;
   int key_row;                            // row of the run's key table that belongs to this step
-  unsigned int ticket;                    // last-CTA election of the moveout kernel
+  unsigned int ticket[2];                 // last-CTA election of the moveout / forward kernel
   unsigned int prefix[kMaxPeers + 1];     // rank q's unsatisfied cells are U[prefix[q] .. prefix[q+1])
-  unsigned int rcv[2 * kMaxPeers + 1];    // prefix of the received records: cell records of rank 0.., then halo records
+  unsigned int rcvB[kMaxPeers + 1];       // prefix of the received requests, by sender
+  unsigned int rcv[kMaxPeers + 1];        // prefix of the received halo records, by sender
 };
 
 struct GridShardDev {
@@ -62,13 +71,16 @@ struct GridShardDev {
   int X0, X1;                             // rows owned by this rank
   int xb[kMaxPeers + 1];                  // rank q owns rows [xb[q], xb[q+1])
   unsigned int cap, halo_cap;             // records per (parity, rank) segment; its last halo_cap entries take the halo records
-  unsigned int eper;                      // empty-cell slots per rank
-  unsigned long long rec_off;             // byte offset of the record segments in a receive area (after header + slots)
+  unsigned int eper;                      // empty-cell slots per rank = requests per (parity, rank) segment
+  unsigned int nfwd, fchunk;              // CTAs of the forward kernel (the same on every rank); each owns a chunk of fchunk
+                                          // records in its segment of every target: cap = nfwd * fchunk + halo_cap
+  unsigned long long slot_off, req_off, rec_off;    // byte offsets in a receive area: [header][chunk counts u32[2][world][nfwd]]
+                                          // [slots][request segments][record segments]
   unsigned char* peer[kMaxPeers];         // every rank's receive area as mapped here (own = local)
   unsigned char* self;                    // == peer[rank]
   GridStepInfo* info;
   BlkPart* part;                          // [blocks] per-CTA partials of the sweep
-  unsigned int* sendcnt;                  // [2][kMaxPeers] records appended for each target this step (cell / halo)
+  unsigned int* sendcnt;                  // [3][kMaxPeers] appended for each target this step: (unused), halo records, requests
   int blocks;                             // CTAs of the sweep AND the moveout kernel (same row split)
 };
 
@@ -91,18 +103,15 @@ __device__ __forceinline__ int gs_owner(const GridShardDev& gs, int x) {
 __device__ __forceinline__ uint4* gs_seg(unsigned char* base, const GridShardDev& gs, unsigned int par, int from) {
   return (uint4*)(base + gs.rec_off) + ((size_t)par * gs.world + from) * gs.cap;
 }
-// slot jj of the partitioned empty-cell list, wherever it lives
-__device__ __forceinline__ unsigned int* gs_slot(const GridShardDev& gs, unsigned int jj) {
-  const unsigned int q = jj / gs.eper;
-  return (unsigned int*)(gs_peer(gs, (int)q) + sizeof(GridXchgHdr)) + (jj - q * gs.eper);
+// how many records CTA c of rank `from`'s forward kernel left in its chunk of my segment
+__device__ __forceinline__ unsigned int* gs_chunk_cnt(unsigned char* base, const GridShardDev& gs, unsigned int par, int from) {
+  return (unsigned int*)(base + sizeof(GridXchgHdr)) + ((size_t)par * gs.world + from) * gs.nfwd;
 }
-__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ unsigned int* gs_slots(unsigned char* base, const GridShardDev& gs) {
+  return (unsigned int*)(base + gs.slot_off);
 }
-__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ uint4* gs_req(unsigned char* base, const GridShardDev& gs, unsigned int par, int from) {
+  return (uint4*)(base + gs.req_off) + ((size_t)par * gs.world + from) * gs.eper;
 }
 
 // ------------------------------------------------------------------------------------ 1 sweep
@@ -340,8 +349,7 @@ __global__ void __launch_bounds__(kThreads, JXB_GS_MINB) grid_shard_moveout_kern
   __shared__ unsigned int s_ws[8][kWarps];
   __shared__ unsigned int s_rk[8];
   __shared__ unsigned int s_cnt[2][kMaxPeers], s_base[2][kMaxPeers];
-  __shared__ unsigned int* s_slots[kMaxPeers];     // rank q's range of the empty-cell slots
-  __shared__ uint4* s_seg[kMaxPeers];              // my segment of this parity in rank q's receive area
+  __shared__ uint4* s_seg[kMaxPeers];              // my request segment of this parity in rank q's receive area
   __shared__ unsigned int s_prefix, s_last;
   const GridStepInfo* info = gs.info;
   const unsigned int u = info->u, m = info->m, par = info->par;
@@ -358,9 +366,7 @@ __global__ void __launch_bounds__(kThreads, JXB_GS_MINB) grid_shard_moveout_kern
     s_rk[tid] = bits_elem<MODE>(ck, tid, 8);
   }
   if (tid < kMaxPeers) {
-    unsigned char* base = gs_peer(gs, tid < gs.world ? tid : 0);
-    s_slots[tid] = (unsigned int*)(base + sizeof(GridXchgHdr));
-    s_seg[tid] = gs_seg(base, gs, par, gs.rank);
+    s_seg[tid] = gs_req(gs_peer(gs, tid < gs.world ? tid : 0), gs, par, gs.rank);
     s_cnt[0][tid] = 0u; s_cnt[1][tid] = 0u;
   }
   {
@@ -423,8 +429,9 @@ __global__ void __launch_bounds__(kThreads, JXB_GS_MINB) grid_shard_moveout_kern
     }
     __syncthreads();
   }
-  // (b) the moves of the CTA's segment [s_prefix, base), in cell order.  U[j] receives (agent | 1<<31) for a mover
-  // and keeps the cell id of an agent that stays -- what the lazy 'satisfied' column needs.
+  // (b) the movers of the CTA's segment [s_prefix, base), in cell order: the source side of the move happens here,
+  // the rest travels as a request to the owner of the slot.  U[j] receives (agent | 1<<31) for a mover and keeps the
+  // cell id of an agent that stays -- what the lazy 'satisfied' column needs.
   if (m > 0) {
     const Feistel fu = make_feistel(u, s_rk), fe = make_feistel(sd.n_empty, s_rk + 4);
     constexpr int kMv = 4;
@@ -434,9 +441,8 @@ __global__ void __launch_bounds__(kThreads, JXB_GS_MINB) grid_shard_moveout_kern
     const long long words = sd.cells >> 5;
     int it = 0;
     for (unsigned int b0 = s_prefix; b0 < seg_end; b0 += kThreads * kMv, it ^= 1) {     // uniform trip count: barriers inside
-      unsigned int src[kMv], k[kMv], dst[kMv], tw[kMv], li[kMv];
+      unsigned int src[kMv], k[kMv], tw[kMv], li[kMv];
       int2 am[kMv];
-      int tgt[kMv];                      // rank that owns the target cell
       const unsigned int j0 = b0 + tid;
       const int cnt = j0 < seg_end ? (int)min((unsigned int)kMv, (seg_end - j0 + kThreads - 1) / kThreads) : 0;
 #pragma unroll
@@ -446,34 +452,27 @@ __global__ void __launch_bounds__(kThreads, JXB_GS_MINB) grid_shard_moveout_kern
 #pragma unroll
       for (int i = 0; i < kMv; ++i)
         if (i < cnt && k[i] < m) mv |= 1u << i;
-      feistel_permute_masked<kMv>(fe, mv, k);         // k[i] is now the slot index of mover i
-      unsigned int* slot[kMv];
 #pragma unroll
       for (int i = 0; i < kMv; ++i) {
-        dst[i] = 0; tw[i] = 0; am[i] = make_int2(-1, 0); slot[i] = nullptr;
+        tw[i] = 0; am[i] = make_int2(-1, 0);
         if ((mv >> i) & 1u) {
-          const unsigned int q = k[i] / gs.eper;
-          slot[i] = s_slots[q] + (k[i] - q * gs.eper);
-          dst[i] = ld_relaxed_sys(slot[i]);
           am[i] = __ldcg(sb.cell_am + src[i]);
           tw[i] = __ldcg(sb.t1 + (src[i] >> 5));
         }
       }
+      feistel_permute_masked<kMv>(fe, mv, k);         // k[i] is now the slot index of mover i
 #pragma unroll
       for (int i = 0; i < kMv; ++i) {
-        li[i] = 0; tgt[i] = 0;
+        li[i] = 0;
         if (!((mv >> i) & 1u)) continue;
-        const unsigned int s_ = src[i], d_ = dst[i];
+        const unsigned int s_ = src[i];
         const unsigned int sbit = 1u << (s_ & 31);
         const bool ty = (tw[i] & sbit) != 0;
         const int xs = hs >= 0 ? (int)(s_ >> hs) : (int)(s_ / (unsigned int)H);
-        const int xd = hs >= 0 ? (int)(d_ >> hs) : (int)(d_ / (unsigned int)H);
-        st_relaxed_sys(slot[i], s_);
         sd.U[j0 + i * kThreads] = (unsigned int)am[i].x | 0x80000000u;
         atomicAnd(sb.occ + (s_ >> 5), ~sbit);            // the source is a cell of my band
         if (ty) atomicAnd(sb.t1 + (s_ >> 5), ~sbit);
         sb.cell_am[s_] = make_int2(-1, 0);
-        const unsigned int tybit = ty ? 0x80000000u : 0u;
         if (xs == gs.X0 || xs == gs.X1 - 1) {            // boundary row: my wrapped halo copy, the neighbours' halo copies
           if (sd.periodic) {
             if (xs == 0 && gs.X1 == sd.W) gs_plane_write(sb, (long long)(s_ >> 5) + words, sbit, ty, false);
@@ -481,76 +480,71 @@ __global__ void __launch_bounds__(kThreads, JXB_GS_MINB) grid_shard_moveout_kern
           }
           int ha, hb;
           gs_halo_ranks(sd, gs, xs, me, ha, hb);
-          if (ha >= 0) gs_send_halo(gs, par, ha, make_uint4(s_, tybit, 0u, 0u));
-          if (hb >= 0) gs_send_halo(gs, par, hb, make_uint4(s_, tybit, 0u, 0u));
-        }
-        int lo, hi;
-        const int p = gs_owner3(gs, xd, lo, hi);
-        tgt[i] = p;
-        li[i] = atomicAdd(&s_cnt[it][p], 1u);
-        if (xd == lo || xd == hi - 1) {                  // the target row is somebody's halo row
-          int ha, hb;
-          gs_halo_ranks(sd, gs, xd, p, ha, hb);
-          const uint4 rec = make_uint4(d_, (unsigned int)am[i].x | tybit, (unsigned int)(am[i].y + 1), 1u);
+          const uint4 rec = make_uint4(s_, ty ? 0x80000000u : 0u, 0u, 0u);
           if (ha >= 0) gs_send_halo(gs, par, ha, rec);
           if (hb >= 0) gs_send_halo(gs, par, hb, rec);
         }
+        li[i] = atomicAdd(&s_cnt[it][k[i] / gs.eper], 1u);
       }
       __syncthreads();
       if (tid < kMaxPeers) {
         const unsigned int c = s_cnt[it][tid];
-        s_base[it][tid] = c ? atomicAdd(gs.sendcnt + tid, c) : 0u;
+        s_base[it][tid] = c ? atomicAdd(gs.sendcnt + 2 * kMaxPeers + tid, c) : 0u;
         s_cnt[it ^ 1][tid] = 0u;          // the other buffer: read two barriers ago, next written after the barrier below
       }
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < kMv; ++i) {
         if (!((mv >> i) & 1u)) continue;
-        const unsigned int idx = s_base[it][tgt[i]] + li[i];
-        const uint4 rec = make_uint4(dst[i], (unsigned int)am[i].x | (((tw[i] >> (src[i] & 31)) & 1u) << 31),
-                                     (unsigned int)(am[i].y + 1), 1u);
-        if (idx < gs.cap - gs.halo_cap) s_seg[tgt[i]][idx] = rec;
+        const unsigned int q = k[i] / gs.eper;
+        const unsigned int idx = s_base[it][q] + li[i];
+        const uint4 req = make_uint4(k[i] - q * gs.eper, src[i], (unsigned int)am[i].x | (((tw[i] >> (src[i] & 31)) & 1u) << 31),
+                                     (unsigned int)am[i].y);
+        if (idx < gs.eper) s_seg[q][idx] = req;
         else gs_hdr(gs.self)->err = 2u;
       }
     }
-    // the last CTA to finish publishes the counts + flag: the records of ALL CTAs precede it (the block barrier
+    // the last CTA to finish publishes the counts + flag: the requests of ALL CTAs precede it (the block barrier
     // orders every thread's stores before thread 0's system-scope fence, which is cumulative)
     __syncthreads();
     if (tid == 0) {
       __threadfence_system();
-      s_last = (atomicAdd(&gs.info->ticket, 1u) == (unsigned int)(B - 1)) ? 1u : 0u;
+      s_last = (atomicAdd(&gs.info->ticket[0], 1u) == (unsigned int)(B - 1)) ? 1u : 0u;
     }
     __syncthreads();
     if (s_last) {
-      if (tid == 0) gs.info->ticket = 0u;
+      if (tid == 0) gs.info->ticket[0] = 0u;
       __threadfence_system();
       if (tid < gs.world) {
         GridXchgHdr* ph = gs_hdr(gs_peer(gs, tid));
-        ph->cntC[par][me][0] = atomicExch(gs.sendcnt + tid, 0u);
-        ph->cntC[par][me][1] = atomicExch(gs.sendcnt + kMaxPeers + tid, 0u);
-        st_release_sys(&ph->flagC[par][me], info->tag);
+        ph->cntB[par][me] = atomicExch(gs.sendcnt + 2 * kMaxPeers + tid, 0u);
+        st_release_sys(&ph->flagB[par][me], info->tag);
       }
     }
   }
 }
 
-// ------------------------------------------------------------------------------------ 4 wait
+// ------------------------------------------------------------------------------------ 4 / 6 wait
+// CH = 0: the requests (flag B), 1: the records (flag C; the cell records are counted per chunk by the senders, the
+// halo records here)
+template <int CH>
 __global__ void __launch_bounds__(32) grid_shard_wait_kernel(const GridShardDev gs) {
   const int lane = threadIdx.x;
   GridStepInfo* info = gs.info;
-  if (info->m == 0) { if (lane <= 2 * gs.world) info->rcv[lane] = 0u; return; }
+  unsigned int* out = CH ? info->rcv : info->rcvB;
+  if (info->m == 0) { if (lane <= gs.world) out[lane] = 0u; return; }
   const unsigned int tag = info->tag, par = info->par;
   GridXchgHdr* h = gs_hdr(gs.self);
   unsigned int c = 0;
-  if (lane < 2 * gs.world) {
-    const int from = lane < gs.world ? lane : lane - gs.world;
+  if (lane < gs.world) {
+    const unsigned int* flag = CH ? &h->flagC[par][lane] : &h->flagB[par][lane];
     if (!*(volatile unsigned int*)&h->err) {
       const long long t0 = clock64();
-      while (ld_acquire_sys(&h->flagC[par][from]) != tag) {
+      while (ld_acquire_sys(flag) != tag) {
         if (clock64() - t0 > (20ll << 30)) { h->err = 1u; break; }
       }
     }
-    c = __ldcv(&h->cntC[par][from][lane < gs.world ? 0 : 1]);
+    c = CH ? __ldcv(&h->cntC[par][lane][1]) : __ldcv(&h->cntB[par][lane]);
   }
   __syncwarp();
   unsigned int inc = c;
@@ -559,45 +553,147 @@ __global__ void __launch_bounds__(32) grid_shard_wait_kernel(const GridShardDev 
     const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += v;
   }
-  if (lane <= 2 * gs.world) info->rcv[lane] = inc - c;          // lane 2*world: c = 0 -> the total
+  if (lane <= gs.world) out[lane] = inc - c;          // lane world: c = 0 -> the total
 }
 
-// ------------------------------------------------------------------------------------ 5 apply
-__global__ void __launch_bounds__(256) grid_shard_apply_kernel(const SchellingDev sd, const SchellingBitsDev sb, const GridShardDev gs) {
-  __shared__ unsigned int s_rcv[2 * kMaxPeers + 1];
+// ------------------------------------------------------------------------------------ 5 forward
+// the slot owner's part: slot -> target cell, slot <- source cell, the mover goes on to the owner of the target row.
+// CTA c serves a contiguous block of the received requests and appends its records to ITS chunk of my segment in
+// every target's receive area: positions come from shared-memory counters (one atomic per warp and target), so the
+// loop holds no barrier and no global atomic -- it is a chain of two dependent random accesses per request and
+// needs every warp running free to hide them.
+__global__ void __launch_bounds__(kThreads, 4) grid_shard_forward_kernel(const SchellingDev sd, const GridShardDev gs) {
+  __shared__ unsigned int s_rcv[kMaxPeers + 1];
+  __shared__ unsigned int s_pos[kMaxPeers];
+  __shared__ uint4* s_chunk[kMaxPeers];            // my chunk of my record segment of this parity in rank p's receive area
+  __shared__ unsigned int s_last;
   const GridStepInfo* info = gs.info;
-  if (info->m == 0) return;
-  const int nseg = 2 * gs.world;
-  if ((int)threadIdx.x <= nseg) s_rcv[threadIdx.x] = info->rcv[threadIdx.x];
+  if (info->m == 0) return;              // uniform over the world
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned int par = info->par;
+  const int me = gs.rank, H = sd.H, c = blockIdx.x;
+  if (tid <= gs.world) s_rcv[tid] = info->rcvB[tid];
+  if (tid < kMaxPeers) {
+    s_chunk[tid] = gs_seg(gs_peer(gs, tid < gs.world ? tid : 0), gs, par, me) + (size_t)c * gs.fchunk;
+    s_pos[tid] = 0u;
+  }
   __syncthreads();
-  const unsigned int total = s_rcv[nseg], par = info->par;
-  const int H = sd.H;
+  const unsigned int total = s_rcv[gs.world];
+  const unsigned int per = (total + gridDim.x - 1) / gridDim.x;
+  const unsigned int lo = min(total, (unsigned int)c * per), hi = min(total, lo + per);
+  unsigned int* slots = gs_slots(gs.self, gs);
   const int hs = (H & (H - 1)) == 0 ? __ffs(H) - 1 : -1;
-  constexpr int kRec = 4;                // records in flight per thread: the loop is a chain of dependent random accesses
-  const unsigned int stride = gridDim.x * blockDim.x;
-  for (unsigned int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kRec) {
-    uint4 rec[kRec];
+  constexpr int kRq = 4;
+  for (unsigned int c0 = lo; c0 < hi; c0 += kThreads * kRq) {      // uniform per CTA: the warps stay converged for the votes
+    uint4 rq[kRq];
+    unsigned int dst[kRq];
+    bool ok[kRq];
 #pragma unroll
-    for (int r = 0; r < kRec; ++r) {
-      const unsigned int i = i0 + r * stride;
-      rec[r] = make_uint4(0u, 0u, 0u, 2u);
-      if (i < total) {
-        int s = 0;
-        while (s + 1 < nseg && i >= s_rcv[s + 1]) ++s;
-        const unsigned int off = i - s_rcv[s];
-        const uint4* seg = gs_seg(gs.self, gs, par, s < gs.world ? s : s - gs.world);
-        rec[r] = __ldcg(seg + (s < gs.world ? off : gs.cap - 1u - off));
+    for (int r = 0; r < kRq; ++r) {
+      const unsigned int i = c0 + r * kThreads + tid;
+      ok[r] = i < hi;
+      rq[r] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[r]) {
+        int sq = 0;
+        while (sq + 1 < gs.world && i >= s_rcv[sq + 1]) ++sq;
+        rq[r] = __ldcs(gs_req(gs.self, gs, par, sq) + (i - s_rcv[sq]));
       }
     }
 #pragma unroll
-    for (int r = 0; r < kRec; ++r) {
-      if (rec[r].w > 1u) continue;
-      const unsigned int c = rec[r].x;
-      const bool ty = (rec[r].y >> 31) != 0, set = rec[r].w != 0u;
-      const int x = hs >= 0 ? (int)(c >> hs) : (int)(c / (unsigned int)H);
-      gs_flip(sd, sb, gs, c, x, ty, set);
-      if (set && x >= gs.X0 && x < gs.X1) sb.cell_am[c] = make_int2((int)(rec[r].y & 0x7FFFFFFFu), (int)rec[r].z);
+    for (int r = 0; r < kRq; ++r) dst[r] = ok[r] ? __ldcg(slots + rq[r].x) : 0u;
+#pragma unroll
+    for (int r = 0; r < kRq; ++r) {
+      int p = -1;
+      const unsigned int d_ = dst[r];
+      if (ok[r]) {
+        slots[rq[r].x] = rq[r].y;
+        const int xd = hs >= 0 ? (int)(d_ >> hs) : (int)(d_ / (unsigned int)H);
+        int blo, bhi;
+        p = gs_owner3(gs, xd, blo, bhi);
+        if (xd == blo || xd == bhi - 1) {                // the target row is somebody's halo row
+          int ha, hb;
+          gs_halo_ranks(sd, gs, xd, p, ha, hb);
+          const uint4 rec = make_uint4(d_, rq[r].z, rq[r].w + 1u, 1u);
+          if (ha >= 0) gs_send_halo(gs, par, ha, rec);
+          if (hb >= 0) gs_send_halo(gs, par, hb, rec);
+        }
+      }
+      // one shared-memory atomic per (warp, target): the lanes of a group take consecutive positions
+      const unsigned int grp = __match_any_sync(0xffffffffu, p);
+      const int leader = __ffs(grp) - 1;
+      unsigned int pos = 0;
+      if (lane == leader && p >= 0) pos = atomicAdd(&s_pos[p], (unsigned int)__popc(grp));
+      pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(grp & ((1u << lane) - 1u));
+      if (p >= 0) {
+        if (pos < gs.fchunk) s_chunk[p][pos] = make_uint4(d_, rq[r].z, rq[r].w + 1u, 1u);
+        else gs_hdr(gs.self)->err = 2u;
+      }
     }
+  }
+  __syncthreads();
+  if (tid < gs.world) gs_chunk_cnt(gs_peer(gs, tid), gs, par, me)[c] = s_pos[tid];
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(&gs.info->ticket[1], 1u) == gridDim.x - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    if (tid == 0) gs.info->ticket[1] = 0u;
+    __threadfence_system();
+    if (tid < gs.world) {
+      GridXchgHdr* ph = gs_hdr(gs_peer(gs, tid));
+      ph->cntC[par][me][1] = atomicExch(gs.sendcnt + kMaxPeers + tid, 0u);
+      st_release_sys(&ph->flagC[par][me], info->tag);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ 7 apply
+__device__ __forceinline__ void gs_apply_record(const SchellingDev& sd, const SchellingBitsDev& sb, const GridShardDev& gs,
+                                                const uint4 rec, int hs) {
+  const unsigned int c = rec.x;
+  const bool ty = (rec.y >> 31) != 0, set = rec.w != 0u;
+  const int x = hs >= 0 ? (int)(c >> hs) : (int)(c / (unsigned int)sd.H);
+  gs_flip(sd, sb, gs, c, x, ty, set);
+  if (set && x >= gs.X0 && x < gs.X1) sb.cell_am[c] = make_int2((int)(rec.y & 0x7FFFFFFFu), (int)rec.z);
+}
+
+__global__ void __launch_bounds__(256) grid_shard_apply_kernel(const SchellingDev sd, const SchellingBitsDev sb, const GridShardDev gs) {
+  __shared__ unsigned int s_rcv[kMaxPeers + 1];
+  const GridStepInfo* info = gs.info;
+  if (info->m == 0) return;
+  const int tid = threadIdx.x;
+  if (tid <= gs.world) s_rcv[tid] = info->rcv[tid];
+  __syncthreads();
+  const unsigned int par = info->par;
+  const int H = sd.H;
+  const int hs = (H & (H - 1)) == 0 ? __ffs(H) - 1 : -1;
+  constexpr int kRec = 4;                // records in flight per thread: the loop is a chain of dependent random accesses
+  // the cell records: one (sender, chunk) pair per CTA at a time
+  const int pairs = gs.world * (int)gs.nfwd;
+  for (int pi = blockIdx.x; pi < pairs; pi += gridDim.x) {
+    const int from = pi / (int)gs.nfwd, c = pi - from * (int)gs.nfwd;
+    const unsigned int n = __ldcv(gs_chunk_cnt(gs.self, gs, par, from) + c);
+    const uint4* chunk = gs_seg(gs.self, gs, par, from) + (size_t)c * gs.fchunk;
+    for (unsigned int i0 = tid; i0 < n; i0 += 256 * kRec) {
+      uint4 rec[kRec];
+#pragma unroll
+      for (int r = 0; r < kRec; ++r) {
+        const unsigned int i = i0 + r * 256;
+        rec[r] = i < n ? __ldcs(chunk + i) : make_uint4(0u, 0u, 0u, 2u);
+      }
+#pragma unroll
+      for (int r = 0; r < kRec; ++r)
+        if (rec[r].w <= 1u) gs_apply_record(sd, sb, gs, rec[r], hs);
+    }
+  }
+  // the halo records (boundary rows only)
+  const unsigned int total = s_rcv[gs.world];
+  for (unsigned int i = blockIdx.x * blockDim.x + tid; i < total; i += gridDim.x * blockDim.x) {
+    int sq = 0;
+    while (sq + 1 < gs.world && i >= s_rcv[sq + 1]) ++sq;
+    gs_apply_record(sd, sb, gs, __ldcg(gs_seg(gs.self, gs, par, sq) + (gs.cap - 1u - (i - s_rcv[sq]))), hs);
   }
 }
 

@@ -12,8 +12,8 @@ That pins the design decisions the kernels rely on without a GPU:
     (including the wrapped rows of a periodic grid): no halo exchange besides the movers themselves;
   * the ordered per-band unsatisfied lists, concatenated in rank order, are the global list ``U``, so a rank
     can walk ITS movers alone: entry j of its segment is mover k = piU^-1(j);
-  * ``empty_cells`` can be partitioned by slot range: a slot is matched to exactly one mover per step, whose
-    rank reads and rewrites it in place wherever it lives;
+  * ``empty_cells`` can be partitioned by slot range: a slot is matched to exactly one mover per step, so its
+    owner can serve the movers' requests in any order and forward each mover to the owner of the target row;
   * the agent id and its move count travel with the cell (the record), so no rank needs a per-agent column
     during the run; columns combine as position = max, satisfied = min, moves = sum over the ranks' views;
   * a node range of the SIR network only needs its own rows + the global infected bitmap.
@@ -59,6 +59,7 @@ class _BandRank:
         own = (positions[:, 0] >= self.X0) & (positions[:, 0] < self.X1)
         self.cell_agent[positions[own, 0], positions[own, 1]] = np.flatnonzero(own)
         self.inbox = []                                             # records received this step
+        self.requests = []                                          # movers that take one of my slots this step
         self.last_unsat = np.zeros(0, dtype=np.int64)
 
     def _kept_rows(self):
@@ -118,8 +119,8 @@ class _BandRank:
         return len(self.U), int(sel.sum()), num
 
     def moveout(self, ranks, prefix, u, m, rk):
-        """Walk MY movers: entry j of my segment is mover k with piU(k) = j; it takes slot piE(k), wherever that
-        slot lives.  The source cell is cleared here; everything else travels as records."""
+        """Walk MY movers: entry j of my segment is mover k with piU(k) = j; it takes slot piE(k).  The source cell
+        is cleared here; the mover leaves as a request to the rank that holds the slot."""
         k = np.arange(m, dtype=np.uint32)
         j = jl.feistel_permute(k, u, rk[0:4]).astype(np.int64)
         mine = (j >= prefix[self.rank]) & (j < prefix[self.rank + 1])
@@ -127,10 +128,7 @@ class _BandRank:
         H = self.H
         for jj, sl in zip(j[mine] - prefix[self.rank], slots):
             s_ = int(self.U[jj])
-            q, off = divmod(int(sl), self.eper)
-            d_ = int(ranks[q].E[off])                              # peer load + store: nobody else touches this slot
-            ranks[q].E[off] = s_
-            xs, xd = s_ // H, d_ // H
+            xs = s_ // H
             a, mv, ty = self.cell_agent[xs, s_ % H], self.cell_moves[xs, s_ % H], self.grid[xs, s_ % H]
             assert a >= 0 and ty >= 0
             self._flip(s_, -1)
@@ -138,11 +136,22 @@ class _BandRank:
             self.cell_moves[xs, s_ % H] = 0
             for p in self._halo_ranks(xs, self.rank):
                 ranks[p].inbox.append((s_, -1, 0, -1))
+            q, off = divmod(int(sl), self.eper)
+            ranks[q].requests.append((off, s_, int(a), int(mv), int(ty)))
+
+    def forward(self, ranks):
+        """The slot owner's part: slot -> target cell, slot <- source cell; the mover goes on to the owner of the
+        target row, plane-only copies to the ranks that keep that row as a halo."""
+        for off, s_, a, mv, ty in self.requests:
+            d_ = int(self.E[off])
+            self.E[off] = s_
+            xd = d_ // self.H
             p = self._owner(xd)
-            rec = (d_, int(a), int(mv) + 1, int(ty))
+            rec = (d_, a, mv + 1, ty)
             ranks[p].inbox.append(rec)
             for ph in self._halo_ranks(xd, p):
                 ranks[ph].inbox.append(rec)
+        self.requests = []
 
     def _flip(self, c, value):
         x = c // self.H
@@ -192,6 +201,8 @@ def schelling_bands_run(grid_size, types, positions, world, steps, seed_key, mod
         if m > 0:
             for r in ranks:
                 r.moveout(ranks, prefix, u, m, rk)
+            for r in ranks:
+                r.forward(ranks)
             for r in ranks:
                 r.apply()
         total_moves += m

@@ -168,7 +168,7 @@ def test_grid_shard_rejects_bad_shapes():
         DeviceModel(d)
     d = make_desc("schelling", [TypeSpec("schelling", 100)], [0.5], grid=(64, 64, False), world_size=2, rank=0)
     dev = DeviceModel(d)
-    h = np.zeros(72, dtype=np.uint8)
+    h = np.zeros(80, dtype=np.uint8)
     with pytest.raises(nat.JxbError, match="consecutive rows"):
         nat.check(nat.lib().jxb_model_grid_shard_export(dev.handle, 0, 40, nat.ptr(h), h.nbytes))
     with pytest.raises(nat.JxbError, match="export"):
