@@ -1647,15 +1647,11 @@ static int enqueue_step(jxb_model* m, cudaStream_t s, bool timed) {
       if (part) grid_shard_moveout_kernel<1><<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
       else grid_shard_moveout_kernel<0><<<m->gs.blocks, kThreads, 0, s>>>(m->sd, m->sb, m->gs, m->dev);
       mark();
-      grid_shard_wait_kernel<0><<<1, 32, 0, s>>>(m->gs);
-      mark();
       grid_shard_forward_kernel<<<m->gs.nfwd, kThreads, 0, s>>>(m->sd, m->gs);
-      mark();
-      grid_shard_wait_kernel<1><<<1, 32, 0, s>>>(m->gs);
       mark();
       grid_shard_apply_kernel<<<eng->sms * 8, 256, 0, s>>>(m->sd, m->sb, m->gs);
       mark();
-      eng->launches += 7;
+      eng->launches += 5;
       break;
     }
     case JXB_PROGRAM_TRACED: {
@@ -1777,7 +1773,7 @@ static int launches_per_step_all(jxb_model* m) {
   return launches_per_step(m) + extra;
 }
 static int launches_per_step(jxb_model* m) {
-  if (m->grid_sharded) return 7;
+  if (m->grid_sharded) return 5;
   if (m->net_sharded) return 2;
   if (m->desc.program == JXB_PROGRAM_SIR) return m->sir_mode == 3 ? 4 : (m->sir_mode == 1 ? 2 : 1);
   if (m->desc.program == JXB_PROGRAM_ECONOMY) return m->desc.n_types + (m->eco_hh >= 0 ? (m->dev.world_size > 1 ? 6 : 5) : 1);
@@ -1969,19 +1965,19 @@ extern "C" int jxb_model_run(jxb_model* m, int steps, int collect_interval, doub
   }
   if (!m->gs_trace.empty()) {
     // per-kernel device time of the band steps, summed over the run and for the first steps
-    static const char* names[7] = {"sweep", "counts", "moveout", "waitB", "forward", "waitC", "apply"};
-    const size_t nst = m->gs_trace.size() / 8;
-    double sum[7] = {0, 0, 0, 0, 0, 0, 0};
+    static const char* names[5] = {"sweep", "counts", "moveout", "forward", "apply"};
+    const size_t nst = m->gs_trace.size() / 6;
+    double sum[5] = {0, 0, 0, 0, 0};
     std::string first;
     for (size_t st = 0; st < nst; ++st)
-      for (int k = 0; k < 7; ++k) {
+      for (int k = 0; k < 5; ++k) {
         float us = 0;
-        cudaEventElapsedTime(&us, m->gs_trace[st * 8 + k], m->gs_trace[st * 8 + k + 1]);
+        cudaEventElapsedTime(&us, m->gs_trace[st * 6 + k], m->gs_trace[st * 6 + k + 1]);
         sum[k] += us * 1e3;
         if (st < 2) { char b[64]; snprintf(b, sizeof b, " %s[%zu]=%.1f", names[k], st, us * 1e3); first += b; }
       }
-    fprintf(stderr, "[jxb gs_trace] rank %d, %zu steps, us: sweep %.1f counts %.1f moveout %.1f waitB %.1f forward %.1f waitC %.1f apply %.1f |%s\n",
-            m->dev.rank, nst, sum[0], sum[1], sum[2], sum[3], sum[4], sum[5], sum[6], first.c_str());
+    fprintf(stderr, "[jxb gs_trace] rank %d, %zu steps, us: sweep %.1f counts %.1f moveout %.1f forward %.1f apply %.1f |%s\n",
+            m->dev.rank, nst, sum[0], sum[1], sum[2], sum[3], sum[4], first.c_str());
     for (auto e : m->gs_trace) cudaEventDestroy(e);
     m->gs_trace.clear();
   }

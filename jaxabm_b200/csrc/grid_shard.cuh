@@ -10,7 +10,7 @@
 //           U[prefix[r] .. prefix[r+1]) -- its own rows, compacted CTA-locally;
 //   E       the empty-cell slots: rank q holds slots [q * eper, (q+1) * eper) inside its receive area.
 //
-// A step is seven launches per rank, graph-captured, with no host round trip and no NCCL call:
+// A step is five launches per rank, graph-captured, with no host round trip and no NCCL call:
 //   1 sweep    bit-sliced neighbour counts of the band (eval_row of schelling_bits.cuh): unsatisfied
 //              mask + exact integer partials per CTA.
 //   2 counts   one CTA: folds the partials, stores the band's counts + flag A into every rank's
@@ -24,15 +24,14 @@
 //              mover leaves as a 16-byte request (slot, source cell, agent | type<<31, moves) stored
 //              into segment [parity][me] of the SLOT OWNER's receive area; the last CTA releases the
 //              per-target counts + flag B.
-//   4 wait B   one warp spins on the world's B flags in its OWN area and leaves the request counts.
-//   5 forward  the slot owner reads each request's slot (the target cell), rewrites it with the source
-//              cell, and forwards (target cell, agent | type<<31, moves + 1, set) to the rank that
-//              owns the target row -- plus a plane-only copy to the ranks that hold that row as a
-//              halo; the last CTA releases the counts + flag C.
-//   6 wait C   as 4, for the records.
-//   7 apply    every received record sets / clears the plane bits wherever this rank keeps that row
-//              (band, halo, wrapped halo of a periodic grid) and, for a cell of the band, writes the
-//              payload.
+//   4 forward  (every CTA first waits for the world's B flags in its OWN area.)  The slot owner reads
+//              each request's slot (the target cell), rewrites it with the source cell, and forwards
+//              (target cell, agent | type<<31, moves + 1, set) to the rank that owns the target row --
+//              plus a plane-only copy to the ranks that hold that row as a halo; the last CTA
+//              releases flag C.
+//   5 apply    (waits for the C flags.)  Every received record sets / clears the plane bits wherever
+//              this rank keeps that row (band, halo, wrapped halo of a periodic grid) and, for a cell
+//              of the band, writes the payload.
 // (A first version let the mover's rank read and rewrite the slot in place over NVLink: half of the
 // slot reads at 2 GPUs being remote loads cost more than the halved work saved -- measured,
 // profiles/r02_grid_bands_v2.txt -- so the slot owner became a party of its own.)
@@ -62,8 +61,6 @@ struct GridStepInfo {
   int key_row;                            // row of the run's key table that belongs to this step
   unsigned int ticket[2];                 // last-CTA election of the moveout / forward kernel
   unsigned int prefix[kMaxPeers + 1];     // rank q's unsatisfied cells are U[prefix[q] .. prefix[q+1])
-  unsigned int rcvB[kMaxPeers + 1];       // prefix of the received requests, by sender
-  unsigned int rcv[kMaxPeers + 1];        // prefix of the received halo records, by sender
 };
 
 struct GridShardDev {
@@ -524,36 +521,33 @@ __global__ void __launch_bounds__(kThreads, JXB_GS_MINB) grid_shard_moveout_kern
   }
 }
 
-// ------------------------------------------------------------------------------------ 4 / 6 wait
-// CH = 0: the requests (flag B), 1: the records (flag C; the cell records are counted per chunk by the senders, the
-// halo records here)
+// ------------------------------------------------------------------------------------ waiting for the peers
+// Every CTA of the consuming kernel waits for the world's flags itself (thread p spins on rank p's flag in this
+// rank's OWN area, ld.acquire.sys) and leaves the prefix of the senders' counts in s_rcv[0 .. world]: no separate
+// wait launch.  CH = 0: the requests (flag B), 1: the records (flag C; the cell records are counted per chunk by
+// the senders, the halo records here).
 template <int CH>
-__global__ void __launch_bounds__(32) grid_shard_wait_kernel(const GridShardDev gs) {
-  const int lane = threadIdx.x;
-  GridStepInfo* info = gs.info;
-  unsigned int* out = CH ? info->rcv : info->rcvB;
-  if (info->m == 0) { if (lane <= gs.world) out[lane] = 0u; return; }
+__device__ __forceinline__ void gs_wait(const GridShardDev& gs, const GridStepInfo* info, unsigned int* s_rcv) {
+  const int tid = threadIdx.x;
   const unsigned int tag = info->tag, par = info->par;
   GridXchgHdr* h = gs_hdr(gs.self);
-  unsigned int c = 0;
-  if (lane < gs.world) {
-    const unsigned int* flag = CH ? &h->flagC[par][lane] : &h->flagB[par][lane];
+  if (tid < gs.world) {
+    const unsigned int* flag = CH ? &h->flagC[par][tid] : &h->flagB[par][tid];
     if (!*(volatile unsigned int*)&h->err) {
       const long long t0 = clock64();
       while (ld_acquire_sys(flag) != tag) {
-        if (clock64() - t0 > (20ll << 30)) { h->err = 1u; break; }
+        if (clock64() - t0 > (20ll << 30)) { h->err = 1u; break; }     // ~10 s: a peer is gone
       }
     }
-    c = CH ? __ldcv(&h->cntC[par][lane][1]) : __ldcv(&h->cntB[par][lane]);
+    s_rcv[tid + 1] = CH ? __ldcv(&h->cntC[par][tid][1]) : __ldcv(&h->cntB[par][tid]);
   }
-  __syncwarp();
-  unsigned int inc = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int acc = 0;
+    s_rcv[0] = 0u;
+    for (int q = 1; q <= gs.world; ++q) { acc += s_rcv[q]; s_rcv[q] = acc; }
   }
-  if (lane <= gs.world) out[lane] = inc - c;          // lane world: c = 0 -> the total
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------ 5 forward
@@ -572,12 +566,11 @@ __global__ void __launch_bounds__(kThreads, 4) grid_shard_forward_kernel(const S
   const int tid = threadIdx.x, lane = tid & 31;
   const unsigned int par = info->par;
   const int me = gs.rank, H = sd.H, c = blockIdx.x;
-  if (tid <= gs.world) s_rcv[tid] = info->rcvB[tid];
   if (tid < kMaxPeers) {
     s_chunk[tid] = gs_seg(gs_peer(gs, tid < gs.world ? tid : 0), gs, par, me) + (size_t)c * gs.fchunk;
     s_pos[tid] = 0u;
   }
-  __syncthreads();
+  gs_wait<0>(gs, info, s_rcv);
   const unsigned int total = s_rcv[gs.world];
   const unsigned int per = (total + gridDim.x - 1) / gridDim.x;
   const unsigned int lo = min(total, (unsigned int)c * per), hi = min(total, lo + per);
@@ -664,8 +657,7 @@ __global__ void __launch_bounds__(256) grid_shard_apply_kernel(const SchellingDe
   const GridStepInfo* info = gs.info;
   if (info->m == 0) return;
   const int tid = threadIdx.x;
-  if (tid <= gs.world) s_rcv[tid] = info->rcv[tid];
-  __syncthreads();
+  gs_wait<1>(gs, info, s_rcv);
   const unsigned int par = info->par;
   const int H = sd.H;
   const int hs = (H & (H - 1)) == 0 ? __ffs(H) - 1 : -1;
