@@ -78,8 +78,9 @@ class SchellingWorkload:
         self.name = f"schelling_{grid}x{grid}_{n / 1e6:.3g}M" if (grid, n) != (4096, 13_000_000) else self.name
         if shard:
             self.kernel = "grid_shard_sweep_kernel"
-            self.l2_note = ("no flush; 4 launches per step and rank (band sweep, compaction + peer stores, flag wait, "
-                            "movers); the band's bit planes are L2-resident, the active-phase working set is not")
+            self.l2_note = ("no flush; 5 launches per step and rank (band sweep, counts + flag wait, movers out as requests "
+                            "to the slot owners, slot owners forward to the cell owners, apply); the band's bit planes "
+                            "are L2-resident, the active-phase working set is not")
         self.types, self.positions = schelling.initial_layout(grid, n, 0.5, self.seed)
         self.agents = n
         self._pins = None

@@ -13,9 +13,10 @@ sharded run reproduces the unsharded model's state bit for bit; the reduction or
 (per-rank partials folded in rank order), so float32 env trajectories agree to rounding.
 
 Grids (C2, SURVEY.md 8(e) "Grid: row blocks + halo") split by ROW BANDS: rank r owns the rows
-``shard_bounds(W, r, world)`` of the one ``env['grid']``; the per-step exchange (the unsatisfied
-agents' records + three integer counts) is written straight into every peer's receive area over
-NVLink by the compaction kernel (``csrc/grid_shard.cuh``).  :func:`shard_model` on a Schelling model
+``shard_bounds(W, r, world)`` of the one ``env['grid']`` and a range of the empty-cell slots, and walks
+only the movers of its own rows: a mover leaves as a 16-byte request stored into the receive area of the
+rank that holds its slot, which rewrites the slot and forwards the mover to the owner of the target row
+-- posted stores over NVLink and step flags only (``csrc/grid_shard.cuh``).  :func:`shard_model` on a Schelling model
 selects it; state reads combine the ranks' views (``position`` max, ``satisfied`` min, ``moves``
 sum) and are collective calls.  Results are bit-identical to the single-GPU run.
 
