@@ -73,10 +73,13 @@ def test_series_facade_results_keys(mode):
     assert len(series) == 25 and np.array_equal(series[-1], pos[-1])
 
 
+@pytest.mark.parametrize("bands", ["0", "1"])
 @pytest.mark.parametrize("grid,n", [(64, 3100), (1024, 800_000)])
-def test_series_schelling_persistent_kernel(mode, grid, n):
-    """The persistent cooperative kernel is cut at the recording steps: position / moves / the lazily materialised
-    'satisfied' column after every recorded step equal the oracle's, bit for bit; the run itself is unchanged."""
+def test_series_schelling_persistent_kernel(mode, grid, n, bands, monkeypatch):
+    """The persistent cooperative kernel is cut at the recording steps (bands = "1": the band kernels, whose snapshot
+    launches sit between the steps of the captured graph): position / moves / the lazily materialised 'satisfied'
+    column after every recorded step equal the oracle's, bit for bit; the run itself is unchanged."""
+    monkeypatch.setenv("JXB_GRID_BANDS", bands)
     ci, steps = 2, 8
     kw = dict(seed=5, config=jx.ModelConfig(seed=9, rng_mode=mode, collect_interval=ci))
     m = schelling.create_schelling_model(grid, n, **kw)
@@ -173,14 +176,19 @@ def test_filter_matches_oracle_filter(mode):
 
 
 # ------------------------------------------------------------------------------- state edits between runs
-def test_schelling_uploads_between_runs_with_packed_cell_payload(mode):
-    """The persistent bit-sliced kernel keeps (agent, moves) with the cell and derives 'position' / 'moves' on read.
+@pytest.mark.parametrize("bands", ["0", "1"])
+def test_schelling_uploads_between_runs_with_packed_cell_payload(mode, bands, monkeypatch):
+    """The persistent bit-sliced kernel -- and the band kernels with the whole grid as one band (bands = "1") -- keep
+    (agent, moves) with the cell and derive 'position' / 'moves' on read.
     Uploading 'moves' between runs refreshes the counts that travel with the cells WITHOUT rebuilding the grid (the
     empty-cell slot order, hence the trajectory, is unchanged); uploading 'position' rebuilds the cell binning -- with the
     other derived column brought up to date first -- exactly like a fresh model created from those columns."""
+    monkeypatch.setenv("JXB_GRID_BANDS", bands)
+
     def build(**kw):
         return schelling.create_schelling_model(1024, 800_000, seed=5, config=jx.ModelConfig(seed=9, rng_mode=mode), **kw)
     a, b = build(), build()
+    assert (a._dev.profile()[2] == "grid_shard_sweep_kernel") == (bands == "1")
     a.run(steps=4), b.run(steps=4)
     sa, sb = a.agent_collections["agents"].states, b.agent_collections["agents"].states
     moves_before = np.array(sb["moves"])
