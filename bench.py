@@ -652,6 +652,8 @@ def measure(ctx, eng, args, name, K, shard=False, want_e2e=True):
             pm = model if wl.stationary else wl.fresh()
             if name == "schelling":
                 wl.kernel = pm._dev.profile()[2]   # band kernels: whole-grid band on one GPU, or one band per rank
+                if wl.kernel == "grid_shard_sweep_kernel":
+                    wl.kernel = "grid_shard_{sweep,counts,moveout,forward,apply}_kernel (the 5 launches of a step, timed as one unit)"
             pm._dev.set_profile(True)              # events around every launch, no graph
             res = pm.run(steps=K)
             ksecs, klaunches, _ = pm._dev.profile()
@@ -687,7 +689,7 @@ def measure(ctx, eng, args, name, K, shard=False, want_e2e=True):
                         "(frac > 1 on the API figure means the engine moves fewer bytes than the reference layout implies)"}
     par = "single-gpu"
     if world > 1:
-        par = (f"one grid in {world} row bands, one per gpu (per-step records of the unsatisfied agents over NVLink peer memory)"
+        par = (f"one grid in {world} row bands, one per gpu (movers travel source band -> slot owner -> target band as posted stores over NVLink peer memory)"
                if (sharded and name == "schelling") else
                f"one network in {world} node ranges, one per gpu (new infected-bitmap words stored into every rank's copy over NVLink peer memory)"
                if (sharded and name == "sir") else
