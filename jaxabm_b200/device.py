@@ -163,6 +163,16 @@ class DeviceModel:
     def upload(self, t: int, f: int, value) -> None:
         shape, dt = self._shape(t, f)
         a = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), shape))
+        name = self.fields[t][f][0]
+        if self.group is not None and name in ("type", "position"):
+            # a row-band sharded Grid (collective call): the write makes every rank rebuild its cell binning from its
+            # API columns, which only hold the band's view once they were read -- hand every rank the whole
+            # 'position' / 'moves' columns first (the agents' move counts travel with them into the rebuilt bands)
+            for other in ("position", "moves"):
+                if other != name:
+                    fo = self.field_index(t, other)
+                    whole = self.download(t, fo)
+                    nat.check(self._lib.jxb_model_upload(self.handle, t, fo, nat.ptr(whole), whole.nbytes))
         nat.check(self._lib.jxb_model_upload(self.handle, t, f, nat.ptr(a), a.nbytes))
         if self.net_group is not None:
             self.net_shard_sync()
