@@ -50,7 +50,8 @@ struct GridXchgHdr {
   unsigned int flagB[2][kMaxPeers];       // step tag: rank p's requests of this parity are complete
   unsigned int cntB[2][kMaxPeers];        // how many requests rank p sent here
   unsigned int flagC[2][kMaxPeers];       // step tag: rank p's records of this parity are complete
-  unsigned int cntC[2][kMaxPeers][2];     // how many records rank p sent here: cell records (front), halo records (back)
+  unsigned int cntC[2][kMaxPeers][2];     // [1]: how many halo records rank p left at the back of its segment ([0] is not used:
+                                          // the cell records are counted per chunk, gs_chunk_cnt)
   unsigned int err;                       // 1: a peer's flag did not arrive within the spin budget, 2: a segment overflowed
   unsigned int pad[256 - 20 * kMaxPeers - 1];
 };
@@ -77,7 +78,8 @@ struct GridShardDev {
   unsigned char* self;                    // == peer[rank]
   GridStepInfo* info;
   BlkPart* part;                          // [blocks] per-CTA partials of the sweep
-  unsigned int* sendcnt;                  // [3][kMaxPeers] appended for each target this step: (unused), halo records, requests
+  unsigned int* sendcnt;                  // [3][kMaxPeers] appended for each target this step: row 1 halo records, row 2 requests
+                                          // (row 0 is not used)
   int blocks;                             // CTAs of the sweep AND the moveout kernel (same row split)
 };
 
@@ -550,7 +552,7 @@ __device__ __forceinline__ void gs_wait(const GridShardDev& gs, const GridStepIn
   __syncthreads();
 }
 
-// ------------------------------------------------------------------------------------ 5 forward
+// ------------------------------------------------------------------------------------ 4 forward
 // the slot owner's part: slot -> target cell, slot <- source cell, the mover goes on to the owner of the target row.
 // CTA c serves a contiguous block of the received requests and appends its records to ITS chunk of my segment in
 // every target's receive area: positions come from shared-memory counters (one atomic per warp and target), so the
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 4) grid_shard_forward_kernel(const S
   }
 }
 
-// ------------------------------------------------------------------------------------ 7 apply
+// ------------------------------------------------------------------------------------ 5 apply
 __device__ __forceinline__ void gs_apply_record(const SchellingDev& sd, const SchellingBitsDev& sb, const GridShardDev& gs,
                                                 const uint4 rec, int hs) {
   const unsigned int c = rec.x;
