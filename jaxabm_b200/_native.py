@@ -55,6 +55,9 @@ _lib: Optional[C.CDLL] = None
 
 # name -> (restype, argtypes); every symbol declared in include/jxb.h
 _P = C.c_void_p
+IPC_HANDLE_BYTES = 64        # include/jxb.h: JXB_IPC_HANDLE_BYTES
+GRID_HANDLE_BYTES = 80       # include/jxb.h: JXB_GRID_HANDLE_BYTES (IPC handle + band + launch shape)
+
 SIGNATURES = {
     "jxb_version": (C.c_int, []),
     "jxb_last_error": (C.c_char_p, []),

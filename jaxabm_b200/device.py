@@ -136,7 +136,7 @@ class DeviceModel:
         """Row band of this rank + receive areas of all ranks (``jxb_model_grid_shard_export/attach``)."""
         from .dist import shard_bounds
         lo, hi = shard_bounds(int(self.desc.grid_w), group.rank, group.world)
-        handle = np.zeros(80, dtype=np.uint8)          # JXB_GRID_HANDLE_BYTES: IPC handle + the band
+        handle = np.zeros(nat.GRID_HANDLE_BYTES, dtype=np.uint8)          # IPC handle + the band
         nat.check(self._lib.jxb_model_grid_shard_export(self.handle, lo, hi, nat.ptr(handle), handle.nbytes))
         table = np.ascontiguousarray(group.all_gather_bytes(handle))
         nat.check(self._lib.jxb_model_grid_shard_attach(self.handle, nat.ptr(table), table.shape[1], group.world))

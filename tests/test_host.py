@@ -492,3 +492,12 @@ def test_facade_step_with_host_side_state_is_not_frozen_into_the_kernel():
     assert m._host_env_keys == {"time"} and m.env.state["time"] == 0           # the trace left the host state alone
     assert "time" not in variants[-1].env_out and "growth_rate" in variants[-1].env_out
     assert dict(variants[-1].metrics)["efficiency"].op != "const"               # 1 / (time * g + 1) reads the env slot
+
+
+def test_handle_sizes_match_the_header():
+    """The host shim sizes the buffers it all-gathers from constants that must follow include/jxb.h."""
+    import re
+    from jaxabm_b200 import _native as nat
+    header = open(os.path.join(ROOT, "include", "jxb.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(JXB_\w+_HANDLE_BYTES)\s+(\d+)", header)}
+    assert defs == {"JXB_IPC_HANDLE_BYTES": nat.IPC_HANDLE_BYTES, "JXB_GRID_HANDLE_BYTES": nat.GRID_HANDLE_BYTES}
