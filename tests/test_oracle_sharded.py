@@ -31,6 +31,28 @@ def test_schelling_row_bands_equal_the_single_grid(world, periodic, mode):
     assert rows[-1][2] > 0
 
 
+@pytest.mark.parametrize("grid,n,world", [(24, 430, 8), (24, 430, 5), (8, 45, 8), (9, 60, 4)])
+@pytest.mark.parametrize("periodic", [False, True])
+def test_schelling_row_bands_many_ranks_uneven_and_one_row_bands(grid, n, world, periodic):
+    """8 ranks (what the 8-GPU runs use), bands of unequal height, and bands of ONE row -- where a row is its
+    owner's first and last row at once and both neighbours hold it as a halo (or, periodic with few rows, the same
+    neighbour twice): the records that keep the halo copies coherent must still go out exactly once per holder."""
+    steps, thr, mode = 6, 0.6, 1
+    om = orules.create_schelling_model(grid, n, seed=3, similarity_threshold=thr, periodic=periodic,
+                                       config=ort.ModelConfig(seed=11, rng_mode=mode))
+    types, pos = orules.schelling_initial_layout(grid, n, 0.5, 3)
+    ores = om.run(steps=steps)
+    ost = om.agent_collections["agents"].states
+    st, rows, E = sharded.schelling_bands_run(grid, types, pos, world, steps, jl.PRNGKey(11), mode, threshold=thr,
+                                              periodic=periodic)
+    for k in ("type", "position", "satisfied", "moves"):
+        assert np.array_equal(st[k], np.asarray(ost[k])), (world, periodic, k)
+    assert [r[2] for r in rows] == [int(v) for v in ores["total_moves"]]
+    ec = np.asarray(om._env_state["empty_cells"])
+    assert np.array_equal(E, ec[:, 0].astype(np.int64) * grid + ec[:, 1])
+    assert rows[-1][2] > 0
+
+
 def test_a_band_never_reads_outside_its_halo():
     """The restatement poisons every row outside [X0-1, X1] of a rank's copy; the sweep asserts it never sees
     one -- here the poison is checked to be in place (so the assertion above is not vacuous)."""
